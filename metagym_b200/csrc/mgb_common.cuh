@@ -1,0 +1,135 @@
+// Shared helpers of libmgb200: error reporting, counter-based RNG, bulk (TMA) copies.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "mgb200.h"
+
+void mgb_set_error(const char *fmt, ...);
+
+#define MGB_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            mgb_set_error("%s -> %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);      \
+            return MGB_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+#define MGB_REQUIRE(cond, msg)                                                                           \
+    do {                                                                                                 \
+        if (!(cond)) {                                                                                   \
+            mgb_set_error("%s: %s", __func__, msg);                                                      \
+            return MGB_ERR_ARG;                                                                          \
+        }                                                                                                \
+    } while (0)
+
+// RAII "make this device current for the duration of the call"
+struct MgbDeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit MgbDeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        want = dev;
+    }
+    ~MgbDeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    int want = -1;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so every env owns a stream keyed by its GLOBAL index and the
+// results do not depend on how envs are sharded over GPUs or blocks.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mgb_mulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 mgb_philox4x32_10(uint4 ctr, uint2 key)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mgb_mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = mgb_mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+// 24-bit uniform in [0, 1)
+__host__ __device__ __forceinline__ float mgb_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// RNG stream ids (ctr.w)
+#define MGB_STREAM_RESET 0x100u   // + j, j = 0..2: twelve reset draws
+#define MGB_STREAM_ACTION 0x200u  // rollout actions
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (the TMA engine's 1-D form: cp.async.bulk, SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mgb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// generic-proxy writes to smem -> visible to the async proxy (must precede a bulk store reading that smem)
+__device__ __forceinline__ void mgb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// smem -> global, bytes % 16 == 0, both 16 B aligned.  Issued by ONE thread.
+__device__ __forceinline__ void mgb_bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(mgb_smem_addr(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mgb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the smem SOURCE of all but the newest n groups has been read (smem reusable)
+template <int N> __device__ __forceinline__ void mgb_bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void mgb_bulk_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// mbarrier + global -> smem bulk load
+__device__ __forceinline__ void mgb_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mgb_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mgb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mgb_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mgb_smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mgb_bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     mgb_smem_addr(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(mgb_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mgb_mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mgb_smem_addr(bar)),
+        "r"(phase)
+        : "memory");
+}

@@ -1,0 +1,917 @@
+// Quadrotor hot path for sm_100a: one thread = one env; the 22-float rigid-body state, the adjugate of the rotation
+// matrix and every substep intermediate live in registers for the whole env.step().
+//
+// Replaces (reference file:line, PaddlePaddle/MetaGym):
+//   QuadrotorSim._run_internal / _check_failure / step      metagym/quadrotor/quadrotorsim.py:122-221, 295-304
+//   QuadrotorSim.get_state / get_sensor / reset              metagym/quadrotor/quadrotorsim.py:239-293
+//   Quadrotor.step / _get_reward / _check_collision / _update_state / _convert_state_to_ndarray
+//                                                             metagym/quadrotor/env.py:127-165, 193-281
+//
+// Data layout in HBM (DESIGN.md "state planes"): six planes of float4, plane k at base + k * n_pad, so that every
+// load/store is one coalesced 128-bit access per thread (512 B contiguous per warp):
+//   P0 = p.x p.y p.z v.x | P1 = v.y v.z w.x w.y | P2 = w.z m0 m1 m2 | P3 = m3 R00 R01 R02
+//   P4 = R10 R11 R12 R20 | P5 = R21 R22 ct(int) episode(int)
+// (p position, v velocity, w body angular velocity, m propeller speeds, R rotation matrix)
+// Observations leave through a shared-memory tile and ONE bulk (TMA) store per CTA, so the [n][obs_dim] row-major
+// array the gym API wants is written with full 128 B lines even though obs_dim*4 (64 or 76 B) is not a line.
+#include <math.h>
+#include <string.h>
+#include <new>
+
+#include "mgb_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kMaxObs = 19;
+
+// Constants derived on the host (double arithmetic, rounded once to float32 -- numpy's "weak python scalar" rule).
+struct QuadConst {
+    float h;         // substep
+    float k1phi;     // (phi/ra)*phi
+    float k1;        // phi/ra
+    float inv_phi;   // 1/phi
+    float hjm;       // h/jm
+    float mm;
+    float ct0, ct1, ct2;
+    float vmin, vmax;
+    float A[4], B[4];      // py*|p|, px*|p|   (inflow term, quadrotorsim.py:149-151)
+    float px[4], py[4], pz[4];
+    float Df[3], Dm[3];
+    float cg[3];
+    float hI[9];           // h * inverse inertia
+    float gm;              // -9.8 * mass
+    float c_hm;            // h / mass
+    float c_h2m;           // 0.5 h^2 / mass
+    float fail_r2, fail_v2, fail_w2;
+    float dt, healthy, z_off;
+    float init_v[3], init_w[3], noise_v, noise_w;
+    int nt, task, substeps, obs_dim;
+    int simple;            // propeller z == 0, cg == 0, diagonal inertia, ct2 == 0
+};
+
+struct QuadArgs {
+    float4 *planes;
+    int64_t n_pad;
+    int64_t n;
+    int64_t env_base;          // global index of local env 0
+    const float *act;          // [n][4]  (rollout: [T][n][4] or null)
+    float *obs;                // [n][D]
+    float *rew;
+    uint8_t *done;
+    int32_t *fail;
+    float *final_obs;
+    const float *targets;      // [n_tasks][nt][3]
+    const int32_t *env2task;   // [n]
+    uint64_t seed;
+    int auto_reset;
+    // rollout only
+    int T;
+    uint64_t act_seed;
+    uint32_t t_base;
+    float *act_out;
+};
+
+struct QState {
+    float p[3], v[3], om[3], w[4], R[9];
+    int ct, ep;
+};
+
+__device__ __forceinline__ void load_state(const QuadArgs &a, int64_t e, QState &s)
+{
+    const float4 q0 = a.planes[0 * a.n_pad + e], q1 = a.planes[1 * a.n_pad + e], q2 = a.planes[2 * a.n_pad + e],
+                 q3 = a.planes[3 * a.n_pad + e], q4 = a.planes[4 * a.n_pad + e], q5 = a.planes[5 * a.n_pad + e];
+    s.p[0] = q0.x; s.p[1] = q0.y; s.p[2] = q0.z; s.v[0] = q0.w;
+    s.v[1] = q1.x; s.v[2] = q1.y; s.om[0] = q1.z; s.om[1] = q1.w;
+    s.om[2] = q2.x; s.w[0] = q2.y; s.w[1] = q2.z; s.w[2] = q2.w;
+    s.w[3] = q3.x; s.R[0] = q3.y; s.R[1] = q3.z; s.R[2] = q3.w;
+    s.R[3] = q4.x; s.R[4] = q4.y; s.R[5] = q4.z; s.R[6] = q4.w;
+    s.R[7] = q5.x; s.R[8] = q5.y; s.ct = __float_as_int(q5.z); s.ep = __float_as_int(q5.w);
+}
+
+__device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const QState &s)
+{
+    a.planes[0 * a.n_pad + e] = make_float4(s.p[0], s.p[1], s.p[2], s.v[0]);
+    a.planes[1 * a.n_pad + e] = make_float4(s.v[1], s.v[2], s.om[0], s.om[1]);
+    a.planes[2 * a.n_pad + e] = make_float4(s.om[2], s.w[0], s.w[1], s.w[2]);
+    a.planes[3 * a.n_pad + e] = make_float4(s.w[3], s.R[0], s.R[1], s.R[2]);
+    a.planes[4 * a.n_pad + e] = make_float4(s.R[3], s.R[4], s.R[5], s.R[6]);
+    a.planes[5 * a.n_pad + e] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct), __int_as_float(s.ep));
+}
+
+// adjugate of R (unscaled inverse) and 1/det; R^-1 = adj * id.  R drifts away from orthogonality (the reference never
+// re-orthonormalises, quadrotorsim.py:193-202), so this is a genuine inverse, not a transpose.
+__device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &id)
+{
+    adj[0] = R[4] * R[8] - R[5] * R[7];
+    adj[3] = R[5] * R[6] - R[3] * R[8];
+    adj[6] = R[3] * R[7] - R[4] * R[6];
+    const float det = R[0] * adj[0] + R[1] * adj[3] + R[2] * adj[6];
+    adj[1] = R[2] * R[7] - R[1] * R[8];
+    adj[2] = R[1] * R[5] - R[2] * R[4];
+    adj[4] = R[0] * R[8] - R[2] * R[6];
+    adj[5] = R[2] * R[3] - R[0] * R[5];
+    adj[7] = R[1] * R[6] - R[0] * R[7];
+    adj[8] = R[0] * R[4] - R[1] * R[3];
+    id = 1.0f / det;
+}
+
+// `substeps` calls of _run_internal.  Returns the fail code (0 = none); power = last substep's electrical power.
+template <bool SIMPLE>
+__device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
+                                         float &power)
+{
+    // voltage clamp (quadrotorsim.py:130-134) and the per-step rotor constants
+    float V[4] = {act.x, act.y, act.z, act.w};
+    float kV[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        V[i] = V[i] > c.vmax ? c.vmax : (V[i] < c.vmin ? c.vmin : V[i]);
+        kV[i] = c.k1 * V[i];
+    }
+    float me[4] = {0.f, 0.f, 0.f, 0.f};
+    int fail = 0;
+    float vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
+    float osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+
+#pragma unroll 1
+    for (int k = 0; k < c.substeps; ++k) {
+        // body-frame velocity R^-1 v (quadrotorsim.py:147-148), shared by the four rotors and the drag term
+        const float bvx = (adj[0] * s.v[0] + adj[1] * s.v[1] + adj[2] * s.v[2]) * id;
+        const float bvy = (adj[3] * s.v[0] + adj[4] * s.v[1] + adj[5] * s.v[2]) * id;
+        const float bvz = (adj[6] * s.v[0] + adj[7] * s.v[1] + adj[8] * s.v[2]) * id;
+        const float vn = sqrtf(vsq);
+        const float on = sqrtf(osq);
+
+        float fz = 0.f, tx = 0.f, ty = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            me[i] = fmaf(-c.k1phi, s.w[i], kV[i]);                         // :136-138
+            const float wm = fmaf(c.hjm, me[i] - c.mm, s.w[i]);            // :141-145
+            const float v1 = fmaf(s.om[0], c.A[i], fmaf(-s.om[1], c.B[i], bvz));  // :146-151
+            float th = wm * fmaf(c.ct0, wm, c.ct1 * v1);                   // :154-156
+            if (!SIMPLE) th = fmaf(c.ct2 * v1, fabsf(v1), th);
+            s.w[i] = wm;
+            fz += th;
+            tx = fmaf(th, c.py[i], tx);                                    // -(0,0,th) x p_i, :160-162
+            ty = fmaf(-th, c.px[i], ty);
+        }
+        const float tz = (me[1] - me[0]) + (me[3] - me[2]);                // :164
+
+        // force: thrust + gravity (R^-1 g m) + drag (-|v| Df R^-1 v), :166-180
+        const float idgm = id * c.gm;
+        const float nvn = -vn, non = -on;
+        const float Fx = fmaf(nvn * c.Df[0], bvx, adj[2] * idgm);
+        const float Fy = fmaf(nvn * c.Df[1], bvy, adj[5] * idgm);
+        const float Fz = fmaf(nvn * c.Df[2], bvz, fmaf(adj[8], idgm, fz));
+        float Tx = fmaf(non * c.Dm[0], s.om[0], tx);
+        float Ty = fmaf(non * c.Dm[1], s.om[1], ty);
+        float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
+        if (!SIMPLE) {  // gravity torque -(f_grav x cg), :177-178
+            const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
+            Tx -= gy * c.cg[2] - gz * c.cg[1];
+            Ty -= gz * c.cg[0] - gx * c.cg[2];
+            Tz -= gx * c.cg[1] - gy * c.cg[0];
+        }
+
+        // translation, :183-187 (1/mass folded into the step constants)
+        const float ax = s.R[0] * Fx + s.R[1] * Fy + s.R[2] * Fz;
+        const float ay = s.R[3] * Fx + s.R[4] * Fy + s.R[5] * Fz;
+        const float az = s.R[6] * Fx + s.R[7] * Fy + s.R[8] * Fz;
+        s.p[0] = fmaf(ax, c.c_h2m, fmaf(s.v[0], c.h, s.p[0]));
+        s.p[1] = fmaf(ay, c.c_h2m, fmaf(s.v[1], c.h, s.p[1]));
+        s.p[2] = fmaf(az, c.c_h2m, fmaf(s.v[2], c.h, s.p[2]));
+        s.v[0] = fmaf(ax, c.c_hm, s.v[0]);
+        s.v[1] = fmaf(ay, c.c_hm, s.v[1]);
+        s.v[2] = fmaf(az, c.c_hm, s.v[2]);
+
+        // rotation, :190-204
+        float ahx, ahy, ahz;  // h * I^-1 * torque
+        if (SIMPLE) {
+            ahx = Tx * c.hI[0]; ahy = Ty * c.hI[4]; ahz = Tz * c.hI[8];
+        } else {
+            ahx = c.hI[0] * Tx + c.hI[1] * Ty + c.hI[2] * Tz;
+            ahy = c.hI[3] * Tx + c.hI[4] * Ty + c.hI[5] * Tz;
+            ahz = c.hI[6] * Tx + c.hI[7] * Ty + c.hI[8] * Tz;
+        }
+        const float hwx = c.h * fmaf(0.5f, ahx, s.om[0]);
+        const float hwy = c.h * fmaf(0.5f, ahy, s.om[1]);
+        const float hwz = c.h * fmaf(0.5f, ahz, s.om[2]);
+        s.om[0] += ahx; s.om[1] += ahy; s.om[2] += ahz;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {   // R += h R [w]x
+            const float r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
+            s.R[3 * r + 0] = fmaf(r1, hwz, fmaf(-r2, hwy, r0));
+            s.R[3 * r + 1] = fmaf(r2, hwx, fmaf(-r0, hwz, r1));
+            s.R[3 * r + 2] = fmaf(r0, hwy, fmaf(-r1, hwx, r2));
+        }
+        adjugate(s.R, adj, id);                                            // :206-208
+
+        // _check_failure, :212-221 (evaluated every substep like the reference)
+        const float psq = s.p[0] * s.p[0] + s.p[1] * s.p[1] + s.p[2] * s.p[2];
+        vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
+        osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+        // the negated form also catches NaN
+        if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {
+            fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR);
+            break;
+        }
+    }
+    // :139,188  power = sum_i |me_i / phi * V_i| of the last executed substep
+    power = ((fabsf(me[0] * c.inv_phi * V[0]) + fabsf(me[1] * c.inv_phi * V[1])) + fabsf(me[2] * c.inv_phi * V[2])) +
+            fabsf(me[3] * c.inv_phi * V[3]);
+    return fail;
+}
+
+// get_state + get_sensor + _convert_state_to_ndarray (quadrotorsim.py:260-293, env.py:193-209)
+// key order: b_v xyz, b xyz, acc xyz, gyro xyz, pitch, roll, yaw, z (+ z_offset)
+__device__ __forceinline__ void observe(const QuadConst &c, const QState &s, const float adj[9], float id, float *o,
+                                        float bv[3], float Ri[9])
+{
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ri[k] = adj[k] * id;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        bv[r] = Ri[3 * r] * s.v[0] + Ri[3 * r + 1] * s.v[1] + Ri[3 * r + 2] * s.v[2];
+        o[r] = bv[r];
+        o[3 + r] = Ri[3 * r] * s.p[0] + Ri[3 * r + 1] * s.p[1] + Ri[3 * r + 2] * s.p[2];
+        o[6 + r] = Ri[3 * r + 2] * -9.8f;    // body_acceleration is never updated (:22,:278): IMU = R^-1 g only
+        o[9 + r] = s.om[r];
+    }
+    o[12] = atan2f(-s.R[6], sqrtf(s.R[7] * s.R[7] + s.R[8] * s.R[8]));   // pitch, :111-120
+    o[13] = atan2f(s.R[7], s.R[8]);                                       // roll
+    o[14] = atan2f(s.R[3], s.R[0]);                                       // yaw
+    o[15] = s.p[2] + c.z_off;
+}
+
+// QuadrotorSim.reset applied to one env with the twelve uniform draws u[12] (quadrotorsim.py:239-258)
+__device__ __forceinline__ void reset_env(const QuadConst &c, QState &s, const double u[12])
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s.p[k] = 0.f;
+        const double sv = u[k] > 0.5 ? 1.0 : -1.0, sw = u[6 + k] > 0.5 ? 1.0 : -1.0;
+        s.v[k] = (float)((double)c.init_v[k] + ((double)c.noise_v * u[3 + k]) * sv);
+        s.om[k] = (float)((double)c.init_w[k] + ((double)c.noise_w * u[9 + k]) * sw);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.w[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s.R[k] = (k % 4 == 0) ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ void philox_reset_draws(uint64_t seed, int64_t genv, int ep, double u[12])
+{
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint4 r = mgb_philox4x32_10(
+            make_uint4((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)ep, MGB_STREAM_RESET + j), key);
+        u[4 * j + 0] = (double)mgb_u01(r.x);
+        u[4 * j + 1] = (double)mgb_u01(r.y);
+        u[4 * j + 2] = (double)mgb_u01(r.z);
+        u[4 * j + 3] = (double)mgb_u01(r.w);
+    }
+}
+
+// Task logic after the integrator: observation, reward, collision, done, counters, optional auto-reset.
+// o[] receives the observation to publish; fo[] the terminal observation (valid iff *had_final).
+__device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &a, int64_t e, QState &s,
+                                            const float adj[9], float id, float z_old, float power, int fail,
+                                            float *o, float &reward, int &done_flag, bool &write_final)
+{
+    float bv[3], Ri[9];
+    observe(c, s, adj, id, o, bv, Ri);
+    const float *trow = nullptr;
+    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
+        trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
+        const int t = s.ct < c.nt - 1 ? s.ct : c.nt - 1;      // env.py:270-274 (ct already incremented)
+        o[16] = __ldg(trow + 3 * t);
+        o[17] = __ldg(trow + 3 * t + 1);
+        o[18] = __ldg(trow + 3 * t + 2);
+    }
+    // energy term, env.py:217
+    reward = -fminf(c.dt * power, c.healthy);
+    int done = 0;
+    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
+        const float *g = trow + 3 * (s.ct - 1);               // env.py:153-157
+        const float g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+        float diff = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) diff += fabsf((Ri[3 * r] * g0 + Ri[3 * r + 1] * g1 + Ri[3 * r + 2] * g2) - bv[r]);
+        reward += -0.001f * diff;
+    } else {
+        // flat-map collision, env.py:248-260: `z_min < np.any(taken_pos)` compares against False == 0
+        const float z_new = s.p[2] + c.z_off;
+        const bool coll = fminf(z_old, z_new) < 0.f;
+        float tr = coll ? 0.f : c.healthy;
+        if (c.task == MGB_TASK_HOVERING_CONTROL) {            // env.py:222-243
+            const float vn = sqrtf(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
+            const float on = sqrtf(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
+            tr -= vn + on;
+            const float zm = fabsf(0.f - s.p[2]);             // pos_0[2] is always 0 (env.py:123, :26)
+            tr += zm < 0.5f ? 10.f : fmaxf(-20.f, 0.5f - zm);
+        }
+        reward += tr;
+        if (coll) { done = 1; s.ct = 0; }                    // env.py:147-150
+    }
+    if (s.ct == c.nt) { done = 1; s.ct = 0; }                // env.py:159-161
+    if (fail) { done = 1; s.ct = 0; }                        // the reference raises (quadrotorsim.py:212-221)
+    done_flag = done;
+    write_final = false;
+    if (done && a.auto_reset) {
+        write_final = true;
+        s.ep += 1;
+        double u[12];
+        philox_reset_draws(a.seed, a.env_base + e, s.ep, u);
+        reset_env(c, s, u);
+    }
+}
+
+// Observation of a freshly reset env (R = I): cheap closed form of observe().
+__device__ __forceinline__ void observe_reset(const QuadConst &c, const QuadArgs &a, int64_t e, const QState &s,
+                                              float *o)
+{
+    o[0] = s.v[0]; o[1] = s.v[1]; o[2] = s.v[2];
+    o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;
+    o[6] = 0.f * -9.8f; o[7] = 0.f * -9.8f; o[8] = -9.8f;
+    o[9] = s.om[0]; o[10] = s.om[1]; o[11] = s.om[2];
+    o[12] = atan2f(-0.f, 1.f); o[13] = 0.f; o[14] = 0.f;
+    o[15] = 0.f + c.z_off;
+    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
+        const float *trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
+        const int t = s.ct < c.nt - 1 ? s.ct : c.nt - 1;
+        o[16] = __ldg(trow + 3 * t); o[17] = __ldg(trow + 3 * t + 1); o[18] = __ldg(trow + 3 * t + 2);
+    }
+}
+
+// Publish a CTA's observation tile: rows of D floats for envs [e0, e0+rows) are contiguous in global memory, so the
+// whole tile is ONE bulk store (UBLKCP) when it is 16-byte sized/aligned; ragged tails fall back to scalar stores.
+__device__ __forceinline__ void publish_tile(float *gobs, const float *tile, int64_t e0, int rows, int D)
+{
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+    float *dst = gobs + e0 * D;
+    if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        mgb_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mgb_bulk_store(dst, tile, bytes);
+            mgb_bulk_commit();
+        }
+    } else {
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tile[i];
+    }
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_constant__ QuadConst c,
+                                                             const __grid_constant__ QuadArgs a)
+{
+    __shared__ __align__(128) float tile[kThreads * kMaxObs];
+    __shared__ __align__(128) float ftile[kThreads * kMaxObs];
+    const int64_t e0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t e = e0 + threadIdx.x;
+    const int rows = (int)((a.n - e0) < kThreads ? (a.n - e0) : kThreads);
+    const int D = c.obs_dim;
+    const bool active = e < a.n;
+    bool any_final = false;
+
+    if (active) {
+        QState s;
+        load_state(a, e, s);
+        const float4 act = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
+        float adj[9], id, power;
+        adjugate(s.R, adj, id);
+        s.ct += 1;                                              // env.py:128
+        const float z_old = s.p[2] + c.z_off;                   // env.py:131-133
+        const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
+        float o[kMaxObs], reward;
+        int done;
+        bool wf;
+        finish_step(c, a, e, s, adj, id, z_old, power, fail, o, reward, done, wf);
+        store_state(a, e, s);
+        a.rew[e] = reward;
+        a.done[e] = (uint8_t)done;
+        if (a.fail) a.fail[e] = fail;
+        float *trow = tile + threadIdx.x * D;
+        if (wf) {
+            if (a.final_obs) {
+                float *frow = ftile + threadIdx.x * D;
+                for (int k = 0; k < D; ++k) frow[k] = o[k];
+                any_final = true;
+            }
+            observe_reset(c, a, e, s, o);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) trow[k] = o[k];
+        if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
+    }
+    publish_tile(a.obs, tile, e0, rows, D);
+    // terminal observations are rare: only CTAs that saw one write them (rows of other envs are left untouched)
+    if (a.final_obs) {
+        if (__syncthreads_or(any_final ? 1 : 0)) {
+            if (active && any_final) {
+                float *dst = a.final_obs + e * D;
+                const float *frow = ftile + threadIdx.x * D;
+                for (int k = 0; k < D; ++k) dst[k] = frow[k];
+            }
+        }
+    }
+    if (threadIdx.x == 0) mgb_bulk_wait<0>();
+}
+
+// T env.step()s in one launch: the state never leaves registers; per step the kernel reads 16 B of action (or draws
+// it) and writes obs/reward/done.  Observation tiles are double-buffered so the bulk store of step t overlaps the
+// arithmetic of step t+1.
+template <bool SIMPLE>
+__global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_constant__ QuadConst c,
+                                                                const __grid_constant__ QuadArgs a)
+{
+    __shared__ __align__(128) float tiles[2][kThreads * kMaxObs];
+    const int64_t e0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t e = e0 + threadIdx.x;
+    const int rows = (int)((a.n - e0) < kThreads ? (a.n - e0) : kThreads);
+    const int D = c.obs_dim;
+    const bool active = e < a.n;
+    QState s;
+    float adj[9], id = 1.f;
+    if (active) {
+        load_state(a, e, s);
+        adjugate(s.R, adj, id);
+    }
+    const uint2 akey = make_uint2((uint32_t)a.act_seed, (uint32_t)(a.act_seed >> 32));
+    const int64_t genv = a.env_base + e;
+    for (int t = 0; t < a.T; ++t) {
+        float *tile = tiles[t & 1];
+        // the bulk store issued two steps ago must have finished READING this tile before we overwrite it
+        if (threadIdx.x == 0) mgb_bulk_wait_read<1>();
+        __syncthreads();
+        if (active) {
+            float4 act;
+            if (a.act) {
+                act = __ldg(reinterpret_cast<const float4 *>(a.act) + (int64_t)t * a.n + e);
+            } else {
+                const uint4 r = mgb_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32),
+                                                             a.t_base + (uint32_t)t, MGB_STREAM_ACTION),
+                                                  akey);
+                const float span = c.vmax - c.vmin;
+                act = make_float4(fmaf(span, mgb_u01(r.x), c.vmin), fmaf(span, mgb_u01(r.y), c.vmin),
+                                  fmaf(span, mgb_u01(r.z), c.vmin), fmaf(span, mgb_u01(r.w), c.vmin));
+                if (a.act_out) reinterpret_cast<float4 *>(a.act_out)[(int64_t)t * a.n + e] = act;
+            }
+            s.ct += 1;
+            const float z_old = s.p[2] + c.z_off;
+            float power;
+            const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
+            float o[kMaxObs], reward;
+            int done;
+            bool wf;
+            finish_step(c, a, e, s, adj, id, z_old, power, fail, o, reward, done, wf);
+            if (wf) {
+                observe_reset(c, a, e, s, o);
+                adjugate(s.R, adj, id);
+            }
+            if (a.rew) a.rew[(int64_t)t * a.n + e] = reward;
+            if (a.done) a.done[(int64_t)t * a.n + e] = (uint8_t)done;
+            if (a.obs) {
+                float *trow = tile + threadIdx.x * D;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) trow[k] = o[k];
+                if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
+            }
+        }
+        if (a.obs) publish_tile(a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
+    }
+    if (active) store_state(a, e, s);
+    if (threadIdx.x == 0) mgb_bulk_wait<0>();
+}
+
+// QuadrotorSim.reset for masked envs + observation of every env (env.py:116-125)
+__global__ void __launch_bounds__(kThreads) quad_reset_kernel(const __grid_constant__ QuadConst c,
+                                                              const __grid_constant__ QuadArgs a,
+                                                              const uint8_t *__restrict__ mask,
+                                                              const double *__restrict__ noise)
+{
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= a.n) return;
+    QState s;
+    load_state(a, e, s);
+    if (!mask || mask[e]) {
+        double u[12];
+        if (noise) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) u[k] = noise[e * 12 + k];
+        } else {
+            s.ep += 1;
+            philox_reset_draws(a.seed, a.env_base + e, s.ep, u);
+        }
+        reset_env(c, s, u);
+        store_state(a, e, s);
+    }
+    if (a.obs) {
+        float adj[9], id, o[kMaxObs], bv[3], Ri[9];
+        adjugate(s.R, adj, id);
+        observe(c, s, adj, id, o, bv, Ri);
+        if (c.task == MGB_TASK_VELOCITY_CONTROL) {
+            const float *trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
+            const int t = s.ct < c.nt - 1 ? s.ct : c.nt - 1;
+            o[16] = trow[3 * t]; o[17] = trow[3 * t + 1]; o[18] = trow[3 * t + 2];
+        }
+        float *dst = a.obs + e * c.obs_dim;
+        for (int k = 0; k < c.obs_dim; ++k) dst[k] = o[k];
+    }
+}
+
+// [n][22] row-major float32 + ct  <->  state planes
+__global__ void quad_state_kernel(QuadArgs a, float *state, int32_t *ct, int load)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    QState s;
+    load_state(a, e, s);
+    float *row = state + e * 22;
+    if (load) {
+        for (int k = 0; k < 3; ++k) { s.p[k] = row[k]; s.v[k] = row[3 + k]; s.om[k] = row[6 + k]; }
+        for (int k = 0; k < 4; ++k) s.w[k] = row[9 + k];
+        for (int k = 0; k < 9; ++k) s.R[k] = row[13 + k];
+        if (ct) s.ct = ct[e];
+        store_state(a, e, s);
+    } else {
+        for (int k = 0; k < 3; ++k) { row[k] = s.p[k]; row[3 + k] = s.v[k]; row[6 + k] = s.om[k]; }
+        for (int k = 0; k < 4; ++k) row[9 + k] = s.w[k];
+        for (int k = 0; k < 9; ++k) row[13 + k] = s.R[k];
+        if (ct) ct[e] = s.ct;
+    }
+}
+
+__global__ void quad_init_kernel(QuadArgs a)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_pad) return;
+    QState s;
+    for (int k = 0; k < 3; ++k) s.p[k] = s.v[k] = s.om[k] = 0.f;
+    for (int k = 0; k < 4; ++k) s.w[k] = 0.f;
+    for (int k = 0; k < 9; ++k) s.R[k] = (k % 4 == 0) ? 1.f : 0.f;
+    s.ct = 0;
+    s.ep = 0;
+    store_state(a, e, s);
+}
+
+// define_velocity_control_task (quadrotorsim.py:306-319): one thread per task seed integrates nt steps from the zero
+// state with host-replayed actions and records global_velocity after every step.
+template <bool SIMPLE>
+__global__ void quad_targets_kernel(const __grid_constant__ QuadConst c, const float *__restrict__ act, int n_tasks,
+                                    float *__restrict__ tbl)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tasks) return;
+    QState s;
+    for (int q = 0; q < 3; ++q) s.p[q] = s.v[q] = s.om[q] = 0.f;
+    for (int q = 0; q < 4; ++q) s.w[q] = 0.f;
+    for (int q = 0; q < 9; ++q) s.R[q] = (q % 4 == 0) ? 1.f : 0.f;
+    s.ct = 0; s.ep = 0;
+    float adj[9], id, power;
+    adjugate(s.R, adj, id);
+    for (int t = 0; t < c.nt; ++t) {
+        const float4 a4 = reinterpret_cast<const float4 *>(act)[(int64_t)k * c.nt + t];
+        const int fail = integrate<SIMPLE>(c, s, a4, adj, id, power);
+        float *dst = tbl + ((int64_t)k * c.nt + t) * 3;
+        dst[0] = s.v[0]; dst[1] = s.v[1]; dst[2] = s.v[2];
+        if (fail) {   // the reference would raise here; fill the rest with NaN so the caller notices
+            for (int r = t + 1; r < c.nt; ++r) {
+                float *d2 = tbl + ((int64_t)k * c.nt + r) * 3;
+                d2[0] = d2[1] = d2[2] = __int_as_float(0x7fc00000);
+            }
+            return;
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// handle + C ABI
+// ---------------------------------------------------------------------------------------------------------------
+struct mgb_quad {
+    int device = 0;
+    int64_t n = 0, n_pad = 0, env_base = 0;
+    mgb_quad_cfg cfg;
+    QuadConst c;
+    float4 *planes = nullptr;
+    float *targets = nullptr;
+    int32_t *env2task = nullptr;
+    int n_tasks = 0;
+    int auto_reset = 0;
+    uint64_t seed = 0;
+    uint32_t t_base = 0;
+    int64_t launches = 0;
+    // host staging for *_host entry points
+    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+    uint8_t *h_done = nullptr;
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+    uint8_t *d_done = nullptr;
+    cudaStream_t hstream[2] = {nullptr, nullptr};
+    cudaEvent_t hevent[2] = {nullptr, nullptr};
+};
+
+static QuadArgs base_args(const mgb_quad *h)
+{
+    QuadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.planes = h->planes;
+    a.n_pad = h->n_pad;
+    a.n = h->n;
+    a.env_base = h->env_base;
+    a.targets = h->targets;
+    a.env2task = h->env2task;
+    a.seed = h->seed;
+    a.auto_reset = h->auto_reset;
+    return a;
+}
+
+static int derive_constants(const mgb_quad_cfg *g, QuadConst *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->h = (float)g->precision;
+    c->k1 = (float)(g->phi / g->ra);
+    c->k1phi = (float)(g->phi / g->ra * g->phi);
+    c->inv_phi = (float)(1.0 / g->phi);
+    c->hjm = (float)(g->precision / g->jm);
+    c->mm = (float)g->mm;
+    c->ct0 = (float)g->ct[0]; c->ct1 = (float)g->ct[1]; c->ct2 = (float)g->ct[2];
+    c->vmin = (float)g->min_voltage; c->vmax = (float)g->max_voltage;
+    bool simple = (g->ct[2] == 0.0);
+    for (int i = 0; i < 4; ++i) {
+        c->px[i] = g->propeller[3 * i]; c->py[i] = g->propeller[3 * i + 1]; c->pz[i] = g->propeller[3 * i + 2];
+        c->A[i] = (float)((double)c->py[i] * (double)g->propeller_norm[i]);
+        c->B[i] = (float)((double)c->px[i] * (double)g->propeller_norm[i]);
+        if (c->pz[i] != 0.f) simple = false;
+    }
+    for (int k = 0; k < 3; ++k) {
+        c->Df[k] = g->drag_f[k]; c->Dm[k] = g->drag_m[k]; c->cg[k] = g->gravity_center[k];
+        if (c->cg[k] != 0.f) simple = false;
+        c->init_v[k] = g->init_velocity[k]; c->init_w[k] = g->init_angular_velocity[k];
+    }
+    for (int k = 0; k < 9; ++k) {
+        c->hI[k] = (float)(g->precision * (double)g->inv_inertia[k]);
+        if (k % 4 != 0 && g->inv_inertia[k] != 0.f) simple = false;
+    }
+    c->gm = (float)((double)(float)-9.8 * g->quality);
+    c->c_hm = (float)(g->precision / g->quality);
+    c->c_h2m = (float)(0.5 * g->precision * g->precision / g->quality);
+    c->fail_r2 = (float)(g->fail_range * g->fail_range);
+    c->fail_v2 = (float)(g->fail_velocity * g->fail_velocity);
+    c->fail_w2 = (float)(g->fail_w * g->fail_w);
+    c->dt = (float)g->dt; c->healthy = (float)g->healthy_reward; c->z_off = (float)g->z_offset;
+    c->noise_v = (float)g->init_velocity_noise; c->noise_w = (float)g->init_angular_velocity_noise;
+    c->nt = g->nt; c->task = g->task;
+    c->substeps = (int)(g->dt / g->precision);          // quadrotorsim.py:302, evaluated in double like python
+    c->obs_dim = g->task == MGB_TASK_VELOCITY_CONTROL ? 19 : 16;
+    c->simple = simple ? 1 : 0;
+    return 0;
+}
+
+extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cfg *cfg, int device,
+                               int64_t env_index_base)
+{
+    MGB_REQUIRE(out && cfg, "null argument");
+    MGB_REQUIRE(n_envs > 0, "n_envs must be positive");
+    MGB_REQUIRE(cfg->task >= 0 && cfg->task <= 2, "invalid task");                 // env.py:55-56
+    MGB_REQUIRE(cfg->nt > 0, "nt must be positive");
+    // quadrotorsim.py:299-300
+    MGB_REQUIRE(!(cfg->precision < 1e-8 || cfg->precision > cfg->dt), "Inproper parameter of precision");
+    int ndev = 0;
+    MGB_CUDA(cudaGetDeviceCount(&ndev));
+    MGB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    MgbDeviceGuard guard(device);
+    mgb_quad *h = new (std::nothrow) mgb_quad();
+    MGB_REQUIRE(h, "out of host memory");
+    h->device = device;
+    h->n = n_envs;
+    h->n_pad = (n_envs + 127) / 128 * 128;
+    h->env_base = env_index_base;
+    h->cfg = *cfg;
+    derive_constants(cfg, &h->c);
+    cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
+    if (e != cudaSuccess) {
+        mgb_set_error("cudaMalloc(state planes, %lld envs) -> %s", (long long)n_envs, cudaGetErrorString(e));
+        delete h;
+        return MGB_ERR_CUDA;
+    }
+    QuadArgs a = base_args(h);
+    quad_init_kernel<<<(unsigned)((h->n_pad + 255) / 256), 256>>>(a);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        mgb_set_error("state init -> %s", cudaGetErrorString(e));
+        cudaFree(h->planes);
+        delete h;
+        return MGB_ERR_CUDA;
+    }
+    h->launches += 1;
+    *out = h;
+    return MGB_OK;
+}
+
+extern "C" void mgb_quad_destroy(mgb_quad *h)
+{
+    if (!h) return;
+    MgbDeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->planes);
+    cudaFree(h->targets);
+    cudaFree(h->env2task);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done);
+    for (int i = 0; i < 2; ++i) {
+        if (h->hstream[i]) cudaStreamDestroy(h->hstream[i]);
+        if (h->hevent[i]) cudaEventDestroy(h->hevent[i]);
+    }
+    delete h;
+}
+
+extern "C" int mgb_quad_obs_dim(const mgb_quad *h) { return h ? h->c.obs_dim : MGB_ERR_ARG; }
+extern "C" int64_t mgb_quad_num_envs(const mgb_quad *h) { return h ? h->n : MGB_ERR_ARG; }
+extern "C" int64_t mgb_quad_launch_count(const mgb_quad *h) { return h ? h->launches : MGB_ERR_ARG; }
+
+extern "C" int mgb_quad_set_options(mgb_quad *h, int auto_reset, uint64_t seed)
+{
+    MGB_REQUIRE(h, "null handle");
+    h->auto_reset = auto_reset ? 1 : 0;
+    h->seed = seed;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_set_targets(mgb_quad *h, const float *tbl_dev, int32_t n_tasks, const int32_t *env2task_dev)
+{
+    MGB_REQUIRE(h && tbl_dev && env2task_dev, "null argument");
+    MGB_REQUIRE(n_tasks > 0, "n_tasks must be positive");
+    MgbDeviceGuard guard(h->device);
+    MGB_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->targets); h->targets = nullptr;
+    cudaFree(h->env2task); h->env2task = nullptr;
+    const size_t tb = sizeof(float) * 3 * (size_t)h->c.nt * (size_t)n_tasks;
+    MGB_CUDA(cudaMalloc(&h->targets, tb));
+    MGB_CUDA(cudaMalloc(&h->env2task, sizeof(int32_t) * h->n));
+    MGB_CUDA(cudaMemcpy(h->targets, tbl_dev, tb, cudaMemcpyDeviceToDevice));
+    MGB_CUDA(cudaMemcpy(h->env2task, env2task_dev, sizeof(int32_t) * h->n, cudaMemcpyDeviceToDevice));
+    h->n_tasks = n_tasks;
+    return MGB_OK;
+}
+
+static int check_ready(const mgb_quad *h)
+{
+    if (h->c.task == MGB_TASK_VELOCITY_CONTROL && !h->targets) {
+        mgb_set_error("velocity_control: call mgb_quad_set_targets before reset/step");
+        return MGB_ERR_STATE;
+    }
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_make_targets(mgb_quad *h, const float *act_dev, int32_t n_tasks, float *tbl_dev, void *stream)
+{
+    MGB_REQUIRE(h && act_dev && tbl_dev, "null argument");
+    MGB_REQUIRE(n_tasks > 0, "n_tasks must be positive");
+    MgbDeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 32, blocks = (n_tasks + threads - 1) / threads;
+    if (h->c.simple) quad_targets_kernel<true><<<blocks, threads, 0, st>>>(h->c, act_dev, n_tasks, tbl_dev);
+    else quad_targets_kernel<false><<<blocks, threads, 0, st>>>(h->c, act_dev, n_tasks, tbl_dev);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_reset(mgb_quad *h, const uint8_t *mask_dev, const double *noise_dev, float *obs_dev,
+                              void *stream)
+{
+    MGB_REQUIRE(h, "null handle");
+    int rc = check_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    QuadArgs a = base_args(h);
+    a.obs = obs_dev;
+    quad_reset_kernel<<<(unsigned)((h->n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        h->c, a, mask_dev, noise_dev);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}
+
+static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
+{
+    const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
+    if (h->c.simple) quad_step_kernel<true><<<blocks, kThreads, 0, st>>>(h->c, a);
+    else quad_step_kernel<false><<<blocks, kThreads, 0, st>>>(h->c, a);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_step(mgb_quad *h, const float *act_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev,
+                             int32_t *fail_dev, float *final_obs_dev, void *stream)
+{
+    MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
+    MGB_REQUIRE((reinterpret_cast<uintptr_t>(act_dev) & 15u) == 0, "act_dev must be 16-byte aligned");
+    int rc = check_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    QuadArgs a = base_args(h);
+    a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev; a.fail = fail_dev;
+    a.final_obs = final_obs_dev;
+    return launch_step(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, uint64_t act_seed, float *act_out_dev,
+                                float *obs_dev, float *rew_dev, uint8_t *done_dev, void *stream)
+{
+    MGB_REQUIRE(h, "null handle");
+    MGB_REQUIRE(T > 0, "T must be positive");
+    MGB_REQUIRE((reinterpret_cast<uintptr_t>(act_dev) & 15u) == 0, "act_dev must be 16-byte aligned");
+    int rc = check_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    QuadArgs a = base_args(h);
+    a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev;
+    a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
+    const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
+    if (h->c.simple) quad_rollout_kernel<true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    else quad_rollout_kernel<false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    MGB_CUDA(cudaGetLastError());
+    h->t_base += (uint32_t)T;
+    h->launches += 1;
+    return MGB_OK;
+}
+
+static int ensure_host_staging(mgb_quad *h)
+{
+    if (h->d_act) return MGB_OK;
+    const size_t n = (size_t)h->n, D = (size_t)h->c.obs_dim;
+    MGB_CUDA(cudaMalloc(&h->d_act, n * 16));
+    MGB_CUDA(cudaMalloc(&h->d_obs, n * D * 4));
+    MGB_CUDA(cudaMalloc(&h->d_rew, n * 4));
+    MGB_CUDA(cudaMalloc(&h->d_done, n));
+    MGB_CUDA(cudaMallocHost(&h->h_act, n * 16));
+    MGB_CUDA(cudaMallocHost(&h->h_obs, n * D * 4));
+    MGB_CUDA(cudaMallocHost(&h->h_rew, n * 4));
+    MGB_CUDA(cudaMallocHost(&h->h_done, n));
+    for (int i = 0; i < 2; ++i) {
+        MGB_CUDA(cudaStreamCreateWithFlags(&h->hstream[i], cudaStreamNonBlocking));
+        MGB_CUDA(cudaEventCreateWithFlags(&h->hevent[i], cudaEventDisableTiming));
+    }
+    return MGB_OK;
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host,
+                                  uint8_t *done_host)
+{
+    MGB_REQUIRE(h && act_host && obs_host && rew_host && done_host, "null argument");
+    int rc = check_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->n, D = (size_t)h->c.obs_dim;
+    cudaStream_t st = h->hstream[0];
+    // Pinned caller buffers are DMA'd directly; pageable ones go through the handle's pinned staging area.
+    const bool pin_in = is_pinned(act_host);
+    const bool pin_out = is_pinned(obs_host) && is_pinned(rew_host) && is_pinned(done_host);
+    const float *src = act_host;
+    if (!pin_in) { memcpy(h->h_act, act_host, n * 16); src = h->h_act; }
+    MGB_CUDA(cudaMemcpyAsync(h->d_act, src, n * 16, cudaMemcpyHostToDevice, st));
+    QuadArgs a = base_args(h);
+    a.act = h->d_act; a.obs = h->d_obs; a.rew = h->d_rew; a.done = h->d_done;
+    rc = launch_step(h, a, st);
+    if (rc) return rc;
+    float *o = pin_out ? obs_host : h->h_obs;
+    float *r = pin_out ? rew_host : h->h_rew;
+    uint8_t *d = pin_out ? done_host : h->h_done;
+    MGB_CUDA(cudaMemcpyAsync(o, h->d_obs, n * D * 4, cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaMemcpyAsync(r, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaMemcpyAsync(d, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaStreamSynchronize(st));
+    if (!pin_out) {
+        memcpy(obs_host, h->h_obs, n * D * 4);
+        memcpy(rew_host, h->h_rew, n * 4);
+        memcpy(done_host, h->h_done, n);
+    }
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_state(mgb_quad *h, float *state_dev, int32_t *ct_dev, int load, void *stream)
+{
+    MGB_REQUIRE(h && state_dev, "null argument");
+    MgbDeviceGuard guard(h->device);
+    QuadArgs a = base_args(h);
+    quad_state_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, state_dev, ct_dev, load);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}

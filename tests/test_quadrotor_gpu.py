@@ -1,0 +1,323 @@
+"""GPU parity tests of the quadrotor path: libmgb200 (through the C ABI / BatchedQuadrotor) against
+ (a) golden vectors recorded from the unmodified reference (tests/golden/quadrotor_golden.npz), and
+ (b) the CPU oracle (oracle/quad_oracle.c) on seeded random batches,
+plus size-independent properties at the BASELINE.json sizes (65 536 envs).
+
+Tolerance: the north star asks for 1e-5 relative fp32 per step; teacher-forced single steps are asserted at 1e-5
+(typically ~3e-7), free runs with an envelope that grows with the horizon (SURVEY.md 8c measured the reference's own
+f32-vs-f64 drift at 7e-6 after 100 steps).
+"""
+import numpy as np
+import pytest
+
+from util import OBS_GROUPS, QUAD_RUNS, STATE_GROUPS, golden_run, group_rel_err, scalar_rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL_STEP = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_mod(cuda_device):
+    import torch
+    return torch
+
+
+def make_env(n, task="hovering_control", **kw):
+    from metagym_b200 import BatchedQuadrotor
+    return BatchedQuadrotor(task=task, num_envs=n, device=0, squeeze=False, **kw)
+
+
+def set_state(env, state, ct):
+    import torch
+    env.load_state_dict({"state": torch.as_tensor(np.asarray(state, dtype=np.float32)),
+                         "ct": torch.as_tensor(np.asarray(ct, dtype=np.int32))})
+
+
+def get_state(env):
+    sd = env.state_dict()
+    return sd["state"].cpu().numpy().astype(np.float64), sd["ct"].cpu().numpy()
+
+
+def test_kat_zero_state(torch_mod, quad_golden):
+    torch = torch_mod
+    env = make_env(1, "no_collision")
+    act = torch.tensor([[5.0, 6.0, 7.0, 8.0]], device="cuda")
+    env.step(act)
+    st, ct = get_state(env)
+    assert group_rel_err(st, quad_golden["kat1_state"][None], STATE_GROUPS, floor=1e-12) < RTOL_STEP
+    assert ct[0] == 1
+    env.close()
+
+
+def test_kat_200_steps(torch_mod, quad_golden):
+    torch = torch_mod
+    env = make_env(1, "velocity_control", nt=1000, seed=0)   # velocity_control: no floor, so the fall continues
+    ref = quad_golden["kat2_states"]
+    act = torch.full((1, 4), 5.0, device="cuda")
+    for t in range(200):
+        env.step(act)
+        if t % 20 == 19:
+            st, _ = get_state(env)
+            assert group_rel_err(st, ref[t][None], STATE_GROUPS) < 5e-5
+    env.close()
+
+
+@pytest.mark.parametrize("name", QUAD_RUNS)
+def test_teacher_forced_vs_reference(torch_mod, quad_golden, name):
+    """Every recorded (state, ct, action) of a reference episode becomes one env of a batch; one step; compare."""
+    torch = torch_mod
+    r = golden_run(quad_golden, name)
+    n = r["pre_state"].shape[0]
+    kw = dict(dt=r["dt"], nt=r["nt"])
+    if r["task"] == "velocity_control":
+        kw["seed"] = r["seed"]
+    env = make_env(n, r["task"], **kw)
+    if r["task"] == "velocity_control":
+        tbl = env.velocity_targets.cpu().numpy()[0]
+        assert np.abs(tbl - r["targets"]).max() < 1e-5 * max(1.0, np.abs(r["targets"]).max())
+        # use the reference's own table so the comparison below isolates the step
+        env._lib.mgb_quad_set_targets(env._h, torch.as_tensor(r["targets"][None]).cuda().contiguous().data_ptr(), 1,
+                                      env.env2task.data_ptr())
+    set_state(env, r["pre_state"], r["pre_ct"])
+    obs, rew, done, info = env.step(torch.as_tensor(r["act"]).cuda())
+    st, ct = get_state(env)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    assert group_rel_err(st, r["post_state"], STATE_GROUPS) < RTOL_STEP
+    assert group_rel_err(obs[:, :16], r["obs"][:, :16], OBS_GROUPS) < RTOL_STEP
+    if r["task"] == "velocity_control":
+        assert np.array_equal(obs[:, 16:], r["obs"][:, 16:])
+    assert scalar_rel_err(rew, r["rew"]) < RTOL_STEP
+    assert np.array_equal(done, r["done"])
+    assert np.array_equal(ct, r["post_ct"])
+    assert not env.fail_code.cpu().numpy().any()
+    assert "next_target_g_v_x" in info or r["task"] != "velocity_control"     # reference test_env.py:37
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["hover_a", "hover_fall", "nocol_a", "vel_a", "vel_c"])
+def test_free_run_vs_reference(torch_mod, quad_golden, name):
+    """Whole reference episodes (reset noise replayed, ct carried across episodes like the reference object)."""
+    torch = torch_mod
+    r = golden_run(quad_golden, name)
+    kw = dict(dt=r["dt"], nt=r["nt"])
+    if r["task"] == "velocity_control":
+        kw["seed"] = r["seed"]
+    env = make_env(1, r["task"], **kw)
+    ep = r["ep"]
+    for k in range(int(ep.max()) + 1):
+        idx = np.nonzero(ep == k)[0]
+        o0 = env.reset(noise=r["reset_noise"][k][None]).cpu().numpy()
+        assert group_rel_err(o0[:, :16], r["reset_obs"][k][None, :16], OBS_GROUPS) < 1e-6
+        if r["task"] == "velocity_control":
+            assert np.abs(o0[0, 16:] - r["reset_obs"][k][16:]).max() < 1e-5
+        for j, i in enumerate(idx):
+            obs, rew, done, _ = env.step(torch.as_tensor(r["act"][i][None]).cuda())
+            tol = 5e-6 * (1 + j)
+            o = obs.cpu().numpy()
+            assert group_rel_err(o[:, :16], r["obs"][i][None, :16], OBS_GROUPS) < tol, (k, j)
+            assert bool(done.cpu().numpy()[0]) == bool(r["done"][i]), (k, j)
+            assert scalar_rel_err(rew.cpu().numpy(), r["rew"][i]) < max(tol, 1e-5), (k, j)
+        _, ct = get_state(env)
+        assert ct[0] == r["post_ct"][idx[-1]]
+    env.close()
+
+
+@pytest.mark.parametrize("task,dt", [("hovering_control", 0.01), ("velocity_control", 0.005), ("no_collision", 0.01)])
+@pytest.mark.parametrize("n", [1, 127, 129, 4096])
+def test_random_batch_vs_oracle(torch_mod, task, dt, n):
+    """Seeded random batch: 20 free-running steps on GPU vs the CPU oracle (mixed-precision mode)."""
+    torch = torch_mod
+    from oracle import quad_oracle as qo
+    cfg = qo.make_cfg()
+    rng = np.random.RandomState(1234 + n)
+    nt = 30
+    env = make_env(n, task, dt=dt, nt=nt, seed=[0, 1, 2])
+    noise = rng.random_sample((n, 12))
+    env.reset(noise=noise)
+    state = qo.reset_state(None, noise)
+    ct = np.zeros(n, np.int32)
+    kw = {}
+    if task == "velocity_control":
+        kw = dict(targets=env.velocity_targets.cpu().numpy(), env2task=env.env2task.cpu().numpy())
+    for t in range(20):
+        act = rng.uniform(-1.0, 16.0, (n, 4)).astype(np.float32)
+        obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
+        o_ref, r_ref, d_ref, f_ref, _ = qo.env_step(cfg, state, ct, act, task, dt, nt, mode="mix", **kw)
+        tol = 3e-6 * (1 + t)
+        assert group_rel_err(obs.cpu().numpy()[:, :16], o_ref[:, :16], OBS_GROUPS) < tol, t
+        assert scalar_rel_err(rew.cpu().numpy(), r_ref) < max(tol, 1e-5), t
+        assert np.array_equal(done.cpu().numpy(), d_ref.astype(bool)), t
+    st, ct_gpu = get_state(env)
+    assert group_rel_err(st, state, STATE_GROUPS) < 1e-4
+    assert np.array_equal(ct_gpu, ct)
+    env.close()
+
+
+def test_general_config_path_vs_oracle(torch_mod, tmp_path):
+    """A config that leaves the specialised kernel (off-diagonal inertia, raised rotors, cg offset, CT2 != 0)."""
+    import copy
+    import json
+    torch = torch_mod
+    from oracle import quad_oracle as qo
+    from metagym_b200.quadrotor import DEFAULT_SIMULATOR_CONF
+    conf = copy.deepcopy(DEFAULT_SIMULATOR_CONF)
+    conf["inertia"].update(xy=0.001, xz=-0.0005, yz=0.0007)
+    conf["gravity_center"] = {"x": 0.01, "y": -0.02, "z": 0.015}
+    conf["thrust"]["CT"][2] = "1.0e-3"
+    for i, z in enumerate([0.02, -0.01, 0.03, 0.0]):
+        conf["propeller"][i]["z"] = z
+    path = tmp_path / "conf.json"
+    path.write_text(json.dumps(conf))
+    cfg = qo.make_cfg(conf)
+    n, dt, nt = 512, 0.01, 1000
+    rng = np.random.RandomState(5)
+    env = make_env(n, "hovering_control", dt=dt, nt=nt, simulator_conf=str(path))
+    noise = rng.random_sample((n, 12))
+    env.reset(noise=noise)
+    state = qo.reset_state(conf, noise)
+    ct = np.zeros(n, np.int32)
+    for t in range(10):
+        act = rng.uniform(0.1, 15.0, (n, 4)).astype(np.float32)
+        obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
+        o_ref, r_ref, d_ref, _, _ = qo.env_step(cfg, state, ct, act, "hovering_control", dt, nt, mode="mix")
+        assert group_rel_err(obs.cpu().numpy(), o_ref, OBS_GROUPS) < 3e-6 * (1 + t)
+        assert scalar_rel_err(rew.cpu().numpy(), r_ref) < 1e-5
+    env.close()
+
+
+def test_velocity_task_generator_vs_reference(torch_mod, quad_golden):
+    """mgb_quad_make_targets == define_velocity_control_task (quadrotorsim.py:306-319) for seeds 0..5."""
+    env = make_env(6, "velocity_control", dt=0.005, nt=40, seed=list(range(6)))
+    tbl = env.velocity_targets.cpu().numpy()
+    ref = quad_golden["veltask_tables"]
+    scale = np.maximum(np.abs(ref).max(axis=2, keepdims=True), 1e-3)
+    assert (np.abs(tbl - ref) / scale).max() < 2e-5
+    env.close()
+
+
+def test_failure_codes(torch_mod):
+    torch = torch_mod
+    env = make_env(4, "hovering_control")
+    st = np.zeros((4, 22), np.float32)
+    st[:, 13] = st[:, 17] = st[:, 21] = 1.0
+    st[0, 3] = 150.0
+    st[1, 6] = 2000.0
+    st[2, 0] = 1500.0
+    set_state(env, st, np.zeros(4, np.int32))
+    obs, rew, done, _ = env.step(torch.full((4, 4), 5.0, device="cuda"))
+    assert env.fail_code.cpu().tolist() == [2, 3, 1, 0]
+    assert done.cpu().tolist() == [True, True, True, False]
+    with pytest.raises(Exception, match="too large velocity"):
+        env.raise_on_failure()
+    env.close()
+
+
+def test_host_path_equals_device_path(torch_mod):
+    torch = torch_mod
+    n = 1000
+    rng = np.random.RandomState(3)
+    noise = rng.random_sample((n, 12))
+    a = make_env(n)
+    b = make_env(n)
+    a.reset(noise=noise)
+    b.reset(noise=noise)
+    for t in range(3):
+        act = rng.uniform(0.1, 15, (n, 4)).astype(np.float32)
+        o1, r1, d1, _ = a.step(torch.as_tensor(act).cuda())
+        o2, r2, d2, _ = b.step(act)                       # numpy in -> host path -> numpy out
+        assert isinstance(o2, np.ndarray)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+    a.close()
+    b.close()
+
+
+def test_single_env_is_reference_shaped(torch_mod):
+    from metagym_b200 import BatchedQuadrotor
+    env = BatchedQuadrotor(task="velocity_control", num_envs=1, nt=10, dt=0.01)
+    o = env.reset()
+    assert tuple(o.shape) == (19,)
+    step = 0
+    done = False
+    while not done:                                        # reference tests/test_env.py:31-40
+        o, r, done, info = env.step(env.action_space.sample())
+        assert "next_target_g_v_x" in info
+        done = bool(done)
+        step += 1
+    assert step == env.nt
+    env.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: properties that do not need the oracle
+# ----------------------------------------------------------------------------------------------------------------
+def test_full_size_sharding_invariance_and_rollout(torch_mod):
+    """65 536 envs (config 3): (i) two half-size handles with env_index_base reproduce one full handle bit for bit,
+    auto-reset noise included; (ii) the fused T-step rollout kernel equals T single-step launches bit for bit."""
+    torch = torch_mod
+    N, T = 65536, 12
+    kw = dict(dt=0.005, nt=8, seed=list(range(64)), auto_reset=True, rng_seed=77)
+    full = make_env(N, "velocity_control", **kw)
+    lo = make_env(N // 2, "velocity_control", env_index_base=0, **kw)
+    hi = make_env(N // 2, "velocity_control", env_index_base=N // 2, **kw)
+    fused = make_env(N, "velocity_control", **kw)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.rand((T, N, 4), device="cuda", generator=g) * 14.9 + 0.1
+    for e in (full, lo, hi, fused):
+        e.reset()
+    out = fused.rollout(T, actions=acts)
+    n_done = 0
+    for t in range(T):
+        o, r, d, _ = full.step(acts[t])
+        o1, r1, d1, _ = lo.step(acts[t, : N // 2])
+        o2, r2, d2, _ = hi.step(acts[t, N // 2:])
+        assert torch.equal(o, torch.cat([o1, o2])) and torch.equal(r, torch.cat([r1, r2]))
+        assert torch.equal(d, torch.cat([d1, d2]))
+        assert torch.equal(out["obs"][t], o) and torch.equal(out["rew"][t], r)
+        assert torch.equal(out["done"][t].bool(), d)
+        assert torch.isfinite(o).all()
+        n_done += int(d.sum())
+    assert n_done == N                      # nt = 8: every env finishes exactly once in 12 steps
+    s1, s2 = full.state_dict(), fused.state_dict()
+    assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
+    for e in (full, lo, hi, fused):
+        e.close()
+
+
+def test_full_size_hover_invariants(torch_mod):
+    """4096- and 65 536-env hovering batches: outputs finite, done <=> floor contact or time limit, determinism."""
+    torch = torch_mod
+    for N in (4096, 65536):
+        a = make_env(N, "hovering_control", nt=50, auto_reset=True, rng_seed=5)
+        b = make_env(N, "hovering_control", nt=50, auto_reset=True, rng_seed=5)
+        a.reset()
+        b.reset()
+        ra = a.rollout(60, act_seed=9, want_actions=True)
+        rb = b.rollout(60, act_seed=9)
+        assert torch.equal(ra["obs"], rb["obs"]) and torch.equal(ra["rew"], rb["rew"])
+        assert torch.isfinite(ra["obs"]).all() and torch.isfinite(ra["rew"]).all()
+        assert float(ra["act"].min()) >= 0.1 and float(ra["act"].max()) <= 15.0
+        # every env hits the nt = 50 limit once (random actions do not reach the floor 5 m below in 0.5 s)
+        assert int(ra["done"].sum()) >= N
+        a.close()
+        b.close()
+
+
+def test_auto_reset_publishes_first_obs_and_final_obs(torch_mod):
+    torch = torch_mod
+    n = 256
+    env = make_env(n, "no_collision", nt=3, auto_reset=True, rng_seed=1)
+    env.reset()
+    act = torch.full((n, 4), 5.0, device="cuda")
+    for t in range(3):
+        obs, rew, done, _ = env.step(act)
+    assert bool(done.all())
+    # after auto-reset: R = I, position 0 -> body position 0, z = 5, |v| <= 2*sqrt(3), episode counter restarted
+    o = obs.cpu().numpy()
+    assert np.all(o[:, 3:6] == 0) and np.all(o[:, 15] == 5.0) and np.all(np.abs(o[:, 0:3]) <= 2.0)
+    f = env.final_observation.cpu().numpy()
+    assert np.all(np.abs(f[:, 15] - 5.0) > 0) and np.isfinite(f).all()
+    st, ct = get_state(env)
+    assert np.all(ct == 0) and np.all(st[:, 0:3] == 0)
+    env.close()

@@ -1,0 +1,103 @@
+"""CPU: pin the oracle (oracle/quad_oracle.c) against golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+from oracle import quad_oracle as qo
+from util import OBS_GROUPS, QUAD_RUNS, STATE_GROUPS, golden_run, group_rel_err, scalar_rel_err
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return qo.make_cfg()
+
+
+def test_kat_zero_state_one_step(quad_golden, cfg):
+    # never-reset simulator: all-float32 mode; agreement is at the float32 rounding level
+    s = qo.zero_state(1)
+    power, fail = qo.sim_step(cfg, s, np.array([[5, 6, 7, 8]], np.float32), 10, "f32")
+    assert group_rel_err(s, quad_golden["kat1_state"][None], STATE_GROUPS, floor=1e-12) < 2e-6
+    assert abs(power[0] - float(quad_golden["kat1_power"])) < 1e-3
+    assert fail[0] == 0
+
+
+def test_kat_200_steps(quad_golden, cfg):
+    s = qo.zero_state(1)
+    ref = quad_golden["kat2_states"]
+    for t in range(200):
+        qo.sim_step(cfg, s, np.array([[5, 5, 5, 5]], np.float32), 10, "f32")
+        assert group_rel_err(s, ref[t][None], STATE_GROUPS) < 2e-5
+    # SURVEY.md 8c quotes p_z=-2.3465273, v_z=-0.5655445, prop_w=283.22287 for this trajectory
+    assert abs(ref[-1][2] - (-2.3465273)) < 1e-5 and abs(ref[-1][9] - 283.22287) < 1e-3
+
+
+@pytest.mark.parametrize("name", QUAD_RUNS)
+def test_teacher_forced_step(quad_golden, cfg, name):
+    """One env.step from every recorded pre-step state of the reference (mixed precision after reset())."""
+    r = golden_run(quad_golden, name)
+    state = np.array(r["pre_state"], dtype=np.float64)
+    ct = np.array(r["pre_ct"], dtype=np.int32)
+    n = state.shape[0]
+    kw = {}
+    if r["task"] == "velocity_control":
+        kw = dict(targets=r["targets"][None], env2task=np.zeros(n, np.int32))
+    obs, rew, done, fail, power = qo.env_step(cfg, state, ct, r["act"], r["task"], r["dt"], r["nt"], mode="mix", **kw)
+    assert group_rel_err(state, r["post_state"], STATE_GROUPS) < 1e-6
+    assert group_rel_err(obs[:, :16], r["obs"][:, :16], OBS_GROUPS) < 1e-6
+    if r["task"] == "velocity_control":
+        assert np.array_equal(obs[:, 16:], r["obs"][:, 16:])
+    assert scalar_rel_err(rew, r["rew"]) < 1e-6
+    assert np.array_equal(done.astype(bool), r["done"])
+    assert np.array_equal(ct, r["post_ct"])
+    assert scalar_rel_err(power, r["power"]) < 1e-6
+    assert not fail.any()
+
+
+@pytest.mark.parametrize("name", ["hover_a", "vel_a", "nocol_a"])
+def test_free_run_with_reset_replay(quad_golden, cfg, name):
+    """Whole episodes from the replayed reset noise; the envelope grows with the horizon."""
+    r = golden_run(quad_golden, name)
+    ep = r["ep"]
+    for k in range(int(ep.max()) + 1):
+        idx = np.nonzero(ep == k)[0]
+        state = qo.reset_state(None, r["reset_noise"][k][None])
+        ct = np.array([r["reset_ct"][k]], np.int32)
+        assert np.array_equal(state[0], r["pre_state"][idx[0]])
+        kw = {}
+        if r["task"] == "velocity_control":
+            kw = dict(targets=r["targets"][None], env2task=np.zeros(1, np.int32))
+        for j, i in enumerate(idx[:100]):
+            obs, rew, done, fail, _ = qo.env_step(cfg, state, ct, r["act"][i][None], r["task"], r["dt"], r["nt"],
+                                                  mode="mix", **kw)
+            tol = 2e-6 * (1 + j)
+            assert group_rel_err(obs[:, :16], r["obs"][i][None, :16], OBS_GROUPS) < tol
+            assert bool(done[0]) == bool(r["done"][i])
+
+
+def test_f64_arbiter_close_to_mix(quad_golden, cfg):
+    r = golden_run(quad_golden, "hover_a")
+    for mode, tol in (("f32", 3e-6), ("f64", 3e-6)):
+        state = np.array(r["pre_state"], dtype=np.float64)
+        ct = np.array(r["pre_ct"], dtype=np.int32)
+        qo.env_step(cfg, state, ct, r["act"], r["task"], r["dt"], r["nt"], mode=mode)
+        assert group_rel_err(state, r["post_state"], STATE_GROUPS) < tol
+
+
+def test_velocity_task_tables(quad_golden, cfg):
+    """define_velocity_control_task (quadrotorsim.py:306-319) re-derived: seeded actions + float32 integration."""
+    from metagym_b200.quadrotor import DEFAULT_SIMULATOR_CONF, velocity_task_actions
+    ref = quad_golden["veltask_tables"]
+    for seed in range(ref.shape[0]):
+        acts = velocity_task_actions(DEFAULT_SIMULATOR_CONF, 40, seed)
+        s = qo.zero_state(1)
+        for t in range(40):
+            qo.sim_step(cfg, s, acts[t][None], 5, "f32")
+            assert np.abs(s[0, 3:6] - ref[seed, t]).max() < 1e-5 * max(1.0, np.abs(ref[seed, t]).max())
+
+
+def test_failure_detection(cfg):
+    s = qo.zero_state(3)
+    s[0, 3] = 150.0      # |v| > 100
+    s[1, 6] = 2000.0     # |w| > 1000
+    s[2, 0] = 1500.0     # |p| > 1000
+    _, fail = qo.sim_step(cfg, s, np.full((3, 4), 5, np.float32), 10, "mix")
+    assert list(fail) == [2, 3, 1]
