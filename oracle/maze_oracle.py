@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE -- ctypes front end of oracle/maze_oracle.c (CPU restatement of the MetaMaze path).
+
+`OracleMaze` mirrors the call sequence of the reference envs (metagym/metamaze/envs/maze_env.py:16-75,155-206):
+set_task(TaskConfig-like) -> reset() -> step(action) -> (obs, reward, done, info).  One instance = one env.
+"""
+import ctypes
+
+import numpy as np
+
+from . import build as _build
+
+c_i32, c_f64 = ctypes.c_int32, ctypes.c_double
+MAX_N = 31
+
+
+class _Cfg(ctypes.Structure):
+    _fields_ = [("n", c_i32), ("task_type", c_i32), ("max_steps", c_i32), ("view_grid", c_i32), ("res_h", c_i32),
+                ("res_v", c_i32), ("max_vision", c_f64), ("fov", c_f64), ("l_focal", c_f64), ("text_size", c_f64)]
+
+
+class _Task(ctypes.Structure):
+    _fields_ = [("start", c_i32 * 2), ("goal", c_i32 * 2), ("cell_size", c_f64), ("wall_height", c_f64),
+                ("agent_height", c_f64), ("initial_life", c_f64), ("max_life", c_f64), ("step_reward", c_f64),
+                ("goal_reward", c_f64)]
+
+
+class _Env(ctypes.Structure):
+    _fields_ = [("gx", c_i32), ("gy", c_i32), ("ori", c_i32), ("steps", c_i32), ("life", c_f64),
+                ("cur_food", c_f64 * (MAX_N * MAX_N)), ("revival", c_i32 * (MAX_N * MAX_N)),
+                ("wait", c_i32 * (MAX_N * MAX_N))]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(_build.build())
+        assert _lib.mo_env_size() == ctypes.sizeof(_Env)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class OracleMaze(object):
+    def __init__(self, kind, task_type="SURVIVAL", max_steps=200, view_grid=1, resolution=(128, 128), textures=None,
+                 max_vision=12.0, fov=0.6 * 3.1415926, l_focal=0.20, text_size=1.0):
+        assert kind in ("2D", "3D")
+        self.kind = kind
+        self.cfg = _Cfg()
+        self.cfg.task_type = {"SURVIVAL": 0, "ESCAPE": 1}[task_type]
+        self.cfg.max_steps = max_steps
+        self.cfg.view_grid = view_grid
+        self.cfg.res_h, self.cfg.res_v = resolution
+        self.cfg.max_vision, self.cfg.fov, self.cfg.l_focal, self.cfg.text_size = max_vision, fov, l_focal, text_size
+        if kind == "3D":
+            grounds, ceil = textures
+            self.tex = np.ascontiguousarray(grounds, dtype=np.uint8)
+            self.ceil = np.ascontiguousarray(ceil, dtype=np.uint8)
+            self.ts = self.tex.shape[1]
+            assert self.tex.shape[1:] == (self.ts, self.ts, 3) and self.ceil.shape == (self.ts, self.ts, 3)
+        self.env = _Env()
+        self.need_task = True
+
+    def set_task(self, task):
+        n = int(np.shape(task.cell_walls)[0])
+        assert n <= MAX_N
+        self.cfg.n = n
+        self.walls = np.ascontiguousarray(task.cell_walls, dtype=np.int8)
+        self.texts = np.ascontiguousarray(task.cell_texts, dtype=np.int8)
+        self.food = np.ascontiguousarray(task.food_rewards, dtype=np.float64)
+        self.interval = np.ascontiguousarray(task.food_interval, dtype=np.int32)
+        t = _Task()
+        t.start[:] = [int(task.start[0]), int(task.start[1])]
+        t.goal[:] = [int(task.goal[0]), int(task.goal[1])]
+        t.cell_size, t.wall_height, t.agent_height = task.cell_size, task.wall_height, task.agent_height
+        t.initial_life, t.max_life = task.initial_life, task.max_life
+        t.step_reward, t.goal_reward = task.step_reward, task.goal_reward
+        self.task = t
+        self.need_task = False
+
+    def _observe(self):
+        L = lib()
+        if self.kind == "2D":
+            w = 2 * self.cfg.view_grid + 1
+            obs = np.zeros((w, w), dtype=np.float32)
+            L.mo_observe_2d(ctypes.byref(self.cfg), ctypes.byref(self.task), ctypes.byref(self.env), _p(self.walls),
+                            _p(obs))
+            return obs
+        H, V = self.cfg.res_h, self.cfg.res_v
+        obs = np.zeros((H, V, 3), dtype=np.int32)
+        scratch = np.zeros((H, V), dtype=np.float32)
+        L.mo_observe_3d(ctypes.byref(self.cfg), ctypes.byref(self.task), ctypes.byref(self.env), _p(self.walls),
+                        _p(self.texts), _p(self.tex), _p(self.ceil), ctypes.c_int(self.ts), _p(obs), _p(scratch))
+        return obs
+
+    def reset(self):
+        if self.need_task:
+            raise Exception("Must call \"set_task\" before reset")
+        lib().mo_reset(ctypes.byref(self.cfg), ctypes.byref(self.task), _p(self.food), _p(self.interval),
+                       ctypes.byref(self.env))
+        return self._observe()
+
+    def step(self, action, render=True):
+        rew = c_f64(0.0)
+        done = ctypes.c_int(0)
+        fn = lib().mo_step_2d if self.kind == "2D" else lib().mo_step_3d
+        fn(ctypes.byref(self.cfg), ctypes.byref(self.task), _p(self.walls), _p(self.food), _p(self.interval),
+           ctypes.byref(self.env), ctypes.c_int(int(action)), ctypes.byref(rew), ctypes.byref(done))
+        obs = self._observe() if render else None
+        return obs, rew.value, bool(done.value), {"steps": self.env.steps}
+
+    @property
+    def agent(self):
+        return (self.env.gx, self.env.gy, self.env.ori, self.env.steps)
+
+    @property
+    def life(self):
+        return self.env.life

@@ -26,3 +26,9 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return 0
+
+
+@pytest.fixture(scope="session")
+def maze_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "maze_golden.npz"), allow_pickle=False)

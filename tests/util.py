@@ -4,7 +4,9 @@ import numpy as np
 # state row = p3 v3 w3 prop4 R9
 STATE_GROUPS = [(0, 3), (3, 6), (6, 9), (9, 13), (13, 22)]
 # obs row = b_v3 b_p3 acc3 gyro3 (pitch roll yaw) z [target3]
-OBS_GROUPS = [(0, 3), (3, 6), (6, 9), (9, 12), (12, 15), (15, 16)]
+# third entry = scale floor of the group: angles are compared against 1 rad, the barometer z = p_z + z_offset against the
+# 5 m offset it contains (near the floor z -> 0 by cancellation while p_z itself is ~5)
+OBS_GROUPS = [(0, 3), (3, 6), (6, 9), (9, 12), (12, 15, 1.0), (15, 16, 5.0)]
 TASK_NAMES = {0: "no_collision", 1: "hovering_control", 2: "velocity_control"}
 
 
@@ -16,8 +18,10 @@ def group_rel_err(a, ref, groups, floor=1e-3):
     a = a.reshape(-1, a.shape[-1])
     ref = ref.reshape(-1, ref.shape[-1])
     worst = 0.0
-    for lo, hi in groups:
-        scale = np.maximum(np.abs(ref[:, lo:hi]).max(axis=1, keepdims=True), floor)
+    for grp in groups:
+        lo, hi = grp[0], grp[1]
+        gfloor = grp[2] if len(grp) > 2 else floor
+        scale = np.maximum(np.abs(ref[:, lo:hi]).max(axis=1, keepdims=True), gfloor)
         err = np.abs(a[:, lo:hi] - ref[:, lo:hi]) / scale
         if err.size:
             worst = max(worst, float(np.nanmax(err)))
@@ -41,3 +45,35 @@ def golden_run(g, name):
 
 
 QUAD_RUNS = ["hover_a", "hover_b", "hover_fall", "nocol_fall", "nocol_a", "vel_a", "vel_b", "vel_c"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# maze fixtures
+# ---------------------------------------------------------------------------------------------------------------
+from collections import namedtuple  # noqa: E402
+
+MazeTask = namedtuple("MazeTask", ["start", "goal", "cell_walls", "cell_texts", "cell_size", "wall_height",
+                                   "agent_height", "initial_life", "max_life", "step_reward", "goal_reward",
+                                   "food_rewards", "food_interval"])
+MAZE_CASES = ["m2d_surv", "m2d_surv_g2", "m2d_esc", "m3d_surv", "m3d_esc", "m3d_big"]
+
+
+def task_from_arrays(walls, texts, food, interval, scalars):
+    s = scalars
+    return MazeTask(start=(int(s[0]), int(s[1])), goal=(int(s[2]), int(s[3])), cell_walls=np.asarray(walls),
+                    cell_texts=np.asarray(texts), cell_size=float(s[4]), wall_height=float(s[5]),
+                    agent_height=float(s[6]), initial_life=float(s[7]), max_life=float(s[8]),
+                    step_reward=float(s[9]), goal_reward=float(s[10]), food_rewards=np.asarray(food),
+                    food_interval=np.asarray(interval))
+
+
+def maze_case(g, name):
+    pre = name + "."
+    d = {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+    kind, tt, max_steps, view_grid, rh, rv = [int(x) for x in d["meta"]]
+    d["kind"] = "2D" if kind == 0 else "3D"
+    d["task_type"] = "SURVIVAL" if tt == 0 else "ESCAPE"
+    d["max_steps"], d["view_grid"], d["resolution"] = max_steps, view_grid, (rh, rv)
+    d["task"] = task_from_arrays(d["task.walls"], d["task.texts"], d["task.food"], d["task.interval"],
+                                 d["task.scalars"])
+    return d
