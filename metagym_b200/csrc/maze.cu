@@ -1,14 +1,917 @@
-// placeholder until the maze kernels land (this file is replaced in the next milestone)
+// MetaMaze hot path for sm_100a: 2-D grid step (one thread = one env) and discrete-3D step + first-person raycast
+// render (one persistent CTA per SM, textures staged ONCE into shared memory by TMA bulk copy, every env's maze tile
+// staged by TMA + mbarrier, pixels leave through double-buffered shared-memory chunks and TMA bulk stores).
+//
+// Replaces (reference file:line, PaddlePaddle/MetaGym):
+//   MazeBase.set_task / reset / evaluation_rule      metagym/metamaze/envs/maze_base.py:19-95, 191-202
+//   MazeCore2D.do_action / update_observation        metagym/metamaze/envs/maze_2d.py:21-34, 89-121
+//   MazeCoreDiscrete3D.turn / move / do_action / update_observation
+//                                                    metagym/metamaze/envs/maze_discrete_3d.py:39-81, 113-127
+//   DDA_2D / maze_view                               metagym/metamaze/envs/ray_caster_utils.py:11-62, 66-209
+//
+// Exactness: grid state, done flags, float64 rewards/life and the rendered integers are bit-identical to the reference.
+// The renderer therefore computes pixel geometry in float64 with the reference's operation order, float32 column
+// tables, truncating float->int conversions and NO fused multiply-add (this file is compiled with -fmad=false).
+// Food respawn is evaluated lazily from per-food "eaten at step s" stamps: a cell eaten at step s is
+// edible again at the check of step t iff t > s + interval and visible after step t iff t >= s + interval, which is
+// what maze_base.py:74-75,83-88 does with its whole-grid countdown arrays.
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
 #include "mgb_common.cuh"
-#define NYI() do { mgb_set_error("%s: maze path not built yet", __func__); return MGB_ERR_STATE; } while (0)
-extern "C" int mgb_maze_create(mgb_maze **, int64_t, const mgb_maze_cfg *, int, int64_t) { NYI(); }
-extern "C" void mgb_maze_destroy(mgb_maze *) {}
-extern "C" int64_t mgb_maze_obs_bytes_per_env(const mgb_maze *) { return -1; }
-extern "C" int mgb_maze_set_textures(mgb_maze *, const uint8_t *, int32_t, const uint8_t *, int32_t) { NYI(); }
-extern "C" int mgb_maze_set_task(mgb_maze *, int32_t, const int8_t *, const int8_t *, const double *, const int32_t *,
-                                 const mgb_maze_task_scalars *, const int32_t *) { NYI(); }
-extern "C" int mgb_maze_reset(mgb_maze *, const uint8_t *, void *, void *) { NYI(); }
-extern "C" int mgb_maze_step(mgb_maze *, const int32_t *, void *, double *, uint8_t *, void *) { NYI(); }
-extern "C" int mgb_maze_set_options(mgb_maze *, int) { NYI(); }
-extern "C" int mgb_maze_state(mgb_maze *, int32_t *, double *, void *) { NYI(); }
-extern "C" int64_t mgb_maze_launch_count(const mgb_maze *) { return -1; }
+
+namespace {
+
+constexpr int kMaxN = 31;
+constexpr int kNever = INT_MIN / 2;
+constexpr int kRenderThreads = 512;
+constexpr int kChunkPixels = 2048;
+constexpr int kMaxHitsCap = 48;
+
+struct TaskHdr {                 // 80 bytes, head of every task blob
+    int32_t start[2], goal[2];
+    double cell_size, wall_height, agent_height, initial_life, max_life, step_reward, goal_reward;
+    int32_t n_food, pad;
+};
+
+struct MazeConst {
+    int kind, task_type, n, max_steps, view_grid, res_h, res_v, obs_dtype;
+    int n_tex, ts;
+    int f_max;                   // food slots per env
+    int max_hits;                // transparent crossings kept per column
+    int blob_bytes;              // bytes of one task blob (multiple of 16)
+    int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
+    double max_vision, l_focal, text_size;
+    double half_h, half_v, pixel_size;                        // host-computed like ray_caster_utils.py:68-70
+    // life bar (maze_discrete_3d.py:42-45)
+    double lb_sx, lb_sy, lb_w, lb_l;
+};
+
+struct MazeArgs {
+    int64_t n, n_pad, env_base;
+    int4 *agent;                 // gx, gy, ori, steps
+    double *life;
+    int32_t *eaten;              // [f_max][n_pad]
+    const int32_t *env2task;
+    const uint8_t *blobs;        // [n_tasks][blob_bytes]
+    const uint32_t *tex;         // packed 0x00BBGGRR, (n_tex + 1) * ts * ts, ceiling last
+    const float *coltab;         // [4][3][res_h]: cos_hp, cos_abs, sin_abs per heading
+    const int32_t *act;
+    void *obs;
+    double *rew;
+    uint8_t *done;
+    const uint8_t *mask;
+    int do_step;                 // 0: observe only (reset), 1: step then observe
+    int auto_reset;
+};
+
+struct Env {
+    int gx, gy, ori, steps;
+    double life;
+};
+
+__device__ __forceinline__ const TaskHdr *blob_hdr(const uint8_t *b) { return reinterpret_cast<const TaskHdr *>(b); }
+
+// action + evaluation_rule for one env (single thread).  `eaten` is strided by `estride` (SoA in HBM).
+__device__ __forceinline__ void maze_logic(const MazeConst &c, const uint8_t *blob, int32_t *eaten, int64_t estride,
+                                           Env &e, int action, double &reward, int &done)
+{
+    const TaskHdr *th = blob_hdr(blob);
+    const int8_t *walls = reinterpret_cast<const int8_t *>(blob + c.off_walls);
+    const int n = c.n;
+    action &= 3;
+    if (c.kind == MGB_MAZE_2D) {                                  // maze_2d.py:21-34 with DISCRETE_ACTIONS (dx, dy)
+        int tx = e.gx + (action == 0 ? -1 : (action == 1 ? 1 : 0));
+        int ty = e.gy + (action == 2 ? -1 : (action == 3 ? 1 : 0));
+        if (tx < 0) tx += n;                                      // numpy negative index; unreachable (border walls)
+        if (ty < 0) ty += n;
+        if (tx < n && ty < n && walls[tx * n + ty] < 1) { e.gx = tx; e.gy = ty; }
+    } else {                                                      // maze_discrete_3d.py:51-81, (turn, move)
+        const int turn = action == 0 ? -1 : (action == 1 ? 1 : 0);
+        const int mv = action == 2 ? -1 : (action == 3 ? 1 : 0);
+        e.ori = (e.ori + turn + 4) & 3;
+        int tx = e.gx, ty = e.gy;
+        if (e.ori == 0) tx += mv; else if (e.ori == 1) ty += mv; else if (e.ori == 2) tx -= mv; else ty -= mv;
+        if (tx >= 0 && tx < n && ty >= 0 && ty < n && walls[tx * n + ty] == 0) { e.gx = tx; e.gy = ty; }
+    }
+    e.steps += 1;                                                 // maze_base.py:66
+    const bool over = e.steps > c.max_steps - 1;                  // :191-192
+    if (c.task_type == MGB_MAZE_SURVIVAL) {
+        double r = 0.0;
+        const int8_t *fidx = reinterpret_cast<const int8_t *>(blob + c.off_fidx);
+        const int f = fidx[e.gx * n + e.gy];
+        if (f >= 0) {
+            const double val = reinterpret_cast<const double *>(blob + c.off_fval)[f];
+            const int itv = reinterpret_cast<const int32_t *>(blob + c.off_fint)[f];
+            const int ea = eaten[f * estride];
+            const bool present = (ea == kNever) || (e.steps > ea + itv);
+            if (present && val > 1.0e-2) {                        // :71-75
+                r = val;
+                eaten[f * estride] = e.steps;
+            }
+        }
+        e.life = e.life + (r + th->step_reward);                  // :78
+        e.life = e.life < th->max_life ? e.life : th->max_life;   // :79
+        done = (e.life < 0.0) || over;                            // :80
+        reward = r;
+    } else {
+        const int goal = (e.gx == th->goal[0] && e.gy == th->goal[1]);
+        reward = th->step_reward + (double)goal * th->goal_reward;   // :91-92
+        done = goal || over;
+    }
+}
+
+__device__ __forceinline__ void env_reset(const MazeConst &c, const uint8_t *blob, int32_t *eaten, int64_t estride,
+                                          Env &e)
+{
+    const TaskHdr *th = blob_hdr(blob);
+    e.gx = th->start[0]; e.gy = th->start[1]; e.ori = 0; e.steps = 0;
+    e.life = th->initial_life;
+    for (int f = 0; f < c.f_max; ++f) eaten[f * estride] = kNever;
+}
+
+// current transparent value of cell (i, j): SURVIVAL = remaining food (alias at maze_base.py:57), ESCAPE = goal one-hot
+__device__ __forceinline__ double food_now(const MazeConst &c, const uint8_t *blob, const int32_t *eaten,
+                                           int64_t estride, int steps, int cell)
+{
+    const int8_t *fidx = reinterpret_cast<const int8_t *>(blob + c.off_fidx);
+    const int f = fidx[cell];
+    if (f < 0) return 0.0;
+    const int itv = reinterpret_cast<const int32_t *>(blob + c.off_fint)[f];
+    const int ea = eaten[f * estride];
+    const bool visible = (ea == kNever) || (steps >= ea + itv);
+    return visible ? reinterpret_cast<const double *>(blob + c.off_fval)[f] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// state-only kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void maze_reset_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    if (a.mask && !a.mask[e]) return;
+    const uint8_t *blob = a.blobs + (int64_t)a.env2task[e] * c.blob_bytes;
+    Env s;
+    env_reset(c, blob, a.eaten + e, a.n_pad, s);
+    a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+    a.life[e] = s.life;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-D: one thread per env; observation tile of the CTA leaves through shared memory + one bulk store
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int k2dThreads = 128;
+
+__global__ void __launch_bounds__(k2dThreads) maze2d_kernel(const __grid_constant__ MazeConst c,
+                                                            const __grid_constant__ MazeArgs a)
+{
+    extern __shared__ __align__(128) float tile2d[];
+    const int64_t e0 = (int64_t)blockIdx.x * k2dThreads;
+    const int64_t e = e0 + threadIdx.x;
+    const int W = 2 * c.view_grid + 1, D = W * W;
+    const int rows = (int)((a.n - e0) < k2dThreads ? (a.n - e0) : k2dThreads);
+    if (e < a.n) {
+        const uint8_t *blob = a.blobs + (int64_t)a.env2task[e] * c.blob_bytes;
+        const TaskHdr *th = blob_hdr(blob);
+        const int4 ag = a.agent[e];
+        Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
+        int32_t *eaten = a.eaten + e;
+        if (a.do_step) {
+            double reward;
+            int done;
+            maze_logic(c, blob, eaten, a.n_pad, s, a.act[e], reward, done);
+            a.rew[e] = reward;
+            a.done[e] = (uint8_t)done;
+            if (done && a.auto_reset) env_reset(c, blob, eaten, a.n_pad, s);
+            a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+            a.life[e] = s.life;
+        }
+        // update_observation, maze_2d.py:89-121
+        const int8_t *walls = reinterpret_cast<const int8_t *>(blob + c.off_walls);
+        const int n = c.n, g = c.view_grid;
+        float *row = tile2d + threadIdx.x * D;
+        for (int p = 0; p < W; ++p)
+            for (int q = 0; q < W; ++q) {
+                const int x = s.gx - g + p, y = s.gy - g + q;
+                float v = -1.0f;
+                if (x >= 0 && x < n && y >= 0 && y < n) {
+                    v = (float)(-(int)walls[x * n + y]);
+                    if (c.task_type == MGB_MAZE_SURVIVAL)
+                        v = (float)((double)v + food_now(c, blob, eaten, a.n_pad, s.steps, x * n + y));
+                    else
+                        v = (float)((double)v + ((x == th->goal[0] && y == th->goal[1]) ? 1.0 : 0.0));
+                }
+                row[p * W + q] = v;
+            }
+        if (c.task_type == MGB_MAZE_SURVIVAL) row[g * W + g] = (float)s.life;
+    }
+    float *dst = reinterpret_cast<float *>(a.obs) + e0 * D;
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+    if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        mgb_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mgb_bulk_store(dst, tile2d, bytes);
+            mgb_bulk_commit();
+            mgb_bulk_wait<0>();
+        }
+    } else {
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tile2d[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// discrete 3-D: persistent CTA, step logic + raycast render
+// ---------------------------------------------------------------------------------------------------------------
+struct ColRec {                  // one screen column (ray), 64 bytes
+    double cos_hp, cos_abs, sin_abs;   // float32 table values promoted (ray_caster_utils.py:82-92)
+    double light, oma, ratio;          // wall shading: |cos/sin|, 1 - alpha, hit_dist * cos_hp / l_focal
+    int16_t v_s, v_e;                  // wall span [v_s, v_e)
+    int16_t ti, text_id;               // texture column, texture id
+    int16_t n_hits, wall;              // transparent crossings, wall hit within max_vision
+    int32_t pad;
+};
+struct RowRec {                  // one screen row, 24 bytes
+    double distance, light;
+    int32_t kind;                // 0 none, 1 floor, 2 ceiling
+    int32_t pad;
+};
+struct HitRec {                  // one transparent crossing of a column, 16 bytes
+    double tf;
+    int16_t v_s, v_e;
+    int32_t pad;
+};
+
+__device__ __forceinline__ int trunc_i(double x) { return (int)x; }   // cvt.rzi: python/numba int()
+
+// rgb = light * (alpha * FAR_RGB + (1 - alpha) * texel), FAR_RGB = 0 (ray_caster_utils.py:7,118)
+__device__ __forceinline__ void shade(int rgb[3], double light, double oma, uint32_t texel)
+{
+    rgb[0] = trunc_i(light * (oma * (double)(texel & 0xffu)));
+    rgb[1] = trunc_i(light * (oma * (double)((texel >> 8) & 0xffu)));
+    rgb[2] = trunc_i(light * (oma * (double)((texel >> 16) & 0xffu)));
+}
+// rgb = (1 - tf) * rgb + tf * (0, 255, 0)  (ray_caster_utils.py:8,121-123)
+__device__ __forceinline__ void blend(int rgb[3], double tf)
+{
+    const double k = 1.0 - tf;
+    rgb[0] = trunc_i(k * (double)rgb[0] + tf * 0.0);
+    rgb[1] = trunc_i(k * (double)rgb[1] + tf * 255.0);
+    rgb[2] = trunc_i(k * (double)rgb[2] + tf * 0.0);
+}
+
+__device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_constant__ MazeConst c,
+                                                                   const __grid_constant__ MazeArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int n = c.n, H = c.res_h, V = c.res_v, ts = c.ts;
+    const int tex_words = (c.n_tex + 1) * ts * ts;
+    // ---- shared memory carve-up (mirrors maze3d_smem_bytes on the host)
+    size_t off = 0;
+    uint32_t *s_tex = reinterpret_cast<uint32_t *>(smem + off);          off = align_up(off + (size_t)tex_words * 4, 128);
+    uint8_t *s_blob = smem + off;                                         off = align_up(off + c.blob_bytes, 128);
+    double *s_transp = reinterpret_cast<double *>(smem + off);           off = align_up(off + (size_t)n * n * 8, 128);
+    ColRec *s_col = reinterpret_cast<ColRec *>(smem + off);              off = align_up(off + (size_t)H * sizeof(ColRec), 128);
+    RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
+    HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);              off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
+    const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
+    uint8_t *s_out0 = smem + off;                                         off = align_up(off + (size_t)kChunkPixels * px_bytes, 128);
+    uint8_t *s_out1 = smem + off;                                         off = align_up(off + (size_t)kChunkPixels * px_bytes, 128);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 16;
+    int *s_env = reinterpret_cast<int *>(smem + off);                    // [0..3] gx gy ori steps, [4] lifebar end
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mgb_mbar_init(&s_bar[0], 1);   // textures
+        mgb_mbar_init(&s_bar[1], 1);   // task blob
+        mgb_fence_mbar_init();
+    }
+    __syncthreads();
+    // ---- textures: ONE bulk (TMA) copy per CTA for the whole launch, in <= 64 KB pieces
+    if (tid == 0) {
+        const uint32_t total = (uint32_t)tex_words * 4u;
+        mgb_mbar_expect_tx(&s_bar[0], total);
+        for (uint32_t o = 0; o < total; o += 65536u) {
+            const uint32_t len = total - o < 65536u ? total - o : 65536u;
+            mgb_bulk_load(reinterpret_cast<uint8_t *>(s_tex) + o, reinterpret_cast<const uint8_t *>(a.tex) + o, len,
+                          &s_bar[0]);
+        }
+    }
+    uint32_t blob_phase = 0;
+    bool tex_ready = false;
+    int chunk_parity = 0;
+
+    for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x) {
+        const bool live = !(a.mask && !a.mask[e]) || a.do_step;   // reset with a mask renders only the masked envs
+        if (!live) continue;
+        // ---- stage this env's maze tile (walls, textures ids, food table) by TMA
+        if (tid == 0) {
+            const uint8_t *src = a.blobs + (int64_t)a.env2task[e] * c.blob_bytes;
+            mgb_mbar_expect_tx(&s_bar[1], (uint32_t)c.blob_bytes);
+            mgb_bulk_load(s_blob, src, (uint32_t)c.blob_bytes, &s_bar[1]);
+        }
+        mgb_mbar_wait(&s_bar[1], blob_phase);
+        blob_phase ^= 1u;
+        const TaskHdr *th = blob_hdr(s_blob);
+
+        // ---- step logic (one thread), then publish agent pose to the CTA
+        if (tid == 0) {
+            const int4 ag = a.agent[e];
+            Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
+            int32_t *eaten = a.eaten + e;
+            if (a.do_step) {
+                double reward;
+                int done;
+                maze_logic(c, s_blob, eaten, a.n_pad, s, a.act[e], reward, done);
+                a.rew[e] = reward;
+                a.done[e] = (uint8_t)done;
+                if (done && a.auto_reset) env_reset(c, s_blob, eaten, a.n_pad, s);
+                a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+                a.life[e] = s.life;
+            }
+            s_env[0] = s.gx; s_env[1] = s.gy; s_env[2] = s.ori; s_env[3] = s.steps;
+            // life bar extent, maze_discrete_3d.py:118-126 (python slice semantics on the end index)
+            int ex = trunc_i(c.lb_sx + s.life / th->max_life * c.lb_l);
+            if (ex < 0) { ex += H; if (ex < 0) ex = 0; }
+            if (ex > H) ex = H;
+            s_env[4] = ex;
+        }
+        __syncthreads();
+        const int gx = s_env[0], gy = s_env[1], ori = s_env[2], steps = s_env[3];
+        const double cell_size = th->cell_size, vision_height = th->agent_height, ceil_height = th->wall_height;
+        const double pos_x = gx * cell_size + 0.5 * cell_size;       // get_cell_center, maze_base.py:194-197
+        const double pos_y = gy * cell_size + 0.5 * cell_size;
+        const double text_to_cell = c.text_size / cell_size;
+
+        // ---- transparent map + row table
+        for (int k = tid; k < n * n; k += blockDim.x) {
+            double v;
+            if (c.task_type == MGB_MAZE_SURVIVAL) v = food_now(c, s_blob, a.eaten + e, a.n_pad, steps, k);
+            else v = (k == th->goal[0] * n + th->goal[1]) ? 1.0 : 0.0;
+            s_transp[k] = v;
+        }
+        for (int d_v = tid; d_v < V; d_v += blockDim.x) {
+            RowRec r;
+            r.kind = 0; r.distance = 0.0; r.light = 0.0; r.pad = 0;
+            if (d_v > V / 2) {                                       // floor rows, ray_caster_utils.py:95-101
+                const double v_screen = (d_v + 0.5) * c.pixel_size - c.half_v;
+                r.distance = vision_height / v_screen * c.l_focal;
+                r.light = v_screen / c.l_focal;
+                r.kind = r.distance > c.max_vision ? 0 : 1;
+            } else if (d_v < V / 2) {                                // ceiling rows, :129-135
+                const double v_screen = c.half_v - (d_v + 0.5) * c.pixel_size;
+                r.distance = (ceil_height - vision_height) / v_screen * c.l_focal;
+                r.light = v_screen / c.l_focal;
+                r.kind = r.distance > c.max_vision ? 0 : 2;
+            }
+            s_row[d_v] = r;
+        }
+        __syncthreads();
+
+        // ---- one ray per column: DDA_2D (ray_caster_utils.py:11-62) + wall span set-up (:156-182)
+        const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
+        const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
+        const float *ct = a.coltab + (size_t)ori * 3 * H;
+        for (int d_h = tid; d_h < H; d_h += blockDim.x) {
+            ColRec cr;
+            cr.cos_hp = (double)ct[d_h];
+            cr.cos_abs = (double)ct[H + d_h];
+            cr.sin_abs = (double)ct[2 * H + d_h];
+            const double cos_ori = cr.cos_abs, sin_ori = cr.sin_abs;
+            const int i0 = trunc_i(pos_x / cell_size), j0 = trunc_i(pos_y / cell_size);
+            const double delta_dist_x = fabs(cos_ori) < 1.0e-6 ? 1.0e+6 : fabs(cell_size / cos_ori);
+            const double delta_dist_y = fabs(sin_ori) < 1.0e-6 ? 1.0e+6 : fabs(cell_size / sin_ori);
+            const double d_x = cos_ori > 0 ? ((i0 + 1) * cell_size - pos_x) : (i0 * cell_size - pos_x);
+            const double d_y = sin_ori > 0 ? ((j0 + 1) * cell_size - pos_y) : (j0 * cell_size - pos_y);
+            double side_x = fabs(cos_ori) < 1.0e-6 ? 1.0e+6 : d_x / cos_ori;
+            double side_y = fabs(sin_ori) < 1.0e-6 ? 1.0e+6 : d_y / sin_ori;
+            const int delta_i = cos_ori > 0 ? 1 : -1, delta_j = sin_ori > 0 ? 1 : -1;
+            int hit_i = i0, hit_j = j0, hit_side = 0, nh = 0;
+            double hit_dist = 0.0;
+            HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
+            // a transparent crossing at distance d paints the span of a wall standing there (:191-198)
+            auto record_hit = [&](double d, double strength) {
+                if (nh >= c.max_hits) return;
+                const double ratio = d * cr.cos_hp / c.l_focal;
+                const double tv = (ceil_height - vision_height) / ratio, bv = vision_height / ratio;
+                const int s0 = trunc_i((c.half_v - tv) / c.pixel_size), s1 = trunc_i((c.half_v + bv) / c.pixel_size);
+                HitRec hr;
+                hr.tf = strength * 0.50 + 0.10;
+                hr.v_s = (int16_t)(s0 < 0 ? 0 : s0);
+                hr.v_e = (int16_t)(s1 > V ? V : s1);
+                hr.pad = 0;
+                hits[nh++] = hr;
+            };
+            if (s_transp[hit_i * n + hit_j] > 0.01)                   // start cell, :25-29
+                record_hit(side_x < side_y ? side_x : side_y, s_transp[hit_i * n + hit_j]);
+            while (hit_dist < c.max_vision) {
+                if (side_x < side_y) {
+                    hit_i += delta_i;
+                    side_y -= side_x;
+                    hit_dist += side_x;
+                    if (hit_i < 0 || hit_i >= n) {
+                        if (hit_j < 0 || hit_j >= n) { hit_dist = 1.0e+6; break; }
+                    } else if (hit_j >= 0 && hit_j < n) {
+                        const double tv = s_transp[hit_i * n + hit_j];
+                        if (tv > 0.01) record_hit(hit_dist, tv);
+                        if (walls[hit_i * n + hit_j] > 0) { hit_side = 0; break; }
+                    }
+                    side_x = delta_dist_x;
+                } else {
+                    hit_j += delta_j;
+                    side_x -= side_y;
+                    hit_dist += side_y;
+                    if (hit_i < 0 || hit_i >= n) {
+                        if (hit_j < 0 || hit_j >= n) { hit_dist = 1.0e+6; break; }
+                    } else if (hit_j >= 0 && hit_j < n) {
+                        const double tv = s_transp[hit_i * n + hit_j];
+                        if (tv > 0.01) record_hit(hit_dist, tv);
+                        if (walls[hit_i * n + hit_j] > 0) { hit_side = 1; break; }
+                    }
+                    side_y = delta_dist_y;
+                }
+            }
+            cr.wall = hit_dist > c.max_vision ? 0 : 1;               // :162-163 (skips overlays too)
+            cr.n_hits = 0; cr.v_s = 0; cr.v_e = 0; cr.ti = 0; cr.text_id = 0;
+            cr.light = 0.0; cr.oma = 0.0; cr.ratio = 1.0; cr.pad = 0;
+            if (cr.wall) {
+                const double alpha = fmin(1.0, fmax(2.0 * hit_dist / c.max_vision - 1.0, 0.0));
+                const int ci = hit_i < 0 ? 0 : (hit_i >= n ? n - 1 : hit_i);
+                const int cj = hit_j < 0 ? 0 : (hit_j >= n ? n - 1 : hit_j);
+                cr.text_id = texts[ci * n + cj];
+                const double hit_pt_x = hit_dist * cos_ori + pos_x;
+                const double hit_pt_y = hit_dist * sin_ori + pos_y;
+                double local_h;
+                if (hit_side == 0) {
+                    local_h = hit_pt_y / cell_size; local_h -= floor(local_h);
+                    cr.light = fabs(cos_ori);
+                } else {
+                    local_h = hit_pt_x / cell_size; local_h -= floor(local_h);
+                    cr.light = fabs(sin_ori);
+                }
+                double d_i = local_h / c.text_size;
+                d_i -= floor(d_i);
+                cr.ti = (int16_t)trunc_i(ts * d_i);
+                cr.oma = 1.0 - alpha;
+                cr.ratio = hit_dist * cr.cos_hp / c.l_focal;
+                const double top_v = (ceil_height - vision_height) / cr.ratio, bot_v = vision_height / cr.ratio;
+                int v_s = trunc_i((c.half_v - top_v) / c.pixel_size), v_e = trunc_i((c.half_v + bot_v) / c.pixel_size);
+                cr.v_s = (int16_t)(v_s < 0 ? 0 : v_s);
+                cr.v_e = (int16_t)(v_e > V ? V : v_e);
+                cr.n_hits = (int16_t)nh;
+            }
+            s_col[d_h] = cr;
+        }
+        if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
+        __syncthreads();
+
+        // ---- pixels: q = d_h * V + d_v in chunks of kChunkPixels, double-buffered, TMA bulk store per chunk
+        const int total_px = H * V;
+        const int lb_sx = trunc_i(c.lb_sx), lb_ex = s_env[4];
+        const int lb_sy = trunc_i(c.lb_sy);
+        int lb_ey = trunc_i(c.lb_sy + c.lb_w);
+        if (lb_ey > V) lb_ey = V;
+        uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
+        for (int base = 0; base < total_px; base += kChunkPixels) {
+            uint8_t *buf = chunk_parity ? s_out1 : s_out0;
+            const int cnt = total_px - base < kChunkPixels ? total_px - base : kChunkPixels;
+            // the bulk store that last used this buffer (two chunks ago) must have finished reading it
+            if (tid == 0) mgb_bulk_wait_read<1>();
+            __syncthreads();
+            for (int p = tid; p < cnt; p += blockDim.x) {
+                const int q = base + p;
+                const int d_h = q / V, d_v = q - d_h * V;
+                const ColRec &cr = s_col[d_h];
+                const RowRec &rr = s_row[d_v];
+                int rgb[3] = {0, 0, 0};
+                bool mark = false;
+                const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
+                if (rr.kind != 0 && (!in_wall || cr.n_hits > 0)) {
+                    const double eff = rr.distance / cr.cos_hp;
+                    const double hit_x = eff * cr.cos_abs + pos_x;
+                    const double hit_y = eff * cr.sin_abs + pos_y;
+                    if (rr.kind == 1) {                                   // floor, :103-126
+                        const double alpha = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0)) * rr.light;
+                        const double fi = hit_x / cell_size, fj = hit_y / cell_size;
+                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                        const int i = trunc_i(fi), j = trunc_i(fj);
+                        if (i < n && i >= 0 && j < n && j >= 0) {
+                            const int text_id = texts[i * n + j];
+                            d_i /= text_to_cell; d_j /= text_to_cell;
+                            d_i -= floor(d_i); d_j -= floor(d_j);
+                            d_i *= ts; d_j *= ts;
+                            shade(rgb, rr.light, 1.0 - alpha, s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                            const double tv = s_transp[i * n + j];
+                            if (tv > 0.01) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+                        }
+                    } else {                                              // ceiling, :137-153
+                        const double alpha = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
+                        const int t_i = trunc_i(hit_x / cell_size), t_j = trunc_i(hit_y / cell_size);
+                        const double fi = hit_x / c.text_size, fj = hit_y / c.text_size;
+                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                        d_i *= ts; d_j *= ts;
+                        shade(rgb, rr.light, 1.0 - alpha, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                        if (t_i >= 0 && t_i < n && t_j >= 0 && t_j < n) {
+                            const double tv = s_transp[t_i * n + t_j];
+                            if (tv > 0) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+                        }
+                    }
+                }
+                if (in_wall) {                                            // wall texel, :184-189
+                    const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
+                    double d_j = local_v / c.text_size;
+                    d_j -= floor(d_j);
+                    shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(ts * d_j)]);
+                }
+                if (cr.n_hits > 0 && !mark) {                             // transparent overlays, :191-205
+                    const HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
+                    for (int k = 0; k < cr.n_hits; ++k)
+                        if (d_v >= hits[k].v_s && d_v < hits[k].v_e) blend(rgb, hits[k].tf);
+                }
+                if (c.task_type == MGB_MAZE_SURVIVAL && d_h >= lb_sx && d_h < lb_ex && d_v >= lb_sy && d_v < lb_ey) {
+                    rgb[0] = 255; rgb[1] = 0; rgb[2] = 0;                 // life bar, maze_discrete_3d.py:118-126
+                }
+                if (c.obs_dtype == MGB_OBS_U8) {
+                    buf[p * 3 + 0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
+                    buf[p * 3 + 1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
+                    buf[p * 3 + 2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
+                } else {
+                    int32_t *o = reinterpret_cast<int32_t *>(buf) + p * 3;
+                    o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
+                }
+            }
+            uint8_t *dst = gobs + (size_t)base * px_bytes;
+            const uint32_t bytes = (uint32_t)cnt * (uint32_t)px_bytes;
+            if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                mgb_fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    mgb_bulk_store(dst, buf, bytes);
+                    mgb_bulk_commit();
+                }
+            } else {
+                __syncthreads();
+                for (uint32_t i = tid; i < bytes; i += blockDim.x) dst[i] = buf[i];
+            }
+            chunk_parity ^= 1;
+        }
+        __syncthreads();   // s_col / s_row / s_transp / s_blob are rewritten by the next env
+    }
+    if (!tex_ready && tid == 0) mgb_mbar_wait(&s_bar[0], 0);   // never leave a TMA load in flight
+    if (tid == 0) mgb_bulk_wait<0>();
+}
+
+__global__ void maze_state_kernel(MazeArgs a, int32_t *agent_out, double *life_out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const int4 ag = a.agent[e];
+    agent_out[4 * e + 0] = ag.x; agent_out[4 * e + 1] = ag.y; agent_out[4 * e + 2] = ag.z; agent_out[4 * e + 3] = ag.w;
+    if (life_out) life_out[e] = a.life[e];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// handle + C ABI
+// ---------------------------------------------------------------------------------------------------------------
+struct mgb_maze {
+    int device = 0;
+    int64_t n = 0, n_pad = 0, env_base = 0;
+    mgb_maze_cfg cfg;
+    MazeConst c;
+    int4 *agent = nullptr;
+    double *life = nullptr;
+    int32_t *eaten = nullptr;
+    int32_t *env2task = nullptr;
+    uint8_t *blobs = nullptr;
+    uint32_t *tex = nullptr;
+    float *coltab = nullptr;
+    int n_tasks = 0;
+    int auto_reset = 0;
+    bool has_task = false, has_tex = false;
+    size_t smem3d = 0;
+    int num_sms = 0;
+    int64_t launches = 0;
+};
+
+static size_t maze3d_smem_bytes(const MazeConst &c)
+{
+    auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
+    size_t off = 0;
+    off = up(off + (size_t)(c.n_tex + 1) * c.ts * c.ts * 4, 128);
+    off = up(off + c.blob_bytes, 128);
+    off = up(off + (size_t)c.n * c.n * 8, 128);
+    off = up(off + (size_t)c.res_h * sizeof(ColRec), 128);
+    off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
+    off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
+    const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
+    off = up(off + (size_t)kChunkPixels * px, 128);
+    off = up(off + (size_t)kChunkPixels * px, 128);
+    off += 16 + 32;
+    return off;
+}
+
+static MazeArgs maze_args(const mgb_maze *h)
+{
+    MazeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = h->n; a.n_pad = h->n_pad; a.env_base = h->env_base;
+    a.agent = h->agent; a.life = h->life; a.eaten = h->eaten; a.env2task = h->env2task; a.blobs = h->blobs;
+    a.tex = h->tex; a.coltab = h->coltab; a.auto_reset = h->auto_reset;
+    return a;
+}
+
+extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cfg *cfg, int device,
+                               int64_t env_index_base)
+{
+    MGB_REQUIRE(out && cfg, "null argument");
+    MGB_REQUIRE(n_envs > 0, "n_envs must be positive");
+    MGB_REQUIRE(cfg->kind == MGB_MAZE_2D || cfg->kind == MGB_MAZE_DISCRETE_3D, "invalid kind");
+    MGB_REQUIRE(cfg->task_type == MGB_MAZE_SURVIVAL || cfg->task_type == MGB_MAZE_ESCAPE, "invalid task_type");
+    MGB_REQUIRE(cfg->n_cells >= 3 && cfg->n_cells <= kMaxN, "n_cells must be in [3, 31]");
+    MGB_REQUIRE(cfg->max_steps > 0, "max_steps must be positive");
+    if (cfg->kind == MGB_MAZE_2D) MGB_REQUIRE(cfg->view_grid >= 0 && cfg->view_grid <= 8, "view_grid out of range");
+    if (cfg->kind == MGB_MAZE_DISCRETE_3D) {
+        MGB_REQUIRE(cfg->res_h > 0 && cfg->res_h <= 1024 && cfg->res_v > 0 && cfg->res_v <= 1024, "resolution out of range");
+        MGB_REQUIRE(cfg->obs_dtype == MGB_OBS_U8 || cfg->obs_dtype == MGB_OBS_I32, "invalid obs_dtype");
+        MGB_REQUIRE(cfg->max_vision > 0 && cfg->l_focal > 0 && cfg->text_size > 0 && cfg->fov > 0, "invalid optics");
+    }
+    int ndev = 0;
+    MGB_CUDA(cudaGetDeviceCount(&ndev));
+    MGB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    MgbDeviceGuard guard(device);
+    mgb_maze *h = new (std::nothrow) mgb_maze();
+    MGB_REQUIRE(h, "out of host memory");
+    h->device = device; h->n = n_envs; h->n_pad = (n_envs + 127) / 128 * 128; h->env_base = env_index_base;
+    h->cfg = *cfg;
+    MazeConst &c = h->c;
+    memset(&c, 0, sizeof(c));
+    c.kind = cfg->kind; c.task_type = cfg->task_type; c.n = cfg->n_cells; c.max_steps = cfg->max_steps;
+    c.view_grid = cfg->view_grid; c.res_h = cfg->res_h; c.res_v = cfg->res_v; c.obs_dtype = cfg->obs_dtype;
+    c.max_vision = cfg->max_vision; c.l_focal = cfg->l_focal; c.text_size = cfg->text_size;
+    cudaDeviceProp prop;
+    MGB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    MGB_CUDA(cudaMalloc(&h->agent, sizeof(int4) * h->n_pad));
+    MGB_CUDA(cudaMalloc(&h->life, sizeof(double) * h->n_pad));
+    MGB_CUDA(cudaMalloc(&h->env2task, sizeof(int32_t) * h->n_pad));
+    MGB_CUDA(cudaMemset(h->agent, 0, sizeof(int4) * h->n_pad));
+    MGB_CUDA(cudaMemset(h->life, 0, sizeof(double) * h->n_pad));
+    if (cfg->kind == MGB_MAZE_DISCRETE_3D) {
+        // screen geometry and the per-heading column tables, exactly as maze_view computes them
+        // (ray_caster_utils.py:68-92): float64 arithmetic, float32 sin/cos of the float32 heading, float32 tables.
+        const int H = cfg->res_h, V = cfg->res_v;
+        volatile double half_h = tan(cfg->fov / 2) * cfg->l_focal;
+        volatile double half_v = half_h * V / H;
+        volatile double pixel_size = 2.0 * half_h / H;
+        volatile double pixel_factor = pixel_size / cfg->l_focal;
+        c.half_h = half_h; c.half_v = half_v; c.pixel_size = pixel_size;
+        c.lb_sx = 0.10 * V; c.lb_sy = 0.10 * V; c.lb_w = 0.05 * H; c.lb_l = 0.80 * V;   // maze_discrete_3d.py:42-45
+        std::vector<float> tab((size_t)4 * 3 * H);
+        const float choice[4] = {0.0f, 0.5f, 1.0f, 1.5f};
+        for (int k = 0; k < 4; ++k) {
+            volatile float ori = choice[k] * (float)3.1415926;          // maze_discrete_3d.py:46
+            volatile float s_ori = sinf(ori), c_ori = cosf(ori);
+            volatile double tan_hp = (-0.5 - (double)H / 2) * pixel_factor;
+            for (int d = 0; d < H; ++d) {
+                tan_hp = tan_hp + pixel_factor;
+                volatile double t2 = tan_hp * tan_hp;
+                volatile double cos_hp = sqrt(1.0 / (1.0 + t2));
+                volatile double sin_hp = tan_hp * cos_hp;
+                volatile double a1 = sin_hp * (double)c_ori, a2 = cos_hp * (double)s_ori;
+                volatile double b1 = cos_hp * (double)c_ori, b2 = sin_hp * (double)s_ori;
+                tab[((size_t)k * 3 + 0) * H + d] = (float)cos_hp;
+                tab[((size_t)k * 3 + 1) * H + d] = (float)(b1 - b2);
+                tab[((size_t)k * 3 + 2) * H + d] = (float)(a1 + a2);
+            }
+        }
+        MGB_CUDA(cudaMalloc(&h->coltab, tab.size() * sizeof(float)));
+        MGB_CUDA(cudaMemcpy(h->coltab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    *out = h;
+    return MGB_OK;
+}
+
+extern "C" void mgb_maze_destroy(mgb_maze *h)
+{
+    if (!h) return;
+    MgbDeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
+    cudaFree(h->tex); cudaFree(h->coltab);
+    delete h;
+}
+
+extern "C" int64_t mgb_maze_obs_bytes_per_env(const mgb_maze *h)
+{
+    if (!h) return MGB_ERR_ARG;
+    if (h->c.kind == MGB_MAZE_2D) { const int w = 2 * h->c.view_grid + 1; return (int64_t)w * w * 4; }
+    return (int64_t)h->c.res_h * h->c.res_v * 3 * (h->c.obs_dtype == MGB_OBS_U8 ? 1 : 4);
+}
+
+extern "C" int64_t mgb_maze_launch_count(const mgb_maze *h) { return h ? h->launches : MGB_ERR_ARG; }
+
+extern "C" int mgb_maze_set_options(mgb_maze *h, int auto_reset)
+{
+    MGB_REQUIRE(h, "null handle");
+    h->auto_reset = auto_reset ? 1 : 0;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_set_textures(mgb_maze *h, const uint8_t *grounds_host, int32_t n_tex, const uint8_t *ceil_host,
+                                     int32_t tex_size)
+{
+    MGB_REQUIRE(h && grounds_host && ceil_host, "null argument");
+    MGB_REQUIRE(h->c.kind == MGB_MAZE_DISCRETE_3D, "textures only apply to the 3-D maze");
+    MGB_REQUIRE(n_tex >= 1 && n_tex <= 15, "n_tex must be in [1, 15]");
+    MGB_REQUIRE(tex_size >= 1 && tex_size <= 128, "tex_size must be in [1, 128]");
+    MgbDeviceGuard guard(h->device);
+    MGB_CUDA(cudaDeviceSynchronize());
+    const size_t px = (size_t)tex_size * tex_size;
+    std::vector<uint32_t> packed((size_t)(n_tex + 1) * px);
+    for (size_t i = 0; i < (size_t)n_tex * px; ++i)
+        packed[i] = (uint32_t)grounds_host[3 * i] | ((uint32_t)grounds_host[3 * i + 1] << 8) |
+                    ((uint32_t)grounds_host[3 * i + 2] << 16);
+    for (size_t i = 0; i < px; ++i)
+        packed[(size_t)n_tex * px + i] = (uint32_t)ceil_host[3 * i] | ((uint32_t)ceil_host[3 * i + 1] << 8) |
+                                         ((uint32_t)ceil_host[3 * i + 2] << 16);
+    cudaFree(h->tex); h->tex = nullptr;
+    MGB_CUDA(cudaMalloc(&h->tex, packed.size() * 4));
+    MGB_CUDA(cudaMemcpy(h->tex, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    h->c.n_tex = n_tex; h->c.ts = tex_size;
+    h->has_tex = true;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *walls_host, const int8_t *texts_host,
+                                 const double *food_rewards_host, const int32_t *food_interval_host,
+                                 const mgb_maze_task_scalars *scalars_host, const int32_t *env2task_host)
+{
+    MGB_REQUIRE(h && walls_host && texts_host && food_rewards_host && food_interval_host && scalars_host &&
+                    env2task_host, "null argument");
+    MGB_REQUIRE(n_tasks > 0, "n_tasks must be positive");
+    MgbDeviceGuard guard(h->device);
+    MGB_CUDA(cudaDeviceSynchronize());
+    MazeConst &c = h->c;
+    const int n = c.n, nn = n * n;
+    // food slots: every cell with a positive reward (the ceiling tint of ray_caster_utils.py:150 tests "> 0")
+    int f_max = 0;
+    for (int t = 0; t < n_tasks; ++t) {
+        int cnt = 0;
+        for (int k = 0; k < nn; ++k) cnt += food_rewards_host[(size_t)t * nn + k] > 0.0 ? 1 : 0;
+        f_max = cnt > f_max ? cnt : f_max;
+        const mgb_maze_task_scalars &s = scalars_host[t];
+        MGB_REQUIRE(s.start[0] >= 0 && s.start[0] < n && s.start[1] >= 0 && s.start[1] < n, "start outside the maze");
+        MGB_REQUIRE(s.goal[0] >= 0 && s.goal[0] < n && s.goal[1] >= 0 && s.goal[1] < n, "goal outside the maze");
+        // maze_base.py:36
+        MGB_REQUIRE(s.agent_height < s.wall_height && s.agent_height > 0, "the agent height must be > 0 and < wall height");
+        MGB_REQUIRE(s.cell_size > 0, "cell_size must be positive");
+    }
+    MGB_REQUIRE(f_max <= 127, "at most 127 food cells per task are supported");
+    for (int e = 0; e < h->n; ++e) MGB_REQUIRE(env2task_host[e] >= 0 && env2task_host[e] < n_tasks, "env2task out of range");
+    c.f_max = f_max;
+    int mh = (f_max < 2 * n + 2 ? f_max : 2 * n + 2) + 1;
+    if (c.task_type == MGB_MAZE_ESCAPE) mh = 2;
+    c.max_hits = mh > kMaxHitsCap ? kMaxHitsCap : mh;
+    // blob layout
+    size_t off = sizeof(TaskHdr);
+    c.off_walls = (int)off; off += nn;
+    c.off_texts = (int)off; off += nn;
+    c.off_fidx = (int)off;  off += nn;
+    off = (off + 7) / 8 * 8;
+    c.off_fval = (int)off;  off += (size_t)(f_max > 0 ? f_max : 1) * 8;
+    c.off_fint = (int)off;  off += (size_t)(f_max > 0 ? f_max : 1) * 4;
+    c.blob_bytes = (int)((off + 15) / 16 * 16);
+    std::vector<uint8_t> blobs((size_t)n_tasks * c.blob_bytes, 0);
+    for (int t = 0; t < n_tasks; ++t) {
+        uint8_t *b = blobs.data() + (size_t)t * c.blob_bytes;
+        TaskHdr hd;
+        memset(&hd, 0, sizeof(hd));
+        const mgb_maze_task_scalars &s = scalars_host[t];
+        hd.start[0] = s.start[0]; hd.start[1] = s.start[1]; hd.goal[0] = s.goal[0]; hd.goal[1] = s.goal[1];
+        hd.cell_size = s.cell_size; hd.wall_height = s.wall_height; hd.agent_height = s.agent_height;
+        hd.initial_life = s.initial_life; hd.max_life = s.max_life; hd.step_reward = s.step_reward;
+        hd.goal_reward = s.goal_reward;
+        int cnt = 0;
+        int8_t *fidx = reinterpret_cast<int8_t *>(b + c.off_fidx);
+        double *fval = reinterpret_cast<double *>(b + c.off_fval);
+        int32_t *fint = reinterpret_cast<int32_t *>(b + c.off_fint);
+        for (int k = 0; k < nn; ++k) {
+            b[c.off_walls + k] = (uint8_t)walls_host[(size_t)t * nn + k];
+            b[c.off_texts + k] = (uint8_t)texts_host[(size_t)t * nn + k];
+            const double fv = food_rewards_host[(size_t)t * nn + k];
+            if (fv > 0.0) {
+                fidx[k] = (int8_t)cnt; fval[cnt] = fv; fint[cnt] = food_interval_host[(size_t)t * nn + k];
+                ++cnt;
+            } else fidx[k] = -1;
+        }
+        hd.n_food = cnt;
+        memcpy(b, &hd, sizeof(hd));
+    }
+    if (c.kind == MGB_MAZE_DISCRETE_3D) {
+        for (int t = 0; t < n_tasks; ++t)
+            for (int k = 0; k < nn; ++k) {
+                const int id = texts_host[(size_t)t * nn + k];
+                MGB_REQUIRE(id >= 0 && (!h->has_tex || id < c.n_tex), "cell_texts refers to a texture that is not loaded");
+            }
+    }
+    cudaFree(h->blobs); h->blobs = nullptr;
+    cudaFree(h->eaten); h->eaten = nullptr;
+    MGB_CUDA(cudaMalloc(&h->blobs, blobs.size()));
+    MGB_CUDA(cudaMemcpy(h->blobs, blobs.data(), blobs.size(), cudaMemcpyHostToDevice));
+    MGB_CUDA(cudaMalloc(&h->eaten, sizeof(int32_t) * (size_t)(f_max > 0 ? f_max : 1) * h->n_pad));
+    MGB_CUDA(cudaMemcpy(h->env2task, env2task_host, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice));
+    h->n_tasks = n_tasks;
+    h->has_task = true;
+    // set_task leaves the env in "need reset" state (maze_env.py:44-50): initialise it so a stray step is harmless
+    MazeArgs a = maze_args(h);
+    maze_reset_kernel<<<(unsigned)((h->n + 255) / 256), 256>>>(c, a);
+    MGB_CUDA(cudaDeviceSynchronize());
+    h->launches += 1;
+    return MGB_OK;
+}
+
+static int maze_ready(const mgb_maze *h)
+{
+    if (!h->has_task) { mgb_set_error("Must call \"set_task\" before reset"); return MGB_ERR_STATE; }   // maze_env.py:49-50
+    if (h->c.kind == MGB_MAZE_DISCRETE_3D && !h->has_tex) {
+        mgb_set_error("3-D maze: call mgb_maze_set_textures first");
+        return MGB_ERR_STATE;
+    }
+    return MGB_OK;
+}
+
+static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
+{
+    const MazeConst &c = h->c;
+    if (c.kind == MGB_MAZE_2D) {
+        const int W = 2 * c.view_grid + 1;
+        const size_t sm = (size_t)k2dThreads * W * W * 4;
+        maze2d_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, st>>>(c, a);
+    } else {
+        const size_t sm = maze3d_smem_bytes(c);
+        if (sm != h->smem3d) {
+            if (sm > 227 * 1024) {
+                mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
+                return MGB_ERR_ARG;
+            }
+            MGB_CUDA(cudaFuncSetAttribute(maze3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            h->smem3d = sm;
+        }
+        const unsigned grid = (unsigned)(h->n < h->num_sms ? h->n : h->num_sms);
+        maze3d_kernel<<<grid, kRenderThreads, sm, st>>>(c, a);
+    }
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_dev, void *stream)
+{
+    MGB_REQUIRE(h, "null handle");
+    int rc = maze_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    MazeArgs a = maze_args(h);
+    a.mask = mask_dev;
+    maze_reset_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, st>>>(h->c, a);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (obs_dev) {
+        a.obs = obs_dev; a.do_step = 0; a.mask = nullptr;
+        return launch_observe(h, a, st);
+    }
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_step(mgb_maze *h, const int32_t *act_dev, void *obs_dev, double *rew_dev, uint8_t *done_dev,
+                             void *stream)
+{
+    MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
+    int rc = maze_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    MazeArgs a = maze_args(h);
+    a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev; a.do_step = 1;
+    return launch_observe(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int mgb_maze_state(mgb_maze *h, int32_t *agent_dev, double *life_dev, void *stream)
+{
+    MGB_REQUIRE(h && agent_dev, "null argument");
+    MgbDeviceGuard guard(h->device);
+    MazeArgs a = maze_args(h);
+    maze_state_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, agent_dev, life_dev);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}

@@ -1,0 +1,357 @@
+"""Batched drop-ins for metagym.metamaze.MetaMaze2D / MetaMazeDiscrete3D
+(reference: metagym/metamaze/envs/maze_env.py:16-75, 155-206) plus a host-side task sampler.
+
+Same constructor kwargs, `set_task` / `reset` / `step` protocol and error messages as the reference, with a leading
+batch axis over `num_envs` independent instances stepped by libmgb200 (metagym_b200/csrc/maze.cu).  A task is the
+reference's `TaskConfig` namedtuple (metagym/metamaze/envs/maze_task.py:15-17); objects produced by the reference's own
+`MazeTaskSampler` are accepted as they are (duck-typed by field name).
+"""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+from .spaces import Box, Discrete
+from .textures import synthetic_textures
+
+PI = 3.1415926                                       # metagym/metamaze/envs/dynamics.py:6
+DISCRETE_ACTIONS = [(-1, 0), (1, 0), (0, -1), (0, 1)]   # maze_env.py:14
+
+TaskConfig = namedtuple("TaskConfig", ["start", "goal", "cell_walls", "cell_texts", "cell_size", "wall_height",
+                                       "agent_height", "initial_life", "max_life", "step_reward", "goal_reward",
+                                       "food_rewards", "food_interval"])
+
+
+class _DSU(object):
+    def __init__(self, n):
+        self.p = list(range(n))
+
+    def find(self, x):
+        while self.p[x] != x:
+            self.p[x] = self.p[self.p[x]]
+            x = self.p[x]
+        return x
+
+    def union(self, a, b):
+        a, b = self.find(a), self.find(b)
+        if a == b:
+            return False
+        self.p[a] = b
+        return True
+
+
+def MazeTaskSampler(n=15, allow_loops=True, cell_size=2.0, wall_height=3.2, agent_height=1.6, step_reward=-0.01,
+                    goal_reward=None, food_reward=0.50, initial_life=1.0, max_life=2.0, food_density=0.010,
+                    food_interval=100, crowd_ratio=0.0, n_texts=7, rng=None):
+    """Random maze task with the reference sampler's schema, defaults and constraints (maze_task.py:41-190).
+
+    Host-side and once per task, so it is written for clarity: rooms sit on odd coordinates, a random spanning tree
+    (Kruskal over the room lattice) connects them, and with `allow_loops` further interior walls are knocked out
+    until at most `crowd_ratio` of the interior is wall.  It draws from its own RandomState, so it reproduces the
+    reference's DISTRIBUTION of mazes (size, connectivity, wall density, food statistics), not its exact samples;
+    feed tasks from the reference sampler through `set_task` when sample-level identity matters.
+    """
+    assert n > 6, "Minimum required cells are 7"
+    assert n % 2 != 0, "Cell Numbers can only be odd"
+    assert step_reward < 0, "step_reward must be < 0"
+    rs = rng if rng is not None else np.random.RandomState()
+    walls = np.ones((n, n), dtype=np.int32)
+    walls[1:n:2, 1:n:2] = 0
+    m = (n - 1) // 2
+    dsu = _DSU(m * m)
+    edges = []
+    for a in range(m):
+        for b in range(m):
+            if a + 1 < m:
+                edges.append((2 * a + 2, 2 * b + 1, a * m + b, (a + 1) * m + b))
+            if b + 1 < m:
+                edges.append((2 * a + 1, 2 * b + 2, a * m + b, a * m + b + 1))
+    for k in rs.permutation(len(edges)):
+        i, j, u, v = edges[k]
+        if dsu.union(u, v):
+            walls[i, j] = 0
+    if allow_loops:
+        interior = walls[1:-1, 1:-1]
+        budget = interior.size * crowd_ratio
+        cand = [(i, j) for i in range(1, n - 1) for j in range(1, n - 1) if walls[i, j] > 0]
+        for k in rs.permutation(len(cand)):
+            if interior.sum() <= budget:
+                break
+            i, j = cand[k]
+            if walls[i - 1, j] == 0 or walls[i + 1, j] == 0 or walls[i, j - 1] == 0 or walls[i, j + 1] == 0:
+                walls[i, j] = 0
+    texts = rs.randint(1, n_texts, size=(n, n))
+    texts[walls < 1] = 0
+    start = (int(rs.randint(0, m)) * 2 + 1, int(rs.randint(0, m)) * 2 + 1)
+    goal = (n - 2, n - 2)
+    for _ in range(m * m):
+        cand = (int(rs.randint(0, m)) * 2 + 1, int(rs.randint(0, m)) * 2 + 1)
+        if np.hypot(cand[0] - start[0], cand[1] - start[1]) > 0.45 * n:
+            goal = cand
+            break
+    def_goal_reward = -np.sqrt(n) * n * step_reward if goal_reward is None else goal_reward
+    assert def_goal_reward > 0, "goal reward must be > 0"
+    food = np.clip(rs.rand(n, n) * food_reward, 0.10, food_reward) * (1.0 - walls)
+    expected = (n - 1) * (n - 1) * food_density
+    while food.sum() > expected:
+        food *= (rs.rand(n, n) < 0.90).astype("float32")
+    interval = food_interval * (food > 1.0e-3).astype("int32")
+    return TaskConfig(start=start, goal=goal, cell_walls=walls, cell_texts=texts, cell_size=cell_size,
+                      step_reward=step_reward, goal_reward=def_goal_reward, wall_height=wall_height,
+                      agent_height=agent_height, initial_life=initial_life, max_life=max_life, food_rewards=food,
+                      food_interval=interval)
+
+
+class _BatchedMazeBase(object):
+    KIND = None
+
+    def _setup(self, num_envs, device, task_type, max_steps, auto_reset, env_index_base, squeeze):
+        import torch
+        assert task_type in ("SURVIVAL", "ESCAPE")
+        self._torch = torch
+        self.num_envs = int(num_envs)
+        self.task_type = task_type
+        self.max_steps = max_steps
+        self.auto_reset = bool(auto_reset)
+        self.env_index_base = int(env_index_base)
+        self._squeeze = bool(squeeze) and self.num_envs == 1
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.MgbError("metagym_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _lib.load()
+        self._h = None
+        self._n_cells = None
+        self.action_space = Discrete(4)
+        self.need_reset = True                         # maze_env.py:41-42
+        self.need_set_task = True
+        self._rew = torch.empty((self.num_envs,), dtype=torch.float64, device=self.device)
+        self._done = torch.empty((self.num_envs,), dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def _make_cfg(self, n_cells):
+        raise NotImplementedError
+
+    def _after_create(self):
+        pass
+
+    def _create(self, n_cells):
+        if self._h is not None:
+            if n_cells == self._n_cells:
+                return
+            self._lib.mgb_maze_destroy(self._h)
+            self._h = None
+        cfg = self._make_cfg(n_cells)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.mgb_maze_create(ctypes.byref(h), self.num_envs, ctypes.byref(cfg), self.device.index,
+                                             self.env_index_base))
+        self._h, self._n_cells = h, n_cells
+        _lib.check(self._lib.mgb_maze_set_options(self._h, int(self.auto_reset)))
+        self._after_create()
+
+    def set_task(self, task_config, env2task=None):
+        """MazeBase.set_task (maze_base.py:19-38).  `task_config`: one TaskConfig (all envs) or a sequence of them;
+        env i then runs task env2task[i] (default: (env_index_base + i) % n_tasks)."""
+        tasks = [task_config] if hasattr(task_config, "cell_walls") else list(task_config)
+        n = int(np.shape(tasks[0].cell_walls)[0])
+        for t in tasks:
+            w = np.asarray(t.cell_walls)
+            assert t.agent_height < t.wall_height and t.agent_height > 0, \
+                "the agent height must be > 0 and < wall height"
+            assert w.shape == np.shape(t.cell_texts), "the dimension of walls must be equal to textures"
+            assert w.shape[0] == w.shape[1], "only support square shape"
+            assert w.shape[0] == n, "all tasks of one batch must share the maze size"
+        self._create(n)
+        K = len(tasks)
+        walls = np.ascontiguousarray(np.stack([np.asarray(t.cell_walls) for t in tasks]).astype(np.int8))
+        texts = np.ascontiguousarray(np.stack([np.asarray(t.cell_texts) for t in tasks]).astype(np.int8))
+        food = np.ascontiguousarray(np.stack([np.asarray(t.food_rewards, dtype=np.float64) for t in tasks]))
+        itv = np.ascontiguousarray(np.stack([np.asarray(t.food_interval) for t in tasks]).astype(np.int32))
+        sc = (_lib.MazeTaskScalars * K)()
+        for k, t in enumerate(tasks):
+            sc[k].start[:] = [int(t.start[0]), int(t.start[1])]
+            sc[k].goal[:] = [int(t.goal[0]), int(t.goal[1])]
+            sc[k].cell_size, sc[k].wall_height, sc[k].agent_height = t.cell_size, t.wall_height, t.agent_height
+            sc[k].initial_life, sc[k].max_life = t.initial_life, t.max_life
+            sc[k].step_reward, sc[k].goal_reward = t.step_reward, t.goal_reward
+        if env2task is None:
+            env2task = (np.arange(self.num_envs, dtype=np.int64) + self.env_index_base) % K
+        e2t = np.ascontiguousarray(np.asarray(env2task, dtype=np.int32))
+        assert e2t.shape == (self.num_envs,)
+        self._torch.cuda.synchronize(self.device)
+        _lib.check(self._lib.mgb_maze_set_task(self._h, K, walls.ctypes.data, texts.ctypes.data, food.ctypes.data,
+                                               itv.ctypes.data, sc, e2t.ctypes.data))
+        self.tasks, self.env2task = tasks, e2t
+        self.need_set_task = False
+        self.need_reset = True
+
+    def sample_task(self, **kwargs):
+        """Convenience: draw one task with the host sampler (reference usage: MazeTaskSampler(...), test.py:12)."""
+        return MazeTaskSampler(**kwargs)
+
+    def _out(self, t):
+        return t[0] if self._squeeze else t
+
+    def reset(self, mask=None):
+        if self.need_set_task:
+            raise Exception("Must call \"set_task\" before reset")                  # maze_env.py:49-50
+        m = None
+        if mask is not None:
+            m = self._torch.as_tensor(mask, device=self.device).to(self._torch.uint8).contiguous()
+        _lib.check(self._lib.mgb_maze_reset(self._h, _lib.ptr(m), self._obs.data_ptr(), self._stream()))
+        self.need_reset = False
+        return self._out(self._obs)
+
+    def step(self, action=None):
+        if self.need_reset:
+            raise Exception("Must \"reset\" before doing any actions")              # maze_env.py:60-61
+        if action is None:
+            raise NotImplementedError("keyboard control (action=None) is display-only in the reference")
+        torch = self._torch
+        if not (hasattr(action, "is_cuda") and action.is_cuda):
+            action = torch.as_tensor(np.asarray(action).reshape(self.num_envs), device=self.device)
+        act = action.to(torch.int32).reshape(self.num_envs).contiguous()
+        _lib.check(self._lib.mgb_maze_step(self._h, act.data_ptr(), self._obs.data_ptr(), self._rew.data_ptr(),
+                                           self._done.data_ptr(), self._stream()))
+        info = _LazySteps(self)
+        return self._out(self._obs), self._out(self._rew), self._out(self._done.view(torch.bool)), info
+
+    def agent_state(self):
+        """-> (agent [N,4] int32 = grid_x, grid_y, ori_index, steps ; life [N] float64)."""
+        torch = self._torch
+        ag = torch.empty((self.num_envs, 4), dtype=torch.int32, device=self.device)
+        life = torch.empty((self.num_envs,), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.mgb_maze_state(self._h, ag.data_ptr(), life.data_ptr(), self._stream()))
+        return ag, life
+
+    @property
+    def launch_count(self):
+        return int(self._lib.mgb_maze_launch_count(self._h)) if self._h else 0
+
+    def render(self, mode="human"):
+        raise NotImplementedError("the pygame god-view (maze_base.py:100-189) is out of scope for the batched engine")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.mgb_maze_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _LazySteps(dict):
+    """info = {"steps": n} (maze_env.py:73): fetched from the device only when somebody looks."""
+
+    def __init__(self, env):
+        dict.__init__(self)
+        self._env = env
+
+    def __missing__(self, k):
+        if k != "steps":
+            raise KeyError(k)
+        ag, _ = self._env.agent_state()
+        v = ag[:, 3]
+        self[k] = v[0] if self._env._squeeze else v
+        return self[k]
+
+    def __contains__(self, k):
+        return k == "steps"
+
+
+class BatchedMetaMaze2D(_BatchedMazeBase):
+    """MetaMaze2D(enable_render, render_scale, max_steps, task_type, view_grid) x num_envs (maze_env.py:155-172)."""
+    KIND = 0
+
+    def __init__(self, enable_render=False, render_scale=480, max_steps=5000, task_type="SURVIVAL", view_grid=2,
+                 num_envs=1, device=0, auto_reset=False, env_index_base=0, squeeze=True):
+        if enable_render:
+            raise NotImplementedError("enable_render=True needs a display; the batched engine is headless")
+        self.enable_render = False
+        self.view_grid = int(view_grid)
+        self._setup(num_envs, device, task_type, max_steps, auto_reset, env_index_base, squeeze)
+        w = 2 * self.view_grid + 1
+        # the reference declares Box(-1, 1, (3,3), int32) but returns float32 (2g+1)^2 arrays (maze_2d.py:92)
+        self.observation_space = Box(low=-1, high=1, shape=(w, w), dtype=np.float32)
+        self._obs = self._torch.empty((self.num_envs, w, w), dtype=self._torch.float32, device=self.device)
+
+    def _make_cfg(self, n_cells):
+        cfg = _lib.MazeCfg()
+        cfg.kind, cfg.task_type = 0, {"SURVIVAL": 0, "ESCAPE": 1}[self.task_type]
+        cfg.n_cells, cfg.max_steps, cfg.view_grid = n_cells, self.max_steps, self.view_grid
+        return cfg
+
+
+class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
+    """MetaMazeDiscrete3D(enable_render, render_scale, resolution, max_steps, task_type) x num_envs
+    (maze_env.py:16-42).  obs_dtype: 'int32' = exact reference values, 'uint8' = min(value, 255).
+    textures: (grounds uint8 [n_tex,64,64,3], ceil uint8 [64,64,3]); default = procedural set."""
+    KIND = 1
+
+    def __init__(self, enable_render=False, render_scale=480, resolution=(320, 320), max_steps=5000,
+                 task_type="SURVIVAL", num_envs=1, device=0, auto_reset=False, env_index_base=0, squeeze=True,
+                 obs_dtype="int32", textures=None, max_vision_range=12.0, fol_angle=0.6 * PI):
+        if enable_render:
+            raise NotImplementedError("enable_render=True needs a display; the batched engine is headless")
+        self.enable_render = False
+        self.resolution = (int(resolution[0]), int(resolution[1]))
+        assert obs_dtype in ("int32", "uint8")
+        self.obs_dtype = obs_dtype
+        self.max_vision_range, self.fol_angle = max_vision_range, fol_angle
+        self.textures = textures if textures is not None else synthetic_textures(seed=0)
+        self._setup(num_envs, device, task_type, max_steps, auto_reset, env_index_base, squeeze)
+        torch = self._torch
+        h, v = self.resolution
+        self.observation_space = Box(low=0, high=256, shape=(h, v, 3), dtype=np.float32)     # maze_env.py:37-39
+        self._obs = torch.empty((self.num_envs, h, v, 3), dtype=torch.int32 if obs_dtype == "int32" else torch.uint8,
+                                device=self.device)
+
+    def _make_cfg(self, n_cells):
+        cfg = _lib.MazeCfg()
+        cfg.kind, cfg.task_type = 1, {"SURVIVAL": 0, "ESCAPE": 1}[self.task_type]
+        cfg.n_cells, cfg.max_steps, cfg.view_grid = n_cells, self.max_steps, 0
+        cfg.res_h, cfg.res_v = self.resolution
+        cfg.obs_dtype = 1 if self.obs_dtype == "int32" else 0
+        cfg.max_vision, cfg.fov = self.max_vision_range, self.fol_angle       # maze_discrete_3d.py:22-23
+        cfg.l_focal, cfg.text_size = 0.20, 1.0                                # maze_discrete_3d.py:116
+        return cfg
+
+    def _after_create(self):
+        grounds = np.ascontiguousarray(self.textures[0], dtype=np.uint8)
+        ceil = np.ascontiguousarray(self.textures[1], dtype=np.uint8)
+        ts = grounds.shape[1]
+        assert grounds.shape[1:] == (ts, ts, 3) and ceil.shape == (ts, ts, 3)
+        _lib.check(self._lib.mgb_maze_set_textures(self._h, grounds.ctypes.data, grounds.shape[0], ceil.ctypes.data,
+                                                   ts))
+
+
+MetaMaze2D = BatchedMetaMaze2D
+MetaMazeDiscrete3D = BatchedMetaMazeDiscrete3D
+
+
+def smoke():
+    """Tiny 3-D + 2-D maze episode on cuda:0 checked bit for bit against the CPU oracle (called by smoke())."""
+    import torch
+    from oracle.maze_oracle import OracleMaze
+    rs = np.random.RandomState(3)
+    task = MazeTaskSampler(n=9, food_density=0.05, food_interval=4, rng=rs)
+    tex = synthetic_textures(seed=0)
+    env = BatchedMetaMazeDiscrete3D(resolution=(32, 24), max_steps=30, num_envs=2, squeeze=False, textures=tex)
+    ora = OracleMaze("3D", "SURVIVAL", 30, 1, (32, 24), textures=tex)
+    env.set_task(task)
+    ora.set_task(task)
+    assert np.array_equal(env.reset().cpu().numpy()[0], ora.reset())
+    for t in range(12):
+        a = int(rs.randint(4))
+        obs, rew, done, _ = env.step(torch.full((2,), a, device="cuda", dtype=torch.int32))
+        o2, r2, d2, _ = ora.step(a)
+        assert np.array_equal(obs.cpu().numpy()[1], o2) and float(rew[0]) == r2 and bool(done[0]) == d2
+    env.close()
+    print("smoke ok: maze3d 32x24 render bit-exact vs oracle")

@@ -1,0 +1,68 @@
+"""CPU: the C-ABI library loads and exports exactly the functions include/mgb200.h declares (no compute calls)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "mgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from metagym_b200 import _lib
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libmgb200.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and include/mgb200.h disagree"
+    assert b"sm_100a" in lib.mgb_version()
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the ABI structs have the C sizes (checked against a tiny gcc-compiled sizeof program)."""
+    import ctypes
+    import subprocess
+    import tempfile
+    from metagym_b200 import _lib
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write('#include <stdio.h>\n#include "mgb200.h"\nint main(){printf("%zu %zu %zu\\n",'
+                             'sizeof(mgb_quad_cfg),sizeof(mgb_maze_task_scalars),sizeof(mgb_maze_cfg));return 0;}\n')
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.QuadCfg), ctypes.sizeof(_lib.MazeTaskScalars), ctypes.sizeof(_lib.MazeCfg)]
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run (this container has none); with one, this is a no-op."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from metagym_b200 import BatchedQuadrotor, MgbError
+    with pytest.raises(MgbError):
+        BatchedQuadrotor(num_envs=4)
+    from metagym_b200 import _lib
+    assert _lib.load().mgb_device_count() < 0 or _lib.load().mgb_device_count() == 0
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the product package may reference it, except the smoke helper
+    (metamaze.smoke, called only from __graft_entry__.smoke)."""
+    pkg = os.path.join(ROOT, "metagym_b200")
+    for fn in os.listdir(pkg):
+        if not fn.endswith(".py"):
+            continue
+        src = open(os.path.join(pkg, fn)).read()
+        for m in re.finditer(r"^\s*(from|import)\s+oracle\b.*$", src, flags=re.M):
+            line_no = src[: m.start()].count("\n")
+            context = src[: m.start()]
+            assert fn == "metamaze.py" and context.rfind("def smoke()") > context.rfind("\nclass "), (fn, line_no)

@@ -1,0 +1,178 @@
+"""GPU parity tests of the MetaMaze path: libmgb200 against golden episodes recorded from the unmodified reference
+(tests/golden/maze_golden.npz) and against the CPU oracle (oracle/maze_oracle.c).  Everything is compared bit for bit:
+grid indices, heading, step counters, done flags, float64 rewards / life, float32 2-D observations, int32 raycast images
+(and the uint8 mode as min(reference, 255))."""
+import numpy as np
+import pytest
+
+from util import MAZE_CASES, maze_case, task_from_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod(cuda_device):
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def textures():
+    from metagym_b200.textures import synthetic_textures
+    return synthetic_textures(seed=0)
+
+
+def make_env(c, n, textures, **kw):
+    from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D
+    if c["kind"] == "2D":
+        return BatchedMetaMaze2D(max_steps=c["max_steps"], task_type=c["task_type"], view_grid=c["view_grid"],
+                                 num_envs=n, squeeze=False, **kw)
+    return BatchedMetaMazeDiscrete3D(resolution=c["resolution"], max_steps=c["max_steps"], task_type=c["task_type"],
+                                     num_envs=n, squeeze=False, textures=textures, **kw)
+
+
+@pytest.mark.parametrize("name", MAZE_CASES)
+@pytest.mark.parametrize("n", [1, 3])
+def test_reference_episode(torch_mod, maze_golden, textures, name, n):
+    """Replay the recorded reference episode on n identical envs (manual reset after done, like the reference user)."""
+    torch = torch_mod
+    c = maze_case(maze_golden, name)
+    env = make_env(c, n, textures)
+    with pytest.raises(Exception, match="set_task"):
+        env.reset()
+    env.set_task(c["task"])
+    with pytest.raises(Exception, match="reset"):
+        env.step(torch.zeros(n, dtype=torch.int32, device="cuda"))
+    obs0 = env.reset().cpu().numpy()
+    for k in range(n):
+        assert np.array_equal(obs0[k], c["reset_obs"].astype(obs0.dtype))
+    kept = {int(t): k for k, t in enumerate(c["obs_idx"])}
+    for t, a in enumerate(c["act"]):
+        obs, rew, done, info = env.step(torch.full((n,), int(a), dtype=torch.int32, device="cuda"))
+        ag, life = env.agent_state()
+        ag, life, rew_h, done_h = ag.cpu().numpy(), life.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for k in range(n):
+            assert rew_h[k] == c["rew"][t], (t, rew_h[k], c["rew"][t])
+            assert bool(done_h[k]) == bool(c["done"][t]), t
+            assert tuple(ag[k]) == tuple(int(x) for x in c["agent"][t]), (t, ag[k], c["agent"][t])
+            if c["task_type"] == "SURVIVAL":
+                assert life[k] == c["life"][t], t
+        if t in kept:
+            o = obs.cpu().numpy()
+            ref = c["obs"][kept[t]]
+            for k in range(n):
+                assert np.array_equal(o[k], ref.astype(o.dtype)), (t, int((o[k] != ref).sum()))
+        assert int(info["steps"][0]) == int(c["agent"][t][3])
+        if c["done"][t]:
+            env.reset()
+    env.close()
+
+
+def test_uint8_mode_is_clamped_reference(torch_mod, maze_golden, textures):
+    torch = torch_mod
+    c = maze_case(maze_golden, "m3d_big")
+    bright = (textures[0].copy(), textures[1])
+    bright[0][0] = 255          # bright ground -> exact values exceed 255 near the bottom of the screen
+    a = make_env(c, 1, bright, obs_dtype="int32")
+    b = make_env(c, 1, bright, obs_dtype="uint8")
+    for e in (a, b):
+        e.set_task(c["task"])
+        e.reset()
+    for t in range(10):
+        act = torch.full((1,), int(c["act"][t]), dtype=torch.int32, device="cuda")
+        o32 = a.step(act)[0].cpu().numpy()
+        o8 = b.step(act)[0].cpu().numpy()
+        assert o8.dtype == np.uint8 and np.array_equal(o8, np.minimum(o32, 255).astype(np.uint8))
+    assert o32.max() > 255
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("kind,task_type", [("2D", "SURVIVAL"), ("2D", "ESCAPE"), ("3D", "SURVIVAL"), ("3D", "ESCAPE")])
+def test_random_batch_vs_oracle(torch_mod, maze_golden, textures, kind, task_type):
+    """Many envs, several tasks, independent random actions, auto-reset on: every env equals its own oracle instance."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D
+    from oracle.maze_oracle import OracleMaze
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 10, g["tasks15.scalars"][k]) for k in range(4)]
+    n, T, max_steps, res = (96, 120, 40, None) if kind == "2D" else (20, 45, 25, (40, 24))
+    if kind == "2D":
+        env = BatchedMetaMaze2D(max_steps=max_steps, task_type=task_type, view_grid=2, num_envs=n, squeeze=False,
+                                auto_reset=True)
+    else:
+        env = BatchedMetaMazeDiscrete3D(resolution=res, max_steps=max_steps, task_type=task_type, num_envs=n,
+                                        squeeze=False, auto_reset=True, textures=textures)
+    env.set_task(tasks)
+    oracles = []
+    for e in range(n):
+        o = OracleMaze(kind, task_type, max_steps, 2, res or (8, 8), textures=textures if kind == "3D" else None)
+        o.set_task(tasks[e % 4])
+        oracles.append(o)
+    obs = env.reset().cpu().numpy()
+    for e in range(n):
+        assert np.array_equal(obs[e], oracles[e].reset())
+    rng = np.random.RandomState(7)
+    n_done = 0
+    for t in range(T):
+        act = rng.randint(0, 4, n)
+        obs, rew, done, _ = env.step(torch.as_tensor(act, dtype=torch.int32).cuda())
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for e in range(n):
+            o2, r2, d2, _ = oracles[e].step(int(act[e]))
+            assert rew[e] == r2 and bool(done[e]) == d2, (t, e)
+            if d2:
+                o2 = oracles[e].reset()         # auto-reset publishes the first observation of the next episode
+                n_done += 1
+            assert np.array_equal(obs[e], o2), (t, e)
+    assert n_done > 0
+    env.close()
+
+
+def test_masked_reset(torch_mod, maze_golden):
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D
+    c = maze_case(maze_golden, "m2d_surv")
+    env = BatchedMetaMaze2D(max_steps=60, view_grid=1, num_envs=4, squeeze=False)
+    env.set_task(c["task"])
+    env.reset()
+    for a in c["act"][:10]:
+        env.step(torch.full((4,), int(a), dtype=torch.int32, device="cuda"))
+    before, _ = env.agent_state()
+    env.reset(mask=torch.tensor([1, 0, 0, 1], device="cuda"))
+    after, life = env.agent_state()
+    after, before = after.cpu().numpy(), before.cpu().numpy()
+    assert tuple(after[0]) == (c["task"].start[0], c["task"].start[1], 0, 0) and np.array_equal(after[0], after[3])
+    assert np.array_equal(after[1], before[1]) and np.array_equal(after[2], before[2])
+    env.close()
+
+
+def test_config4_shape_properties(torch_mod, maze_golden, textures):
+    """BASELINE config 4 shape per GPU (1024 envs, 15x15, 128x128, uint8): sharding invariance + determinism."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k], g["tasks15.scalars"][k]) for k in range(8)]
+    N = 1024
+    kw = dict(resolution=(128, 128), max_steps=200, task_type="SURVIVAL", squeeze=False, auto_reset=True,
+              obs_dtype="uint8", textures=textures)
+    full = BatchedMetaMazeDiscrete3D(num_envs=N, **kw)
+    lo = BatchedMetaMazeDiscrete3D(num_envs=N // 2, env_index_base=0, **kw)
+    hi = BatchedMetaMazeDiscrete3D(num_envs=N // 2, env_index_base=N // 2, **kw)
+    for e in (full, lo, hi):
+        e.set_task(tasks)
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(6):
+        act = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        o, r, d, _ = full.step(act)
+        o1, r1, d1, _ = lo.step(act[: N // 2])
+        o2, r2, d2, _ = hi.step(act[N // 2:])
+        assert torch.equal(o, torch.cat([o1, o2])) and torch.equal(r, torch.cat([r1, r2]))
+        assert torch.equal(d, torch.cat([d1, d2]))
+    # envs that share a task and received the same actions render the same image: env i and i+8 differ only by action
+    assert int(o.max()) <= 255 and int(o.float().mean()) > 5
+    for e in (full, lo, hi):
+        e.close()
