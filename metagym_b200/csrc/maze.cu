@@ -28,7 +28,6 @@ namespace {
 constexpr int kMaxN = 31;
 constexpr int kNever = INT_MIN / 2;
 constexpr int kRenderThreads = 512;
-constexpr int kChunkPixels = 2048;
 constexpr int kMaxHitsCap = 48;
 
 struct TaskHdr {                 // 80 bytes, head of every task blob
@@ -42,6 +41,7 @@ struct MazeConst {
     int n_tex, ts;
     int f_max;                   // food slots per env
     int max_hits;                // transparent crossings kept per column
+    int chunk_px;                // pixels per output chunk (shared-memory staging buffer, double-buffered)
     int blob_bytes;              // bytes of one task blob (multiple of 16)
     int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
     double max_vision, l_focal, text_size;
@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
     HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);              off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
     const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
-    uint8_t *s_out0 = smem + off;                                         off = align_up(off + (size_t)kChunkPixels * px_bytes, 128);
-    uint8_t *s_out1 = smem + off;                                         off = align_up(off + (size_t)kChunkPixels * px_bytes, 128);
+    uint8_t *s_out0 = smem + off;                                         off = align_up(off + (size_t)c.chunk_px * px_bytes, 128);
+    uint8_t *s_out1 = smem + off;                                         off = align_up(off + (size_t)c.chunk_px * px_bytes, 128);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 16;
     int *s_env = reinterpret_cast<int *>(smem + off);                    // [0..3] gx gy ori steps, [4] lifebar end
 
@@ -472,16 +472,16 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
         __syncthreads();
 
-        // ---- pixels: q = d_h * V + d_v in chunks of kChunkPixels, double-buffered, TMA bulk store per chunk
+        // ---- pixels: q = d_h * V + d_v in chunks of c.chunk_px, double-buffered, TMA bulk store per chunk
         const int total_px = H * V;
         const int lb_sx = trunc_i(c.lb_sx), lb_ex = s_env[4];
         const int lb_sy = trunc_i(c.lb_sy);
         int lb_ey = trunc_i(c.lb_sy + c.lb_w);
         if (lb_ey > V) lb_ey = V;
         uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
-        for (int base = 0; base < total_px; base += kChunkPixels) {
+        for (int base = 0; base < total_px; base += c.chunk_px) {
             uint8_t *buf = chunk_parity ? s_out1 : s_out0;
-            const int cnt = total_px - base < kChunkPixels ? total_px - base : kChunkPixels;
+            const int cnt = total_px - base < c.chunk_px ? total_px - base : c.chunk_px;
             // the bulk store that last used this buffer (two chunks ago) must have finished reading it
             if (tid == 0) mgb_bulk_wait_read<1>();
             __syncthreads();
@@ -613,8 +613,8 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
     off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
-    off = up(off + (size_t)kChunkPixels * px, 128);
-    off = up(off + (size_t)kChunkPixels * px, 128);
+    off = up(off + (size_t)c.chunk_px * px, 128);
+    off = up(off + (size_t)c.chunk_px * px, 128);
     off += 16 + 32;
     return off;
 }
@@ -778,9 +778,16 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     MGB_REQUIRE(f_max <= 127, "at most 127 food cells per task are supported");
     for (int e = 0; e < h->n; ++e) MGB_REQUIRE(env2task_host[e] >= 0 && env2task_host[e] < n_tasks, "env2task out of range");
     c.f_max = f_max;
-    int mh = (f_max < 2 * n + 2 ? f_max : 2 * n + 2) + 1;
+    // A ray is followed for max_vision at most, i.e. through <= 2 * max_vision / cell_size + 2 cells (one per DDA step
+    // plus the start cell): that bounds the transparent crossings a column can record (ray_caster_utils.py:24-61).
+    double min_cell = scalars_host[0].cell_size;
+    for (int t = 1; t < n_tasks; ++t) min_cell = scalars_host[t].cell_size < min_cell ? scalars_host[t].cell_size : min_cell;
+    const int geo = (int)ceil(2.0 * c.max_vision / min_cell) + 3;
+    int mh = f_max < geo ? f_max : geo;
+    if (mh < 1) mh = 1;
     if (c.task_type == MGB_MAZE_ESCAPE) mh = 2;
     c.max_hits = mh > kMaxHitsCap ? kMaxHitsCap : mh;
+    c.chunk_px = c.obs_dtype == MGB_OBS_U8 ? 2048 : 1024;
     // blob layout
     size_t off = sizeof(TaskHdr);
     c.off_walls = (int)off; off += nn;

@@ -15,6 +15,7 @@
 // Observations leave through a shared-memory tile and ONE bulk (TMA) store per CTA, so the [n][obs_dim] row-major
 // array the gym API wants is written with full 128 B lines even though obs_dim*4 (64 or 76 B) is not a line.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -22,7 +23,7 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 64;   // 65 536 envs -> 1024 CTAs = 6.9 per SM: 1 % tail imbalance (128 -> 15 %)
 constexpr int kMaxObs = 19;
 
 // Constants derived on the host (double arithmetic, rounded once to float32 -- numpy's "weak python scalar" rule).
@@ -32,6 +33,7 @@ struct QuadConst {
     float k1;        // phi/ra
     float inv_phi;   // 1/phi
     float hjm;       // h/jm
+    float hk;        // (h/jm)*(phi/ra)*phi : per-substep relative decay of a rotor's speed
     float mm;
     float ct0, ct1, ct2;
     float vmin, vmax;
@@ -99,8 +101,48 @@ __device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const 
     a.planes[5 * a.n_pad + e] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct), __int_as_float(s.ep));
 }
 
+// ---- fast float32 primitives.  The reference's own float32 noise (1.3e-7 relative per step against a
+// float64 restatement) is larger than the error of any of these, and each replaces a 10-60 instruction IEEE sequence.
+__device__ __forceinline__ float fast_sqrt(float x)      // sqrt.approx: MUFU.SQRT, <= 1 ulp-ish, sqrt(0) = 0
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x)       // MUFU.RCP + one Newton step (~0.5 ulp)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+// atan2 with a degree-7 minimax polynomial in a^2 on [0,1] (max abs error 7.5e-8 rad evaluated in float32, fitted for
+// this file) instead of libdevice's ~65-instruction atan2f.  atan2(+-0, x>0) = +-0 like numpy.
+__device__ __forceinline__ float fast_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+    float a = mn * rc;
+    a = fmaf(fmaf(-a, mx, mn), rc, a);                  // one correction step of the quotient
+    a = mx > 0.f ? a : 0.f;
+    const float q = a * a;
+    float r = 0.0026222404558211565f;
+    r = fmaf(r, q, -0.015132519416511059f);
+    r = fmaf(r, q, 0.04112182930111885f);
+    r = fmaf(r, q, -0.07366703450679779f);
+    r = fmaf(r, q, 0.10573931038379669f);
+    r = fmaf(r, q, -0.1418597549200058f);
+    r = fmaf(r, q, 0.1999039649963379f);
+    r = fmaf(r, q, -0.33332985639572144f);
+    r = fmaf(r * q, a, a);
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+}
+
 // adjugate of R (unscaled inverse) and 1/det; R^-1 = adj * id.  R drifts away from orthogonality (the reference never
-// re-orthonormalises, quadrotorsim.py:193-202), so this is a genuine inverse, not a transpose.
+// re-orthonormalises, quadrotorsim.py:193-202), so this is a genuine inverse, not a transpose.  det = 1 +- a few 1e-3.
 __device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &id)
 {
     adj[0] = R[4] * R[8] - R[5] * R[7];
@@ -113,113 +155,137 @@ __device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &
     adj[5] = R[2] * R[3] - R[0] * R[5];
     adj[7] = R[1] * R[6] - R[0] * R[7];
     adj[8] = R[0] * R[4] - R[1] * R[3];
-    id = 1.0f / det;
+    id = fast_rcp(det);
 }
 
-// `substeps` calls of _run_internal.  Returns the fail code (0 = none); power = last substep's electrical power.
+// One call of _run_internal (quadrotorsim.py:122-208) on register state.  Algebra used (exact in real arithmetic):
+//   me_i  = (phi/ra)(V_i - phi w_i) = kV_i - k1phi w_i                                   :136-138
+//   w_i' = w_i + (h/jm)(me_i - Mm) = (w_i + cw_i) - hk w_i,  hk = (h/jm) k1phi, cw_i = (h/jm)(kV_i - Mm)   :141-145
+//   yaw reaction -me0+me1-me2+me3 = Kz - k1phi((w1-w0)+(w3-w2)),  Kz = (kV1-kV0)+(kV3-kV2)               :164
+// so the per-rotor work is 2 ops for the speed, 2 for the inflow, 3 for the thrust, 2 for the torque arm.
+template <bool SIMPLE>
+__device__ __forceinline__ void substep(const QuadConst &c, QState &s, const float cw[4], float Kz, float adj[9],
+                                        float &id, float &vsq, float &osq)
+{
+    // body-frame velocity R^-1 v (:147-148), shared by the four rotors and the drag term
+    const float bvx = (adj[0] * s.v[0] + adj[1] * s.v[1] + adj[2] * s.v[2]) * id;
+    const float bvy = (adj[3] * s.v[0] + adj[4] * s.v[1] + adj[5] * s.v[2]) * id;
+    const float bvz = (adj[6] * s.v[0] + adj[7] * s.v[1] + adj[8] * s.v[2]) * id;
+    const float nvn = -fast_sqrt(vsq), non = -fast_sqrt(osq);
+    const float tz = fmaf(-c.k1phi, (s.w[1] - s.w[0]) + (s.w[3] - s.w[2]), Kz);
+    float th[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float v1 = fmaf(s.om[0], c.A[i], fmaf(-s.om[1], c.B[i], bvz));      // inflow, :146-151
+        const float wm = fmaf(-c.hk, s.w[i], s.w[i] + cw[i]);  // NOT w*(1-hk)+cw: rounding 1-hk would bias the steady state
+        th[i] = wm * fmaf(c.ct0, wm, c.ct1 * v1);                                 // :154-156
+        if (!SIMPLE) th[i] = fmaf(c.ct2 * v1, fabsf(v1), th[i]);
+        s.w[i] = wm;
+    }
+    const float fz = (th[0] + th[1]) + (th[2] + th[3]);
+    // -(0,0,th) x p_i summed over the rotors, :160-162
+    const float tx = fmaf(th[0], c.py[0], fmaf(th[1], c.py[1], fmaf(th[2], c.py[2], th[3] * c.py[3])));
+    const float ty = -fmaf(th[0], c.px[0], fmaf(th[1], c.px[1], fmaf(th[2], c.px[2], th[3] * c.px[3])));
+
+    // force: thrust + gravity (R^-1 g m) + drag (-|v| Df R^-1 v), :166-180
+    const float idgm = id * c.gm;
+    const float Fx = fmaf(nvn * c.Df[0], bvx, adj[2] * idgm);
+    const float Fy = fmaf(nvn * c.Df[1], bvy, adj[5] * idgm);
+    const float Fz = fmaf(nvn * c.Df[2], bvz, fmaf(adj[8], idgm, fz));
+    float Tx = fmaf(non * c.Dm[0], s.om[0], tx);
+    float Ty = fmaf(non * c.Dm[1], s.om[1], ty);
+    float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
+    if (!SIMPLE) {  // gravity torque -(f_grav x cg), :177-178
+        const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
+        Tx -= gy * c.cg[2] - gz * c.cg[1];
+        Ty -= gz * c.cg[0] - gx * c.cg[2];
+        Tz -= gx * c.cg[1] - gy * c.cg[0];
+    }
+
+    // translation, :183-187 (1/mass folded into the step constants)
+    const float ax = s.R[0] * Fx + s.R[1] * Fy + s.R[2] * Fz;
+    const float ay = s.R[3] * Fx + s.R[4] * Fy + s.R[5] * Fz;
+    const float az = s.R[6] * Fx + s.R[7] * Fy + s.R[8] * Fz;
+    s.p[0] = fmaf(ax, c.c_h2m, fmaf(s.v[0], c.h, s.p[0]));
+    s.p[1] = fmaf(ay, c.c_h2m, fmaf(s.v[1], c.h, s.p[1]));
+    s.p[2] = fmaf(az, c.c_h2m, fmaf(s.v[2], c.h, s.p[2]));
+    s.v[0] = fmaf(ax, c.c_hm, s.v[0]);
+    s.v[1] = fmaf(ay, c.c_hm, s.v[1]);
+    s.v[2] = fmaf(az, c.c_hm, s.v[2]);
+
+    // rotation, :190-204
+    float ahx, ahy, ahz;  // h * I^-1 * torque
+    if (SIMPLE) {
+        ahx = Tx * c.hI[0]; ahy = Ty * c.hI[4]; ahz = Tz * c.hI[8];
+    } else {
+        ahx = c.hI[0] * Tx + c.hI[1] * Ty + c.hI[2] * Tz;
+        ahy = c.hI[3] * Tx + c.hI[4] * Ty + c.hI[5] * Tz;
+        ahz = c.hI[6] * Tx + c.hI[7] * Ty + c.hI[8] * Tz;
+    }
+    const float hwx = c.h * fmaf(0.5f, ahx, s.om[0]);
+    const float hwy = c.h * fmaf(0.5f, ahy, s.om[1]);
+    const float hwz = c.h * fmaf(0.5f, ahz, s.om[2]);
+    s.om[0] += ahx; s.om[1] += ahy; s.om[2] += ahz;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {   // R += h R [w]x
+        const float r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
+        s.R[3 * r + 0] = fmaf(r1, hwz, fmaf(-r2, hwy, r0));
+        s.R[3 * r + 1] = fmaf(r2, hwx, fmaf(-r0, hwz, r1));
+        s.R[3 * r + 2] = fmaf(r0, hwy, fmaf(-r1, hwx, r2));
+    }
+    adjugate(s.R, adj, id);                                                  // :206-208
+    vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
+    osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+}
+
+// `substeps` calls of _run_internal (quadrotorsim.py:295-304).  Returns the fail code (0 = none); power = electrical
+// power of the last executed substep (:139,188).  The loop is unrolled by 5 when substeps % 5 == 0 (dt = 0.005, 0.01)
+// so the ~40 step constants stay in uniform registers across the unrolled body.
 template <bool SIMPLE>
 __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
                                          float &power)
 {
-    // voltage clamp (quadrotorsim.py:130-134) and the per-step rotor constants
+    // voltage clamp (:130-134) and the per-step rotor constants
     float V[4] = {act.x, act.y, act.z, act.w};
-    float kV[4];
+    float kV[4], cw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         V[i] = V[i] > c.vmax ? c.vmax : (V[i] < c.vmin ? c.vmin : V[i]);
         kV[i] = c.k1 * V[i];
+        cw[i] = c.hjm * (kV[i] - c.mm);
     }
-    float me[4] = {0.f, 0.f, 0.f, 0.f};
+    const float Kz = (kV[1] - kV[0]) + (kV[3] - kV[2]);
     int fail = 0;
     float vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
     float osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+    float wl[4] = {s.w[0], s.w[1], s.w[2], s.w[3]};     // rotor speeds entering the last executed substep
 
-#pragma unroll 1
-    for (int k = 0; k < c.substeps; ++k) {
-        // body-frame velocity R^-1 v (quadrotorsim.py:147-148), shared by the four rotors and the drag term
-        const float bvx = (adj[0] * s.v[0] + adj[1] * s.v[1] + adj[2] * s.v[2]) * id;
-        const float bvy = (adj[3] * s.v[0] + adj[4] * s.v[1] + adj[5] * s.v[2]) * id;
-        const float bvz = (adj[6] * s.v[0] + adj[7] * s.v[1] + adj[8] * s.v[2]) * id;
-        const float vn = sqrtf(vsq);
-        const float on = sqrtf(osq);
-
-        float fz = 0.f, tx = 0.f, ty = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            me[i] = fmaf(-c.k1phi, s.w[i], kV[i]);                         // :136-138
-            const float wm = fmaf(c.hjm, me[i] - c.mm, s.w[i]);            // :141-145
-            const float v1 = fmaf(s.om[0], c.A[i], fmaf(-s.om[1], c.B[i], bvz));  // :146-151
-            float th = wm * fmaf(c.ct0, wm, c.ct1 * v1);                   // :154-156
-            if (!SIMPLE) th = fmaf(c.ct2 * v1, fabsf(v1), th);
-            s.w[i] = wm;
-            fz += th;
-            tx = fmaf(th, c.py[i], tx);                                    // -(0,0,th) x p_i, :160-162
-            ty = fmaf(-th, c.px[i], ty);
-        }
-        const float tz = (me[1] - me[0]) + (me[3] - me[2]);                // :164
-
-        // force: thrust + gravity (R^-1 g m) + drag (-|v| Df R^-1 v), :166-180
-        const float idgm = id * c.gm;
-        const float nvn = -vn, non = -on;
-        const float Fx = fmaf(nvn * c.Df[0], bvx, adj[2] * idgm);
-        const float Fy = fmaf(nvn * c.Df[1], bvy, adj[5] * idgm);
-        const float Fz = fmaf(nvn * c.Df[2], bvz, fmaf(adj[8], idgm, fz));
-        float Tx = fmaf(non * c.Dm[0], s.om[0], tx);
-        float Ty = fmaf(non * c.Dm[1], s.om[1], ty);
-        float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
-        if (!SIMPLE) {  // gravity torque -(f_grav x cg), :177-178
-            const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
-            Tx -= gy * c.cg[2] - gz * c.cg[1];
-            Ty -= gz * c.cg[0] - gx * c.cg[2];
-            Tz -= gx * c.cg[1] - gy * c.cg[0];
-        }
-
-        // translation, :183-187 (1/mass folded into the step constants)
-        const float ax = s.R[0] * Fx + s.R[1] * Fy + s.R[2] * Fz;
-        const float ay = s.R[3] * Fx + s.R[4] * Fy + s.R[5] * Fz;
-        const float az = s.R[6] * Fx + s.R[7] * Fy + s.R[8] * Fz;
-        s.p[0] = fmaf(ax, c.c_h2m, fmaf(s.v[0], c.h, s.p[0]));
-        s.p[1] = fmaf(ay, c.c_h2m, fmaf(s.v[1], c.h, s.p[1]));
-        s.p[2] = fmaf(az, c.c_h2m, fmaf(s.v[2], c.h, s.p[2]));
-        s.v[0] = fmaf(ax, c.c_hm, s.v[0]);
-        s.v[1] = fmaf(ay, c.c_hm, s.v[1]);
-        s.v[2] = fmaf(az, c.c_hm, s.v[2]);
-
-        // rotation, :190-204
-        float ahx, ahy, ahz;  // h * I^-1 * torque
-        if (SIMPLE) {
-            ahx = Tx * c.hI[0]; ahy = Ty * c.hI[4]; ahz = Tz * c.hI[8];
-        } else {
-            ahx = c.hI[0] * Tx + c.hI[1] * Ty + c.hI[2] * Tz;
-            ahy = c.hI[3] * Tx + c.hI[4] * Ty + c.hI[5] * Tz;
-            ahz = c.hI[6] * Tx + c.hI[7] * Ty + c.hI[8] * Tz;
-        }
-        const float hwx = c.h * fmaf(0.5f, ahx, s.om[0]);
-        const float hwy = c.h * fmaf(0.5f, ahy, s.om[1]);
-        const float hwz = c.h * fmaf(0.5f, ahz, s.om[2]);
-        s.om[0] += ahx; s.om[1] += ahy; s.om[2] += ahz;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {   // R += h R [w]x
-            const float r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
-            s.R[3 * r + 0] = fmaf(r1, hwz, fmaf(-r2, hwy, r0));
-            s.R[3 * r + 1] = fmaf(r2, hwx, fmaf(-r0, hwz, r1));
-            s.R[3 * r + 2] = fmaf(r0, hwy, fmaf(-r1, hwx, r2));
-        }
-        adjugate(s.R, adj, id);                                            // :206-208
-
-        // _check_failure, :212-221 (evaluated every substep like the reference)
-        const float psq = s.p[0] * s.p[0] + s.p[1] * s.p[1] + s.p[2] * s.p[2];
-        vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
-        osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
-        // the negated form also catches NaN
-        if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {
-            fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR);
-            break;
-        }
+    // _check_failure after every substep (:210-221); the negated comparisons also catch NaN
+#define MGB_QUAD_ONE_SUBSTEP()                                                                                   \
+    {                                                                                                            \
+        wl[0] = s.w[0]; wl[1] = s.w[1]; wl[2] = s.w[2]; wl[3] = s.w[3];                                          \
+        substep<SIMPLE>(c, s, cw, Kz, adj, id, vsq, osq);                                                        \
+        const float psq = s.p[0] * s.p[0] + s.p[1] * s.p[1] + s.p[2] * s.p[2];                                   \
+        if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {                                 \
+            fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR); \
+            break;                                                                                               \
+        }                                                                                                        \
     }
-    // :139,188  power = sum_i |me_i / phi * V_i| of the last executed substep
-    power = ((fabsf(me[0] * c.inv_phi * V[0]) + fabsf(me[1] * c.inv_phi * V[1])) + fabsf(me[2] * c.inv_phi * V[2])) +
-            fabsf(me[3] * c.inv_phi * V[3]);
+    if (c.substeps % 5 == 0) {
+#pragma unroll 1
+        for (int k = 0; k < c.substeps && !fail; k += 5) {
+#pragma unroll
+            for (int u = 0; u < 5; ++u) MGB_QUAD_ONE_SUBSTEP()
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < c.substeps; ++k) MGB_QUAD_ONE_SUBSTEP()
+    }
+#undef MGB_QUAD_ONE_SUBSTEP
+    float pw = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pw += fabsf(fmaf(-c.k1phi, wl[i], kV[i]) * c.inv_phi * V[i]);
+    power = pw;
     return fail;
 }
 
@@ -238,9 +304,9 @@ __device__ __forceinline__ void observe(const QuadConst &c, const QState &s, con
         o[6 + r] = Ri[3 * r + 2] * -9.8f;    // body_acceleration is never updated (:22,:278): IMU = R^-1 g only
         o[9 + r] = s.om[r];
     }
-    o[12] = atan2f(-s.R[6], sqrtf(s.R[7] * s.R[7] + s.R[8] * s.R[8]));   // pitch, :111-120
-    o[13] = atan2f(s.R[7], s.R[8]);                                       // roll
-    o[14] = atan2f(s.R[3], s.R[0]);                                       // yaw
+    o[12] = fast_atan2(-s.R[6], fast_sqrt(s.R[7] * s.R[7] + s.R[8] * s.R[8]));   // pitch, :111-120
+    o[13] = fast_atan2(s.R[7], s.R[8]);                                       // roll
+    o[14] = fast_atan2(s.R[3], s.R[0]);                                       // yaw
     o[15] = s.p[2] + c.z_off;
 }
 
@@ -306,8 +372,8 @@ __device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &
         const bool coll = fminf(z_old, z_new) < 0.f;
         float tr = coll ? 0.f : c.healthy;
         if (c.task == MGB_TASK_HOVERING_CONTROL) {            // env.py:222-243
-            const float vn = sqrtf(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
-            const float on = sqrtf(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
+            const float vn = fast_sqrt(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
+            const float on = fast_sqrt(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
             tr -= vn + on;
             const float zm = fabsf(0.f - s.p[2]);             // pos_0[2] is always 0 (env.py:123, :26)
             tr += zm < 0.5f ? 10.f : fmaxf(-20.f, 0.5f - zm);
@@ -336,7 +402,7 @@ __device__ __forceinline__ void observe_reset(const QuadConst &c, const QuadArgs
     o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;
     o[6] = 0.f * -9.8f; o[7] = 0.f * -9.8f; o[8] = -9.8f;
     o[9] = s.om[0]; o[10] = s.om[1]; o[11] = s.om[2];
-    o[12] = atan2f(-0.f, 1.f); o[13] = 0.f; o[14] = 0.f;
+    o[12] = -0.f; o[13] = 0.f; o[14] = 0.f;   // arctan2(-0, 1) = -0 (quadrotorsim.py:114-117 at R = I)
     o[15] = 0.f + c.z_off;
     if (c.task == MGB_TASK_VELOCITY_CONTROL) {
         const float *trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
@@ -377,6 +443,12 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
     const bool active = e < a.n;
     bool any_final = false;
 
+    // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now (its CTAs park at their own
+    // griddepcontrol.wait), and this kernel waits here until the PREVIOUS one has completed and flushed -- the
+    // launch latency of back-to-back env steps (the 2-3 us that dominate a 65k-env step) overlaps the previous step.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     if (active) {
         QState s;
         load_state(a, e, s);
@@ -398,7 +470,9 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
         if (wf) {
             if (a.final_obs) {
                 float *frow = ftile + threadIdx.x * D;
-                for (int k = 0; k < D; ++k) frow[k] = o[k];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) frow[k] = o[k];
+                if (D == 19) { frow[16] = o[16]; frow[17] = o[17]; frow[18] = o[18]; }
                 any_final = true;
             }
             observe_reset(c, a, e, s, o);
@@ -519,7 +593,9 @@ __global__ void __launch_bounds__(kThreads) quad_reset_kernel(const __grid_const
             o[16] = trow[3 * t]; o[17] = trow[3 * t + 1]; o[18] = trow[3 * t + 2];
         }
         float *dst = a.obs + e * c.obs_dim;
-        for (int k = 0; k < c.obs_dim; ++k) dst[k] = o[k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[k] = o[k];
+        if (c.obs_dim == 19) { dst[16] = o[16]; dst[17] = o[17]; dst[18] = o[18]; }
     }
 }
 
@@ -603,6 +679,7 @@ struct mgb_quad {
     int32_t *env2task = nullptr;
     int n_tasks = 0;
     int auto_reset = 0;
+    int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     uint64_t seed = 0;
     uint32_t t_base = 0;
     int64_t launches = 0;
@@ -638,6 +715,7 @@ static int derive_constants(const mgb_quad_cfg *g, QuadConst *c)
     c->k1phi = (float)(g->phi / g->ra * g->phi);
     c->inv_phi = (float)(1.0 / g->phi);
     c->hjm = (float)(g->precision / g->jm);
+    c->hk = (float)(g->precision / g->jm * (g->phi / g->ra * g->phi));
     c->mm = (float)g->mm;
     c->ct0 = (float)g->ct[0]; c->ct1 = (float)g->ct[1]; c->ct2 = (float)g->ct[2];
     c->vmin = (float)g->min_voltage; c->vmax = (float)g->max_voltage;
@@ -693,6 +771,7 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     h->env_base = env_index_base;
     h->cfg = *cfg;
     derive_constants(cfg, &h->c);
+    if (const char *ev = getenv("MGB_PDL")) h->pdl = atoi(ev) != 0;
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
     if (e != cudaSuccess) {
         mgb_set_error("cudaMalloc(state planes, %lld envs) -> %s", (long long)n_envs, cudaGetErrorString(e));
@@ -801,8 +880,18 @@ extern "C" int mgb_quad_reset(mgb_quad *h, const uint8_t *mask_dev, const double
 static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
 {
     const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
-    if (h->c.simple) quad_step_kernel<true><<<blocks, kThreads, 0, st>>>(h->c, a);
-    else quad_step_kernel<false><<<blocks, kThreads, 0, st>>>(h->c, a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true>, h->c, a));
+    else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false>, h->c, a));
     MGB_CUDA(cudaGetLastError());
     h->launches += 1;
     return MGB_OK;

@@ -219,8 +219,11 @@ class BatchedQuadrotor(object):
         _lib.check(self._lib.mgb_quad_reset(self._h, _lib.ptr(m), _lib.ptr(nz), self._obs.data_ptr(), self._stream()))
         return self._out(self._obs)
 
-    def step(self, action):
+    def step(self, action, out=None):
         """Quadrotor.step (env.py:127-165) -> (obs [N,D], reward [N], done [N] bool, info).
+
+        out: optional (obs, rew, done_u8) CUDA tensors to write into (e.g. slot t of a rollout buffer) instead of the
+        env's own output tensors.
 
         A CUDA tensor action runs fully on the device (stream-ordered, no host sync).  A numpy / host action takes
         the host path (`mgb_quad_step_host`): copies in, steps, copies out, returns numpy arrays.
@@ -229,11 +232,12 @@ class BatchedQuadrotor(object):
         if not (hasattr(action, "is_cuda") and action.is_cuda):
             return self._step_host(action)
         act = action.to(torch.float32).reshape(self.num_envs, 4).contiguous()
-        _lib.check(self._lib.mgb_quad_step(self._h, act.data_ptr(), self._obs.data_ptr(), self._rew.data_ptr(),
-                                           self._done.data_ptr(), self._fail.data_ptr(), _lib.ptr(self._final_obs),
+        obs, rew, done = (self._obs, self._rew, self._done) if out is None else out
+        _lib.check(self._lib.mgb_quad_step(self._h, act.data_ptr(), obs.data_ptr(), rew.data_ptr(),
+                                           done.data_ptr(), self._fail.data_ptr(), _lib.ptr(self._final_obs),
                                            self._stream()))
-        info = QuadInfo(self._obs, self.obs_keys)
-        return self._out(self._obs), self._out(self._rew), self._out(self._done.view(torch.bool)), info
+        info = QuadInfo(obs, self.obs_keys)
+        return self._out(obs), self._out(rew), self._out(done.view(torch.bool)), info
 
     def _step_host(self, action):
         act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(self.num_envs, 4))
