@@ -865,14 +865,17 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
         maze2d_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, st>>>(c, a);
     } else {
         const size_t sm = maze3d_smem_bytes(c);
-        if (sm != h->smem3d) {
-            if (sm > 227 * 1024) {
-                mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
-                return MGB_ERR_ARG;
-            }
-            MGB_CUDA(cudaFuncSetAttribute(maze3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            h->smem3d = sm;
+        if (sm > 227 * 1024) {
+            mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
+            return MGB_ERR_ARG;
         }
+        // the opt-in limit is a property of the kernel (per device), shared by every handle: only ever raise it
+        static size_t g_smem_limit[64] = {0};
+        if (sm > g_smem_limit[h->device & 63]) {
+            MGB_CUDA(cudaFuncSetAttribute(maze3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            g_smem_limit[h->device & 63] = sm;
+        }
+        h->smem3d = sm;
         const unsigned grid = (unsigned)(h->n < h->num_sms ? h->n : h->num_sms);
         maze3d_kernel<<<grid, kRenderThreads, sm, st>>>(c, a);
     }

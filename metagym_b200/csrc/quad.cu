@@ -160,7 +160,7 @@ __device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &
 
 // One call of _run_internal (quadrotorsim.py:122-208) on register state.  Algebra used (exact in real arithmetic):
 //   me_i  = (phi/ra)(V_i - phi w_i) = kV_i - k1phi w_i                                   :136-138
-//   w_i' = w_i + (h/jm)(me_i - Mm) = (w_i + cw_i) - hk w_i,  hk = (h/jm) k1phi, cw_i = (h/jm)(kV_i - Mm)   :141-145
+//   w_i' = w_i + (h/jm)(me_i - Mm) = w_i + (cw_i - hk w_i),  hk = (h/jm) k1phi, cw_i = (h/jm)(kV_i - Mm)   :141-145
 //   yaw reaction -me0+me1-me2+me3 = Kz - k1phi((w1-w0)+(w3-w2)),  Kz = (kV1-kV0)+(kV3-kV2)               :164
 // so the per-rotor work is 2 ops for the speed, 2 for the inflow, 3 for the thrust, 2 for the torque arm.
 template <bool SIMPLE>
@@ -177,7 +177,10 @@ __device__ __forceinline__ void substep(const QuadConst &c, QState &s, const flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float v1 = fmaf(s.om[0], c.A[i], fmaf(-s.om[1], c.B[i], bvz));      // inflow, :146-151
-        const float wm = fmaf(-c.hk, s.w[i], s.w[i] + cw[i]);  // NOT w*(1-hk)+cw: rounding 1-hk would bias the steady state
+        // increment first, then ONE rounding at the magnitude of w -- the reference's rounding structure (:144-145).  Near
+        // its fixed point a rotor's float32 speed stagnates within +-ulp/2 of increment; any other association
+        // (w*(1-hk)+cw, (w+cw)-hk*w) stagnates elsewhere and biases thrust by ~1e-5.
+        const float wm = s.w[i] + fmaf(-c.hk, s.w[i], cw[i]);
         th[i] = wm * fmaf(c.ct0, wm, c.ct1 * v1);                                 // :154-156
         if (!SIMPLE) th[i] = fmaf(c.ct2 * v1, fabsf(v1), th[i]);
         s.w[i] = wm;
@@ -680,6 +683,7 @@ struct mgb_quad {
     int n_tasks = 0;
     int auto_reset = 0;
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
+    int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
     uint64_t seed = 0;
     uint32_t t_base = 0;
     int64_t launches = 0;
@@ -772,6 +776,7 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     h->cfg = *cfg;
     derive_constants(cfg, &h->c);
     if (const char *ev = getenv("MGB_PDL")) h->pdl = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev) != 0;
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
     if (e != cudaSuccess) {
         mgb_set_error("cudaMalloc(state planes, %lld envs) -> %s", (long long)n_envs, cudaGetErrorString(e));
@@ -951,11 +956,13 @@ static int ensure_host_staging(mgb_quad *h)
     return MGB_OK;
 }
 
-static bool is_pinned(const void *p)
+// Device-visible alias of a pinned (page-locked, UVA-mapped) host buffer, or nullptr for pageable memory.
+static void *pinned_device_alias(const void *p)
 {
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    return at.devicePointer;
 }
 
 extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host,
@@ -969,9 +976,22 @@ extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs
     if (rc) return rc;
     const size_t n = (size_t)h->n, D = (size_t)h->c.obs_dim;
     cudaStream_t st = h->hstream[0];
-    // Pinned caller buffers are DMA'd directly; pageable ones go through the handle's pinned staging area.
-    const bool pin_in = is_pinned(act_host);
-    const bool pin_out = is_pinned(obs_host) && is_pinned(rew_host) && is_pinned(done_host);
+    // Zero-copy path: when all four caller buffers are pinned, the step kernel reads the actions from and writes
+    // obs/reward/done to host memory ITSELF (UVA aliases): the PCIe traffic of both directions overlaps the arithmetic
+    // inside one launch, and no copy call sits between the user and the result.  MGB_HOST_ZEROCOPY=0 forces copies.
+    void *da = pinned_device_alias(act_host), *dob = pinned_device_alias(obs_host), *dr = pinned_device_alias(rew_host),
+         *dd = pinned_device_alias(done_host);
+    if (h->zerocopy && da && dob && dr && dd && (reinterpret_cast<uintptr_t>(da) & 15u) == 0) {
+        QuadArgs a = base_args(h);
+        a.act = (const float *)da; a.obs = (float *)dob; a.rew = (float *)dr; a.done = (uint8_t *)dd;
+        rc = launch_step(h, a, st);
+        if (rc) return rc;
+        MGB_CUDA(cudaStreamSynchronize(st));
+        return MGB_OK;
+    }
+    // Copy path: pinned caller buffers are DMA'd directly; pageable ones go through the handle's pinned staging area.
+    const bool pin_in = da != nullptr;
+    const bool pin_out = dob && dr && dd;
     const float *src = act_host;
     if (!pin_in) { memcpy(h->h_act, act_host, n * 16); src = h->h_act; }
     MGB_CUDA(cudaMemcpyAsync(h->d_act, src, n * 16, cudaMemcpyHostToDevice, st));

@@ -101,3 +101,23 @@ def test_failure_detection(cfg):
     s[2, 0] = 1500.0     # |p| > 1000
     _, fail = qo.sim_step(cfg, s, np.full((3, 4), 5, np.float32), 10, "mix")
     assert list(fail) == [2, 3, 1]
+
+
+@pytest.mark.parametrize("name,np_seed", [("hover_a", 0), ("hover_fall", 2), ("nocol_a", 4), ("vel_a", 5)])
+def test_numpy_port_is_bit_identical_to_reference(quad_golden, name, np_seed):
+    """oracle/quadrotor_np.py (the CPU baseline of bench.py) replays whole reference episodes, global-RNG resets
+    included, to the last bit: it issues the same numpy operations on the same dtypes as the reference."""
+    from oracle.quadrotor_np import NumpyQuadrotorEnv
+    r = golden_run(quad_golden, name)
+    env = NumpyQuadrotorEnv(dt=r["dt"], nt=r["nt"], seed=r["seed"], task=r["task"])
+    if r["task"] == "velocity_control":
+        assert np.array_equal(np.asarray(env.targets, dtype=np.float32), r["targets"])
+    np.random.seed(np_seed)           # tests/golden/gen_quadrotor.py seeds the global RNG once per recorded run
+    ep = -1
+    for i in range(len(r["rew"])):
+        if r["ep"][i] != ep:
+            ep = int(r["ep"][i])
+            assert np.array_equal(env.reset(), r["reset_obs"][ep])
+        obs, rew, done, _ = env.step(r["act"][i])
+        assert np.array_equal(obs, r["obs"][i]) and float(rew) == r["rew"][i] and bool(done) == bool(r["done"][i])
+        assert np.array_equal(env.st.as_row(), r["post_state"][i])
