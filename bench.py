@@ -338,7 +338,7 @@ def main():
                        "integrator": "semi-implicit Euler substeps (the reference's integrator); BASELINE's 'RK4' has "
                                      "no reference counterpart (SURVEY.md fact 2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "quad_step_kernel<true>",
+                         "traffic": None, "peak_source": peak_src, "kernel": "quad_step_kernel<true,true>",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n,
                          "us_per_launch": us_per_launch},
             "gpu_launches": K,

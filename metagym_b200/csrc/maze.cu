@@ -30,10 +30,15 @@ constexpr int kNever = INT_MIN / 2;
 constexpr int kRenderThreads = 512;
 constexpr int kMaxHitsCap = 48;
 
-struct TaskHdr {                 // 80 bytes, head of every task blob
+struct TaskHdr {                 // 112 bytes, head of every task blob
     int32_t start[2], goal[2];
     double cell_size, wall_height, agent_height, initial_life, max_life, step_reward, goal_reward;
-    int32_t n_food, pad;
+    int32_t n_food;
+    int32_t cls;                 // index of the (agent_height, wall_height) class -> pose-independent eff table
+    // x / d == x * (1/d) exactly when d is a power of two: the renderer's divisions by cell_size (2.0) and
+    // text_size / cell_size (0.5) then cost one multiply instead of a ~40-instruction IEEE division.
+    double inv_cell, inv_t2c;
+    int32_t cell_pow2, t2c_pow2;
 };
 
 struct MazeConst {
@@ -41,7 +46,10 @@ struct MazeConst {
     int n_tex, ts;
     int f_max;                   // food slots per env
     int max_hits;                // transparent crossings kept per column
-    int chunk_px;                // pixels per output chunk (shared-memory staging buffer, double-buffered)
+    int run_px;                  // pixels per warp run (768 B of output): one bulk store per run
+    int text_pow2;               // text_size is a power of two
+    double inv_text;
+    int n_cls;                   // height classes with a precomputed eff table (0 = compute per pixel)
     int blob_bytes;              // bytes of one task blob (multiple of 16)
     int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
     double max_vision, l_focal, text_size;
@@ -59,6 +67,7 @@ struct MazeArgs {
     const uint8_t *blobs;        // [n_tasks][blob_bytes]
     const uint32_t *tex;         // packed 0x00BBGGRR, (n_tex + 1) * ts * ts, ceiling last
     const float *coltab;         // [4][3][res_h]: cos_hp, cos_abs, sin_abs per heading
+    const double *efftab;        // [n_cls][res_h * res_v]: distance(d_v) / cos_hp(d_h), pose independent
     const int32_t *act;
     void *obs;
     double *rew;
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_kernel(const __grid_constan
         if (threadIdx.x == 0) {
             mgb_bulk_store(dst, tile2d, bytes);
             mgb_bulk_commit();
-            mgb_bulk_wait<0>();
+            mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
         }
     } else {
         __syncthreads();
@@ -282,8 +291,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
     HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);              off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
     const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
-    uint8_t *s_out0 = smem + off;                                         off = align_up(off + (size_t)c.chunk_px * px_bytes, 128);
-    uint8_t *s_out1 = smem + off;                                         off = align_up(off + (size_t)c.chunk_px * px_bytes, 128);
+    const int run_bytes = c.run_px * px_bytes;                           // 768
+    const int n_slots = c.obs_dtype == MGB_OBS_U8 ? 2 : 1;               // int32 runs are 4x larger: single slot
+    uint8_t *s_out = smem + off;                                          off = align_up(off + (size_t)(kRenderThreads / 32) * n_slots * run_bytes, 128);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 16;
     int *s_env = reinterpret_cast<int *>(smem + off);                    // [0..3] gx gy ori steps, [4] lifebar end
 
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     }
     uint32_t blob_phase = 0;
     bool tex_ready = false;
-    int chunk_parity = 0;
+    int run_parity = 0;
 
     for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x) {
         const bool live = !(a.mask && !a.mask[e]) || a.do_step;   // reset with a mask renders only the masked envs
@@ -472,100 +482,149 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
         __syncthreads();
 
-        // ---- pixels: q = d_h * V + d_v in chunks of c.chunk_px, double-buffered, TMA bulk store per chunk
+        // ---- pixels.  Each WARP owns runs of whole screen columns (c.run_px / V of them, 768 B of output): the column
+        // record is warp-uniform (one broadcast read, held in registers), lanes take rows d_v = lane, lane + 32, ...,
+        // write into the warp's private staging slot, and lane 0 issues ONE bulk (TMA) store per run; the slot is
+        // double-buffered.  No block-wide barrier inside an env: a warp with cheap pixels (walls) simply moves on.
         const int total_px = H * V;
         const int lb_sx = trunc_i(c.lb_sx), lb_ex = s_env[4];
         const int lb_sy = trunc_i(c.lb_sy);
         int lb_ey = trunc_i(c.lb_sy + c.lb_w);
         if (lb_ey > V) lb_ey = V;
+        const bool has_bar = c.task_type == MGB_MAZE_SURVIVAL;
         uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
-        for (int base = 0; base < total_px; base += c.chunk_px) {
-            uint8_t *buf = chunk_parity ? s_out1 : s_out0;
-            const int cnt = total_px - base < c.chunk_px ? total_px - base : c.chunk_px;
-            // the bulk store that last used this buffer (two chunks ago) must have finished reading it
-            if (tid == 0) mgb_bulk_wait_read<1>();
-            __syncthreads();
-            for (int p = tid; p < cnt; p += blockDim.x) {
-                const int q = base + p;
-                const int d_h = q / V, d_v = q - d_h * V;
-                const ColRec &cr = s_col[d_h];
-                const RowRec &rr = s_row[d_v];
-                int rgb[3] = {0, 0, 0};
-                bool mark = false;
-                const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
-                if (rr.kind != 0 && (!in_wall || cr.n_hits > 0)) {
-                    const double eff = rr.distance / cr.cos_hp;
-                    const double hit_x = eff * cr.cos_abs + pos_x;
-                    const double hit_y = eff * cr.sin_abs + pos_y;
-                    if (rr.kind == 1) {                                   // floor, :103-126
-                        const double alpha = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0)) * rr.light;
-                        const double fi = hit_x / cell_size, fj = hit_y / cell_size;
-                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
-                        const int i = trunc_i(fi), j = trunc_i(fj);
-                        if (i < n && i >= 0 && j < n && j >= 0) {
-                            const int text_id = texts[i * n + j];
-                            d_i /= text_to_cell; d_j /= text_to_cell;
-                            d_i -= floor(d_i); d_j -= floor(d_j);
-                            d_i *= ts; d_j *= ts;
-                            shade(rgb, rr.light, 1.0 - alpha, s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
-                            const double tv = s_transp[i * n + j];
-                            if (tv > 0.01) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
-                        }
-                    } else {                                              // ceiling, :137-153
-                        const double alpha = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
-                        const int t_i = trunc_i(hit_x / cell_size), t_j = trunc_i(hit_y / cell_size);
-                        const double fi = hit_x / c.text_size, fj = hit_y / c.text_size;
-                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
-                        d_i *= ts; d_j *= ts;
-                        shade(rgb, rr.light, 1.0 - alpha, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
-                        if (t_i >= 0 && t_i < n && t_j >= 0 && t_j < n) {
-                            const double tv = s_transp[t_i * n + t_j];
-                            if (tv > 0) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+        const int lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+        const double inv_cell = th->inv_cell, inv_t2c = th->inv_t2c;
+        const bool cell_p2 = th->cell_pow2 != 0, t2c_p2 = th->t2c_pow2 != 0, text_p2 = c.text_pow2 != 0;
+        const double *efft = (c.n_cls > 0 && th->cls >= 0) ? a.efftab + (size_t)th->cls * total_px : nullptr;
+        const double fog_from = 0.4999 * c.max_vision;
+        const double dts = (double)ts;
+        const int cols_per_run = c.run_px / V > 0 ? c.run_px / V : 1;
+        const int n_runs = (H + cols_per_run - 1) / cols_per_run;
+        for (int run = warp; run < n_runs; run += n_warps) {
+            uint8_t *buf = s_out + ((size_t)warp * n_slots + (n_slots == 2 ? run_parity : 0)) * run_bytes;
+            const int h0 = run * cols_per_run;
+            const int ncol = H - h0 < cols_per_run ? H - h0 : cols_per_run;
+            // the bulk store that last used this slot (two runs ago) must have finished reading it
+            if (lane == 0) { if (n_slots == 2) mgb_bulk_wait_read<1>(); else mgb_bulk_wait_read<0>(); }
+            __syncwarp();
+            for (int cc = 0; cc < ncol; ++cc) {
+                const int d_h = h0 + cc;
+                const ColRec cr = s_col[d_h];                              // warp-uniform
+                const HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
+                const bool bar_col = has_bar && d_h >= lb_sx && d_h < lb_ex;
+                const double *effc = efft ? efft + (size_t)d_h * V : nullptr;
+                for (int d_v = lane; d_v < V; d_v += 32) {
+                    int rgb[3] = {0, 0, 0};
+                    bool mark = false;
+                    const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
+                    if (!in_wall || cr.n_hits > 0) {
+                        const RowRec rr = s_row[d_v];
+                        if (rr.kind != 0) {
+                            const double eff = effc ? __ldg(effc + d_v) : rr.distance / cr.cos_hp;
+                            // alpha = clip(2 eff / max_vision - 1, 0, 1) is exactly 0 while 2 eff / max_vision < 1; the
+                            // margin keeps the shortcut independent of the division's rounding
+                            double fog = 0.0;
+                            if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
+                            const double hit_x = eff * cr.cos_abs + pos_x;
+                            const double hit_y = eff * cr.sin_abs + pos_y;
+                            const double ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
+                            const double cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
+                            const int i = trunc_i(ci), j = trunc_i(cj);
+                            const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
+                            if (rr.kind == 1) {                               // floor, :103-126
+                                if (inside) {
+                                    double d_i = ci - floor(ci), d_j = cj - floor(cj);
+                                    const int text_id = texts[i * n + j];
+                                    d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
+                                    d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
+                                    d_i -= floor(d_i); d_j -= floor(d_j);
+                                    d_i *= dts; d_j *= dts;
+                                    shade(rgb, rr.light, 1.0 - fog * rr.light,
+                                          s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                                    const double tv = s_transp[i * n + j];
+                                    if (tv > 0.01) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+                                }
+                            } else {                                          // ceiling, :137-153
+                                const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
+                                const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
+                                double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                                d_i *= dts; d_j *= dts;
+                                shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                                if (inside) {
+                                    const double tv = s_transp[i * n + j];
+                                    if (tv > 0) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+                                }
+                            }
                         }
                     }
-                }
-                if (in_wall) {                                            // wall texel, :184-189
-                    const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
-                    double d_j = local_v / c.text_size;
-                    d_j -= floor(d_j);
-                    shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(ts * d_j)]);
-                }
-                if (cr.n_hits > 0 && !mark) {                             // transparent overlays, :191-205
-                    const HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
-                    for (int k = 0; k < cr.n_hits; ++k)
-                        if (d_v >= hits[k].v_s && d_v < hits[k].v_e) blend(rgb, hits[k].tf);
-                }
-                if (c.task_type == MGB_MAZE_SURVIVAL && d_h >= lb_sx && d_h < lb_ex && d_v >= lb_sy && d_v < lb_ey) {
-                    rgb[0] = 255; rgb[1] = 0; rgb[2] = 0;                 // life bar, maze_discrete_3d.py:118-126
-                }
-                if (c.obs_dtype == MGB_OBS_U8) {
-                    buf[p * 3 + 0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
-                    buf[p * 3 + 1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
-                    buf[p * 3 + 2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
-                } else {
-                    int32_t *o = reinterpret_cast<int32_t *>(buf) + p * 3;
-                    o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
+                    if (in_wall) {                                            // wall texel, :184-189
+                        const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
+                        double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
+                        d_j -= floor(d_j);
+                        shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
+                    }
+                    if (cr.n_hits > 0 && !mark) {                             // transparent overlays, :191-205
+                        for (int k = 0; k < cr.n_hits; ++k)
+                            if (d_v >= hits[k].v_s && d_v < hits[k].v_e) blend(rgb, hits[k].tf);
+                    }
+                    if (bar_col && d_v >= lb_sy && d_v < lb_ey) {             // life bar, maze_discrete_3d.py:118-126
+                        rgb[0] = 255; rgb[1] = 0; rgb[2] = 0;
+                    }
+                    const int p = cc * V + d_v;
+                    if (c.obs_dtype == MGB_OBS_U8) {
+                        buf[p * 3 + 0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
+                        buf[p * 3 + 1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
+                        buf[p * 3 + 2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
+                    } else {
+                        int32_t *o = reinterpret_cast<int32_t *>(buf) + p * 3;
+                        o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
+                    }
                 }
             }
-            uint8_t *dst = gobs + (size_t)base * px_bytes;
-            const uint32_t bytes = (uint32_t)cnt * (uint32_t)px_bytes;
+            uint8_t *dst = gobs + (size_t)h0 * V * px_bytes;
+            const uint32_t bytes = (uint32_t)(ncol * V) * (uint32_t)px_bytes;
             if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
                 mgb_fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) {
+                __syncwarp();
+                if (lane == 0) {
                     mgb_bulk_store(dst, buf, bytes);
                     mgb_bulk_commit();
                 }
             } else {
-                __syncthreads();
-                for (uint32_t i = tid; i < bytes; i += blockDim.x) dst[i] = buf[i];
+                __syncwarp();
+                for (uint32_t i = lane; i < bytes; i += 32) dst[i] = buf[i];
             }
-            chunk_parity ^= 1;
+            run_parity ^= 1;
         }
         __syncthreads();   // s_col / s_row / s_transp / s_blob are rewritten by the next env
     }
     if (!tex_ready && tid == 0) mgb_mbar_wait(&s_bar[0], 0);   // never leave a TMA load in flight
-    if (tid == 0) mgb_bulk_wait<0>();
+    if ((tid & 31) == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copies; the kernel boundary flushes the writes
+}
+
+// Pose-independent part of the floor/ceiling geometry: eff(d_h, d_v) = distance(d_v) / cos_hp(d_h)
+// (ray_caster_utils.py:97-104,131-138) depends only on the screen, the optics and the two heights of a task, so it is
+// tabulated once per (agent_height, wall_height) class with the SAME float64 division the renderer would execute.
+__global__ void maze_efftab_kernel(const __grid_constant__ MazeConst c, const float *coltab, const double *cls_heights,
+                                   int n_cls, double *efftab)
+{
+    const int H = c.res_h, V = c.res_v;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_cls * H * V) return;
+    const int k = (int)(idx / ((int64_t)H * V));
+    const int q = (int)(idx - (int64_t)k * H * V);
+    const int d_h = q / V, d_v = q - d_h * V;
+    const double vision_height = cls_heights[2 * k], ceil_height = cls_heights[2 * k + 1];
+    double distance = 0.0;
+    if (d_v > V / 2) {
+        const double v_screen = (d_v + 0.5) * c.pixel_size - c.half_v;
+        distance = vision_height / v_screen * c.l_focal;
+    } else if (d_v < V / 2) {
+        const double v_screen = c.half_v - (d_v + 0.5) * c.pixel_size;
+        distance = (ceil_height - vision_height) / v_screen * c.l_focal;
+    }
+    efftab[idx] = distance / (double)coltab[d_h];     // cos_hp does not depend on the heading: use heading 0
 }
 
 __global__ void maze_state_kernel(MazeArgs a, int32_t *agent_out, double *life_out)
@@ -594,6 +653,7 @@ struct mgb_maze {
     uint8_t *blobs = nullptr;
     uint32_t *tex = nullptr;
     float *coltab = nullptr;
+    double *efftab = nullptr;
     int n_tasks = 0;
     int auto_reset = 0;
     bool has_task = false, has_tex = false;
@@ -613,8 +673,7 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
     off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
-    off = up(off + (size_t)c.chunk_px * px, 128);
-    off = up(off + (size_t)c.chunk_px * px, 128);
+    off = up(off + (size_t)(kRenderThreads / 32) * (c.obs_dtype == MGB_OBS_U8 ? 2 : 1) * c.run_px * px, 128);
     off += 16 + 32;
     return off;
 }
@@ -625,7 +684,7 @@ static MazeArgs maze_args(const mgb_maze *h)
     memset(&a, 0, sizeof(a));
     a.n = h->n; a.n_pad = h->n_pad; a.env_base = h->env_base;
     a.agent = h->agent; a.life = h->life; a.eaten = h->eaten; a.env2task = h->env2task; a.blobs = h->blobs;
-    a.tex = h->tex; a.coltab = h->coltab; a.auto_reset = h->auto_reset;
+    a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.auto_reset = h->auto_reset;
     return a;
 }
 
@@ -657,6 +716,11 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     c.kind = cfg->kind; c.task_type = cfg->task_type; c.n = cfg->n_cells; c.max_steps = cfg->max_steps;
     c.view_grid = cfg->view_grid; c.res_h = cfg->res_h; c.res_v = cfg->res_v; c.obs_dtype = cfg->obs_dtype;
     c.max_vision = cfg->max_vision; c.l_focal = cfg->l_focal; c.text_size = cfg->text_size;
+    {
+        int ex = 0;
+        c.text_pow2 = (cfg->text_size > 0 && frexp(cfg->text_size, &ex) == 0.5) ? 1 : 0;
+        c.inv_text = cfg->text_size > 0 ? 1.0 / cfg->text_size : 0.0;
+    }
     cudaDeviceProp prop;
     MGB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
@@ -706,7 +770,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     MgbDeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
-    cudaFree(h->tex); cudaFree(h->coltab);
+    cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab);
     delete h;
 }
 
@@ -787,7 +851,12 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     if (mh < 1) mh = 1;
     if (c.task_type == MGB_MAZE_ESCAPE) mh = 2;
     c.max_hits = mh > kMaxHitsCap ? kMaxHitsCap : mh;
-    c.chunk_px = c.obs_dtype == MGB_OBS_U8 ? 2048 : 1024;
+    // a warp run = whole columns, about 768 B of output (u8: 256 px, i32: 64 px), never less than one column
+    c.run_px = c.obs_dtype == MGB_OBS_U8 ? 256 : 64;
+    if (c.kind == MGB_MAZE_DISCRETE_3D) {
+        if (c.run_px < c.res_v) c.run_px = c.res_v;
+        c.run_px = c.run_px / c.res_v * c.res_v;
+    }
     // blob layout
     size_t off = sizeof(TaskHdr);
     c.off_walls = (int)off; off += nn;
@@ -798,6 +867,7 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     c.off_fint = (int)off;  off += (size_t)(f_max > 0 ? f_max : 1) * 4;
     c.blob_bytes = (int)((off + 15) / 16 * 16);
     std::vector<uint8_t> blobs((size_t)n_tasks * c.blob_bytes, 0);
+    std::vector<double> cls_heights;   // distinct (agent_height, wall_height) pairs, at most 8 get an eff table
     for (int t = 0; t < n_tasks; ++t) {
         uint8_t *b = blobs.data() + (size_t)t * c.blob_bytes;
         TaskHdr hd;
@@ -807,6 +877,22 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
         hd.cell_size = s.cell_size; hd.wall_height = s.wall_height; hd.agent_height = s.agent_height;
         hd.initial_life = s.initial_life; hd.max_life = s.max_life; hd.step_reward = s.step_reward;
         hd.goal_reward = s.goal_reward;
+        {
+            int ex = 0;
+            const double t2c = c.text_size / s.cell_size;
+            hd.cell_pow2 = frexp(s.cell_size, &ex) == 0.5 ? 1 : 0;
+            hd.t2c_pow2 = frexp(t2c, &ex) == 0.5 ? 1 : 0;
+            hd.inv_cell = 1.0 / s.cell_size;
+            hd.inv_t2c = 1.0 / t2c;
+            hd.cls = -1;
+            for (size_t k = 0; k < cls_heights.size() / 2; ++k)
+                if (cls_heights[2 * k] == s.agent_height && cls_heights[2 * k + 1] == s.wall_height) hd.cls = (int)k;
+            if (hd.cls < 0 && cls_heights.size() / 2 < 8) {
+                hd.cls = (int)(cls_heights.size() / 2);
+                cls_heights.push_back(s.agent_height);
+                cls_heights.push_back(s.wall_height);
+            }
+        }
         int cnt = 0;
         int8_t *fidx = reinterpret_cast<int8_t *>(b + c.off_fidx);
         double *fval = reinterpret_cast<double *>(b + c.off_fval);
@@ -838,6 +924,21 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     MGB_CUDA(cudaMemcpy(h->env2task, env2task_host, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice));
     h->n_tasks = n_tasks;
     h->has_task = true;
+    cudaFree(h->efftab); h->efftab = nullptr;
+    c.n_cls = 0;
+    if (c.kind == MGB_MAZE_DISCRETE_3D && !cls_heights.empty()) {
+        const int n_cls = (int)(cls_heights.size() / 2);
+        const size_t cells = (size_t)n_cls * c.res_h * c.res_v;
+        double *d_heights = nullptr;
+        MGB_CUDA(cudaMalloc(&h->efftab, cells * sizeof(double)));
+        MGB_CUDA(cudaMalloc(&d_heights, cls_heights.size() * sizeof(double)));
+        MGB_CUDA(cudaMemcpy(d_heights, cls_heights.data(), cls_heights.size() * sizeof(double), cudaMemcpyHostToDevice));
+        maze_efftab_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(c, h->coltab, d_heights, n_cls, h->efftab);
+        MGB_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_heights);
+        c.n_cls = n_cls;
+        h->launches += 1;
+    }
     // set_task leaves the env in "need reset" state (maze_env.py:44-50): initialise it so a stray step is harmless
     MazeArgs a = maze_args(h);
     maze_reset_kernel<<<(unsigned)((h->n + 255) / 256), 256>>>(c, a);

@@ -343,28 +343,39 @@ __device__ __forceinline__ void philox_reset_draws(uint64_t seed, int64_t genv, 
     }
 }
 
+// Velocity-target rows an env needs this step, fetched BEFORE the integrator runs so the (dependent: env2task -> row)
+// L2 latency hides under the ~1000 arithmetic instructions of the substeps instead of stalling the epilogue.
+struct TargetRows {
+    float cur[3];    // velocity_targets[ct - 1]         (env.py:153)
+    float nxt[3];    // velocity_targets[min(ct, nt-1)]  (env.py:270-274)
+};
+__device__ __forceinline__ void prefetch_targets(const QuadConst &c, const QuadArgs &a, const float *trow, int ct,
+                                                 TargetRows &tr)
+{
+    if (c.task != MGB_TASK_VELOCITY_CONTROL) return;
+    const int t = ct < c.nt - 1 ? ct : c.nt - 1;
+    const float *g = trow + 3 * (ct - 1), *q = trow + 3 * t;
+    tr.cur[0] = __ldg(g); tr.cur[1] = __ldg(g + 1); tr.cur[2] = __ldg(g + 2);
+    tr.nxt[0] = __ldg(q); tr.nxt[1] = __ldg(q + 1); tr.nxt[2] = __ldg(q + 2);
+}
+
 // Task logic after the integrator: observation, reward, collision, done, counters, optional auto-reset.
 // o[] receives the observation to publish; fo[] the terminal observation (valid iff *had_final).
 __device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &a, int64_t e, QState &s,
                                             const float adj[9], float id, float z_old, float power, int fail,
-                                            float *o, float &reward, int &done_flag, bool &write_final)
+                                            const TargetRows &tr, float *o, float &reward, int &done_flag,
+                                            bool &write_final)
 {
     float bv[3], Ri[9];
     observe(c, s, adj, id, o, bv, Ri);
-    const float *trow = nullptr;
-    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
-        trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
-        const int t = s.ct < c.nt - 1 ? s.ct : c.nt - 1;      // env.py:270-274 (ct already incremented)
-        o[16] = __ldg(trow + 3 * t);
-        o[17] = __ldg(trow + 3 * t + 1);
-        o[18] = __ldg(trow + 3 * t + 2);
+    if (c.task == MGB_TASK_VELOCITY_CONTROL) {                // env.py:270-274 (ct already incremented)
+        o[16] = tr.nxt[0]; o[17] = tr.nxt[1]; o[18] = tr.nxt[2];
     }
     // energy term, env.py:217
     reward = -fminf(c.dt * power, c.healthy);
     int done = 0;
     if (c.task == MGB_TASK_VELOCITY_CONTROL) {
-        const float *g = trow + 3 * (s.ct - 1);               // env.py:153-157
-        const float g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+        const float g0 = tr.cur[0], g1 = tr.cur[1], g2 = tr.cur[2];   // env.py:153-157
         float diff = 0.f;
 #pragma unroll
         for (int r = 0; r < 3; ++r) diff += fabsf((Ri[3 * r] * g0 + Ri[3 * r + 1] * g1 + Ri[3 * r + 2] * g2) - bv[r]);
@@ -433,7 +444,10 @@ __device__ __forceinline__ void publish_tile(float *gobs, const float *tile, int
     }
 }
 
-template <bool SIMPLE>
+// EARLY: fetch the velocity-target rows before the integrator (hides their latency, +8 registers).  Right when one
+// launch is a single wave of CTAs (latency-bound, e.g. 65 536 envs); for multi-wave launches (millions of envs) the
+// extra registers cost one resident CTA per SM and other CTAs already hide the latency, so the host picks EARLY=false.
+template <bool SIMPLE, bool EARLY>
 __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_constant__ QuadConst c,
                                                              const __grid_constant__ QuadArgs a)
 {
@@ -449,6 +463,9 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
     // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now (its CTAs park at their own
     // griddepcontrol.wait), and this kernel waits here until the PREVIOUS one has completed and flushed -- the
     // launch latency of back-to-back env steps (the 2-3 us that dominate a 65k-env step) overlaps the previous step.
+    // (A finer per-tile ticket/flag hand-off between launches was built and measured: 9.8 us/step instead of 6.0 at
+    // 65 536 envs -- all CTAs of one launch are co-resident in a single wave, so there is nothing to overlap and the
+    // spinning early CTAs only steal issue slots.  Rejected; see DESIGN.md.)
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -459,12 +476,18 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
         float adj[9], id, power;
         adjugate(s.R, adj, id);
         s.ct += 1;                                              // env.py:128
+        TargetRows tr;
+        const int ct_now = s.ct;
+        if (EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
+            prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
         const float z_old = s.p[2] + c.z_off;                   // env.py:131-133
         const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
+        if (!EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
+            prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
         float o[kMaxObs], reward;
         int done;
         bool wf;
-        finish_step(c, a, e, s, adj, id, z_old, power, fail, o, reward, done, wf);
+        finish_step(c, a, e, s, adj, id, z_old, power, fail, tr, o, reward, done, wf);
         store_state(a, e, s);
         a.rew[e] = reward;
         a.done[e] = (uint8_t)done;
@@ -495,7 +518,7 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
             }
         }
     }
-    if (threadIdx.x == 0) mgb_bulk_wait<0>();
+    if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
 }
 
 // T env.step()s in one launch: the state never leaves registers; per step the kernel reads 16 B of action (or draws
@@ -519,6 +542,11 @@ __global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_con
     }
     const uint2 akey = make_uint2((uint32_t)a.act_seed, (uint32_t)(a.act_seed >> 32));
     const int64_t genv = a.env_base + e;
+    const float *trow = nullptr;
+    if (active && c.task == MGB_TASK_VELOCITY_CONTROL) trow = a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3;
+    // software pipeline: the action of step t+1 is requested while step t integrates
+    float4 act_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && a.act) act_next = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
     for (int t = 0; t < a.T; ++t) {
         float *tile = tiles[t & 1];
         // the bulk store issued two steps ago must have finished READING this tile before we overwrite it
@@ -527,7 +555,8 @@ __global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_con
         if (active) {
             float4 act;
             if (a.act) {
-                act = __ldg(reinterpret_cast<const float4 *>(a.act) + (int64_t)t * a.n + e);
+                act = act_next;
+                if (t + 1 < a.T) act_next = __ldg(reinterpret_cast<const float4 *>(a.act) + (int64_t)(t + 1) * a.n + e);
             } else {
                 const uint4 r = mgb_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32),
                                                              a.t_base + (uint32_t)t, MGB_STREAM_ACTION),
@@ -538,13 +567,15 @@ __global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_con
                 if (a.act_out) reinterpret_cast<float4 *>(a.act_out)[(int64_t)t * a.n + e] = act;
             }
             s.ct += 1;
+            TargetRows tr;
+            prefetch_targets(c, a, trow, s.ct, tr);
             const float z_old = s.p[2] + c.z_off;
             float power;
             const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
             float o[kMaxObs], reward;
             int done;
             bool wf;
-            finish_step(c, a, e, s, adj, id, z_old, power, fail, o, reward, done, wf);
+            finish_step(c, a, e, s, adj, id, z_old, power, fail, tr, o, reward, done, wf);
             if (wf) {
                 observe_reset(c, a, e, s, o);
                 adjugate(s.R, adj, id);
@@ -561,7 +592,7 @@ __global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_con
         if (a.obs) publish_tile(a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
     }
     if (active) store_state(a, e, s);
-    if (threadIdx.x == 0) mgb_bulk_wait<0>();
+    if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
 }
 
 // QuadrotorSim.reset for masked envs + observation of every env (env.py:116-125)
@@ -682,6 +713,7 @@ struct mgb_quad {
     int32_t *env2task = nullptr;
     int n_tasks = 0;
     int auto_reset = 0;
+    int num_sms = 148;
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
     uint64_t seed = 0;
@@ -776,6 +808,10 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     h->cfg = *cfg;
     derive_constants(cfg, &h->c);
     if (const char *ev = getenv("MGB_PDL")) h->pdl = atoi(ev) != 0;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    }
     if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev) != 0;
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
     if (e != cudaSuccess) {
@@ -895,8 +931,15 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
     attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true>, h->c, a));
-    else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false>, h->c, a));
+    // single wave (<= ~8 resident CTAs per SM) -> latency-bound -> early target fetch; otherwise favour occupancy
+    const bool early = blocks <= (unsigned)h->num_sms * 10u;
+    if (h->c.simple) {
+        if (early) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true, true>, h->c, a));
+        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true, false>, h->c, a));
+    } else {
+        if (early) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false, true>, h->c, a));
+        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false, false>, h->c, a));
+    }
     MGB_CUDA(cudaGetLastError());
     h->launches += 1;
     return MGB_OK;

@@ -1,0 +1,17 @@
+"""Tiny driver for ncu captures: a few maze3d / maze2d steps at the config-4 per-GPU shape."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D, MazeTaskSampler
+rs = np.random.RandomState(0)
+tasks = [MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.35, rng=rs) for _ in range(64)]
+env = BatchedMetaMazeDiscrete3D(resolution=(128, 128), max_steps=200, num_envs=1024, squeeze=False, auto_reset=True,
+                                obs_dtype="uint8")
+env.set_task(tasks); env.reset()
+for t in range(6):
+    env.step(torch.randint(0, 4, (1024,), device="cuda", dtype=torch.int32))
+e2 = BatchedMetaMaze2D(max_steps=200, task_type="ESCAPE", view_grid=1, num_envs=1048576, squeeze=False, auto_reset=True)
+e2.set_task(tasks); e2.reset()
+for t in range(6):
+    e2.step(torch.randint(0, 4, (1048576,), device="cuda", dtype=torch.int32))
+torch.cuda.synchronize()
