@@ -17,6 +17,7 @@
 // what maze_base.py:74-75,83-88 does with its whole-grid countdown arrays.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -68,6 +69,14 @@ struct MazeArgs {
     const uint32_t *tex;         // packed 0x00BBGGRR, (n_tex + 1) * ts * ts, ceiling last
     const float *coltab;         // [4][3][res_h]: cos_hp, cos_abs, sin_abs per heading
     const double *efftab;        // [n_cls][res_h * res_v]: distance(d_v) / cos_hp(d_h), pose independent
+    // pose cache (memoised static layers, see maze3d_compose_kernel)
+    const int4 *poses;           // FILL: [n_slots] task, gx, gy, ori
+    const int32_t *pose_index;   // [n_tasks][n*n*4] -> slot or -1
+    uint32_t *c_px;              // [n_slots][H*V]   10-bit R | G<<10 | B<<20 | in_wall<<30
+    uint8_t *c_fid;              // [n_slots][H*V]   food slot of the floor/ceiling cell under the pixel, 0xFF none
+    uint8_t *c_colhits;          // [n_slots][H]     transparent crossings recorded for the column
+    void *c_hits;                // [n_slots][H][max_hits] HitRec
+    void *dyn;                   // [n] EnvDyn, written by the logic kernel, read by the compose kernel
     const int32_t *act;
     void *obs;
     double *rew;
@@ -253,7 +262,13 @@ struct RowRec {                  // one screen row, 24 bytes
 struct HitRec {                  // one transparent crossing of a column, 16 bytes
     double tf;
     int16_t v_s, v_e;
-    int32_t pad;
+    int32_t fid;                 // food slot of the crossed cell (pose cache: presence is decided per env, per step)
+};
+struct EnvDyn {                  // per env, per step: what the static pose layers must be combined with, 32 bytes
+    int32_t slot;                // pose-cache slot of (task, cell, heading)
+    int32_t bar_end;             // life bar end column (python slice semantics already applied)
+    uint64_t present[2];         // bit f: food slot f is currently visible
+    int32_t task, pad;
 };
 
 __device__ __forceinline__ int trunc_i(double x) { return (int)x; }   // cvt.rzi: python/numba int()
@@ -276,6 +291,12 @@ __device__ __forceinline__ void blend(int rgb[3], double tf)
 
 __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// FILL = false: render the observation of every env directly (step logic + ray cast + paint).
+// FILL = true : render the STATIC layers of every cached pose (task, cell, heading) once, at set_task time: colours
+//               before any transparency, the food slot under every floor/ceiling pixel, every POSSIBLE transparent
+//               crossing of every column.  maze3d_compose_kernel then turns a pose + the env's current food state
+//               into the exact observation with integer work only (the float64 geometry is memoised).
+template <bool FILL>
 __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_constant__ MazeConst c,
                                                                    const __grid_constant__ MazeArgs a)
 {
@@ -319,11 +340,10 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     int run_parity = 0;
 
     for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x) {
-        const bool live = !(a.mask && !a.mask[e]) || a.do_step;   // reset with a mask renders only the masked envs
-        if (!live) continue;
         // ---- stage this env's maze tile (walls, textures ids, food table) by TMA
         if (tid == 0) {
-            const uint8_t *src = a.blobs + (int64_t)a.env2task[e] * c.blob_bytes;
+            const int task_id = FILL ? a.poses[e].x : a.env2task[e];
+            const uint8_t *src = a.blobs + (int64_t)task_id * c.blob_bytes;
             mgb_mbar_expect_tx(&s_bar[1], (uint32_t)c.blob_bytes);
             mgb_bulk_load(s_blob, src, (uint32_t)c.blob_bytes, &s_bar[1]);
         }
@@ -332,7 +352,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const TaskHdr *th = blob_hdr(s_blob);
 
         // ---- step logic (one thread), then publish agent pose to the CTA
-        if (tid == 0) {
+        if (FILL) {
+            if (tid == 0) {
+                const int4 ps = a.poses[e];
+                s_env[0] = ps.y; s_env[1] = ps.z; s_env[2] = ps.w; s_env[3] = 0; s_env[4] = 0;
+            }
+        } else if (tid == 0) {
             const int4 ag = a.agent[e];
             Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
             int32_t *eaten = a.eaten + e;
@@ -363,8 +388,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         // ---- transparent map + row table
         for (int k = tid; k < n * n; k += blockDim.x) {
             double v;
-            if (c.task_type == MGB_MAZE_SURVIVAL) v = food_now(c, s_blob, a.eaten + e, a.n_pad, steps, k);
-            else v = (k == th->goal[0] * n + th->goal[1]) ? 1.0 : 0.0;
+            if (c.task_type == MGB_MAZE_SURVIVAL) {
+                if (FILL) {   // static superset: every food cell at its full value
+                    const int f = reinterpret_cast<const int8_t *>(s_blob + c.off_fidx)[k];
+                    v = f >= 0 ? reinterpret_cast<const double *>(s_blob + c.off_fval)[f] : 0.0;
+                } else v = food_now(c, s_blob, a.eaten + e, a.n_pad, steps, k);
+            } else v = (k == th->goal[0] * n + th->goal[1]) ? 1.0 : 0.0;
             s_transp[k] = v;
         }
         for (int d_v = tid; d_v < V; d_v += blockDim.x) {
@@ -407,7 +436,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             double hit_dist = 0.0;
             HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
             // a transparent crossing at distance d paints the span of a wall standing there (:191-198)
-            auto record_hit = [&](double d, double strength) {
+            const int8_t *fidx_map = reinterpret_cast<const int8_t *>(s_blob + c.off_fidx);
+            auto record_hit = [&](double d, double strength, int cell) {
                 if (nh >= c.max_hits) return;
                 const double ratio = d * cr.cos_hp / c.l_focal;
                 const double tv = (ceil_height - vision_height) / ratio, bv = vision_height / ratio;
@@ -416,11 +446,11 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 hr.tf = strength * 0.50 + 0.10;
                 hr.v_s = (int16_t)(s0 < 0 ? 0 : s0);
                 hr.v_e = (int16_t)(s1 > V ? V : s1);
-                hr.pad = 0;
+                hr.fid = c.task_type == MGB_MAZE_SURVIVAL ? (int)fidx_map[cell] : 0;
                 hits[nh++] = hr;
             };
             if (s_transp[hit_i * n + hit_j] > 0.01)                   // start cell, :25-29
-                record_hit(side_x < side_y ? side_x : side_y, s_transp[hit_i * n + hit_j]);
+                record_hit(side_x < side_y ? side_x : side_y, s_transp[hit_i * n + hit_j], hit_i * n + hit_j);
             while (hit_dist < c.max_vision) {
                 if (side_x < side_y) {
                     hit_i += delta_i;
@@ -430,7 +460,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                         if (hit_j < 0 || hit_j >= n) { hit_dist = 1.0e+6; break; }
                     } else if (hit_j >= 0 && hit_j < n) {
                         const double tv = s_transp[hit_i * n + hit_j];
-                        if (tv > 0.01) record_hit(hit_dist, tv);
+                        if (tv > 0.01) record_hit(hit_dist, tv, hit_i * n + hit_j);
                         if (walls[hit_i * n + hit_j] > 0) { hit_side = 0; break; }
                     }
                     side_x = delta_dist_x;
@@ -442,7 +472,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                         if (hit_j < 0 || hit_j >= n) { hit_dist = 1.0e+6; break; }
                     } else if (hit_j >= 0 && hit_j < n) {
                         const double tv = s_transp[hit_i * n + hit_j];
-                        if (tv > 0.01) record_hit(hit_dist, tv);
+                        if (tv > 0.01) record_hit(hit_dist, tv, hit_i * n + hit_j);
                         if (walls[hit_i * n + hit_j] > 0) { hit_side = 1; break; }
                     }
                     side_y = delta_dist_y;
@@ -478,10 +508,78 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 cr.n_hits = (int16_t)nh;
             }
             s_col[d_h] = cr;
+            if (FILL) {
+                a.c_colhits[(size_t)e * H + d_h] = (uint8_t)cr.n_hits;
+                HitRec *gh = reinterpret_cast<HitRec *>(a.c_hits) + ((size_t)e * H + d_h) * c.max_hits;
+                for (int k = 0; k < cr.n_hits; ++k) gh[k] = hits[k];
+            }
         }
         if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
         __syncthreads();
 
+        if (FILL) {
+            // ---- static layers of this pose: colour before any transparency (wall colour wins inside the wall span),
+            // the food slot of the floor / ceiling cell under every pixel, one word + one byte per pixel, coalesced
+            const int total_px = H * V;
+            const double inv_cell = th->inv_cell, inv_t2c = th->inv_t2c;
+            const bool cell_p2 = th->cell_pow2 != 0, t2c_p2 = th->t2c_pow2 != 0, text_p2 = c.text_pow2 != 0;
+            const double *efft = (c.n_cls > 0 && th->cls >= 0) ? a.efftab + (size_t)th->cls * total_px : nullptr;
+            const double fog_from = 0.4999 * c.max_vision;
+            const double dts = (double)ts;
+            const int8_t *fidx = reinterpret_cast<const int8_t *>(s_blob + c.off_fidx);
+            const int goal_cell = th->goal[0] * n + th->goal[1];
+            uint32_t *gpx = a.c_px + (size_t)e * total_px;
+            uint8_t *gfid = a.c_fid + (size_t)e * total_px;
+            for (int q = tid; q < total_px; q += blockDim.x) {
+                const int d_h = q / V, d_v = q - d_h * V;
+                const ColRec &cr = s_col[d_h];
+                const RowRec &rr = s_row[d_v];
+                int rgb[3] = {0, 0, 0};
+                int fid = 0xFF;
+                const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
+                if (rr.kind != 0 && (!in_wall || cr.n_hits > 0)) {
+                    const double eff = efft ? __ldg(efft + q) : rr.distance / cr.cos_hp;
+                    double fog = 0.0;
+                    if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
+                    const double hit_x = eff * cr.cos_abs + pos_x;
+                    const double hit_y = eff * cr.sin_abs + pos_y;
+                    const double ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
+                    const double cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
+                    const int i = trunc_i(ci), j = trunc_i(cj);
+                    const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
+                    if (inside) {
+                        if (c.task_type == MGB_MAZE_SURVIVAL) { const int f = fidx[i * n + j]; if (f >= 0) fid = f; }
+                        else if (i * n + j == goal_cell) fid = 0;
+                    }
+                    if (rr.kind == 1) {
+                        if (inside) {
+                            double d_i = ci - floor(ci), d_j = cj - floor(cj);
+                            const int text_id = texts[i * n + j];
+                            d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
+                            d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
+                            d_i -= floor(d_i); d_j -= floor(d_j);
+                            d_i *= dts; d_j *= dts;
+                            shade(rgb, rr.light, 1.0 - fog * rr.light,
+                                  s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                        } else fid = 0xFF;
+                    } else {
+                        const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
+                        const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
+                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                        d_i *= dts; d_j *= dts;
+                        shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                    }
+                }
+                if (in_wall) {
+                    const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
+                    double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
+                    d_j -= floor(d_j);
+                    shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
+                }
+                gpx[q] = (uint32_t)rgb[0] | ((uint32_t)rgb[1] << 10) | ((uint32_t)rgb[2] << 20) | (in_wall ? (1u << 30) : 0u);
+                gfid[q] = (uint8_t)fid;
+            }
+        } else {
         // ---- pixels.  Each WARP owns runs of whole screen columns (c.run_px / V of them, 768 B of output): the column
         // record is warp-uniform (one broadcast read, held in registers), lanes take rows d_v = lane, lane + 32, ...,
         // write into the warp's private staging slot, and lane 0 issues ONE bulk (TMA) store per run; the slot is
@@ -597,10 +695,145 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             }
             run_parity ^= 1;
         }
+        }
         __syncthreads();   // s_col / s_row / s_transp / s_blob are rewritten by the next env
     }
     if (!tex_ready && tid == 0) mgb_mbar_wait(&s_bar[0], 0);   // never leave a TMA load in flight
     if ((tid & 31) == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copies; the kernel boundary flushes the writes
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pose cache path: step logic (one thread per env) + compose (static pose layers x current food state -> observation)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void maze3d_logic_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const int task = a.env2task[e];
+    const uint8_t *blob = a.blobs + (int64_t)task * c.blob_bytes;
+    const TaskHdr *th = blob_hdr(blob);
+    const int4 ag = a.agent[e];
+    Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
+    int32_t *eaten = a.eaten + e;
+    if (a.do_step) {
+        double reward;
+        int done;
+        maze_logic(c, blob, eaten, a.n_pad, s, a.act[e], reward, done);
+        a.rew[e] = reward;
+        a.done[e] = (uint8_t)done;
+        if (done && a.auto_reset) env_reset(c, blob, eaten, a.n_pad, s);
+        a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+        a.life[e] = s.life;
+    }
+    EnvDyn d;
+    d.slot = a.pose_index[(size_t)task * c.n * c.n * 4 + (s.gx * c.n + s.gy) * 4 + s.ori];
+    d.task = task; d.pad = 0;
+    d.present[0] = d.present[1] = 0;
+    if (c.task_type == MGB_MAZE_SURVIVAL) {
+        const int32_t *fint = reinterpret_cast<const int32_t *>(blob + c.off_fint);
+        for (int f = 0; f < th->n_food; ++f) {
+            const int ea = eaten[f * a.n_pad];
+            if ((ea == kNever) || (s.steps >= ea + fint[f])) d.present[f >> 6] |= 1ull << (f & 63);
+        }
+        int ex = trunc_i(c.lb_sx + s.life / th->max_life * c.lb_l);      // maze_discrete_3d.py:118-126
+        if (ex < 0) { ex += c.res_h; if (ex < 0) ex = 0; }
+        if (ex > c.res_h) ex = c.res_h;
+        d.bar_end = ex;
+    } else {
+        d.present[0] = 1ull;             // the goal cell is pseudo food slot 0, always present (maze_base.py:59-60)
+        d.bar_end = 0;
+    }
+    reinterpret_cast<EnvDyn *>(a.dyn)[e] = d;
+}
+
+constexpr int kComposeThreads = 256;
+
+// One CTA per env.  Per pixel: one packed word (colour before transparency + in-wall flag) and one byte (food slot
+// under the pixel) of the cached pose, the env's 128-bit food presence mask, and -- only for pixels that really are
+// tinted -- the reference's float64 blend on the integer colour.  Everything else is integer work; the traffic is
+// 5 B read + 3 B written per pixel (uint8 mode), i.e. the renderer has become an HBM-bound gather/scatter.
+__global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
+                                                                         const __grid_constant__ MazeArgs a)
+{
+    const int64_t e = blockIdx.x;
+    const EnvDyn d = reinterpret_cast<const EnvDyn *>(a.dyn)[e];
+    const int H = c.res_h, V = c.res_v, total_px = H * V;
+    const uint8_t *blob = a.blobs + (int64_t)d.task * c.blob_bytes;
+    const double *fval = reinterpret_cast<const double *>(blob + c.off_fval);
+    const uint32_t *gpx = a.c_px + (size_t)d.slot * total_px;
+    const uint8_t *gfid = a.c_fid + (size_t)d.slot * total_px;
+    const uint8_t *colhits = a.c_colhits + (size_t)d.slot * H;
+    const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)d.slot * H * c.max_hits;
+    const bool survival = c.task_type == MGB_MAZE_SURVIVAL;
+    const int lb_sx = trunc_i(c.lb_sx), lb_ex = d.bar_end, lb_sy = trunc_i(c.lb_sy);
+    int lb_ey = trunc_i(c.lb_sy + c.lb_w);
+    if (lb_ey > V) lb_ey = V;
+    const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
+    uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
+
+    auto present = [&](int f) -> bool { return (d.present[f >> 6] >> (f & 63)) & 1ull; };
+    auto food_value = [&](int f) -> double { return survival ? __ldg(fval + f) : 1.0; };
+    // one pixel: static colour -> floor/ceiling tint -> crossings of the column -> life bar (ray_caster_utils.py:118-205)
+    auto finish = [&](uint32_t w, int f, int d_h, int d_v, int n_hits, int rgb[3]) {
+        rgb[0] = (int)(w & 1023u); rgb[1] = (int)((w >> 10) & 1023u); rgb[2] = (int)((w >> 20) & 1023u);
+        const bool in_wall = (w >> 30) & 1u;
+        bool mark = false;
+        if (f != 0xFF && present(f)) {
+            const double tv = food_value(f);
+            if (d_v > V / 2 ? tv > 0.01 : tv > 0) {          // floor tests > 0.01 (:119), ceiling > 0 (:150)
+                if (!in_wall) blend(rgb, tv * 0.50 + 0.10);
+                mark = true;
+            }
+        }
+        if (n_hits > 0 && !mark) {
+            const HitRec *hits = ghits + (size_t)d_h * c.max_hits;
+            for (int k = 0; k < n_hits; ++k) {
+                const HitRec hr = hits[k];
+                if (present(hr.fid) && d_v >= hr.v_s && d_v < hr.v_e) blend(rgb, hr.tf);
+            }
+        }
+        if (survival && d_h >= lb_sx && d_h < lb_ex && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+    };
+
+    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) {
+        // four consecutive rows of one column per thread: 16 B + 4 B in, 12 B (uint8) or 48 B (int32) out;
+        // unrolled so that four independent 20-byte fetches are in flight per thread
+#pragma unroll 4
+        for (int q = threadIdx.x * 4; q < total_px; q += kComposeThreads * 4) {
+            const int d_h = q / V, d_v0 = q - d_h * V;
+            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
+            const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t *>(gfid + q));
+            const int n_hits = colhits[d_h];
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            int out[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) finish(w[k], (int)((f4 >> (8 * k)) & 0xFFu), d_h, d_v0 + k, n_hits, out + 3 * k);
+            if (c.obs_dtype == MGB_OBS_U8) {
+                uint32_t pk[3] = {0u, 0u, 0u};
+#pragma unroll
+                for (int b = 0; b < 12; ++b) pk[b >> 2] |= (uint32_t)(out[b] > 255 ? 255 : out[b]) << (8 * (b & 3));
+                uint32_t *dst = reinterpret_cast<uint32_t *>(gobs + (size_t)q * 3);
+                dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
+            } else {
+                int4 *dst = reinterpret_cast<int4 *>(gobs + (size_t)q * 12);
+                dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+                dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+                dst[2] = make_int4(out[8], out[9], out[10], out[11]);
+            }
+        }
+    } else {
+        for (int q = threadIdx.x; q < total_px; q += kComposeThreads) {
+            const int d_h = q / V, d_v = q - d_h * V;
+            int rgb[3];
+            finish(__ldg(gpx + q), (int)gfid[q], d_h, d_v, colhits[d_h], rgb);
+            if (c.obs_dtype == MGB_OBS_U8) {
+                for (int k = 0; k < 3; ++k) gobs[(size_t)q * 3 + k] = (uint8_t)(rgb[k] > 255 ? 255 : rgb[k]);
+            } else {
+                int32_t *o = reinterpret_cast<int32_t *>(gobs) + (size_t)q * 3;
+                o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
+            }
+        }
+    }
 }
 
 // Pose-independent part of the floor/ceiling geometry: eff(d_h, d_v) = distance(d_v) / cos_hp(d_h)
@@ -654,6 +887,19 @@ struct mgb_maze {
     uint32_t *tex = nullptr;
     float *coltab = nullptr;
     double *efftab = nullptr;
+    // pose cache
+    int cache_enabled = 1;         // MGB_MAZE_CACHE=0 disables (direct renderer only)
+    double cache_budget_gb = 24.0; // MGB_MAZE_CACHE_GB
+    bool cache_ready = false, cache_dirty = true;
+    int64_t n_poses = 0;
+    int4 *poses = nullptr;
+    int32_t *pose_index = nullptr;
+    uint32_t *c_px = nullptr;
+    uint8_t *c_fid = nullptr, *c_colhits = nullptr;
+    HitRec *c_hits = nullptr;
+    EnvDyn *dyn = nullptr;
+    std::vector<int4> host_poses;
+    std::vector<int32_t> host_pose_index;
     int n_tasks = 0;
     int auto_reset = 0;
     bool has_task = false, has_tex = false;
@@ -685,6 +931,8 @@ static MazeArgs maze_args(const mgb_maze *h)
     a.n = h->n; a.n_pad = h->n_pad; a.env_base = h->env_base;
     a.agent = h->agent; a.life = h->life; a.eaten = h->eaten; a.env2task = h->env2task; a.blobs = h->blobs;
     a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.auto_reset = h->auto_reset;
+    a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
+    a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn;
     return a;
 }
 
@@ -724,6 +972,8 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     cudaDeviceProp prop;
     MGB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    if (const char *ev = getenv("MGB_MAZE_CACHE")) h->cache_enabled = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_MAZE_CACHE_GB")) h->cache_budget_gb = atof(ev);
     MGB_CUDA(cudaMalloc(&h->agent, sizeof(int4) * h->n_pad));
     MGB_CUDA(cudaMalloc(&h->life, sizeof(double) * h->n_pad));
     MGB_CUDA(cudaMalloc(&h->env2task, sizeof(int32_t) * h->n_pad));
@@ -771,6 +1021,8 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaDeviceSynchronize();
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
     cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab);
+    cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
+    cudaFree(h->c_hits); cudaFree(h->dyn);
     delete h;
 }
 
@@ -812,6 +1064,7 @@ extern "C" int mgb_maze_set_textures(mgb_maze *h, const uint8_t *grounds_host, i
     MGB_CUDA(cudaMemcpy(h->tex, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
     h->c.n_tex = n_tex; h->c.ts = tex_size;
     h->has_tex = true;
+    h->cache_dirty = true;
     return MGB_OK;
 }
 
@@ -924,6 +1177,24 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     MGB_CUDA(cudaMemcpy(h->env2task, env2task_host, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice));
     h->n_tasks = n_tasks;
     h->has_task = true;
+    // pose list of the cache: every free cell (the agent can never stand inside a wall, maze_discrete_3d.py:63-65) x 4
+    h->host_poses.clear();
+    h->host_pose_index.assign((size_t)n_tasks * nn * 4, -1);
+    h->cache_dirty = true;
+    h->cache_ready = false;
+    if (c.kind == MGB_MAZE_DISCRETE_3D) {
+        for (int t = 0; t < n_tasks; ++t) {
+            const mgb_maze_task_scalars &sc = scalars_host[t];
+            for (int k = 0; k < nn; ++k) {
+                const bool is_start = (k == sc.start[0] * n + sc.start[1]);
+                if (walls_host[(size_t)t * nn + k] != 0 && !is_start) continue;
+                for (int o = 0; o < 4; ++o) {
+                    h->host_pose_index[((size_t)t * nn + k) * 4 + o] = (int32_t)h->host_poses.size();
+                    h->host_poses.push_back(make_int4(t, k / n, k % n, o));
+                }
+            }
+        }
+    }
     cudaFree(h->efftab); h->efftab = nullptr;
     c.n_cls = 0;
     if (c.kind == MGB_MAZE_DISCRETE_3D && !cls_heights.empty()) {
@@ -957,6 +1228,71 @@ static int maze_ready(const mgb_maze *h)
     return MGB_OK;
 }
 
+template <bool FILL>
+static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStream_t st)
+{
+    const MazeConst &c = h->c;
+    const size_t sm = maze3d_smem_bytes(c);
+    if (sm > 227 * 1024) {
+        mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
+        return MGB_ERR_ARG;
+    }
+    // the opt-in limit is a property of the kernel (per device), shared by every handle: only ever raise it
+    static size_t g_smem_limit[64] = {0};
+    if (sm > g_smem_limit[h->device & 63]) {
+        MGB_CUDA(cudaFuncSetAttribute(maze3d_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        g_smem_limit[h->device & 63] = sm;
+    }
+    h->smem3d = sm;
+    maze3d_kernel<FILL><<<grid, kRenderThreads, sm, st>>>(c, a);
+    MGB_CUDA(cudaGetLastError());
+    return MGB_OK;
+}
+
+// (Re)build the pose cache when tasks or textures changed: every free cell x 4 headings of every task is rendered once
+// into its static layers.  Skipped (direct renderer used instead) when disabled or over the memory budget.
+static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
+{
+    if (!h->cache_dirty) return MGB_OK;
+    h->cache_dirty = false;
+    h->cache_ready = false;
+    MazeConst &c = h->c;
+    if (!h->cache_enabled || c.kind != MGB_MAZE_DISCRETE_3D || h->host_poses.empty()) return MGB_OK;
+    const size_t slots = h->host_poses.size(), px = (size_t)c.res_h * c.res_v;
+    const double bytes = (double)slots * (px * 5.0 + c.res_h * (1.0 + (double)c.max_hits * sizeof(HitRec)));
+    if (bytes > h->cache_budget_gb * 1e9) return MGB_OK;
+    // cudaMalloc/cudaFree synchronise; a capture in progress cannot build the cache
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+        mgb_set_error("maze pose cache must be built before stream capture: call reset() once first");
+        return MGB_ERR_STATE;
+    }
+    cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
+    cudaFree(h->c_hits); cudaFree(h->dyn);
+    h->poses = nullptr; h->pose_index = nullptr; h->c_px = nullptr; h->c_fid = nullptr; h->c_colhits = nullptr;
+    h->c_hits = nullptr; h->dyn = nullptr;
+    MGB_CUDA(cudaMalloc(&h->poses, slots * sizeof(int4)));
+    MGB_CUDA(cudaMalloc(&h->pose_index, h->host_pose_index.size() * sizeof(int32_t)));
+    MGB_CUDA(cudaMalloc(&h->c_px, slots * px * sizeof(uint32_t)));
+    MGB_CUDA(cudaMalloc(&h->c_fid, slots * px));
+    MGB_CUDA(cudaMalloc(&h->c_colhits, slots * c.res_h));
+    MGB_CUDA(cudaMalloc(&h->c_hits, slots * c.res_h * c.max_hits * sizeof(HitRec)));
+    MGB_CUDA(cudaMalloc(&h->dyn, (size_t)h->n_pad * sizeof(EnvDyn)));
+    MGB_CUDA(cudaMemcpy(h->poses, h->host_poses.data(), slots * sizeof(int4), cudaMemcpyHostToDevice));
+    MGB_CUDA(cudaMemcpy(h->pose_index, h->host_pose_index.data(), h->host_pose_index.size() * sizeof(int32_t),
+                        cudaMemcpyHostToDevice));
+    MazeArgs a = maze_args(h);
+    a.n = (int64_t)slots;
+    a.do_step = 0;
+    int rc = launch_render<true>(h, a, (unsigned)(slots < (size_t)h->num_sms ? slots : (size_t)h->num_sms), st);
+    if (rc) return rc;
+    MGB_CUDA(cudaStreamSynchronize(st));
+    h->n_poses = (int64_t)slots;
+    h->cache_ready = true;
+    h->launches += 1;
+    return MGB_OK;
+}
+
 static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
 {
     const MazeConst &c = h->c;
@@ -965,20 +1301,20 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
         const size_t sm = (size_t)k2dThreads * W * W * 4;
         maze2d_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, st>>>(c, a);
     } else {
-        const size_t sm = maze3d_smem_bytes(c);
-        if (sm > 227 * 1024) {
-            mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
-            return MGB_ERR_ARG;
+        int rc = ensure_pose_cache(h, st);
+        if (rc) return rc;
+        if (h->cache_ready) {
+            // memoised path: integer step logic, then compose static pose layers with the current food state
+            a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
+            a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn;
+            maze3d_logic_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
+            MGB_CUDA(cudaGetLastError());
+            maze3d_compose_kernel<<<(unsigned)h->n, kComposeThreads, 0, st>>>(c, a);
+            h->launches += 1;
+        } else {
+            rc = launch_render<false>(h, a, (unsigned)(h->n < h->num_sms ? h->n : h->num_sms), st);
+            if (rc) return rc;
         }
-        // the opt-in limit is a property of the kernel (per device), shared by every handle: only ever raise it
-        static size_t g_smem_limit[64] = {0};
-        if (sm > g_smem_limit[h->device & 63]) {
-            MGB_CUDA(cudaFuncSetAttribute(maze3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            g_smem_limit[h->device & 63] = sm;
-        }
-        h->smem3d = sm;
-        const unsigned grid = (unsigned)(h->n < h->num_sms ? h->n : h->num_sms);
-        maze3d_kernel<<<grid, kRenderThreads, sm, st>>>(c, a);
     }
     MGB_CUDA(cudaGetLastError());
     h->launches += 1;

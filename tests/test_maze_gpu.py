@@ -31,12 +31,22 @@ def make_env(c, n, textures, **kw):
                                      num_envs=n, squeeze=False, textures=textures, **kw)
 
 
+@pytest.fixture(params=["pose_cache", "direct_render"])
+def render_path(request, monkeypatch):
+    """3-D observations come either from the memoised pose cache (default) or from the direct float64 renderer
+    (MGB_MAZE_CACHE=0); both must reproduce the reference bit for bit."""
+    monkeypatch.setenv("MGB_MAZE_CACHE", "1" if request.param == "pose_cache" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("name", MAZE_CASES)
 @pytest.mark.parametrize("n", [1, 3])
-def test_reference_episode(torch_mod, maze_golden, textures, name, n):
+def test_reference_episode(torch_mod, maze_golden, textures, name, n, render_path):
     """Replay the recorded reference episode on n identical envs (manual reset after done, like the reference user)."""
     torch = torch_mod
     c = maze_case(maze_golden, name)
+    if c["kind"] == "2D" and render_path == "direct_render":
+        pytest.skip("2-D has a single path")
     env = make_env(c, n, textures)
     with pytest.raises(Exception, match="set_task"):
         env.reset()
@@ -68,7 +78,7 @@ def test_reference_episode(torch_mod, maze_golden, textures, name, n):
     env.close()
 
 
-def test_uint8_mode_is_clamped_reference(torch_mod, maze_golden, textures):
+def test_uint8_mode_is_clamped_reference(torch_mod, maze_golden, textures, render_path):
     torch = torch_mod
     c = maze_case(maze_golden, "m3d_big")
     bright = (textures[0].copy(), textures[1])
@@ -89,9 +99,11 @@ def test_uint8_mode_is_clamped_reference(torch_mod, maze_golden, textures):
 
 
 @pytest.mark.parametrize("kind,task_type", [("2D", "SURVIVAL"), ("2D", "ESCAPE"), ("3D", "SURVIVAL"), ("3D", "ESCAPE")])
-def test_random_batch_vs_oracle(torch_mod, maze_golden, textures, kind, task_type):
+def test_random_batch_vs_oracle(torch_mod, maze_golden, textures, kind, task_type, render_path):
     """Many envs, several tasks, independent random actions, auto-reset on: every env equals its own oracle instance."""
     torch = torch_mod
+    if kind == "2D" and render_path == "direct_render":
+        pytest.skip("2-D has a single path")
     from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D
     from oracle.maze_oracle import OracleMaze
     g = maze_golden
@@ -146,6 +158,34 @@ def test_masked_reset(torch_mod, maze_golden):
     assert tuple(after[0]) == (c["task"].start[0], c["task"].start[1], 0, 0) and np.array_equal(after[0], after[3])
     assert np.array_equal(after[1], before[1]) and np.array_equal(after[2], before[2])
     env.close()
+
+
+def test_pose_cache_equals_direct_render_at_config4_shape(torch_mod, maze_golden, textures, monkeypatch):
+    """1024 envs, 15x15, 128x128 uint8 (BASELINE config 4 per GPU): memoised path == direct float64 renderer."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 20, g["tasks15.scalars"][k]) for k in range(8)]
+    N = 1024
+    kw = dict(resolution=(128, 128), max_steps=60, task_type="SURVIVAL", squeeze=False, auto_reset=True,
+              obs_dtype="uint8", textures=textures, num_envs=N)
+    monkeypatch.setenv("MGB_MAZE_CACHE", "1")
+    a = BatchedMetaMazeDiscrete3D(**kw)
+    monkeypatch.setenv("MGB_MAZE_CACHE", "0")
+    b = BatchedMetaMazeDiscrete3D(**kw)
+    for e in (a, b):
+        e.set_task(tasks)
+    assert torch.equal(a.reset(), b.reset())
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(80):
+        act = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2), (t, int((o1 != o2).sum()))
+        assert torch.equal(r1, r2) and torch.equal(d1, d2)
+    a.close()
+    b.close()
 
 
 def test_config4_shape_properties(torch_mod, maze_golden, textures):
