@@ -74,6 +74,8 @@ struct MazeArgs {
     const int32_t *pose_index;   // [n_tasks][n*n*4] -> slot or -1
     uint32_t *c_px;              // [n_slots][H*V]   10-bit R | G<<10 | B<<20 | in_wall<<30
     uint8_t *c_fid;              // [n_slots][H*V]   food slot of the floor/ceiling cell under the pixel, 0xFF none
+    uint8_t *c_rgb8;             // [n_slots][H*V*3] min(colour, 255): the finished uint8 pixel when nothing is tinted
+    uint32_t *c_gmask;           // [n_slots][ceil(H*V/128)] bit per 4-pixel group: group may be tinted (slow path)
     uint8_t *c_colhits;          // [n_slots][H]     transparent crossings recorded for the column
     void *c_hits;                // [n_slots][H][max_hits] HitRec
     void *dyn;                   // [n] EnvDyn, written by the logic kernel, read by the compose kernel
@@ -83,6 +85,7 @@ struct MazeArgs {
     uint8_t *done;
     const uint8_t *mask;
     int do_step;                 // 0: observe only (reset), 1: step then observe
+    int do_parts;                // compose kernel: image slices per env
     int auto_reset;
 };
 
@@ -578,6 +581,23 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 }
                 gpx[q] = (uint32_t)rgb[0] | ((uint32_t)rgb[1] << 10) | ((uint32_t)rgb[2] << 20) | (in_wall ? (1u << 30) : 0u);
                 gfid[q] = (uint8_t)fid;
+                uint8_t *g8 = a.c_rgb8 + ((size_t)e * total_px + q) * 3;
+                g8[0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
+                g8[1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
+                g8[2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
+                // 4-pixel groups (q / 4) that can ever be tinted: a food cell under a pixel or a crossing span over it
+                bool tintable = fid != 0xFF;
+                if (!tintable && cr.n_hits > 0) {
+                    const HitRec *hh = s_hit + (size_t)d_h * c.max_hits;
+                    for (int k = 0; k < cr.n_hits; ++k) tintable = tintable || (d_v >= hh[k].v_s && d_v < hh[k].v_e);
+                }
+                const unsigned dyn_px = __ballot_sync(__activemask(), tintable);
+                if ((tid & 31) == 0 && dyn_px) {
+                    unsigned gbits = 0;                       // lanes 4g..4g+3 -> group bit g of this warp's 8 groups
+                    for (int g = 0; g < 8; ++g) gbits |= ((dyn_px >> (4 * g)) & 0xFu) ? (1u << g) : 0u;
+                    const int group0 = q >> 2;                // q is the warp's first pixel here (lane 0), a multiple of 32
+                    atomicOr(a.c_gmask + (size_t)e * ((total_px + 127) / 128) + (group0 >> 5), gbits << (group0 & 31));
+                }
             }
         } else {
         // ---- pixels.  Each WARP owns runs of whole screen columns (c.run_px / V of them, 768 B of output): the column
@@ -755,20 +775,35 @@ constexpr int kComposeThreads = 256;
 __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
                                                                          const __grid_constant__ MazeArgs a)
 {
-    const int64_t e = blockIdx.x;
-    const EnvDyn d = reinterpret_cast<const EnvDyn *>(a.dyn)[e];
+    // persistent CTAs: work item = (env, one of kParts slices of its image); grid = resident CTA count, so there is
+    // no partial last wave (1024 envs as 1024 CTAs ran 1.15 waves = almost twice the time of one)
+    const int kParts = a.do_parts;      // 1..4 image slices per env, chosen by the host so that items >> resident CTAs
     const int H = c.res_h, V = c.res_v, total_px = H * V;
+    const bool survival = c.task_type == MGB_MAZE_SURVIVAL;
+    const int lb_sx = trunc_i(c.lb_sx), lb_sy = trunc_i(c.lb_sy);
+    int lb_ey = trunc_i(c.lb_sy + c.lb_w);
+    if (lb_ey > V) lb_ey = V;
+    const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
+    const int part_px = ((total_px / kParts) + 127) / 128 * 128;          // slice boundaries stay 128-pixel aligned
+  const int64_t n_items = a.n * kParts;
+  EnvDyn d_next;
+  if ((int64_t)blockIdx.x < n_items) d_next = reinterpret_cast<const EnvDyn *>(a.dyn)[blockIdx.x / kParts];
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t e = item / kParts;
+    const int part = (int)(item - e * kParts);
+    const int q_begin = part * part_px, q_end = (part + 1) * part_px < total_px ? (part + 1) * part_px : total_px;
+    // software pipeline: the next item's EnvDyn (-> pose slot -> every address below) is requested now, so the
+    // dependent-load bubble at the start of an item overlaps this item's pixels
+    const EnvDyn d = d_next;
+    if (item + gridDim.x < n_items) d_next = reinterpret_cast<const EnvDyn *>(a.dyn)[(item + gridDim.x) / kParts];
+    if (q_begin >= total_px) continue;
     const uint8_t *blob = a.blobs + (int64_t)d.task * c.blob_bytes;
     const double *fval = reinterpret_cast<const double *>(blob + c.off_fval);
     const uint32_t *gpx = a.c_px + (size_t)d.slot * total_px;
     const uint8_t *gfid = a.c_fid + (size_t)d.slot * total_px;
     const uint8_t *colhits = a.c_colhits + (size_t)d.slot * H;
     const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)d.slot * H * c.max_hits;
-    const bool survival = c.task_type == MGB_MAZE_SURVIVAL;
-    const int lb_sx = trunc_i(c.lb_sx), lb_ex = d.bar_end, lb_sy = trunc_i(c.lb_sy);
-    int lb_ey = trunc_i(c.lb_sy + c.lb_w);
-    if (lb_ey > V) lb_ey = V;
-    const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
+    const int lb_ex = d.bar_end;
     uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
 
     auto present = [&](int f) -> bool { return (d.present[f >> 6] >> (f & 63)) & 1ull; };
@@ -795,12 +830,34 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
         if (survival && d_h >= lb_sx && d_h < lb_ex && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
     };
 
-    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) {
-        // four consecutive rows of one column per thread: 16 B + 4 B in, 12 B (uint8) or 48 B (int32) out;
-        // unrolled so that four independent 20-byte fetches are in flight per thread
-#pragma unroll 4
-        for (int q = threadIdx.x * 4; q < total_px; q += kComposeThreads * 4) {
-            const int d_h = q / V, d_v0 = q - d_h * V;
+    if ((V & 3) == 0 && (total_px & 127) == 0 && (reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) {
+        // four consecutive rows of one column per thread.  FAST PATH (the cached group can never be tinted and the life
+        // bar does not cross it): uint8 -> copy 12 finished bytes; int32 -> unpack.  Otherwise: 16 B + 4 B in, finish().
+        // (forcing a 4x unroll was measured slower: 87 vs 80 us at 1024 envs)
+        const uint32_t *gmask = a.c_gmask + (size_t)d.slot * (total_px / 128);
+        const uint8_t *g8 = a.c_rgb8 + (size_t)d.slot * total_px * 3;
+        const int v_shift = (V & (V - 1)) == 0 ? 31 - __clz(V) : -1;
+        for (int q = q_begin + threadIdx.x * 4; q < q_end; q += kComposeThreads * 4) {
+            const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
+            const int d_v0 = q - d_h * V;
+            const int group = q >> 2;
+            const bool tintable = (__ldg(gmask + (group >> 5)) >> (group & 31)) & 1u;
+            const bool bar = survival && d_h >= lb_sx && d_h < lb_ex && d_v0 + 3 >= lb_sy && d_v0 < lb_ey;
+            if (!tintable && !bar) {
+                if (c.obs_dtype == MGB_OBS_U8) {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(g8 + (size_t)q * 3);
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(gobs + (size_t)q * 3);
+                    const uint32_t b0 = __ldg(src), b1 = __ldg(src + 1), b2 = __ldg(src + 2);
+                    dst[0] = b0; dst[1] = b1; dst[2] = b2;
+                } else {
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
+                    int4 *dst = reinterpret_cast<int4 *>(gobs + (size_t)q * 12);
+                    dst[0] = make_int4(w4.x & 1023u, (w4.x >> 10) & 1023u, (w4.x >> 20) & 1023u, w4.y & 1023u);
+                    dst[1] = make_int4((w4.y >> 10) & 1023u, (w4.y >> 20) & 1023u, w4.z & 1023u, (w4.z >> 10) & 1023u);
+                    dst[2] = make_int4((w4.z >> 20) & 1023u, w4.w & 1023u, (w4.w >> 10) & 1023u, (w4.w >> 20) & 1023u);
+                }
+                continue;
+            }
             const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
             const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t *>(gfid + q));
             const int n_hits = colhits[d_h];
@@ -822,7 +879,7 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
             }
         }
     } else {
-        for (int q = threadIdx.x; q < total_px; q += kComposeThreads) {
+        for (int q = q_begin + threadIdx.x; q < q_end; q += kComposeThreads) {
             const int d_h = q / V, d_v = q - d_h * V;
             int rgb[3];
             finish(__ldg(gpx + q), (int)gfid[q], d_h, d_v, colhits[d_h], rgb);
@@ -834,6 +891,7 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
             }
         }
     }
+  }
 }
 
 // Pose-independent part of the floor/ceiling geometry: eff(d_h, d_v) = distance(d_v) / cos_hp(d_h)
@@ -895,7 +953,8 @@ struct mgb_maze {
     int4 *poses = nullptr;
     int32_t *pose_index = nullptr;
     uint32_t *c_px = nullptr;
-    uint8_t *c_fid = nullptr, *c_colhits = nullptr;
+    uint8_t *c_fid = nullptr, *c_colhits = nullptr, *c_rgb8 = nullptr;
+    uint32_t *c_gmask = nullptr;
     HitRec *c_hits = nullptr;
     EnvDyn *dyn = nullptr;
     std::vector<int4> host_poses;
@@ -932,7 +991,7 @@ static MazeArgs maze_args(const mgb_maze *h)
     a.agent = h->agent; a.life = h->life; a.eaten = h->eaten; a.env2task = h->env2task; a.blobs = h->blobs;
     a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.auto_reset = h->auto_reset;
     a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
-    a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn;
+    a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gmask = h->c_gmask;
     return a;
 }
 
@@ -1022,7 +1081,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
     cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab);
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
-    cudaFree(h->c_hits); cudaFree(h->dyn);
+    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask);
     delete h;
 }
 
@@ -1259,7 +1318,7 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     MazeConst &c = h->c;
     if (!h->cache_enabled || c.kind != MGB_MAZE_DISCRETE_3D || h->host_poses.empty()) return MGB_OK;
     const size_t slots = h->host_poses.size(), px = (size_t)c.res_h * c.res_v;
-    const double bytes = (double)slots * (px * 5.0 + c.res_h * (1.0 + (double)c.max_hits * sizeof(HitRec)));
+    const double bytes = (double)slots * (px * 8.0 + px / 32.0 + c.res_h * (1.0 + (double)c.max_hits * sizeof(HitRec)));
     if (bytes > h->cache_budget_gb * 1e9) return MGB_OK;
     // cudaMalloc/cudaFree synchronise; a capture in progress cannot build the cache
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1268,9 +1327,9 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
         return MGB_ERR_STATE;
     }
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
-    cudaFree(h->c_hits); cudaFree(h->dyn);
+    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask);
     h->poses = nullptr; h->pose_index = nullptr; h->c_px = nullptr; h->c_fid = nullptr; h->c_colhits = nullptr;
-    h->c_hits = nullptr; h->dyn = nullptr;
+    h->c_hits = nullptr; h->dyn = nullptr; h->c_rgb8 = nullptr; h->c_gmask = nullptr;
     MGB_CUDA(cudaMalloc(&h->poses, slots * sizeof(int4)));
     MGB_CUDA(cudaMalloc(&h->pose_index, h->host_pose_index.size() * sizeof(int32_t)));
     MGB_CUDA(cudaMalloc(&h->c_px, slots * px * sizeof(uint32_t)));
@@ -1278,6 +1337,10 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     MGB_CUDA(cudaMalloc(&h->c_colhits, slots * c.res_h));
     MGB_CUDA(cudaMalloc(&h->c_hits, slots * c.res_h * c.max_hits * sizeof(HitRec)));
     MGB_CUDA(cudaMalloc(&h->dyn, (size_t)h->n_pad * sizeof(EnvDyn)));
+    const size_t mask_words = (px + 127) / 128;
+    MGB_CUDA(cudaMalloc(&h->c_rgb8, slots * px * 3));
+    MGB_CUDA(cudaMalloc(&h->c_gmask, slots * mask_words * sizeof(uint32_t)));
+    MGB_CUDA(cudaMemsetAsync(h->c_gmask, 0, slots * mask_words * sizeof(uint32_t), st));
     MGB_CUDA(cudaMemcpy(h->poses, h->host_poses.data(), slots * sizeof(int4), cudaMemcpyHostToDevice));
     MGB_CUDA(cudaMemcpy(h->pose_index, h->host_pose_index.data(), h->host_pose_index.size() * sizeof(int32_t),
                         cudaMemcpyHostToDevice));
@@ -1306,10 +1369,27 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
         if (h->cache_ready) {
             // memoised path: integer step logic, then compose static pose layers with the current food state
             a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
-            a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn;
+            a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gmask = h->c_gmask;
             maze3d_logic_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
             MGB_CUDA(cudaGetLastError());
-            maze3d_compose_kernel<<<(unsigned)h->n, kComposeThreads, 0, st>>>(c, a);
+            {
+                static int ctas_per_sm = 0;
+                if (!ctas_per_sm) {
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, maze3d_compose_kernel, kComposeThreads, 0) !=
+                            cudaSuccess || ctas_per_sm < 1) ctas_per_sm = 4;
+                }
+                const int64_t resident = (int64_t)h->num_sms * ctas_per_sm;
+                int64_t parts = (4 * resident + h->n - 1) / h->n;  // aim at >= 4 work items per resident CTA
+                parts = parts < 1 ? 1 : (parts > 4 ? 4 : parts);
+                a.do_parts = (int)parts;
+                int64_t items = h->n * parts;
+                static int persistent = -1;
+                if (persistent < 0) { const char *ev = getenv("MGB_COMPOSE_PERSISTENT"); persistent = ev ? atoi(ev) : 0; }   // measured: plain grid 65/295 us vs persistent 72/319 us (1024/8192 envs)
+                if (!persistent) items = items < resident ? items : 0x7fffffff;   // plain grid: one CTA per item
+                if (!persistent) { maze3d_compose_kernel<<<(unsigned)(h->n * parts), kComposeThreads, 0, st>>>(c, a); }
+                else
+                maze3d_compose_kernel<<<(unsigned)(items < resident ? items : resident), kComposeThreads, 0, st>>>(c, a);
+            }
             h->launches += 1;
         } else {
             rc = launch_render<false>(h, a, (unsigned)(h->n < h->num_sms ? h->n : h->num_sms), st);
