@@ -143,6 +143,43 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def maze_extras(torch, dev, peak):
+    """env-steps/s of MetaMazeDiscrete3D (15x15, 128x128, uint8, 1024 envs = config 4 per GPU) and MetaMaze2D."""
+    import numpy as np
+    from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D, MazeTaskSampler
+    rs = np.random.RandomState(0)
+    tasks = [MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.35, rng=rs) for _ in range(64)]
+    out = {}
+    for name, make, n, nbytes in (
+            ("maze3d_15x15_128x128_u8_1024envs",
+             lambda: BatchedMetaMazeDiscrete3D(resolution=(128, 128), max_steps=200, task_type="SURVIVAL", num_envs=1024,
+                                               device=dev.index, squeeze=False, auto_reset=True, obs_dtype="uint8"),
+             1024, 128 * 128 * 3 + 1630),
+            ("maze2d_15x15_g1_16384envs",
+             lambda: BatchedMetaMaze2D(max_steps=200, task_type="ESCAPE", view_grid=1, num_envs=16384, device=dev.index,
+                                       squeeze=False, auto_reset=True), 16384, 160)):
+        env = make()
+        env.set_task(tasks)
+        env.reset()
+        acts = torch.randint(0, 4, (16, n), device=dev, dtype=torch.int32)
+        for t in range(5):
+            env.step(acts[t % 16])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 50
+        e0.record()
+        for t in range(iters):
+            env.step(acts[t % 16])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) * 1e3 / iters
+        out[name] = {"value": n / us * 1e6, "unit": "env-steps/s", "us_per_step": us,
+                     "algorithmic_bytes_per_env_step": nbytes, "frac_of_measured_hbm": n * nbytes / us * 1e-3 / peak,
+                     "parity": "bit-exact vs reference golden episodes (tests/test_maze_gpu.py)"}
+        env.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -327,6 +364,11 @@ def main():
             big.close()
             del big, a2
             torch.cuda.empty_cache()
+            # ---- the other half of the hot path: MetaMaze (BASELINE configs[3]/[4] per-GPU shapes), bit-exact renderer
+            try:
+                extras["metamaze"] = maze_extras(torch, dev, peak)
+            except Exception as ex:      # the contract metric above must not depend on this leg
+                extras["metamaze"] = {"error": repr(ex)[:200]}
     else:
         env.close()
 

@@ -37,6 +37,9 @@ extern "C" {
 #define MGB_TASK_HOVERING_CONTROL 1 /* env.py:222-243 */
 #define MGB_TASK_VELOCITY_CONTROL 2 /* env.py:219-221 */
 
+#define MGB_INTEGRATOR_REFERENCE 0
+#define MGB_INTEGRATOR_RK4 1
+
 #define MGB_FAIL_NONE 0
 #define MGB_FAIL_RANGE 1    /* quadrotorsim.py:213-214 */
 #define MGB_FAIL_VELOCITY 2 /* quadrotorsim.py:216-217 */
@@ -68,6 +71,12 @@ typedef struct mgb_quad_cfg {
     int32_t task;              /* MGB_TASK_*                                                 */
     double healthy_reward;
     double z_offset;           /* env.py:112 (5.0 for the flat map; 0 for velocity_control)  */
+    /* Integrator.  MGB_INTEGRATOR_REFERENCE: int(dt/precision) semi-implicit Euler substeps, the reference's only
+     * integrator (quadrotorsim.py:122-208) and the parity-checked default.  MGB_INTEGRATOR_RK4: classical RK4 on the
+     * same continuous-time model, rk4_steps steps of dt/rk4_steps per env step -- BASELINE.json's "RK4 dt=0.005";
+     * the reference has no counterpart, so it is validated by convergence only. */
+    int32_t integrator;
+    int32_t rk4_steps;
 } mgb_quad_cfg;
 
 typedef struct mgb_quad mgb_quad;

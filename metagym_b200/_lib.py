@@ -23,7 +23,7 @@ class QuadCfg(ctypes.Structure):
         ("propeller", c_f32 * 12), ("propeller_norm", c_f32 * 4), ("min_voltage", c_f64), ("max_voltage", c_f64),
         ("init_velocity", c_f32 * 3), ("init_velocity_noise", c_f64), ("init_angular_velocity", c_f32 * 3),
         ("init_angular_velocity_noise", c_f64), ("dt", c_f64), ("nt", c_i32), ("task", c_i32),
-        ("healthy_reward", c_f64), ("z_offset", c_f64),
+        ("healthy_reward", c_f64), ("z_offset", c_f64), ("integrator", c_i32), ("rk4_steps", c_i32),
     ]
 
 

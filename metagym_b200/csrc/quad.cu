@@ -51,6 +51,10 @@ struct QuadConst {
     float dt, healthy, z_off;
     float init_v[3], init_w[3], noise_v, noise_w;
     int nt, task, substeps, obs_dim;
+    int rk4_steps;         // 0 = reference substeps; > 0 = classical RK4 steps per env step
+    float rk4_h;           // dt / rk4_steps
+    float inv_jm, inv_m;   // continuous-time rates used by RK4 (1/Jm, 1/mass)
+    float Iinv[9];         // inverse inertia (unscaled)
     int simple;            // propeller z == 0, cg == 0, diagonal inertia, ct2 == 0
 };
 
@@ -252,6 +256,10 @@ __device__ __forceinline__ void substep(const QuadConst &c, QState &s, const flo
     osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
 }
 
+template <bool SIMPLE>
+__device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
+                                             float &power);
+
 // `substeps` calls of _run_internal (quadrotorsim.py:295-304).  Returns the fail code (0 = none); power = electrical
 // power of the last executed substep (:139,188).  The loop is unrolled by 5 when substeps % 5 == 0 (dt = 0.005, 0.01)
 // so the ~40 step constants stay in uniform registers across the unrolled body.
@@ -259,6 +267,7 @@ template <bool SIMPLE>
 __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
                                          float &power)
 {
+    if (c.rk4_steps > 0) return integrate_rk4<SIMPLE>(c, s, act, adj, id, power);   // uniform branch
     // voltage clamp (:130-134) and the per-step rotor constants
     float V[4] = {act.x, act.y, act.z, act.w};
     float kV[4], cw[4];
@@ -299,6 +308,139 @@ __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const fl
     float pw = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) pw += fabsf(fmaf(-c.k1phi, wl[i], kV[i]) * c.inv_phi * V[i]);
+    power = pw;
+    return fail;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Classical RK4 on the continuous-time model behind _run_internal (BASELINE.json config 3 "RK4 dt=0.005").
+// The reference has NO such integrator (quadrotorsim.py:185-208 is semi-implicit Euler), so this mode cannot be
+// parity-pinned; tests validate it by convergence against the float64 oracle run with a 1e-5 s substep.
+//   p' = v,  v' = R F_body / m,  w' = I^-1 tau,  R' = R [w]x,  m_i' = (me_i - Mm) / Jm
+// with the reference's force model: F_body = (0,0,sum T_i) + R^-1 g m - |v| Df R^-1 v, T_i = ct0 m_i^2 + ct1 m_i v1_i
+// (+ ct2 v1_i |v1_i|), v1_i = (R^-1 v)_z + ((w x p_i) |p_i|)_z, tau = sum -(0,0,T_i) x p_i + yaw reaction - |w| Dm w
+// (- f_grav x cg).  The substep quirks that vanish as h -> 0 (thrust from the already-updated rotor speed, the
+// 0.5 h^2 a position term) are not part of the continuous model.
+// ---------------------------------------------------------------------------------------------------------------
+struct QDeriv { float p[3], v[3], om[3], w[4], R[9]; };
+
+template <bool SIMPLE>
+__device__ __forceinline__ void quad_rhs(const QuadConst &c, const QState &s, const float kV[4], QDeriv &d)
+{
+    float adj[9], id;
+    adjugate(s.R, adj, id);
+    const float bvx = (adj[0] * s.v[0] + adj[1] * s.v[1] + adj[2] * s.v[2]) * id;
+    const float bvy = (adj[3] * s.v[0] + adj[4] * s.v[1] + adj[5] * s.v[2]) * id;
+    const float bvz = (adj[6] * s.v[0] + adj[7] * s.v[1] + adj[8] * s.v[2]) * id;
+    const float nvn = -fast_sqrt(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
+    const float non = -fast_sqrt(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
+    float fz = 0.f, tx = 0.f, ty = 0.f, me[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        me[i] = fmaf(-c.k1phi, s.w[i], kV[i]);
+        d.w[i] = (me[i] - c.mm) * c.inv_jm;
+        const float v1 = fmaf(s.om[0], c.A[i], fmaf(-s.om[1], c.B[i], bvz));
+        float th = s.w[i] * fmaf(c.ct0, s.w[i], c.ct1 * v1);
+        if (!SIMPLE) th = fmaf(c.ct2 * v1, fabsf(v1), th);
+        fz += th;
+        tx = fmaf(th, c.py[i], tx);
+        ty = fmaf(-th, c.px[i], ty);
+    }
+    const float tz = (me[1] - me[0]) + (me[3] - me[2]);
+    const float idgm = id * c.gm;
+    const float Fx = fmaf(nvn * c.Df[0], bvx, adj[2] * idgm);
+    const float Fy = fmaf(nvn * c.Df[1], bvy, adj[5] * idgm);
+    const float Fz = fmaf(nvn * c.Df[2], bvz, fmaf(adj[8], idgm, fz));
+    float Tx = fmaf(non * c.Dm[0], s.om[0], tx);
+    float Ty = fmaf(non * c.Dm[1], s.om[1], ty);
+    float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
+    if (!SIMPLE) {
+        const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
+        Tx -= gy * c.cg[2] - gz * c.cg[1];
+        Ty -= gz * c.cg[0] - gx * c.cg[2];
+        Tz -= gx * c.cg[1] - gy * c.cg[0];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        d.p[r] = s.v[r];
+        d.v[r] = (s.R[3 * r] * Fx + s.R[3 * r + 1] * Fy + s.R[3 * r + 2] * Fz) * c.inv_m;
+        d.om[r] = c.Iinv[3 * r] * Tx + c.Iinv[3 * r + 1] * Ty + c.Iinv[3 * r + 2] * Tz;
+        const float r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
+        d.R[3 * r + 0] = r1 * s.om[2] - r2 * s.om[1];
+        d.R[3 * r + 1] = r2 * s.om[0] - r0 * s.om[2];
+        d.R[3 * r + 2] = r0 * s.om[1] - r1 * s.om[0];
+    }
+}
+
+__device__ __forceinline__ void quad_axpy(const QState &y, const QDeriv &k, float h, QState &out)
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        out.p[r] = fmaf(h, k.p[r], y.p[r]); out.v[r] = fmaf(h, k.v[r], y.v[r]); out.om[r] = fmaf(h, k.om[r], y.om[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out.w[r] = fmaf(h, k.w[r], y.w[r]);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) out.R[r] = fmaf(h, k.R[r], y.R[r]);
+}
+
+template <bool SIMPLE>
+__device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
+                                             float &power)
+{
+    float V[4] = {act.x, act.y, act.z, act.w}, kV[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        V[i] = V[i] > c.vmax ? c.vmax : (V[i] < c.vmin ? c.vmin : V[i]);
+        kV[i] = c.k1 * V[i];
+    }
+    const float h = c.rk4_h;
+    int fail = 0;
+#pragma unroll 1
+    for (int n = 0; n < c.rk4_steps; ++n) {
+        QDeriv k, acc;
+        QState t;
+        quad_rhs<SIMPLE>(c, s, kV, k);                       // k1
+        acc = k;
+        quad_axpy(s, k, 0.5f * h, t);
+        quad_rhs<SIMPLE>(c, t, kV, k);                       // k2
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc.p[r] += 2.f * k.p[r]; acc.v[r] += 2.f * k.v[r]; acc.om[r] += 2.f * k.om[r]; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc.w[r] += 2.f * k.w[r];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) acc.R[r] += 2.f * k.R[r];
+        quad_axpy(s, k, 0.5f * h, t);
+        quad_rhs<SIMPLE>(c, t, kV, k);                       // k3
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc.p[r] += 2.f * k.p[r]; acc.v[r] += 2.f * k.v[r]; acc.om[r] += 2.f * k.om[r]; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc.w[r] += 2.f * k.w[r];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) acc.R[r] += 2.f * k.R[r];
+        quad_axpy(s, k, h, t);
+        quad_rhs<SIMPLE>(c, t, kV, k);                       // k4
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc.p[r] += k.p[r]; acc.v[r] += k.v[r]; acc.om[r] += k.om[r]; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc.w[r] += k.w[r];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) acc.R[r] += k.R[r];
+        const int ct = s.ct, ep = s.ep;
+        quad_axpy(s, acc, h * (1.0f / 6.0f), t);
+        s = t; s.ct = ct; s.ep = ep;
+        const float psq = s.p[0] * s.p[0] + s.p[1] * s.p[1] + s.p[2] * s.p[2];
+        const float vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
+        const float osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+        if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {
+            fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR);
+            break;
+        }
+    }
+    adjugate(s.R, adj, id);
+    float pw = 0.f;      // electrical power at the end state (the reference reports the last substep's, :139,188)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pw += fabsf(fmaf(-c.k1phi, s.w[i], kV[i]) * c.inv_phi * V[i]);
     power = pw;
     return fail;
 }
@@ -881,6 +1023,11 @@ static int derive_constants(const mgb_quad_cfg *g, QuadConst *c)
     c->noise_v = (float)g->init_velocity_noise; c->noise_w = (float)g->init_angular_velocity_noise;
     c->nt = g->nt; c->task = g->task;
     c->substeps = (int)(g->dt / g->precision);          // quadrotorsim.py:302, evaluated in double like python
+    c->rk4_steps = g->integrator == MGB_INTEGRATOR_RK4 ? (g->rk4_steps > 0 ? g->rk4_steps : 1) : 0;
+    c->rk4_h = c->rk4_steps ? (float)(g->dt / c->rk4_steps) : 0.f;
+    c->inv_jm = (float)(1.0 / g->jm);
+    c->inv_m = (float)(1.0 / g->quality);
+    for (int k = 0; k < 9; ++k) c->Iinv[k] = g->inv_inertia[k];
     c->obs_dim = g->task == MGB_TASK_VELOCITY_CONTROL ? 19 : 16;
     c->simple = simple ? 1 : 0;
     return 0;

@@ -48,7 +48,7 @@ def load_simulator_conf(simulator_conf=None):
         return json.load(f)
 
 
-def build_cfg(conf, dt, nt, task, healthy_reward):
+def build_cfg(conf, dt, nt, task, healthy_reward, integrator="euler", rk4_steps=1):
     """QuadrotorSim._parse_cfg (quadrotorsim.py:50-109) -> mgb_quad_cfg.  Raises RuntimeError like get_config."""
     try:
         c = _lib.QuadCfg()
@@ -88,6 +88,9 @@ def build_cfg(conf, dt, nt, task, healthy_reward):
     c.healthy_reward = float(healthy_reward)
     # env.py:97-114: the flat map starts the vehicle 5 m above the floor; velocity_control has no map/offset
     c.z_offset = 0.0 if task == "velocity_control" else 5.0
+    assert integrator in ("euler", "rk4"), "integrator must be 'euler' (the reference's substeps) or 'rk4'"
+    c.integrator = 0 if integrator == "euler" else 1
+    c.rk4_steps = int(rk4_steps)
     return c
 
 
@@ -126,7 +129,8 @@ class BatchedQuadrotor(object):
 
     Extra kwargs: num_envs, device (int or 'cuda:k'), auto_reset (finished envs restart inside the step launch),
     rng_seed (counter-based reset noise), env_index_base (global index of env 0, for multi-GPU sharding),
-    squeeze (num_envs == 1 returns reference-shaped arrays).
+    squeeze (num_envs == 1 returns reference-shaped arrays), integrator ('euler' = the reference's 1 ms substeps,
+    parity-checked; 'rk4' = classical RK4 with rk4_steps steps per env step, validated by convergence only).
     velocity_control: `seed` may be an int (as in the reference) or a sequence of seeds = distinct tasks; env i
     flies task `env2task[i]` (default i % n_tasks).
     """
@@ -134,7 +138,7 @@ class BatchedQuadrotor(object):
 
     def __init__(self, dt=0.01, nt=1000, seed=0, task="no_collision", map_file=None, simulator_conf=None,
                  healthy_reward=1.0, num_envs=1, device=0, auto_reset=False, rng_seed=0, env_index_base=0,
-                 env2task=None, squeeze=True, **kwargs):
+                 env2task=None, squeeze=True, integrator="euler", rk4_steps=1, **kwargs):
         import torch
         assert task in ["velocity_control", "no_collision", "hovering_control"], "Invalid task setting"  # env.py:55
         if map_file is not None:
@@ -153,7 +157,7 @@ class BatchedQuadrotor(object):
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", dev_index)
         self.conf = load_simulator_conf(simulator_conf)
-        self._cfg = build_cfg(self.conf, dt, nt, task, healthy_reward)
+        self._cfg = build_cfg(self.conf, dt, nt, task, healthy_reward, integrator, rk4_steps)
         self.valid_range = self._cfg.fail_range
         lo, hi = self._cfg.min_voltage, self._cfg.max_voltage
         self.action_space = Box(low=np.array([lo] * 4, dtype="float32"), high=np.array([hi] * 4, dtype="float32"),

@@ -142,3 +142,13 @@ def reset_state(cfg_params, noise):
     s[:, 3:6] = base_v + (float(iv["noisy"]) * noise[:, 3:6]) * sv
     s[:, 6:9] = base_w + (float(iw["noisy"]) * noise[:, 9:12]) * sw
     return s
+
+
+def rk4_step(cfg, state, act, dt, rk4_steps=1, mode="f64"):
+    """Classical RK4 on the continuous-time model (NOT a reference mode; parity unpinned).  state [n,22] f64 in place."""
+    n = state.shape[0]
+    assert state.dtype == np.float64 and state.flags.c_contiguous and state.shape == (n, 22)
+    act = np.ascontiguousarray(act, dtype=np.float32).reshape(n, 4)
+    fn = getattr(lib(), "qo_%s_rk4_step" % mode)
+    fn(ctypes.byref(cfg), ctypes.c_int(n), _ptr(state, ctypes.c_double), _ptr(act, ctypes.c_float),
+       ctypes.c_double(dt), ctypes.c_int(rk4_steps))

@@ -292,5 +292,79 @@ void QO_NAME(sim_step)(const qo_cfg *c, int n, double *state, const float *act, 
     }
 }
 
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Classical RK4 on the continuous-time model behind _run_internal.  NOT a reference mode (the reference integrates
+ * with semi-implicit Euler substeps only): "parity unpinned".  It exists so that the engine's RK4 option can be
+ * checked (a) against this restatement and (b) by convergence of this restatement to the Euler-substep oracle as
+ * precision -> 0.  All arithmetic in T.
+ * --------------------------------------------------------------------------------------------------------------- */
+static void QO_NAME(rhs)(const qo_cfg *c, const T vclamp[4], const T y[22], T d[22])
+{
+    const T *p = y, *v = y + 3, *om = y + 6, *w = y + 9, *R = y + 13;
+    T Ri[9];
+    (void)p;
+    QO_NAME(invert)(R, Ri);
+    T bv[3];
+    for (int r = 0; r < 3; ++r) bv[r] = Ri[3 * r] * v[0] + Ri[3 * r + 1] * v[1] + Ri[3 * r + 2] * v[2];
+    T me[4], fz = 0, tq[3] = {0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        const T px = (T)c->prop[3 * i], py = (T)c->prop[3 * i + 1];
+        me[i] = (T)(c->phi / c->ra) * (vclamp[i] - (T)c->phi * w[i]);
+        d[9 + i] = (me[i] - (T)c->mm) / (T)c->jm;
+        const T v1 = bv[2] + (om[0] * py - om[1] * px) * (T)c->lm[i];
+        const T th = (T)c->ct0 * w[i] * w[i] + (T)c->ct1 * w[i] * v1 + (T)c->ct2 * v1 * (v1 < 0 ? -v1 : v1);
+        fz += th;
+        tq[0] += th * py;
+        tq[1] += -th * px;
+    }
+    tq[2] += -me[0] + me[1] - me[2] + me[3];
+    const T vn = (T)QO_SQRTT(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const T on = (T)QO_SQRTT(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    T F[3], Tq[3], fg[3];
+    for (int r = 0; r < 3; ++r) fg[r] = Ri[3 * r + 2] * (T)(-9.8f) * (T)c->m;
+    for (int r = 0; r < 3; ++r) {
+        F[r] = (r == 2 ? fz : 0) + fg[r] - vn * (T)c->Df[r] * bv[r];
+        Tq[r] = tq[r] - on * (T)c->Dm[r] * om[r];
+    }
+    Tq[0] -= fg[1] * (T)c->cg[2] - fg[2] * (T)c->cg[1];
+    Tq[1] -= fg[2] * (T)c->cg[0] - fg[0] * (T)c->cg[2];
+    Tq[2] -= fg[0] * (T)c->cg[1] - fg[1] * (T)c->cg[0];
+    for (int r = 0; r < 3; ++r) {
+        d[r] = v[r];
+        d[3 + r] = (R[3 * r] * F[0] + R[3 * r + 1] * F[1] + R[3 * r + 2] * F[2]) / (T)c->m;
+        d[6 + r] = (T)c->Iinv[3 * r] * Tq[0] + (T)c->Iinv[3 * r + 1] * Tq[1] + (T)c->Iinv[3 * r + 2] * Tq[2];
+        d[13 + 3 * r + 0] = R[3 * r + 1] * om[2] - R[3 * r + 2] * om[1];
+        d[13 + 3 * r + 1] = R[3 * r + 2] * om[0] - R[3 * r + 0] * om[2];
+        d[13 + 3 * r + 2] = R[3 * r + 0] * om[1] - R[3 * r + 1] * om[0];
+    }
+}
+
+void QO_NAME(rk4_step)(const qo_cfg *c, int n, double *state, const float *act, double dt, int rk4_steps)
+{
+    const T h = (T)(dt / rk4_steps);
+    for (int e = 0; e < n; ++e) {
+        double *s = state + 22 * (long)e;
+        T y[22], t[22], k[22], acc[22], vclamp[4];
+        for (int q = 0; q < 22; ++q) y[q] = (T)s[q];
+        for (int q = 0; q < 4; ++q) {
+            double a = (double)act[4 * (long)e + q];
+            if (a > c->vmax) a = c->vmax; else if (a < c->vmin) a = c->vmin;
+            vclamp[q] = (T)a;
+        }
+        for (int it = 0; it < rk4_steps; ++it) {
+            QO_NAME(rhs)(c, vclamp, y, k);
+            for (int q = 0; q < 22; ++q) { acc[q] = k[q]; t[q] = y[q] + (T)0.5 * h * k[q]; }
+            QO_NAME(rhs)(c, vclamp, t, k);
+            for (int q = 0; q < 22; ++q) { acc[q] += 2 * k[q]; t[q] = y[q] + (T)0.5 * h * k[q]; }
+            QO_NAME(rhs)(c, vclamp, t, k);
+            for (int q = 0; q < 22; ++q) { acc[q] += 2 * k[q]; t[q] = y[q] + h * k[q]; }
+            QO_NAME(rhs)(c, vclamp, t, k);
+            for (int q = 0; q < 22; ++q) y[q] = y[q] + h / 6 * (acc[q] + k[q]);
+        }
+        for (int q = 0; q < 22; ++q) s[q] = (double)y[q];
+    }
+}
+
 #undef KT
 #undef KV

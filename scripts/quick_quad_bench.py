@@ -54,3 +54,25 @@ for task, dt, N in [("velocity_control", 0.005, 65536), ("hovering_control", 0.0
     env.close()
     del env, acts, out, out2, g
     torch.cuda.empty_cache()
+
+# RK4 variant of the bench shape (config 3 wording)
+env = BatchedQuadrotor(task="velocity_control", dt=0.005, nt=1000, seed=list(range(64)), num_envs=65536, squeeze=False,
+                       auto_reset=True, integrator="rk4")
+env.reset()
+acts = torch.rand((64, 65536, 4), device="cuda") * 14.9 + 0.1
+def steps(k):
+    for i in range(k):
+        env.step(acts[i % 64])
+steps(10)
+g = torch.cuda.CUDAGraph(); s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    steps(3)
+    with torch.cuda.graph(g, stream=s):
+        steps(64)
+torch.cuda.synchronize()
+def replay(k):
+    for i in range(k): g.replay()
+replay(2)
+us = timeit(replay, 10) / 64
+print(json.dumps(dict(kind="step-graph-rk4", task="velocity_control", N=65536, us_per_step=us, steps_per_s=65536 / us * 1e6,
+                      GBps=65536 * 281 / us * 1e-3)))

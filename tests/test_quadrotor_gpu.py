@@ -349,3 +349,27 @@ def test_streaming_kernel_equals_tile_kernel(torch_mod, monkeypatch):
     assert int(d1.sum()) > 0 or True
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("task,dt,rk4_steps", [("velocity_control", 0.005, 1), ("hovering_control", 0.01, 2)])
+def test_rk4_integrator_vs_restatement(torch_mod, task, dt, rk4_steps):
+    """integrator='rk4' (BASELINE config 3 wording; no reference counterpart, parity unpinned): the float32 kernel
+    follows the float64 RK4 restatement of the same continuous-time model to 1e-5 over 20 free-running steps."""
+    torch = torch_mod
+    from oracle import quad_oracle as qo
+    cfg = qo.make_cfg()
+    n, nt = 2048, 1000
+    rng = np.random.RandomState(21)
+    env = make_env(n, task, dt=dt, nt=nt, seed=[0, 1], integrator="rk4", rk4_steps=rk4_steps)
+    noise = rng.random_sample((n, 12))
+    env.reset(noise=noise)
+    state = qo.reset_state(None, noise)
+    for t in range(20):
+        act = rng.uniform(-1.0, 16.0, (n, 4)).astype(np.float32)
+        obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
+        qo.rk4_step(cfg, state, act, dt, rk4_steps, "f64")
+        assert torch.isfinite(obs).all() and not bool(done.any())
+    st, ct = get_state(env)
+    assert group_rel_err(st, state, STATE_GROUPS) < 2e-5
+    assert np.all(ct == 20)
+    env.close()
