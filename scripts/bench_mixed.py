@@ -1,0 +1,102 @@
+"""BASELINE.json configs[4]: mixed Quadrotor (hovering_control) + MetaMaze2D random-action rollout, envs sharded over
+the GPUs of one node, one NCCL all-gather of every T-step trajectory chunk for the learner.
+
+    python scripts/bench_mixed.py                                  # 1 GPU: 16 384 + 16 384 envs
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
+        scripts/bench_mixed.py                                     # 8 GPUs: 262 144 envs
+
+Prints one JSON line (rank 0): env-steps/s without and with the gather, and the gather's bus bandwidth.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+from metagym_b200 import BatchedMetaMaze2D, BatchedQuadrotor, MazeTaskSampler
+from metagym_b200.rollout import all_gather_rollout, rollout_bytes, shard_range
+
+rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+N_QUAD = N_MAZE = 16384          # per GPU (131 072 + 131 072 over 8 GPUs)
+T, CHUNKS = 32, 8
+qbase, _ = shard_range(N_QUAD * world, rank, world)
+mbase, _ = shard_range(N_MAZE * world, rank, world)
+quad = BatchedQuadrotor(task="hovering_control", dt=0.01, nt=1000, num_envs=N_QUAD, device=local, squeeze=False,
+                        auto_reset=True, env_index_base=qbase)
+rs = np.random.RandomState(0)
+tasks = [MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.35, rng=rs) for _ in range(64)]
+maze = BatchedMetaMaze2D(max_steps=200, task_type="ESCAPE", view_grid=1, num_envs=N_MAZE, device=local, squeeze=False,
+                         auto_reset=True, env_index_base=mbase)
+maze.set_task(tasks)
+quad.reset()
+maze.reset()
+g = torch.Generator(device=dev).manual_seed(rank)
+chunk = {
+    "q_obs": torch.empty((T, N_QUAD, 16), device=dev), "q_act": torch.empty((T, N_QUAD, 4), device=dev),
+    "q_rew": torch.empty((T, N_QUAD), device=dev), "q_done": torch.empty((T, N_QUAD), dtype=torch.uint8, device=dev),
+    "m_obs": torch.empty((T, N_MAZE, 3, 3), device=dev), "m_act": torch.empty((T, N_MAZE), dtype=torch.int32, device=dev),
+    "m_rew": torch.empty((T, N_MAZE), dtype=torch.float64, device=dev),
+    "m_done": torch.empty((T, N_MAZE), dtype=torch.uint8, device=dev),
+}
+
+
+def collect():
+    # quadrotor: T fused steps, device-drawn U(0.1, 15) actions; maze: T single steps with uniform {0..3} actions
+    quad.rollout(T, actions=None, act_seed=7, out={"obs": chunk["q_obs"], "rew": chunk["q_rew"], "done": chunk["q_done"],
+                                                   "act": chunk["q_act"]})
+    chunk["m_act"].copy_(torch.randint(0, 4, (T, N_MAZE), device=dev, generator=g, dtype=torch.int32))
+    for t in range(T):
+        o, r, d, _ = maze.step(chunk["m_act"][t])
+        chunk["m_obs"][t].copy_(o); chunk["m_rew"][t].copy_(r); chunk["m_done"][t].copy_(d)
+
+
+def timed(fn, reps):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t) / reps
+
+
+collect()
+ms_collect = timed(collect, CHUNKS)
+gathered = {}
+
+
+def collect_and_gather():
+    collect()
+    gathered.update(all_gather_rollout(chunk))
+
+
+collect_and_gather()
+ms_both = timed(collect_and_gather, CHUNKS)
+ms_gather = timed(lambda: all_gather_rollout(chunk), CHUNKS)
+steps = (N_QUAD + N_MAZE) * world * T
+nbytes = rollout_bytes(chunk)
+if rank == 0:
+    print(json.dumps({
+        "config": "mixed quadrotor hovering_control + MetaMaze2D ESCAPE, %d envs over %d GPU(s), T=%d chunks" %
+                  ((N_QUAD + N_MAZE) * world, world, T),
+        "env_steps_per_s_no_gather": steps / (ms_collect * 1e-3),
+        "env_steps_per_s_with_gather": steps / (ms_both * 1e-3),
+        "allgather_ms": ms_gather, "chunk_bytes_per_rank": nbytes,
+        "allgather_busbw_GBps": nbytes * (world - 1) / (ms_gather * 1e-3) / 1e9 if world > 1 else None,
+        "gathered_envs": int(gathered["q_obs"].shape[1]) + int(gathered["m_obs"].shape[1]), "n_gpus": world}), flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
