@@ -73,6 +73,7 @@ struct QuadArgs {
     const int32_t *env2task;   // [n]
     uint64_t seed;
     int auto_reset;
+    int per_cta;               // quad_step_wide_kernel: envs per CTA
     // rollout only
     int T;
     uint64_t act_seed;
@@ -682,6 +683,45 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
 }
 
+// "One CTA per SM" variant for launches that fit a single wave (N <= 148 x 512): grid = number of SMs, each CTA owns
+// `per` = ceil(N / grid) envs (rounded to 4 so that every observation tile stays 16-byte aligned for the bulk store).
+// 148 CTA dispatches instead of 1024 and a perfectly balanced wave (444 vs 443 envs per SM at 65 536 envs).
+template <bool SIMPLE>
+__global__ void __launch_bounds__(512, 1) quad_step_wide_kernel(const __grid_constant__ QuadConst c,
+                                                                const __grid_constant__ QuadArgs a)
+{
+    extern __shared__ __align__(128) float wide_smem[];
+    const int per = a.per_cta;
+    float *tile = wide_smem, *ftile = wide_smem + (size_t)per * kMaxObs;
+    const int64_t e0 = (int64_t)blockIdx.x * per;
+    const int64_t e = e0 + threadIdx.x;
+    int rows = (int)((a.n - e0) < per ? (a.n - e0) : per);
+    if (rows < 0) rows = 0;
+    const int D = c.obs_dim;
+    const bool active = (int)threadIdx.x < rows;
+    bool any_final = false;
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (active) {
+        QState s;
+        load_state(a, e, s);
+        const float4 act = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
+        step_body<SIMPLE, true>(c, a, e, s, act, tile + threadIdx.x * D, ftile + threadIdx.x * D, any_final);
+    }
+    if (rows > 0) publish_tile(a.obs, tile, e0, rows, D);
+    else __syncthreads();
+    if (a.final_obs) {
+        if (__syncthreads_or(any_final ? 1 : 0)) {
+            if (active && any_final) {
+                float *dst = a.final_obs + e * D;
+                const float *frow = ftile + threadIdx.x * D;
+                for (int k = 0; k < D; ++k) dst[k] = frow[k];
+            }
+        }
+    }
+    if (threadIdx.x == 0) mgb_bulk_wait_read<0>();
+}
+
 // Streaming variant for multi-wave launches (millions of envs): PERSISTENT CTAs loop over tiles of 128 envs and the state
 // of tile i+1 (six 2 KB plane segments + 2 KB of actions) is fetched by the TMA engine (cp.async.bulk + mbarrier) into
 // the other half of a double-buffered shared-memory stage while tile i integrates, so HBM latency is off the critical
@@ -955,6 +995,7 @@ struct mgb_quad {
     int n_tasks = 0;
     int auto_reset = 0;
     int num_sms = 148;
+    int wide_kernel = 1;       // one-CTA-per-SM step kernel for single-wave launches (MGB_WIDE_KERNEL=0 disables)
     int stream_kernel = 1;     // persistent TMA-pipelined kernel for multi-wave launches (MGB_STREAM_KERNEL=0 disables)
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
@@ -1061,6 +1102,7 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     }
     if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_STREAM_KERNEL")) h->stream_kernel = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_WIDE_KERNEL")) h->wide_kernel = atoi(ev) != 0;
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
     if (e != cudaSuccess) {
         mgb_set_error("cudaMalloc(state planes, %lld envs) -> %s", (long long)n_envs, cudaGetErrorString(e));
@@ -1186,6 +1228,30 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
         cfg.blockDim = dim3(kStreamThreads);
         if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<true>, h->c, a));
         else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<false>, h->c, a));
+        MGB_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return MGB_OK;
+    }
+    // launches that fit one wave of 512-thread CTAs: one CTA per SM (7x fewer CTA dispatches, balanced wave)
+    if (h->wide_kernel && a.n <= (int64_t)h->num_sms * 512 && a.n >= (int64_t)h->num_sms * 64) {
+        int per = (int)((a.n + h->num_sms - 1) / h->num_sms);
+        per = (per + 3) / 4 * 4;
+        QuadArgs aw = a;
+        aw.per_cta = per;
+        const unsigned grid = (unsigned)((a.n + per - 1) / per);
+        const unsigned threads = (unsigned)((per + 31) / 32 * 32);
+        const size_t sm = (size_t)per * kMaxObs * 4 * 2;
+        static size_t g_limit[64] = {0};
+        if (sm > g_limit[h->device & 63]) {
+            MGB_CUDA(cudaFuncSetAttribute(quad_step_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            MGB_CUDA(cudaFuncSetAttribute(quad_step_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            g_limit[h->device & 63] = sm;
+        }
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = sm;
+        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_wide_kernel<true>, h->c, aw));
+        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_wide_kernel<false>, h->c, aw));
         MGB_CUDA(cudaGetLastError());
         h->launches += 1;
         return MGB_OK;

@@ -373,3 +373,29 @@ def test_rk4_integrator_vs_restatement(torch_mod, task, dt, rk4_steps):
     assert group_rel_err(st, state, STATE_GROUPS) < 2e-5
     assert np.all(ct == 20)
     env.close()
+
+
+@pytest.mark.parametrize("N", [9473, 65536, 70001])
+def test_wide_kernel_equals_tile_kernel(torch_mod, monkeypatch, N):
+    """Single-wave launches take the one-CTA-per-SM kernel (quad_step_wide_kernel); it must reproduce the 64-thread
+    tile kernel bit for bit (ragged sizes, auto-reset, terminal observations)."""
+    torch = torch_mod
+    kw = dict(dt=0.005, nt=5, seed=list(range(8)), auto_reset=True, rng_seed=4)
+    a = make_env(N, "velocity_control", **kw)
+    monkeypatch.setenv("MGB_WIDE_KERNEL", "0")
+    b = make_env(N, "velocity_control", **kw)
+    monkeypatch.delenv("MGB_WIDE_KERNEL")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a.reset()
+    b.reset()
+    for t in range(8):
+        act = torch.rand((N, 4), device="cuda", generator=g) * 16.0 - 0.5
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        m = d1.bool()
+        assert torch.equal(a.final_observation[m], b.final_observation[m])
+    s1, s2 = a.state_dict(), b.state_dict()
+    assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
+    a.close()
+    b.close()
