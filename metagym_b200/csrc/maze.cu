@@ -51,6 +51,7 @@ struct MazeConst {
     int text_pow2;               // text_size is a power of two
     double inv_text;
     int n_cls;                   // height classes with a precomputed eff table (0 = compute per pixel)
+    int hits_in_global;          // large screens: the per-column crossing lists live in a global scratch, not smem
     int blob_bytes;              // bytes of one task blob (multiple of 16)
     int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
     double max_vision, l_focal, text_size;
@@ -79,6 +80,7 @@ struct MazeArgs {
     uint8_t *c_colhits;          // [n_slots][H]     transparent crossings recorded for the column
     void *c_hits;                // [n_slots][H][max_hits] HitRec
     void *dyn;                   // [n] EnvDyn, written by the logic kernel, read by the compose kernel
+    void *hit_scratch;           // [grid][H][max_hits] HitRec when c.hits_in_global
     const int32_t *act;
     void *obs;
     double *rew;
@@ -313,7 +315,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     double *s_transp = reinterpret_cast<double *>(smem + off);           off = align_up(off + (size_t)n * n * 8, 128);
     ColRec *s_col = reinterpret_cast<ColRec *>(smem + off);              off = align_up(off + (size_t)H * sizeof(ColRec), 128);
     RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
-    HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);              off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
+    HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);
+    if (c.hits_in_global) s_hit = reinterpret_cast<HitRec *>(a.hit_scratch) + (size_t)blockIdx.x * H * c.max_hits;
+    else off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
     const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     const int run_bytes = c.run_px * px_bytes;                           // 768
     const int n_slots = c.obs_dtype == MGB_OBS_U8 ? 2 : 1;               // int32 runs are 4x larger: single slot
@@ -957,6 +961,8 @@ struct mgb_maze {
     uint32_t *c_gmask = nullptr;
     HitRec *c_hits = nullptr;
     EnvDyn *dyn = nullptr;
+    void *hit_scratch = nullptr;
+    size_t hit_scratch_bytes = 0;
     std::vector<int4> host_poses;
     std::vector<int32_t> host_pose_index;
     int n_tasks = 0;
@@ -976,7 +982,7 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     off = up(off + (size_t)c.n * c.n * 8, 128);
     off = up(off + (size_t)c.res_h * sizeof(ColRec), 128);
     off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
-    off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
+    if (!c.hits_in_global) off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     off = up(off + (size_t)(kRenderThreads / 32) * (c.obs_dtype == MGB_OBS_U8 ? 2 : 1) * c.run_px * px, 128);
     off += 16 + 32;
@@ -1081,7 +1087,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
     cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab);
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
-    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask);
+    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask); cudaFree(h->hit_scratch);
     delete h;
 }
 
@@ -1290,11 +1296,33 @@ static int maze_ready(const mgb_maze *h)
 template <bool FILL>
 static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStream_t st)
 {
-    const MazeConst &c = h->c;
-    const size_t sm = maze3d_smem_bytes(c);
+    MazeConst &c = h->c;
+    c.hits_in_global = 0;
+    size_t sm = maze3d_smem_bytes(c);
+    if (sm > 227 * 1024) {          // e.g. the reference's default 256x256 / 320x320 screens: spill the hit lists
+        c.hits_in_global = 1;
+        sm = maze3d_smem_bytes(c);
+    }
     if (sm > 227 * 1024) {
         mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
         return MGB_ERR_ARG;
+    }
+    MazeArgs a2 = a;
+    if (c.hits_in_global) {
+        const size_t need = (size_t)grid * c.res_h * c.max_hits * sizeof(HitRec);
+        if (need > h->hit_scratch_bytes) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+                mgb_set_error("maze renderer scratch must be allocated before stream capture: call reset() once first");
+                return MGB_ERR_STATE;
+            }
+            MGB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(h->hit_scratch);
+            h->hit_scratch = nullptr;
+            MGB_CUDA(cudaMalloc(&h->hit_scratch, need));
+            h->hit_scratch_bytes = need;
+        }
+        a2.hit_scratch = h->hit_scratch;
     }
     // the opt-in limit is a property of the kernel (per device), shared by every handle: only ever raise it
     static size_t g_smem_limit[64] = {0};
@@ -1303,7 +1331,7 @@ static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStre
         g_smem_limit[h->device & 63] = sm;
     }
     h->smem3d = sm;
-    maze3d_kernel<FILL><<<grid, kRenderThreads, sm, st>>>(c, a);
+    maze3d_kernel<FILL><<<grid, kRenderThreads, sm, st>>>(c, a2);
     MGB_CUDA(cudaGetLastError());
     return MGB_OK;
 }

@@ -216,3 +216,29 @@ def test_config4_shape_properties(torch_mod, maze_golden, textures):
     assert int(o.max()) <= 255 and int(o.float().mean()) > 5
     for e in (full, lo, hi):
         e.close()
+
+
+@pytest.mark.parametrize("res", [(256, 256), (320, 320), (320, 200)])
+def test_reference_default_resolutions_vs_oracle(torch_mod, maze_golden, textures, res, render_path):
+    """The reference registers 256x256 and defaults to 320x320 (metamaze/__init__.py:33-43, maze_env.py:20): screens
+    whose per-column tables no longer fit shared memory next to the textures (hit lists spill to a global scratch)."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D
+    from oracle.maze_oracle import OracleMaze
+    g = maze_golden
+    task = task_from_arrays(g["tasks15.walls"][0], g["tasks15.texts"][0], g["tasks15.food"][0],
+                            g["tasks15.interval"][0] // 20, g["tasks15.scalars"][0])
+    env = BatchedMetaMazeDiscrete3D(resolution=res, max_steps=30, task_type="SURVIVAL", num_envs=2, squeeze=False,
+                                    textures=textures)
+    ora = OracleMaze("3D", "SURVIVAL", 30, 1, res, textures=textures)
+    env.set_task(task)
+    ora.set_task(task)
+    assert np.array_equal(env.reset().cpu().numpy()[1], ora.reset())
+    rng = np.random.RandomState(11)
+    for t in range(8):
+        a = int(rng.randint(4))
+        obs, rew, done, _ = env.step(torch.full((2,), a, dtype=torch.int32, device="cuda"))
+        o2, r2, d2, _ = ora.step(a)
+        assert np.array_equal(obs.cpu().numpy()[0], o2), (t, int((obs.cpu().numpy()[0] != o2).sum()))
+        assert float(rew[1]) == r2 and bool(done[1]) == d2
+    env.close()
