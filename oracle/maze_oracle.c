@@ -113,11 +113,12 @@ static inline void mo_blend(int32_t *px, double tf)
 /*
  * maze_view, ray_caster_utils.py:66-209.
  *   walls, texts int8 [n][n]; transp float64 [n][n]; tex uint8 [n_tex][ts][ts][3]; ceil uint8 [ts][ts][3]
- *   ori_f float32 heading; out int32 [res_h][res_v][3]; transp_mark scratch float [res_h][res_v]
+ *   (s_ori, c_ori): sin/cos of the heading as numba computes them -- float32 libm results promoted for the discrete
+ *   maze (float32 heading), float64 libm results for the continuous maze (python-float heading); out int32 [res_h][res_v][3]; transp_mark scratch float [res_h][res_v]
  */
-void mo_maze_view(const mo_cfg *c, const mo_task *t, const double pos[2], float ori_f, const int8_t *walls,
-                  const double *transp, const int8_t *texts, const uint8_t *tex, const uint8_t *ceil_tex, int ts,
-                  int32_t *out, float *transp_mark)
+void mo_maze_view(const mo_cfg *c, const mo_task *t, const double pos[2], double s_ori, double c_ori,
+                  const int8_t *walls, const double *transp, const int8_t *texts, const uint8_t *tex,
+                  const uint8_t *ceil_tex, int ts, int32_t *out, float *transp_mark)
 {
     const int n = c->n, H = c->res_h, V = c->res_v;
     const double vision_height = t->agent_height, ceil_height = t->wall_height, cell_size = t->cell_size;
@@ -125,7 +126,6 @@ void mo_maze_view(const mo_cfg *c, const mo_task *t, const double pos[2], float 
     const double half_h = tan(c->fov / 2) * l_focal;
     const double half_v = half_h * V / H;
     const double pixel_size = 2.0 * half_h / H;
-    const float s_ori = sinf(ori_f), c_ori = cosf(ori_f);
     const double text_to_cell = text_size / cell_size;
     const double pixel_factor = pixel_size / l_focal;
     float cos_hp_a[4096], cos_abs_a[4096], sin_abs_a[4096];
@@ -269,7 +269,7 @@ void mo_observe_3d(const mo_cfg *c, const mo_task *t, const mo_env *e, const int
     static const float CH[4] = {0.0f, 0.5f, 1.0f, 1.5f};
     const float ori = CH[e->ori] * (float)3.1415926;  /* float32 array * weak python float, maze_discrete_3d.py:46 */
     (void)n;
-    mo_maze_view(c, t, pos, ori, walls, transp, texts, tex, ceil_tex, ts, obs, scratch);
+    mo_maze_view(c, t, pos, (double)sinf(ori), (double)cosf(ori), walls, transp, texts, tex, ceil_tex, ts, obs, scratch);
     if (c->task_type == 0) {
         const double lb_sx = 0.10 * V, lb_sy = 0.10 * V, lb_w = 0.05 * H, lb_l = 0.80 * V;   /* :42-45 */
         const double l = e->life / t->max_life * lb_l;
@@ -363,3 +363,149 @@ void mo_step_2d(const mo_cfg *c, const mo_task *t, const int8_t *walls, const do
 }
 
 int mo_env_size(void) { return (int)sizeof(mo_env); }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MetaMazeContinuous3D: maze_continuous_3d.py:47-56 (do_action), dynamics.py:16-92 (numba + numpy), with the typing
+ * the reference gets for float32 actions (what its action_space.sample() yields): turn_rate / walk_speed float32,
+ * heading float64, position float32.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    float pos[2];
+    int32_t pos_is_list;   /* 1 until the first step: reset() stores the cell centre as python floats */
+    double ori;
+} mo_cont;
+
+static float mo_sum2f(float a, float b) { float c = 0.0f; c += a; c += b; return c; }   /* numba np.sum over float32[2] */
+
+/* nearest_point, dynamics.py:16-29.  pos, l1, l2 float32[2] -> distance (float32), nearest point */
+static float mo_nearest_point(const float pos[2], const float l1[2], const float l2[2], float np_out[2])
+{
+    float u[2] = {l2[0] - l1[0], l2[1] - l1[1]};
+    const float edge_norm = sqrtf(mo_sum2f(u[0] * u[0], u[1] * u[1]));
+    const double den = 1.0e-6 > (double)edge_norm ? 1.0e-6 : (double)edge_norm;
+    u[0] = (float)((double)u[0] / den); u[1] = (float)((double)u[1] / den);
+    const float dist_1 = mo_sum2f((pos[0] - l1[0]) * u[0], (pos[1] - l1[1]) * u[1]);
+    const float *q;
+    float lp[2];
+    if (dist_1 > edge_norm) q = l2;
+    else if (dist_1 < 0) q = l1;
+    else { lp[0] = l1[0] + dist_1 * u[0]; lp[1] = l1[1] + dist_1 * u[1]; q = lp; }
+    const float a = pos[0] - q[0], b = pos[1] - q[1];
+    np_out[0] = q[0]; np_out[1] = q[1];
+    return sqrtf(mo_sum2f(a * a, b * b));
+}
+
+/* collision_force, dynamics.py:31-56 */
+static void mo_collision_force(const float dv[2], double cell_size, double col_dist, float out[2])
+{
+    static const float O10[2] = {0.5f, 0.5f}, O01[2] = {-0.5f, 0.5f}, Om0[2] = {-0.5f, -0.5f}, O0m[2] = {0.5f, -0.5f};
+    double dist = (double)sqrtf(mo_sum2f(dv[0] * dv[0], dv[1] * dv[1]));
+    const double eff = col_dist / cell_size;
+    out[0] = out[1] = 0.0f;
+    if (dist > 0.708 + eff) return;
+    if (fabsf(dv[0]) < 0.5f && fabsf(dv[1]) < 0.5f) {
+        const float k = (float)(0.50 / (dist > 1.0e-6 ? dist : 1.0e-6) * (0.708 + eff - dist) * cell_size);
+        out[0] = k * dv[0]; out[1] = k * dv[1];
+        return;
+    }
+    const int x_pos = (dv[0] + dv[1] > 0), y_pos = (dv[1] - dv[0] > 0);
+    float np[2];
+    if (x_pos && y_pos) dist = (double)mo_nearest_point(dv, O10, O01, np);
+    else if (!x_pos && y_pos) dist = (double)mo_nearest_point(dv, O01, Om0, np);
+    else if (!x_pos && !y_pos) dist = (double)mo_nearest_point(dv, Om0, O0m, np);
+    else dist = (double)mo_nearest_point(dv, O0m, O10, np);
+    if (eff < dist) return;
+    float o[2] = {dv[0] - np[0], dv[1] - np[1]};
+    const float on = sqrtf(mo_sum2f(o[0] * o[0], o[1] * o[1]));
+    const double inv = 1.0 / (1.0e-6 > (double)on ? 1.0e-6 : (double)on);
+    o[0] = (float)((double)o[0] * inv); o[1] = (float)((double)o[1] * inv);
+    const float k = (float)(0.50 * (eff - dist) * cell_size);
+    out[0] = k * o[0]; out[1] = k * o[1];
+}
+
+/* vector_move_with_collision, dynamics.py:58-92, for float32 (turn, walk) already clipped/scaled by do_action */
+static void mo_vector_move_with_collision(mo_cont *st, float turn_rate, float walk_speed, double deta_t, int n,
+                                          const int8_t *walls, double cell_size, double col_dist)
+{
+    if (walk_speed < 0) walk_speed = walk_speed * 0.5f;
+    float tmp[2] = {st->pos[0], st->pos[1]};
+    double ori = st->ori;
+    const int iters = (int)(100 * deta_t);
+    for (int it = 0; it < iters; ++it) {
+        /* vector_move(ori, turn_rate, walk_speed, 0.01) */
+        double fin = ori + (double)turn_rate * 0.01;
+        const double off_ori = 0.5 * (fin + ori);
+        const double off = (double)walk_speed * 0.01;
+        const float d[2] = {(float)(cos(off_ori) * off), (float)(sin(off_ori) * off)};
+        while (fin > 6.2831852) fin -= 6.2831852;
+        while (fin < 0) fin += 6.2831852;
+        ori = fin;
+        const float ex[2] = {tmp[0] + d[0], tmp[1] + d[1]};
+        const float cs = (float)cell_size;
+        const float ec[2] = {ex[0] / cs, ex[1] / cs};
+        float col[2] = {0.0f, 0.0f};
+        for (int i = -1; i < 2; ++i)
+            for (int j = -1; j < 2; ++j) {
+                const int wi = i + (int)ec[0], wj = j + (int)ec[1];
+                if (wi > -1 && wi < n && wj > -1 && wj < n && walls[wi * n + wj] > 0) {
+                    const float dv[2] = {ec[0] - floorf(ec[0]) - (float)(i + 0.5), ec[1] - floorf(ec[1]) - (float)(j + 0.5)};
+                    float f[2];
+                    mo_collision_force(dv, cell_size, col_dist, f);
+                    col[0] += f[0]; col[1] += f[1];
+                }
+            }
+        tmp[0] = col[0] + ex[0]; tmp[1] = col[1] + ex[1];
+    }
+    st->ori = ori;
+    st->pos[0] = tmp[0]; st->pos[1] = tmp[1];
+    st->pos_is_list = 0;
+}
+
+void mo_reset_c3d(const mo_cfg *c, const mo_task *t, const double *food, const int32_t *interval, mo_env *e,
+                  mo_cont *st)
+{
+    mo_reset(c, t, food, interval, e);
+    st->pos[0] = (float)(t->start[0] * t->cell_size + 0.5 * t->cell_size);
+    st->pos[1] = (float)(t->start[1] * t->cell_size + 0.5 * t->cell_size);
+    st->pos_is_list = 1;
+    st->ori = 0.0;
+}
+
+/* MetaMazeContinuous3D.step, maze_env.py:129-146 -> do_action maze_continuous_3d.py:47-56.  tr, ws: float32 actions */
+void mo_step_c3d(const mo_cfg *c, const mo_task *t, const int8_t *walls, const double *food, const int32_t *interval,
+                 mo_env *e, mo_cont *st, float tr, float ws, double *reward, int *done)
+{
+    float turn = tr < -1.0f ? -1.0f : (tr > 1.0f ? 1.0f : tr);
+    turn = turn * (float)3.1415926;                                /* np.clip(float32) * python float -> float32 */
+    const float walk = ws < -1.0f ? -1.0f : (ws > 1.0f ? 1.0f : ws);
+    mo_vector_move_with_collision(st, turn, walk, 0.10, c->n, walls, t->cell_size, 0.20);
+    const float cs = (float)t->cell_size;                          /* get_loc_grid: float32 / python float */
+    e->gx = (int)(st->pos[0] / cs);
+    e->gy = (int)(st->pos[1] / cs);
+    mo_evaluate(c, t, food, interval, e, reward, done);
+}
+
+void mo_observe_c3d(const mo_cfg *c, const mo_task *t, const mo_env *e, const mo_cont *st, const int8_t *walls,
+                    const int8_t *texts, const uint8_t *tex, const uint8_t *ceil_tex, int ts, int32_t *obs,
+                    float *scratch)
+{
+    const int H = c->res_h, V = c->res_v;
+    double transp[MO_MAX_N * MO_MAX_N];
+    mo_transparents(c, t, e, transp);
+    const double pos[2] = {(double)st->pos[0], (double)st->pos[1]};
+    mo_maze_view(c, t, pos, sin(st->ori), cos(st->ori), walls, transp, texts, tex, ceil_tex, ts, obs, scratch);
+    if (c->task_type == 0) {
+        const double lb_sx = 0.10 * V, lb_sy = 0.10 * V, lb_w = 0.05 * H, lb_l = 0.80 * V;
+        const double l = e->life / t->max_life * lb_l;
+        int sx = mo_slice_bound((int)lb_sx, H), ex = mo_slice_bound((int)(lb_sx + l), H);
+        int sy = mo_slice_bound((int)lb_sy, V), ey = mo_slice_bound((int)(lb_sy + lb_w), V);
+        for (int x = sx; x < ex; ++x)
+            for (int y = sy; y < ey; ++y) {
+                int32_t *px = obs + ((size_t)x * V + y) * 3;
+                px[0] = 255; px[1] = 0; px[2] = 0;
+            }
+    }
+}
+
+int mo_cont_size(void) { return (int)sizeof(mo_cont); }
+

@@ -30,6 +30,10 @@ class _Env(ctypes.Structure):
                 ("wait", c_i32 * (MAX_N * MAX_N))]
 
 
+class _Cont(ctypes.Structure):
+    _fields_ = [("pos", ctypes.c_float * 2), ("pos_is_list", c_i32), ("ori", c_f64)]
+
+
 _lib = None
 
 
@@ -37,7 +41,7 @@ def lib():
     global _lib
     if _lib is None:
         _lib = ctypes.CDLL(_build.build())
-        assert _lib.mo_env_size() == ctypes.sizeof(_Env)
+        assert _lib.mo_env_size() == ctypes.sizeof(_Env) and _lib.mo_cont_size() == ctypes.sizeof(_Cont)
     return _lib
 
 
@@ -48,7 +52,8 @@ def _p(a):
 class OracleMaze(object):
     def __init__(self, kind, task_type="SURVIVAL", max_steps=200, view_grid=1, resolution=(128, 128), textures=None,
                  max_vision=12.0, fov=0.6 * 3.1415926, l_focal=0.20, text_size=1.0):
-        assert kind in ("2D", "3D")
+        assert kind in ("2D", "3D", "C3D")
+        self.cont = _Cont()
         self.kind = kind
         self.cfg = _Cfg()
         self.cfg.task_type = {"SURVIVAL": 0, "ESCAPE": 1}[task_type]
@@ -56,7 +61,7 @@ class OracleMaze(object):
         self.cfg.view_grid = view_grid
         self.cfg.res_h, self.cfg.res_v = resolution
         self.cfg.max_vision, self.cfg.fov, self.cfg.l_focal, self.cfg.text_size = max_vision, fov, l_focal, text_size
-        if kind == "3D":
+        if kind in ("3D", "C3D"):
             grounds, ceil = textures
             self.tex = np.ascontiguousarray(grounds, dtype=np.uint8)
             self.ceil = np.ascontiguousarray(ceil, dtype=np.uint8)
@@ -93,6 +98,11 @@ class OracleMaze(object):
         H, V = self.cfg.res_h, self.cfg.res_v
         obs = np.zeros((H, V, 3), dtype=np.int32)
         scratch = np.zeros((H, V), dtype=np.float32)
+        if self.kind == "C3D":
+            L.mo_observe_c3d(ctypes.byref(self.cfg), ctypes.byref(self.task), ctypes.byref(self.env),
+                             ctypes.byref(self.cont), _p(self.walls), _p(self.texts), _p(self.tex), _p(self.ceil),
+                             ctypes.c_int(self.ts), _p(obs), _p(scratch))
+            return obs
         L.mo_observe_3d(ctypes.byref(self.cfg), ctypes.byref(self.task), ctypes.byref(self.env), _p(self.walls),
                         _p(self.texts), _p(self.tex), _p(self.ceil), ctypes.c_int(self.ts), _p(obs), _p(scratch))
         return obs
@@ -100,6 +110,10 @@ class OracleMaze(object):
     def reset(self):
         if self.need_task:
             raise Exception("Must call \"set_task\" before reset")
+        if self.kind == "C3D":
+            lib().mo_reset_c3d(ctypes.byref(self.cfg), ctypes.byref(self.task), _p(self.food), _p(self.interval),
+                               ctypes.byref(self.env), ctypes.byref(self.cont))
+            return self._observe()
         lib().mo_reset(ctypes.byref(self.cfg), ctypes.byref(self.task), _p(self.food), _p(self.interval),
                        ctypes.byref(self.env))
         return self._observe()
@@ -107,6 +121,14 @@ class OracleMaze(object):
     def step(self, action, render=True):
         rew = c_f64(0.0)
         done = ctypes.c_int(0)
+        if self.kind == "C3D":
+            tr, ws = np.float32(action[0]), np.float32(action[1])
+            lib().mo_step_c3d(ctypes.byref(self.cfg), ctypes.byref(self.task), _p(self.walls), _p(self.food),
+                              _p(self.interval), ctypes.byref(self.env), ctypes.byref(self.cont),
+                              ctypes.c_float(float(tr)), ctypes.c_float(float(ws)), ctypes.byref(rew),
+                              ctypes.byref(done))
+            obs = self._observe() if render else None
+            return obs, rew.value, bool(done.value), {"steps": self.env.steps}
         fn = lib().mo_step_2d if self.kind == "2D" else lib().mo_step_3d
         fn(ctypes.byref(self.cfg), ctypes.byref(self.task), _p(self.walls), _p(self.food), _p(self.interval),
            ctypes.byref(self.env), ctypes.c_int(int(action)), ctypes.byref(rew), ctypes.byref(done))
@@ -116,6 +138,10 @@ class OracleMaze(object):
     @property
     def agent(self):
         return (self.env.gx, self.env.gy, self.env.ori, self.env.steps)
+
+    @property
+    def pose(self):
+        return (np.array([self.cont.pos[0], self.cont.pos[1]], dtype=np.float32), float(self.cont.ori))
 
     @property
     def life(self):

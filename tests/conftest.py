@@ -32,3 +32,9 @@ def cuda_device():
 def maze_golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "maze_golden.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def cont_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "maze_continuous_golden.npz"), allow_pickle=False)

@@ -66,6 +66,32 @@ def test_values_can_exceed_uint8(maze_golden):
     assert 300 < int(obs.max()) < 400
 
 
+@pytest.mark.parametrize("name", ["c3d_surv", "c3d_esc"])
+def test_continuous_maze_oracle_matches_reference(cont_golden, name):
+    """MetaMazeContinuous3D: float32 positions, float64 headings, rewards, dones and every
+    recorded frame of the reference episodes, bit for bit (numba/numpy typing of dynamics.py reproduced in C)."""
+    from util import cont_case
+    c = cont_case(cont_golden, name)
+    tex = synthetic_textures(seed=0)
+    env = OracleMaze("C3D", c["task_type"], c["max_steps"], 1, c["resolution"], textures=tex)
+    env.set_task(c["task"])
+    assert np.array_equal(env.reset(), c["reset_obs"].astype(np.int32))
+    kept = {int(t): k for k, t in enumerate(c["obs_idx"])}
+    for t, a in enumerate(c["act"]):
+        obs, rew, done, info = env.step(a)
+        pos, ori = env.pose
+        assert np.array_equal(pos, c["pos"][t]) and ori == c["ori"][t], t
+        assert rew == c["rew"][t] and done == bool(c["done"][t]) and info["steps"] == int(c["steps"][t]), t
+        assert tuple(env.agent[:2]) == tuple(int(x) for x in c["grid"][t])
+        if c["task_type"] == "SURVIVAL":
+            assert env.life == c["life"][t]
+        if t in kept:
+            assert np.array_equal(obs, c["obs"][kept[t]].astype(np.int32)), t
+        if done:
+            env.reset()
+    assert c["done"].sum() >= 1 and (c["rew"] > 0).sum() >= 1
+
+
 @pytest.mark.reference
 def test_oracle_vs_reference_real_textures():
     """Build container only: the reference renderer with its own PNG textures vs the oracle, random poses."""

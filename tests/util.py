@@ -77,3 +77,13 @@ def maze_case(g, name):
     d["task"] = task_from_arrays(d["task.walls"], d["task.texts"], d["task.food"], d["task.interval"],
                                  d["task.scalars"])
     return d
+
+
+def cont_case(g, name):
+    pre = name + "."
+    d = {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+    tt, max_steps, rh, rv = [int(x) for x in d["meta"]]
+    d["task_type"] = "SURVIVAL" if tt == 0 else "ESCAPE"
+    d["max_steps"], d["resolution"] = max_steps, (rh, rv)
+    d["task"] = task_from_arrays(d["task.walls"], d["task.texts"], d["task.food"], d["task.interval"], d["task.scalars"])
+    return d
