@@ -144,6 +144,7 @@ int64_t mgb_quad_launch_count(const mgb_quad *h);
 
 #define MGB_MAZE_2D 0          /* MazeCore2D, maze_2d.py:13          */
 #define MGB_MAZE_DISCRETE_3D 1 /* MazeCoreDiscrete3D, maze_discrete_3d.py:17 */
+#define MGB_MAZE_CONTINUOUS_3D 2 /* MazeCoreContinuous3D, maze_continuous_3d.py:16 (+ dynamics.py) */
 
 #define MGB_MAZE_SURVIVAL 0 /* maze_base.py:52-57,72-88 */
 #define MGB_MAZE_ESCAPE 1   /* maze_base.py:58-60,90-93 */
@@ -205,6 +206,15 @@ int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_dev, void *st
 int mgb_maze_step(mgb_maze *h, const int32_t *act_dev, void *obs_dev, double *rew_dev, uint8_t *done_dev,
                   void *stream);
 int mgb_maze_set_options(mgb_maze *h, int auto_reset);
+
+/* MetaMazeContinuous3D.step (maze_env.py:129-146 -> maze_continuous_3d.py:47-56, dynamics.py:58-92): act_dev [n][2]
+ * float32 = (turn_rate, walk_speed), clipped to [-1, 1] like the reference; ten 10 ms sub-steps of turn/walk with the
+ * soft wall-repulsion collision model, then evaluation_rule and the ray-cast observation (same renderer).  Typing follows
+ * what the reference computes for float32 actions (its action_space.sample()): float32 position, float64 heading. */
+int mgb_maze_step_continuous(mgb_maze *h, const float *act_dev, void *obs_dev, double *rew_dev, uint8_t *done_dev,
+                             void *stream);
+/* Continuous pose: pos_dev [n][2] float32 (_agent_loc), ori_dev [n] float64 (_agent_ori). */
+int mgb_maze_pose(mgb_maze *h, float *pos_dev, double *ori_dev, void *stream);
 
 /* Inspection: agent [n][4] int32 = grid_x, grid_y, ori_index, steps; life [n] float64. */
 int mgb_maze_state(mgb_maze *h, int32_t *agent_dev, double *life_dev, void *stream);

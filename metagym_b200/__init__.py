@@ -4,6 +4,7 @@ Public surface (mirrors the reference's gym.Env classes with a leading batch axi
     BatchedQuadrotor            <- metagym.quadrotor.Quadrotor            (metagym/quadrotor/env.py:30)
     BatchedMetaMaze2D           <- metagym.metamaze.MetaMaze2D            (metagym/metamaze/envs/maze_env.py:155)
     BatchedMetaMazeDiscrete3D   <- metagym.metamaze.MetaMazeDiscrete3D    (metagym/metamaze/envs/maze_env.py:16)
+    BatchedMetaMazeContinuous3D <- metagym.metamaze.MetaMazeContinuous3D  (metagym/metamaze/envs/maze_env.py:85)
 All arithmetic runs in libmgb200.so (hand-written sm_100a CUDA, C ABI in include/mgb200.h); there is no CPU path.
 """
 from ._lib import MgbError  # noqa: F401
@@ -16,8 +17,8 @@ def __getattr__(name):
     if name in ("BatchedQuadrotor", "Quadrotor"):
         from . import quadrotor
         return getattr(quadrotor, name)
-    if name in ("BatchedMetaMaze2D", "BatchedMetaMazeDiscrete3D", "MetaMaze2D", "MetaMazeDiscrete3D",
-                "TaskConfig", "MazeTaskSampler"):
+    if name in ("BatchedMetaMaze2D", "BatchedMetaMazeDiscrete3D", "BatchedMetaMazeContinuous3D", "MetaMaze2D",
+                "MetaMazeDiscrete3D", "MetaMazeContinuous3D", "TaskConfig", "MazeTaskSampler"):
         from . import metamaze
         return getattr(metamaze, name)
     raise AttributeError(name)

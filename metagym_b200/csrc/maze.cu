@@ -82,6 +82,10 @@ struct MazeArgs {
     void *dyn;                   // [n] EnvDyn, written by the logic kernel, read by the compose kernel
     void *hit_scratch;           // [grid][H][max_hits] HitRec when c.hits_in_global
     const int32_t *act;
+    const float *act_c;          // continuous maze: [n][2] (turn_rate, walk_speed)
+    float2 *cpos;                // continuous maze: position (float32, dynamics.py:75)
+    double *cori;                // continuous maze: heading (python float)
+    const double *coltab_d;      // [2][res_h]: cos_hp, sin_hp in float64 (heading independent)
     void *obs;
     double *rew;
     uint8_t *done;
@@ -97,6 +101,9 @@ struct Env {
 };
 
 __device__ __forceinline__ const TaskHdr *blob_hdr(const uint8_t *b) { return reinterpret_cast<const TaskHdr *>(b); }
+
+__device__ __forceinline__ void maze_evaluate(const MazeConst &c, const uint8_t *blob, int32_t *eaten, int64_t estride,
+                                              Env &e, double &reward, int &done);
 
 // action + evaluation_rule for one env (single thread).  `eaten` is strided by `estride` (SoA in HBM).
 __device__ __forceinline__ void maze_logic(const MazeConst &c, const uint8_t *blob, int32_t *eaten, int64_t estride,
@@ -120,6 +127,15 @@ __device__ __forceinline__ void maze_logic(const MazeConst &c, const uint8_t *bl
         if (e.ori == 0) tx += mv; else if (e.ori == 1) ty += mv; else if (e.ori == 2) tx -= mv; else ty -= mv;
         if (tx >= 0 && tx < n && ty >= 0 && ty < n && walls[tx * n + ty] == 0) { e.gx = tx; e.gy = ty; }
     }
+    maze_evaluate(c, blob, eaten, estride, e, reward, done);
+}
+
+// MazeBase.evaluation_rule (maze_base.py:65-95) on the agent's current cell
+__device__ __forceinline__ void maze_evaluate(const MazeConst &c, const uint8_t *blob, int32_t *eaten, int64_t estride,
+                                              Env &e, double &reward, int &done)
+{
+    const TaskHdr *th = blob_hdr(blob);
+    const int n = c.n;
     e.steps += 1;                                                 // maze_base.py:66
     const bool over = e.steps > c.max_steps - 1;                  // :191-192
     if (c.task_type == MGB_MAZE_SURVIVAL) {
@@ -169,6 +185,96 @@ __device__ __forceinline__ double food_now(const MazeConst &c, const uint8_t *bl
     return visible ? reinterpret_cast<const double *>(blob + c.off_fval)[f] : 0.0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// MetaMazeContinuous3D dynamics (dynamics.py:16-92), float32/float64 typing of the numba + numpy original for float32
+// actions: see oracle/maze_oracle.c (mo_vector_move_with_collision) for the line-by-line restatement this mirrors.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sum2f(float a, float b) { float c = 0.0f; c += a; c += b; return c; }
+
+__device__ float nearest_point_dev(const float pos[2], float l1x, float l1y, float l2x, float l2y, float np_out[2])
+{
+    float ux = l2x - l1x, uy = l2y - l1y;
+    const float edge_norm = sqrtf(sum2f(ux * ux, uy * uy));
+    const double den = 1.0e-6 > (double)edge_norm ? 1.0e-6 : (double)edge_norm;
+    ux = (float)((double)ux / den); uy = (float)((double)uy / den);
+    const float dist_1 = sum2f((pos[0] - l1x) * ux, (pos[1] - l1y) * uy);
+    float qx, qy;
+    if (dist_1 > edge_norm) { qx = l2x; qy = l2y; }
+    else if (dist_1 < 0) { qx = l1x; qy = l1y; }
+    else { qx = l1x + dist_1 * ux; qy = l1y + dist_1 * uy; }
+    const float a = pos[0] - qx, b = pos[1] - qy;
+    np_out[0] = qx; np_out[1] = qy;
+    return sqrtf(sum2f(a * a, b * b));
+}
+
+__device__ void collision_force_dev(const float dv[2], double cell_size, double col_dist, float out[2])
+{
+    double dist = (double)sqrtf(sum2f(dv[0] * dv[0], dv[1] * dv[1]));
+    const double eff = col_dist / cell_size;
+    out[0] = out[1] = 0.0f;
+    if (dist > 0.708 + eff) return;
+    if (fabsf(dv[0]) < 0.5f && fabsf(dv[1]) < 0.5f) {
+        const float k = (float)(0.50 / (dist > 1.0e-6 ? dist : 1.0e-6) * (0.708 + eff - dist) * cell_size);
+        out[0] = k * dv[0]; out[1] = k * dv[1];
+        return;
+    }
+    const bool x_pos = (dv[0] + dv[1] > 0), y_pos = (dv[1] - dv[0] > 0);
+    float np[2];
+    if (x_pos && y_pos) dist = (double)nearest_point_dev(dv, 0.5f, 0.5f, -0.5f, 0.5f, np);
+    else if (!x_pos && y_pos) dist = (double)nearest_point_dev(dv, -0.5f, 0.5f, -0.5f, -0.5f, np);
+    else if (!x_pos && !y_pos) dist = (double)nearest_point_dev(dv, -0.5f, -0.5f, 0.5f, -0.5f, np);
+    else dist = (double)nearest_point_dev(dv, 0.5f, -0.5f, 0.5f, 0.5f, np);
+    if (eff < dist) return;
+    float ox = dv[0] - np[0], oy = dv[1] - np[1];
+    const float on = sqrtf(sum2f(ox * ox, oy * oy));
+    const double inv = 1.0 / (1.0e-6 > (double)on ? 1.0e-6 : (double)on);
+    ox = (float)((double)ox * inv); oy = (float)((double)oy * inv);
+    const float k = (float)(0.50 * (eff - dist) * cell_size);
+    out[0] = k * ox; out[1] = k * oy;
+}
+
+// do_action (maze_continuous_3d.py:47-53): clip, scale, ten sub-steps of vector_move + collision forces
+__device__ void continuous_move(const MazeConst &c, const uint8_t *blob, float tr, float ws, float pos[2], double &ori_io)
+{
+    const TaskHdr *th = blob_hdr(blob);
+    const int8_t *walls = reinterpret_cast<const int8_t *>(blob + c.off_walls);
+    const int n = c.n;
+    const double cell_size = th->cell_size;
+    float turn = tr < -1.0f ? -1.0f : (tr > 1.0f ? 1.0f : tr);
+    turn = turn * (float)3.1415926;
+    float walk = ws < -1.0f ? -1.0f : (ws > 1.0f ? 1.0f : ws);
+    if (walk < 0) walk = walk * 0.5f;
+    float tx = pos[0], ty = pos[1];
+    double ori = ori_io;
+    for (int it = 0; it < 10; ++it) {                       // int(100 * 0.10), dynamics.py:76
+        double fin = ori + (double)turn * 0.01;
+        const double off_ori = 0.5 * (fin + ori);
+        const double off = (double)walk * 0.01;
+        const float dx = (float)(cos(off_ori) * off), dy = (float)(sin(off_ori) * off);
+        while (fin > 6.2831852) fin -= 6.2831852;
+        while (fin < 0) fin += 6.2831852;
+        ori = fin;
+        const float ex = tx + dx, ey = ty + dy;
+        const float cs = (float)cell_size;
+        const float ecx = ex / cs, ecy = ey / cs;
+        float cx = 0.0f, cy = 0.0f;
+        for (int i = -1; i < 2; ++i)
+            for (int j = -1; j < 2; ++j) {
+                const int wi = i + (int)ecx, wj = j + (int)ecy;
+                if (wi > -1 && wi < n && wj > -1 && wj < n && walls[wi * n + wj] > 0) {
+                    const float dv[2] = {ecx - floorf(ecx) - (float)(i + 0.5), ecy - floorf(ecy) - (float)(j + 0.5)};
+                    float f[2];
+                    collision_force_dev(dv, cell_size, 0.20, f);   // collision_dist = 0.20, maze_continuous_3d.py:20
+                    cx += f[0]; cy += f[1];
+                }
+            }
+        tx = cx + ex; ty = cy + ey;
+    }
+    pos[0] = tx; pos[1] = ty;
+    ori_io = ori;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // state-only kernels
 // ---------------------------------------------------------------------------------------------------------------
@@ -182,6 +288,12 @@ __global__ void maze_reset_kernel(const __grid_constant__ MazeConst c, const __g
     env_reset(c, blob, a.eaten + e, a.n_pad, s);
     a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
     a.life[e] = s.life;
+    if (c.kind == MGB_MAZE_CONTINUOUS_3D) {             // get_cell_center(start), heading 0 (maze_base.py:41,50)
+        const TaskHdr *th = blob_hdr(blob);
+        a.cpos[e] = make_float2((float)(s.gx * th->cell_size + 0.5 * th->cell_size),
+                                (float)(s.gy * th->cell_size + 0.5 * th->cell_size));
+        a.cori[e] = 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -324,6 +436,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     uint8_t *s_out = smem + off;                                          off = align_up(off + (size_t)(kRenderThreads / 32) * n_slots * run_bytes, 128);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 16;
     int *s_env = reinterpret_cast<int *>(smem + off);                    // [0..3] gx gy ori steps, [4] lifebar end
+    double *s_pose = reinterpret_cast<double *>(smem + off + 32);         // continuous maze: x, y, sin(ori), cos(ori)
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -368,15 +481,37 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             const int4 ag = a.agent[e];
             Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
             int32_t *eaten = a.eaten + e;
+            const bool cont = c.kind == MGB_MAZE_CONTINUOUS_3D;
+            float cp[2] = {0.f, 0.f};
+            double co = 0.0;
+            if (cont) { const float2 p2 = a.cpos[e]; cp[0] = p2.x; cp[1] = p2.y; co = a.cori[e]; }
             if (a.do_step) {
                 double reward;
                 int done;
-                maze_logic(c, s_blob, eaten, a.n_pad, s, a.act[e], reward, done);
+                if (cont) {
+                    continuous_move(c, s_blob, a.act_c[2 * e], a.act_c[2 * e + 1], cp, co);
+                    const float csf = (float)th->cell_size;                 // get_loc_grid, maze_base.py:199-202
+                    s.gx = (int)(cp[0] / csf); s.gy = (int)(cp[1] / csf);
+                    maze_evaluate(c, s_blob, eaten, a.n_pad, s, reward, done);
+                } else {
+                    maze_logic(c, s_blob, eaten, a.n_pad, s, a.act[e], reward, done);
+                }
                 a.rew[e] = reward;
                 a.done[e] = (uint8_t)done;
-                if (done && a.auto_reset) env_reset(c, s_blob, eaten, a.n_pad, s);
+                if (done && a.auto_reset) {
+                    env_reset(c, s_blob, eaten, a.n_pad, s);
+                    if (cont) {
+                        cp[0] = (float)(s.gx * th->cell_size + 0.5 * th->cell_size);
+                        cp[1] = (float)(s.gy * th->cell_size + 0.5 * th->cell_size);
+                        co = 0.0;
+                    }
+                }
                 a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
                 a.life[e] = s.life;
+                if (cont) { a.cpos[e] = make_float2(cp[0], cp[1]); a.cori[e] = co; }
+            }
+            if (cont) {          // publish the pose: position promoted from float32, sin/cos of the float64 heading
+                s_pose[0] = (double)cp[0]; s_pose[1] = (double)cp[1]; s_pose[2] = sin(co); s_pose[3] = cos(co);
             }
             s_env[0] = s.gx; s_env[1] = s.gy; s_env[2] = s.ori; s_env[3] = s.steps;
             // life bar extent, maze_discrete_3d.py:118-126 (python slice semantics on the end index)
@@ -388,8 +523,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         __syncthreads();
         const int gx = s_env[0], gy = s_env[1], ori = s_env[2], steps = s_env[3];
         const double cell_size = th->cell_size, vision_height = th->agent_height, ceil_height = th->wall_height;
-        const double pos_x = gx * cell_size + 0.5 * cell_size;       // get_cell_center, maze_base.py:194-197
-        const double pos_y = gy * cell_size + 0.5 * cell_size;
+        const bool cont_pose = !FILL && c.kind == MGB_MAZE_CONTINUOUS_3D;
+        const double pos_x = cont_pose ? s_pose[0] : gx * cell_size + 0.5 * cell_size;   // get_cell_center, maze_base.py:194-197
+        const double pos_y = cont_pose ? s_pose[1] : gy * cell_size + 0.5 * cell_size;
         const double text_to_cell = c.text_size / cell_size;
 
         // ---- transparent map + row table
@@ -424,12 +560,18 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         // ---- one ray per column: DDA_2D (ray_caster_utils.py:11-62) + wall span set-up (:156-182)
         const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
         const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
-        const float *ct = a.coltab + (size_t)ori * 3 * H;
+        const float *ct = a.coltab + (size_t)(cont_pose ? 0 : ori) * 3 * H;
         for (int d_h = tid; d_h < H; d_h += blockDim.x) {
             ColRec cr;
             cr.cos_hp = (double)ct[d_h];
-            cr.cos_abs = (double)ct[H + d_h];
-            cr.sin_abs = (double)ct[2 * H + d_h];
+            if (cont_pose) {     // float64 heading: tables from the float64 sin/cos, stored as float32 (:82-92)
+                const double ch = a.coltab_d[d_h], sh = a.coltab_d[H + d_h];
+                cr.sin_abs = (double)(float)(sh * s_pose[3] + ch * s_pose[2]);
+                cr.cos_abs = (double)(float)(ch * s_pose[3] - sh * s_pose[2]);
+            } else {
+                cr.cos_abs = (double)ct[H + d_h];
+                cr.sin_abs = (double)ct[2 * H + d_h];
+            }
             const double cos_ori = cr.cos_abs, sin_ori = cr.sin_abs;
             const int i0 = trunc_i(pos_x / cell_size), j0 = trunc_i(pos_y / cell_size);
             const double delta_dist_x = fabs(cos_ori) < 1.0e-6 ? 1.0e+6 : fabs(cell_size / cos_ori);
@@ -949,6 +1091,9 @@ struct mgb_maze {
     uint32_t *tex = nullptr;
     float *coltab = nullptr;
     double *efftab = nullptr;
+    float2 *cpos = nullptr;        // continuous maze pose
+    double *cori = nullptr;
+    double *coltab_d = nullptr;
     // pose cache
     int cache_enabled = 1;         // MGB_MAZE_CACHE=0 disables (direct renderer only)
     double cache_budget_gb = 24.0; // MGB_MAZE_CACHE_GB
@@ -985,7 +1130,7 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     if (!c.hits_in_global) off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     off = up(off + (size_t)(kRenderThreads / 32) * (c.obs_dtype == MGB_OBS_U8 ? 2 : 1) * c.run_px * px, 128);
-    off += 16 + 32;
+    off += 16 + 32 + 32;
     return off;
 }
 
@@ -996,6 +1141,7 @@ static MazeArgs maze_args(const mgb_maze *h)
     a.n = h->n; a.n_pad = h->n_pad; a.env_base = h->env_base;
     a.agent = h->agent; a.life = h->life; a.eaten = h->eaten; a.env2task = h->env2task; a.blobs = h->blobs;
     a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.auto_reset = h->auto_reset;
+    a.cpos = h->cpos; a.cori = h->cori; a.coltab_d = h->coltab_d;
     a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
     a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gmask = h->c_gmask;
     return a;
@@ -1006,12 +1152,13 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
 {
     MGB_REQUIRE(out && cfg, "null argument");
     MGB_REQUIRE(n_envs > 0, "n_envs must be positive");
-    MGB_REQUIRE(cfg->kind == MGB_MAZE_2D || cfg->kind == MGB_MAZE_DISCRETE_3D, "invalid kind");
+    MGB_REQUIRE(cfg->kind == MGB_MAZE_2D || cfg->kind == MGB_MAZE_DISCRETE_3D || cfg->kind == MGB_MAZE_CONTINUOUS_3D,
+                "invalid kind");
     MGB_REQUIRE(cfg->task_type == MGB_MAZE_SURVIVAL || cfg->task_type == MGB_MAZE_ESCAPE, "invalid task_type");
     MGB_REQUIRE(cfg->n_cells >= 3 && cfg->n_cells <= kMaxN, "n_cells must be in [3, 31]");
     MGB_REQUIRE(cfg->max_steps > 0, "max_steps must be positive");
     if (cfg->kind == MGB_MAZE_2D) MGB_REQUIRE(cfg->view_grid >= 0 && cfg->view_grid <= 8, "view_grid out of range");
-    if (cfg->kind == MGB_MAZE_DISCRETE_3D) {
+    if (cfg->kind != MGB_MAZE_2D) {
         MGB_REQUIRE(cfg->res_h > 0 && cfg->res_h <= 1024 && cfg->res_v > 0 && cfg->res_v <= 1024, "resolution out of range");
         MGB_REQUIRE(cfg->obs_dtype == MGB_OBS_U8 || cfg->obs_dtype == MGB_OBS_I32, "invalid obs_dtype");
         MGB_REQUIRE(cfg->max_vision > 0 && cfg->l_focal > 0 && cfg->text_size > 0 && cfg->fov > 0, "invalid optics");
@@ -1044,7 +1191,7 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     MGB_CUDA(cudaMalloc(&h->env2task, sizeof(int32_t) * h->n_pad));
     MGB_CUDA(cudaMemset(h->agent, 0, sizeof(int4) * h->n_pad));
     MGB_CUDA(cudaMemset(h->life, 0, sizeof(double) * h->n_pad));
-    if (cfg->kind == MGB_MAZE_DISCRETE_3D) {
+    if (cfg->kind != MGB_MAZE_2D) {
         // screen geometry and the per-heading column tables, exactly as maze_view computes them
         // (ray_caster_utils.py:68-92): float64 arithmetic, float32 sin/cos of the float32 heading, float32 tables.
         const int H = cfg->res_h, V = cfg->res_v;
@@ -1055,6 +1202,7 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
         c.half_h = half_h; c.half_v = half_v; c.pixel_size = pixel_size;
         c.lb_sx = 0.10 * V; c.lb_sy = 0.10 * V; c.lb_w = 0.05 * H; c.lb_l = 0.80 * V;   // maze_discrete_3d.py:42-45
         std::vector<float> tab((size_t)4 * 3 * H);
+        std::vector<double> tab_d((size_t)2 * H);      // heading-independent cos_hp / sin_hp in float64
         const float choice[4] = {0.0f, 0.5f, 1.0f, 1.5f};
         for (int k = 0; k < 4; ++k) {
             volatile float ori = choice[k] * (float)3.1415926;          // maze_discrete_3d.py:46
@@ -1067,6 +1215,7 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
                 volatile double sin_hp = tan_hp * cos_hp;
                 volatile double a1 = sin_hp * (double)c_ori, a2 = cos_hp * (double)s_ori;
                 volatile double b1 = cos_hp * (double)c_ori, b2 = sin_hp * (double)s_ori;
+                if (k == 0) { tab_d[d] = cos_hp; tab_d[H + d] = sin_hp; }
                 tab[((size_t)k * 3 + 0) * H + d] = (float)cos_hp;
                 tab[((size_t)k * 3 + 1) * H + d] = (float)(b1 - b2);
                 tab[((size_t)k * 3 + 2) * H + d] = (float)(a1 + a2);
@@ -1074,6 +1223,14 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
         }
         MGB_CUDA(cudaMalloc(&h->coltab, tab.size() * sizeof(float)));
         MGB_CUDA(cudaMemcpy(h->coltab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (cfg->kind == MGB_MAZE_CONTINUOUS_3D) {
+            MGB_CUDA(cudaMalloc(&h->coltab_d, tab_d.size() * sizeof(double)));
+            MGB_CUDA(cudaMemcpy(h->coltab_d, tab_d.data(), tab_d.size() * sizeof(double), cudaMemcpyHostToDevice));
+            MGB_CUDA(cudaMalloc(&h->cpos, sizeof(float2) * h->n_pad));
+            MGB_CUDA(cudaMalloc(&h->cori, sizeof(double) * h->n_pad));
+            MGB_CUDA(cudaMemset(h->cpos, 0, sizeof(float2) * h->n_pad));
+            MGB_CUDA(cudaMemset(h->cori, 0, sizeof(double) * h->n_pad));
+        }
     }
     *out = h;
     return MGB_OK;
@@ -1085,7 +1242,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     MgbDeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
-    cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab);
+    cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab); cudaFree(h->cpos); cudaFree(h->cori); cudaFree(h->coltab_d);
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask); cudaFree(h->hit_scratch);
     delete h;
@@ -1111,7 +1268,7 @@ extern "C" int mgb_maze_set_textures(mgb_maze *h, const uint8_t *grounds_host, i
                                      int32_t tex_size)
 {
     MGB_REQUIRE(h && grounds_host && ceil_host, "null argument");
-    MGB_REQUIRE(h->c.kind == MGB_MAZE_DISCRETE_3D, "textures only apply to the 3-D maze");
+    MGB_REQUIRE(h->c.kind != MGB_MAZE_2D, "textures only apply to the 3-D mazes");
     MGB_REQUIRE(n_tex >= 1 && n_tex <= 15, "n_tex must be in [1, 15]");
     MGB_REQUIRE(tex_size >= 1 && tex_size <= 128, "tex_size must be in [1, 128]");
     MgbDeviceGuard guard(h->device);
@@ -1171,7 +1328,7 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     c.max_hits = mh > kMaxHitsCap ? kMaxHitsCap : mh;
     // a warp run = whole columns, about 768 B of output (u8: 256 px, i32: 64 px), never less than one column
     c.run_px = c.obs_dtype == MGB_OBS_U8 ? 256 : 64;
-    if (c.kind == MGB_MAZE_DISCRETE_3D) {
+    if (c.kind != MGB_MAZE_2D) {
         if (c.run_px < c.res_v) c.run_px = c.res_v;
         c.run_px = c.run_px / c.res_v * c.res_v;
     }
@@ -1227,7 +1384,7 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
         hd.n_food = cnt;
         memcpy(b, &hd, sizeof(hd));
     }
-    if (c.kind == MGB_MAZE_DISCRETE_3D) {
+    if (c.kind != MGB_MAZE_2D) {
         for (int t = 0; t < n_tasks; ++t)
             for (int k = 0; k < nn; ++k) {
                 const int id = texts_host[(size_t)t * nn + k];
@@ -1262,7 +1419,7 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     }
     cudaFree(h->efftab); h->efftab = nullptr;
     c.n_cls = 0;
-    if (c.kind == MGB_MAZE_DISCRETE_3D && !cls_heights.empty()) {
+    if (c.kind != MGB_MAZE_2D && !cls_heights.empty()) {
         const int n_cls = (int)(cls_heights.size() / 2);
         const size_t cells = (size_t)n_cls * c.res_h * c.res_v;
         double *d_heights = nullptr;
@@ -1286,7 +1443,7 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
 static int maze_ready(const mgb_maze *h)
 {
     if (!h->has_task) { mgb_set_error("Must call \"set_task\" before reset"); return MGB_ERR_STATE; }   // maze_env.py:49-50
-    if (h->c.kind == MGB_MAZE_DISCRETE_3D && !h->has_tex) {
+    if (h->c.kind != MGB_MAZE_2D && !h->has_tex) {
         mgb_set_error("3-D maze: call mgb_maze_set_textures first");
         return MGB_ERR_STATE;
     }
@@ -1448,10 +1605,45 @@ extern "C" int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_de
     return MGB_OK;
 }
 
+extern "C" int mgb_maze_step_continuous(mgb_maze *h, const float *act_dev, void *obs_dev, double *rew_dev,
+                                        uint8_t *done_dev, void *stream)
+{
+    MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
+    MGB_REQUIRE(h->c.kind == MGB_MAZE_CONTINUOUS_3D, "mgb_maze_step_continuous needs a MGB_MAZE_CONTINUOUS_3D handle");
+    int rc = maze_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    MazeArgs a = maze_args(h);
+    a.act_c = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev; a.do_step = 1;
+    return launch_observe(h, a, (cudaStream_t)stream);
+}
+
+__global__ void maze_pose_kernel(MazeArgs a, float *pos_out, double *ori_out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const float2 p = a.cpos[e];
+    pos_out[2 * e] = p.x; pos_out[2 * e + 1] = p.y;
+    if (ori_out) ori_out[e] = a.cori[e];
+}
+
+extern "C" int mgb_maze_pose(mgb_maze *h, float *pos_dev, double *ori_dev, void *stream)
+{
+    MGB_REQUIRE(h && pos_dev, "null argument");
+    MGB_REQUIRE(h->c.kind == MGB_MAZE_CONTINUOUS_3D, "mgb_maze_pose needs a MGB_MAZE_CONTINUOUS_3D handle");
+    MgbDeviceGuard guard(h->device);
+    MazeArgs a = maze_args(h);
+    maze_pose_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, pos_dev, ori_dev);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}
+
 extern "C" int mgb_maze_step(mgb_maze *h, const int32_t *act_dev, void *obs_dev, double *rew_dev, uint8_t *done_dev,
                              void *stream)
 {
     MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
+    MGB_REQUIRE(h->c.kind != MGB_MAZE_CONTINUOUS_3D, "use mgb_maze_step_continuous for the continuous maze");
     int rc = maze_ready(h);
     if (rc) return rc;
     MgbDeviceGuard guard(h->device);

@@ -332,8 +332,48 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
                                                    ts))
 
 
+class BatchedMetaMazeContinuous3D(BatchedMetaMazeDiscrete3D):
+    """MetaMazeContinuous3D(enable_render, render_scale, resolution, max_steps, task_type) x num_envs
+    (maze_env.py:85-153).  Actions [N, 2] float32 = (turn_rate, walk_speed) in [-1, 1] (clipped like the reference,
+    maze_continuous_3d.py:48-49); float32 position / float64 heading exactly as the reference computes them for
+    float32 actions.  Every pose is unique, so this env always uses the direct float64 renderer."""
+    KIND = 2
+
+    def __init__(self, *args, **kwargs):
+        BatchedMetaMazeDiscrete3D.__init__(self, *args, **kwargs)
+        self.action_space = Box(low=np.array([-1.0, -1.0]), high=np.array([1.0, 1.0]), dtype=np.float32)
+
+    def _make_cfg(self, n_cells):
+        cfg = BatchedMetaMazeDiscrete3D._make_cfg(self, n_cells)
+        cfg.kind = 2
+        return cfg
+
+    def step(self, action=None):
+        if self.need_reset:
+            raise Exception("Must \"reset\" before doing any actions")              # maze_env.py:130-131
+        if action is None:
+            raise NotImplementedError("keyboard control (action=None) is display-only in the reference")
+        torch = self._torch
+        if not (hasattr(action, "is_cuda") and action.is_cuda):
+            action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(self.num_envs, 2), device=self.device)
+        act = action.to(torch.float32).reshape(self.num_envs, 2).contiguous()
+        _lib.check(self._lib.mgb_maze_step_continuous(self._h, act.data_ptr(), self._obs.data_ptr(),
+                                                      self._rew.data_ptr(), self._done.data_ptr(), self._stream()))
+        info = _LazySteps(self)
+        return self._out(self._obs), self._out(self._rew), self._out(self._done.view(torch.bool)), info
+
+    def pose(self):
+        """-> (pos [N,2] float32 = _agent_loc, ori [N] float64 = _agent_ori)."""
+        torch = self._torch
+        pos = torch.empty((self.num_envs, 2), dtype=torch.float32, device=self.device)
+        ori = torch.empty((self.num_envs,), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.mgb_maze_pose(self._h, pos.data_ptr(), ori.data_ptr(), self._stream()))
+        return pos, ori
+
+
 MetaMaze2D = BatchedMetaMaze2D
 MetaMazeDiscrete3D = BatchedMetaMazeDiscrete3D
+MetaMazeContinuous3D = BatchedMetaMazeContinuous3D
 
 
 def smoke():

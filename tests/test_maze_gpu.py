@@ -242,3 +242,76 @@ def test_reference_default_resolutions_vs_oracle(torch_mod, maze_golden, texture
         assert np.array_equal(obs.cpu().numpy()[0], o2), (t, int((obs.cpu().numpy()[0] != o2).sum()))
         assert float(rew[1]) == r2 and bool(done[1]) == d2
     env.close()
+
+
+@pytest.mark.parametrize("name", ["c3d_surv", "c3d_esc"])
+def test_continuous_maze_reference_episode(torch_mod, cont_golden, textures, name):
+    """MetaMazeContinuous3D: reference episodes replayed on the GPU -- float32 positions, float64
+    headings, cells, rewards, dones, life and every recorded frame bit for bit."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeContinuous3D
+    from util import cont_case
+    c = cont_case(cont_golden, name)
+    n = 3
+    env = BatchedMetaMazeContinuous3D(resolution=c["resolution"], max_steps=c["max_steps"], task_type=c["task_type"],
+                                      num_envs=n, squeeze=False, textures=textures)
+    env.set_task(c["task"])
+    obs0 = env.reset().cpu().numpy()
+    assert np.array_equal(obs0[2], c["reset_obs"].astype(np.int32))
+    kept = {int(t): k for k, t in enumerate(c["obs_idx"])}
+    for t, a in enumerate(c["act"]):
+        obs, rew, done, info = env.step(torch.as_tensor(np.tile(a, (n, 1))).cuda())
+        pos, ori = env.pose()
+        ag, life = env.agent_state()
+        pos, ori, ag, life = pos.cpu().numpy(), ori.cpu().numpy(), ag.cpu().numpy(), life.cpu().numpy()
+        for k in range(n):
+            assert np.array_equal(pos[k], c["pos"][t]) and ori[k] == c["ori"][t], (t, pos[k], c["pos"][t], ori[k], c["ori"][t])
+            assert float(rew[k]) == c["rew"][t] and bool(done[k]) == bool(c["done"][t]), t
+            assert tuple(ag[k][:2]) == tuple(int(x) for x in c["grid"][t]) and int(ag[k][3]) == int(c["steps"][t])
+            if c["task_type"] == "SURVIVAL":
+                assert life[k] == c["life"][t]
+        if t in kept:
+            o = obs.cpu().numpy()
+            ref = c["obs"][kept[t]].astype(np.int32)
+            assert np.array_equal(o[0], ref) and np.array_equal(o[n - 1], ref), (t, int((o[0] != ref).sum()))
+        if c["done"][t]:
+            env.reset()
+    env.close()
+
+
+def test_continuous_maze_random_batch_vs_oracle(torch_mod, maze_golden, textures):
+    """64 envs over 4 tasks, independent random float32 actions, auto-reset: every env equals its oracle instance."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeContinuous3D
+    from oracle.maze_oracle import OracleMaze
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 10, g["tasks15.scalars"][k]) for k in range(4)]
+    n, T, max_steps, res = 64, 60, 25, (40, 24)
+    env = BatchedMetaMazeContinuous3D(resolution=res, max_steps=max_steps, task_type="SURVIVAL", num_envs=n,
+                                      squeeze=False, auto_reset=True, textures=textures)
+    env.set_task(tasks)
+    oracles = []
+    for e in range(n):
+        o = OracleMaze("C3D", "SURVIVAL", max_steps, 1, res, textures=textures)
+        o.set_task(tasks[e % 4])
+        oracles.append(o)
+    obs = env.reset().cpu().numpy()
+    for e in range(n):
+        assert np.array_equal(obs[e], oracles[e].reset())
+    rng = np.random.RandomState(17)
+    for t in range(T):
+        act = rng.uniform(-1.3, 1.3, (n, 2)).astype(np.float32)
+        obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        pos, ori = env.pose()
+        pos, ori = pos.cpu().numpy(), ori.cpu().numpy()
+        for e in range(n):
+            o2, r2, d2, _ = oracles[e].step(act[e])
+            assert rew[e] == r2 and bool(done[e]) == d2, (t, e)
+            if d2:
+                o2 = oracles[e].reset()
+            p2, a2 = oracles[e].pose
+            assert np.array_equal(pos[e], p2) and ori[e] == a2, (t, e)
+            assert np.array_equal(obs[e], o2), (t, e, int((obs[e] != o2).sum()))
+    env.close()
