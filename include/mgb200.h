@@ -97,6 +97,13 @@ int64_t mgb_quad_num_envs(const mgb_quad *h);
  * left as is and the caller resets (env.py:116).  Synchronous w.r.t. nothing; takes effect at the next launch. */
 int mgb_quad_set_options(mgb_quad *h, int auto_reset, uint64_t seed);
 
+/* Quadrotor.load_map + the map part of __init__ (env.py:97-114, 293-305): map_host [rows][cols] int32 with exactly one
+ * -1 (the start cell, which becomes 0); x_offset / y_offset are its column / row.  Only the TRUTHINESS of the cells in
+ * the window swept by a step matters to the reference's _check_collision (env.py:248-260: `z < np.any(taken_pos)`),
+ * including python's negative-index slice semantics; both are reproduced.  NULL map = the flat default (env.py:295-298).
+ * no_collision / hovering_control only.  Synchronous. */
+int mgb_quad_set_map(mgb_quad *h, const int32_t *map_host, int32_t rows, int32_t cols);
+
 /* Velocity targets of define_velocity_control_task (quadrotorsim.py:306-319): tbl [n_tasks][nt][3] float32 and the
  * task row of every local env, env2task [n_envs] int32.  Both are COPIED into the handle (synchronous). */
 int mgb_quad_set_targets(mgb_quad *h, const float *tbl_dev, int32_t n_tasks, const int32_t *env2task_dev);

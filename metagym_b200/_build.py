@@ -35,7 +35,8 @@ def needs_build():
 
 
 # per-file extra flags: the maze renderer must reproduce float64 results of code that never fuses multiply-add
-PER_FILE_FLAGS = {"maze.cu": ["-fmad=false"]}
+# quad.cu: every FMA is written out (fmaf / dot3 / det2) so that all kernel variants compute the same bits
+PER_FILE_FLAGS = {"maze.cu": ["-fmad=false"], "quad.cu": ["-fmad=false"]}
 
 
 def build(force=False, verbose=False):

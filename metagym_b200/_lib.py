@@ -48,6 +48,7 @@ SIGNATURES = {
     "mgb_quad_obs_dim": (ctypes.c_int, [vp]),
     "mgb_quad_num_envs": (c_i64, [vp]),
     "mgb_quad_set_options": (ctypes.c_int, [vp, ctypes.c_int, c_u64]),
+    "mgb_quad_set_map": (ctypes.c_int, [vp, vp, c_i32, c_i32]),
     "mgb_quad_set_targets": (ctypes.c_int, [vp, vp, c_i32, vp]),
     "mgb_quad_make_targets": (ctypes.c_int, [vp, vp, c_i32, vp, vp]),
     "mgb_quad_reset": (ctypes.c_int, [vp, vp, vp, vp, vp]),

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 #include "mgb_common.cuh"
 
@@ -70,6 +71,8 @@ struct QuadArgs {
     int32_t *fail;
     float *final_obs;
     const float *targets;      // [n_tasks][nt][3]
+    const int32_t *sat;        // obstacle map: summed-area table of non-zero cells [(rows+1)][(cols+1)], or null (flat)
+    int map_rows, map_cols, x_off, y_off;
     const int32_t *env2task;   // [n]
     uint64_t seed;
     int auto_reset;
@@ -117,6 +120,16 @@ __device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const 
     b[5 * kTileEnvs] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct), __int_as_float(s.ep));
 }
 
+// ---- explicit float32 building blocks.  This file is compiled with -fmad=false and every fused multiply-add is
+// written out, so the arithmetic of an env does not depend on which kernel variant (tile / wide / streaming / rollout)
+// or which inlining context the compiler happened to see: results are bit-identical for any batch size or sharding.
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return fmaf(a2, b2, fmaf(a1, b1, a0 * b0));
+}
+__device__ __forceinline__ float det2(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); }   // ab - cd
+__device__ __forceinline__ float sq3(const float v[3]) { return dot3(v[0], v[0], v[1], v[1], v[2], v[2]); }
+
 // ---- fast float32 primitives.  The reference's own float32 noise (1.3e-7 relative per step against a
 // float64 restatement) is larger than the error of any of these, and each replaces a 10-60 instruction IEEE sequence.
 __device__ __forceinline__ float fast_sqrt(float x)      // sqrt.approx: MUFU.SQRT, <= 1 ulp-ish, sqrt(0) = 0
@@ -161,16 +174,16 @@ __device__ __forceinline__ float fast_atan2(float y, float x)
 // re-orthonormalises, quadrotorsim.py:193-202), so this is a genuine inverse, not a transpose.  det = 1 +- a few 1e-3.
 __device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &id)
 {
-    adj[0] = R[4] * R[8] - R[5] * R[7];
-    adj[3] = R[5] * R[6] - R[3] * R[8];
-    adj[6] = R[3] * R[7] - R[4] * R[6];
-    const float det = R[0] * adj[0] + R[1] * adj[3] + R[2] * adj[6];
-    adj[1] = R[2] * R[7] - R[1] * R[8];
-    adj[2] = R[1] * R[5] - R[2] * R[4];
-    adj[4] = R[0] * R[8] - R[2] * R[6];
-    adj[5] = R[2] * R[3] - R[0] * R[5];
-    adj[7] = R[1] * R[6] - R[0] * R[7];
-    adj[8] = R[0] * R[4] - R[1] * R[3];
+    adj[0] = det2(R[4], R[8], R[5], R[7]);
+    adj[3] = det2(R[5], R[6], R[3], R[8]);
+    adj[6] = det2(R[3], R[7], R[4], R[6]);
+    const float det = dot3(R[0], adj[0], R[1], adj[3], R[2], adj[6]);
+    adj[1] = det2(R[2], R[7], R[1], R[8]);
+    adj[2] = det2(R[1], R[5], R[2], R[4]);
+    adj[4] = det2(R[0], R[8], R[2], R[6]);
+    adj[5] = det2(R[2], R[3], R[0], R[5]);
+    adj[7] = det2(R[1], R[6], R[0], R[7]);
+    adj[8] = det2(R[0], R[4], R[1], R[3]);
     id = fast_rcp(det);
 }
 
@@ -184,9 +197,9 @@ __device__ __forceinline__ void substep(const QuadConst &c, QState &s, const flo
                                         float &id, float &vsq, float &osq)
 {
     // body-frame velocity R^-1 v (:147-148), shared by the four rotors and the drag term
-    const float bvx = (adj[0] * s.v[0] + adj[1] * s.v[1] + adj[2] * s.v[2]) * id;
-    const float bvy = (adj[3] * s.v[0] + adj[4] * s.v[1] + adj[5] * s.v[2]) * id;
-    const float bvz = (adj[6] * s.v[0] + adj[7] * s.v[1] + adj[8] * s.v[2]) * id;
+    const float bvx = dot3(adj[0], s.v[0], adj[1], s.v[1], adj[2], s.v[2]) * id;
+    const float bvy = dot3(adj[3], s.v[0], adj[4], s.v[1], adj[5], s.v[2]) * id;
+    const float bvz = dot3(adj[6], s.v[0], adj[7], s.v[1], adj[8], s.v[2]) * id;
     const float nvn = -fast_sqrt(vsq), non = -fast_sqrt(osq);
     const float tz = fmaf(-c.k1phi, (s.w[1] - s.w[0]) + (s.w[3] - s.w[2]), Kz);
     float th[4];
@@ -216,15 +229,15 @@ __device__ __forceinline__ void substep(const QuadConst &c, QState &s, const flo
     float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
     if (!SIMPLE) {  // gravity torque -(f_grav x cg), :177-178
         const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
-        Tx -= gy * c.cg[2] - gz * c.cg[1];
-        Ty -= gz * c.cg[0] - gx * c.cg[2];
-        Tz -= gx * c.cg[1] - gy * c.cg[0];
+        Tx -= det2(gy, c.cg[2], gz, c.cg[1]);
+        Ty -= det2(gz, c.cg[0], gx, c.cg[2]);
+        Tz -= det2(gx, c.cg[1], gy, c.cg[0]);
     }
 
     // translation, :183-187 (1/mass folded into the step constants)
-    const float ax = s.R[0] * Fx + s.R[1] * Fy + s.R[2] * Fz;
-    const float ay = s.R[3] * Fx + s.R[4] * Fy + s.R[5] * Fz;
-    const float az = s.R[6] * Fx + s.R[7] * Fy + s.R[8] * Fz;
+    const float ax = dot3(s.R[0], Fx, s.R[1], Fy, s.R[2], Fz);
+    const float ay = dot3(s.R[3], Fx, s.R[4], Fy, s.R[5], Fz);
+    const float az = dot3(s.R[6], Fx, s.R[7], Fy, s.R[8], Fz);
     s.p[0] = fmaf(ax, c.c_h2m, fmaf(s.v[0], c.h, s.p[0]));
     s.p[1] = fmaf(ay, c.c_h2m, fmaf(s.v[1], c.h, s.p[1]));
     s.p[2] = fmaf(az, c.c_h2m, fmaf(s.v[2], c.h, s.p[2]));
@@ -237,9 +250,9 @@ __device__ __forceinline__ void substep(const QuadConst &c, QState &s, const flo
     if (SIMPLE) {
         ahx = Tx * c.hI[0]; ahy = Ty * c.hI[4]; ahz = Tz * c.hI[8];
     } else {
-        ahx = c.hI[0] * Tx + c.hI[1] * Ty + c.hI[2] * Tz;
-        ahy = c.hI[3] * Tx + c.hI[4] * Ty + c.hI[5] * Tz;
-        ahz = c.hI[6] * Tx + c.hI[7] * Ty + c.hI[8] * Tz;
+        ahx = dot3(c.hI[0], Tx, c.hI[1], Ty, c.hI[2], Tz);
+        ahy = dot3(c.hI[3], Tx, c.hI[4], Ty, c.hI[5], Tz);
+        ahz = dot3(c.hI[6], Tx, c.hI[7], Ty, c.hI[8], Tz);
     }
     const float hwx = c.h * fmaf(0.5f, ahx, s.om[0]);
     const float hwy = c.h * fmaf(0.5f, ahy, s.om[1]);
@@ -253,8 +266,8 @@ __device__ __forceinline__ void substep(const QuadConst &c, QState &s, const flo
         s.R[3 * r + 2] = fmaf(r0, hwy, fmaf(-r1, hwx, r2));
     }
     adjugate(s.R, adj, id);                                                  // :206-208
-    vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
-    osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+    vsq = sq3(s.v);
+    osq = sq3(s.om);
 }
 
 template <bool SIMPLE>
@@ -280,8 +293,8 @@ __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const fl
     }
     const float Kz = (kV[1] - kV[0]) + (kV[3] - kV[2]);
     int fail = 0;
-    float vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
-    float osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+    float vsq = sq3(s.v);
+    float osq = sq3(s.om);
     float wl[4] = {s.w[0], s.w[1], s.w[2], s.w[3]};     // rotor speeds entering the last executed substep
 
     // _check_failure after every substep (:210-221); the negated comparisons also catch NaN
@@ -289,7 +302,7 @@ __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const fl
     {                                                                                                            \
         wl[0] = s.w[0]; wl[1] = s.w[1]; wl[2] = s.w[2]; wl[3] = s.w[3];                                          \
         substep<SIMPLE>(c, s, cw, Kz, adj, id, vsq, osq);                                                        \
-        const float psq = s.p[0] * s.p[0] + s.p[1] * s.p[1] + s.p[2] * s.p[2];                                   \
+        const float psq = sq3(s.p);                                   \
         if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {                                 \
             fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR); \
             break;                                                                                               \
@@ -330,11 +343,11 @@ __device__ __forceinline__ void quad_rhs(const QuadConst &c, const QState &s, co
 {
     float adj[9], id;
     adjugate(s.R, adj, id);
-    const float bvx = (adj[0] * s.v[0] + adj[1] * s.v[1] + adj[2] * s.v[2]) * id;
-    const float bvy = (adj[3] * s.v[0] + adj[4] * s.v[1] + adj[5] * s.v[2]) * id;
-    const float bvz = (adj[6] * s.v[0] + adj[7] * s.v[1] + adj[8] * s.v[2]) * id;
-    const float nvn = -fast_sqrt(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
-    const float non = -fast_sqrt(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
+    const float bvx = dot3(adj[0], s.v[0], adj[1], s.v[1], adj[2], s.v[2]) * id;
+    const float bvy = dot3(adj[3], s.v[0], adj[4], s.v[1], adj[5], s.v[2]) * id;
+    const float bvz = dot3(adj[6], s.v[0], adj[7], s.v[1], adj[8], s.v[2]) * id;
+    const float nvn = -fast_sqrt(sq3(s.v));
+    const float non = -fast_sqrt(sq3(s.om));
     float fz = 0.f, tx = 0.f, ty = 0.f, me[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -357,19 +370,19 @@ __device__ __forceinline__ void quad_rhs(const QuadConst &c, const QState &s, co
     float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
     if (!SIMPLE) {
         const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
-        Tx -= gy * c.cg[2] - gz * c.cg[1];
-        Ty -= gz * c.cg[0] - gx * c.cg[2];
-        Tz -= gx * c.cg[1] - gy * c.cg[0];
+        Tx -= det2(gy, c.cg[2], gz, c.cg[1]);
+        Ty -= det2(gz, c.cg[0], gx, c.cg[2]);
+        Tz -= det2(gx, c.cg[1], gy, c.cg[0]);
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         d.p[r] = s.v[r];
-        d.v[r] = (s.R[3 * r] * Fx + s.R[3 * r + 1] * Fy + s.R[3 * r + 2] * Fz) * c.inv_m;
-        d.om[r] = c.Iinv[3 * r] * Tx + c.Iinv[3 * r + 1] * Ty + c.Iinv[3 * r + 2] * Tz;
+        d.v[r] = dot3(s.R[3 * r], Fx, s.R[3 * r + 1], Fy, s.R[3 * r + 2], Fz) * c.inv_m;
+        d.om[r] = dot3(c.Iinv[3 * r], Tx, c.Iinv[3 * r + 1], Ty, c.Iinv[3 * r + 2], Tz);
         const float r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
-        d.R[3 * r + 0] = r1 * s.om[2] - r2 * s.om[1];
-        d.R[3 * r + 1] = r2 * s.om[0] - r0 * s.om[2];
-        d.R[3 * r + 2] = r0 * s.om[1] - r1 * s.om[0];
+        d.R[3 * r + 0] = det2(r1, s.om[2], r2, s.om[1]);
+        d.R[3 * r + 1] = det2(r2, s.om[0], r0, s.om[2]);
+        d.R[3 * r + 2] = det2(r0, s.om[1], r1, s.om[0]);
     }
 }
 
@@ -406,19 +419,19 @@ __device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, cons
         quad_axpy(s, k, 0.5f * h, t);
         quad_rhs<SIMPLE>(c, t, kV, k);                       // k2
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { acc.p[r] += 2.f * k.p[r]; acc.v[r] += 2.f * k.v[r]; acc.om[r] += 2.f * k.om[r]; }
+        for (int r = 0; r < 3; ++r) { acc.p[r] = fmaf(2.f, k.p[r], acc.p[r]); acc.v[r] = fmaf(2.f, k.v[r], acc.v[r]); acc.om[r] = fmaf(2.f, k.om[r], acc.om[r]); }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc.w[r] += 2.f * k.w[r];
+        for (int r = 0; r < 4; ++r) acc.w[r] = fmaf(2.f, k.w[r], acc.w[r]);
 #pragma unroll
-        for (int r = 0; r < 9; ++r) acc.R[r] += 2.f * k.R[r];
+        for (int r = 0; r < 9; ++r) acc.R[r] = fmaf(2.f, k.R[r], acc.R[r]);
         quad_axpy(s, k, 0.5f * h, t);
         quad_rhs<SIMPLE>(c, t, kV, k);                       // k3
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { acc.p[r] += 2.f * k.p[r]; acc.v[r] += 2.f * k.v[r]; acc.om[r] += 2.f * k.om[r]; }
+        for (int r = 0; r < 3; ++r) { acc.p[r] = fmaf(2.f, k.p[r], acc.p[r]); acc.v[r] = fmaf(2.f, k.v[r], acc.v[r]); acc.om[r] = fmaf(2.f, k.om[r], acc.om[r]); }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc.w[r] += 2.f * k.w[r];
+        for (int r = 0; r < 4; ++r) acc.w[r] = fmaf(2.f, k.w[r], acc.w[r]);
 #pragma unroll
-        for (int r = 0; r < 9; ++r) acc.R[r] += 2.f * k.R[r];
+        for (int r = 0; r < 9; ++r) acc.R[r] = fmaf(2.f, k.R[r], acc.R[r]);
         quad_axpy(s, k, h, t);
         quad_rhs<SIMPLE>(c, t, kV, k);                       // k4
 #pragma unroll
@@ -430,9 +443,9 @@ __device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, cons
         const int ct = s.ct, ep = s.ep;
         quad_axpy(s, acc, h * (1.0f / 6.0f), t);
         s = t; s.ct = ct; s.ep = ep;
-        const float psq = s.p[0] * s.p[0] + s.p[1] * s.p[1] + s.p[2] * s.p[2];
-        const float vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
-        const float osq = s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2];
+        const float psq = sq3(s.p);
+        const float vsq = sq3(s.v);
+        const float osq = sq3(s.om);
         if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {
             fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR);
             break;
@@ -455,13 +468,13 @@ __device__ __forceinline__ void observe(const QuadConst &c, const QState &s, con
     for (int k = 0; k < 9; ++k) Ri[k] = adj[k] * id;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        bv[r] = Ri[3 * r] * s.v[0] + Ri[3 * r + 1] * s.v[1] + Ri[3 * r + 2] * s.v[2];
+        bv[r] = dot3(Ri[3 * r], s.v[0], Ri[3 * r + 1], s.v[1], Ri[3 * r + 2], s.v[2]);
         o[r] = bv[r];
-        o[3 + r] = Ri[3 * r] * s.p[0] + Ri[3 * r + 1] * s.p[1] + Ri[3 * r + 2] * s.p[2];
+        o[3 + r] = dot3(Ri[3 * r], s.p[0], Ri[3 * r + 1], s.p[1], Ri[3 * r + 2], s.p[2]);
         o[6 + r] = Ri[3 * r + 2] * -9.8f;    // body_acceleration is never updated (:22,:278): IMU = R^-1 g only
         o[9 + r] = s.om[r];
     }
-    o[12] = fast_atan2(-s.R[6], fast_sqrt(s.R[7] * s.R[7] + s.R[8] * s.R[8]));   // pitch, :111-120
+    o[12] = fast_atan2(-s.R[6], fast_sqrt(fmaf(s.R[8], s.R[8], s.R[7] * s.R[7])));   // pitch, :111-120
     o[13] = fast_atan2(s.R[7], s.R[8]);                                       // roll
     o[14] = fast_atan2(s.R[3], s.R[0]);                                       // yaw
     o[15] = s.p[2] + c.z_off;
@@ -513,12 +526,41 @@ __device__ __forceinline__ void prefetch_targets(const QuadConst &c, const QuadA
     tr.nxt[0] = __ldg(q); tr.nxt[1] = __ldg(q + 1); tr.nxt[2] = __ldg(q + 2);
 }
 
+// python slice bound for a[start:stop] on an axis of length len (negative indices wrap once, then clamp)
+__device__ __forceinline__ int slice_bound(double v, int len)
+{
+    long long x = v < -2.0e9 ? -2000000000LL : (v > 2.0e9 ? 2000000000LL : (long long)v);
+    if (x < 0) { x += len; if (x < 0) x = 0; }
+    if (x > len) x = len;
+    return (int)x;
+}
+
+// _check_collision with an obstacle map (env.py:248-260).  x/y are float64 in the reference (float32 position +
+// int64 offset from np.where), z is float32 (+ python float 5.0).
+__device__ __forceinline__ bool map_collision(const QuadArgs &a, float x_old, float y_old, float z_old, float x_new,
+                                              float y_new, float z_new)
+{
+    const double xo = (double)x_old + a.x_off, xn = (double)x_new + a.x_off;
+    const double yo = (double)y_old + a.y_off, yn = (double)y_new + a.y_off;
+    const double x_min = floor(fmin(xo, xn)), x_max = ceil(fmax(xo, xn));
+    const double y_min = floor(fmin(yo, yn)), y_max = ceil(fmax(yo, yn));
+    const int z_lo = (int)floorf(fminf(z_old, z_new)), z_hi = (int)ceilf(fmaxf(z_old, z_new));
+    const int ys = slice_bound(y_min, a.map_rows), ye = slice_bound(y_max + 1.0, a.map_rows);
+    const int xs = slice_bound(x_min, a.map_cols), xe = slice_bound(x_max + 1.0, a.map_cols);
+    int any = 0;
+    if (ys < ye && xs < xe) {
+        const int W = a.map_cols + 1;
+        any = (a.sat[ye * W + xe] - a.sat[ys * W + xe] - a.sat[ye * W + xs] + a.sat[ys * W + xs]) > 0 ? 1 : 0;
+    }
+    return z_lo < any || z_hi < any;
+}
+
 // Task logic after the integrator: observation, reward, collision, done, counters, optional auto-reset.
 // o[] receives the observation to publish; fo[] the terminal observation (valid iff *had_final).
 __device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &a, int64_t e, QState &s,
-                                            const float adj[9], float id, float z_old, float power, int fail,
-                                            const TargetRows &tr, float *o, float &reward, int &done_flag,
-                                            bool &write_final)
+                                            const float adj[9], float id, float z_old, float x_old, float y_old,
+                                            float power, int fail, const TargetRows &tr, float *o, float &reward,
+                                            int &done_flag, bool &write_final)
 {
     float bv[3], Ri[9];
     observe(c, s, adj, id, o, bv, Ri);
@@ -532,16 +574,20 @@ __device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &
         const float g0 = tr.cur[0], g1 = tr.cur[1], g2 = tr.cur[2];   // env.py:153-157
         float diff = 0.f;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) diff += fabsf((Ri[3 * r] * g0 + Ri[3 * r + 1] * g1 + Ri[3 * r + 2] * g2) - bv[r]);
+        for (int r = 0; r < 3; ++r) diff += fabsf(dot3(Ri[3 * r], g0, Ri[3 * r + 1], g1, Ri[3 * r + 2], g2) - bv[r]);
         reward += -0.001f * diff;
     } else {
-        // flat-map collision, env.py:248-260: `z_min < np.any(taken_pos)` compares against False == 0
+        // collision, env.py:248-260: `z_min < np.any(taken_pos) or z_max < np.any(taken_pos)` compares integer
+        // altitudes against a BOOL: 0 over free cells (flat map: always), 1 as soon as the window swept by the step
+        // contains any obstacle cell (the obstacle's height is never used -- reference quirk)
         const float z_new = s.p[2] + c.z_off;
-        const bool coll = fminf(z_old, z_new) < 0.f;
+        bool coll;
+        if (a.sat) coll = map_collision(a, x_old, y_old, z_old, s.p[0], s.p[1], z_new);
+        else coll = fminf(z_old, z_new) < 0.f;
         float tr = coll ? 0.f : c.healthy;
         if (c.task == MGB_TASK_HOVERING_CONTROL) {            // env.py:222-243
-            const float vn = fast_sqrt(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
-            const float on = fast_sqrt(s.om[0] * s.om[0] + s.om[1] * s.om[1] + s.om[2] * s.om[2]);
+            const float vn = fast_sqrt(sq3(s.v));
+            const float on = fast_sqrt(sq3(s.om));
             tr -= vn + on;
             const float zm = fabsf(0.f - s.p[2]);             // pos_0[2] is always 0 (env.py:123, :26)
             tr += zm < 0.5f ? 10.f : fmaxf(-20.f, 0.5f - zm);
@@ -613,13 +659,14 @@ __device__ __forceinline__ void step_body(const QuadConst &c, const QuadArgs &a,
     if (EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
         prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
     const float z_old = s.p[2] + c.z_off;                   // env.py:131-133
+    const float x_old = s.p[0], y_old = s.p[1];
     const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
     if (!EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
         prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
     float o[kMaxObs], reward;
     int done;
     bool wf;
-    finish_step(c, a, e, s, adj, id, z_old, power, fail, tr, o, reward, done, wf);
+    finish_step(c, a, e, s, adj, id, z_old, x_old, y_old, power, fail, tr, o, reward, done, wf);
     store_state(a, e, s);
     a.rew[e] = reward;
     a.done[e] = (uint8_t)done;
@@ -806,7 +853,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __
 // it) and writes obs/reward/done.  Observation tiles are double-buffered so the bulk store of step t overlaps the
 // arithmetic of step t+1.
 template <bool SIMPLE>
-__global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_constant__ QuadConst c,
+__global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_constant__ QuadConst c,
                                                                 const __grid_constant__ QuadArgs a)
 {
     __shared__ __align__(128) float tiles[2][kThreads * kMaxObs];
@@ -851,12 +898,13 @@ __global__ void __launch_bounds__(kThreads) quad_rollout_kernel(const __grid_con
             TargetRows tr;
             prefetch_targets(c, a, trow, s.ct, tr);
             const float z_old = s.p[2] + c.z_off;
+            const float x_old = s.p[0], y_old = s.p[1];
             float power;
             const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
             float o[kMaxObs], reward;
             int done;
             bool wf;
-            finish_step(c, a, e, s, adj, id, z_old, power, fail, tr, o, reward, done, wf);
+            finish_step(c, a, e, s, adj, id, z_old, x_old, y_old, power, fail, tr, o, reward, done, wf);
             if (wf) {
                 observe_reset(c, a, e, s, o);
                 adjugate(s.R, adj, id);
@@ -990,6 +1038,8 @@ struct mgb_quad {
     mgb_quad_cfg cfg;
     QuadConst c;
     float4 *planes = nullptr;
+    int32_t *sat = nullptr;
+    int map_rows = 0, map_cols = 0, x_off = 0, y_off = 0;
     float *targets = nullptr;
     int32_t *env2task = nullptr;
     int n_tasks = 0;
@@ -1020,6 +1070,7 @@ static QuadArgs base_args(const mgb_quad *h)
     a.n = h->n;
     a.env_base = h->env_base;
     a.targets = h->targets;
+    a.sat = h->sat; a.map_rows = h->map_rows; a.map_cols = h->map_cols; a.x_off = h->x_off; a.y_off = h->y_off;
     a.env2task = h->env2task;
     a.seed = h->seed;
     a.auto_reset = h->auto_reset;
@@ -1129,6 +1180,7 @@ extern "C" void mgb_quad_destroy(mgb_quad *h)
     MgbDeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->planes);
+    cudaFree(h->sat);
     cudaFree(h->targets);
     cudaFree(h->env2task);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
@@ -1149,6 +1201,35 @@ extern "C" int mgb_quad_set_options(mgb_quad *h, int auto_reset, uint64_t seed)
     MGB_REQUIRE(h, "null handle");
     h->auto_reset = auto_reset ? 1 : 0;
     h->seed = seed;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_set_map(mgb_quad *h, const int32_t *map_host, int32_t rows, int32_t cols)
+{
+    MGB_REQUIRE(h, "null handle");
+    MgbDeviceGuard guard(h->device);
+    MGB_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->sat);
+    h->sat = nullptr;
+    h->map_rows = h->map_cols = h->x_off = h->y_off = 0;
+    if (!map_host) return MGB_OK;                               // flat default map, env.py:295-298
+    MGB_REQUIRE(h->c.task != MGB_TASK_VELOCITY_CONTROL, "velocity_control has no map (env.py:101-104)");
+    MGB_REQUIRE(rows > 0 && cols > 0 && rows <= 8192 && cols <= 8192, "map size out of range");
+    int starts = 0, sr = 0, sc = 0;
+    for (int r = 0; r < rows; ++r)
+        for (int q = 0; q < cols; ++q)
+            if (map_host[(size_t)r * cols + q] == -1) { ++starts; sr = r; sc = q; }
+    MGB_REQUIRE(starts == 1, "the map must mark exactly one start cell with -1 (env.py:108-109)");
+    std::vector<int32_t> sat((size_t)(rows + 1) * (cols + 1), 0);
+    for (int r = 0; r < rows; ++r)
+        for (int q = 0; q < cols; ++q) {
+            const int v = (r == sr && q == sc) ? 0 : map_host[(size_t)r * cols + q];    // env.py:113
+            sat[(size_t)(r + 1) * (cols + 1) + q + 1] = (v != 0 ? 1 : 0) + sat[(size_t)r * (cols + 1) + q + 1] +
+                                                        sat[(size_t)(r + 1) * (cols + 1) + q] - sat[(size_t)r * (cols + 1) + q];
+        }
+    MGB_CUDA(cudaMalloc(&h->sat, sat.size() * sizeof(int32_t)));
+    MGB_CUDA(cudaMemcpy(h->sat, sat.data(), sat.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->map_rows = rows; h->map_cols = cols; h->x_off = sc; h->y_off = sr;
     return MGB_OK;
 }
 

@@ -141,9 +141,6 @@ class BatchedQuadrotor(object):
                  env2task=None, squeeze=True, integrator="euler", rk4_steps=1, **kwargs):
         import torch
         assert task in ["velocity_control", "no_collision", "hovering_control"], "Invalid task setting"  # env.py:55
-        if map_file is not None:
-            raise NotImplementedError("obstacle maps (map_file) are not on the accelerated path yet; "
-                                      "the flat default map of env.py:295-298 is")
         self.dt, self.nt, self.task, self.healthy_reward = dt, nt, task, healthy_reward
         self.num_envs = int(num_envs)
         self._squeeze = bool(squeeze) and self.num_envs == 1
@@ -166,8 +163,12 @@ class BatchedQuadrotor(object):
         self.observation_space = Space(shape=[len(self.obs_keys)], dtype="float32")
         self.x_offset = self.y_offset = 0
         self.z_offset = self._cfg.z_offset
+        self.map_matrix = None
         if task != "velocity_control":
-            self.x_offset = self.y_offset = 50                       # env.py:296-297,108-111
+            self.map_matrix = self.load_map(map_file)                # env.py:105-113
+            y_offsets, x_offsets = np.where(self.map_matrix == -1)
+            assert len(y_offsets) == 1
+            self.y_offset, self.x_offset = int(y_offsets[0]), int(x_offsets[0])
         h = ctypes.c_void_p()
         _lib.check(self._lib.mgb_quad_create(ctypes.byref(h), self.num_envs, ctypes.byref(self._cfg), dev_index,
                                              int(env_index_base)))
@@ -181,6 +182,12 @@ class BatchedQuadrotor(object):
         self._done = torch.empty((N,), dtype=torch.uint8, device=dev)
         self._fail = torch.zeros((N,), dtype=torch.int32, device=dev)
         self._final_obs = torch.zeros((N, D), dtype=torch.float32, device=dev) if self.auto_reset else None
+        if self.map_matrix is not None and map_file is not None:
+            m = np.ascontiguousarray(self.map_matrix, dtype=np.int32)
+            _lib.check(self._lib.mgb_quad_set_map(self._h, m.ctypes.data, m.shape[0], m.shape[1]))
+        if self.map_matrix is not None:
+            self.map_matrix = self.map_matrix.copy()
+            self.map_matrix[self.y_offset, self.x_offset] = 0         # env.py:113
         self.velocity_targets = None
         if task == "velocity_control":
             seeds = [seed] if np.isscalar(seed) else list(seed)
@@ -206,6 +213,20 @@ class BatchedQuadrotor(object):
         _lib.check(self._lib.mgb_quad_set_targets(self._h, tbl.data_ptr(), len(seeds), e2t.data_ptr()))
         self.velocity_targets = tbl
         self.env2task = e2t
+
+    @staticmethod
+    def load_map(map_file):
+        """Quadrotor.load_map (env.py:293-305): None = 100x100 flat floor with the start at (50, 50); otherwise a text
+        file of space-separated integer rows, -1 marking the start cell."""
+        if map_file is None:
+            flatten_map = np.zeros([100, 100], dtype=np.int32)
+            flatten_map[50, 50] = -1
+            return flatten_map
+        rows = []
+        with open(map_file, "r") as f:
+            for line in f.readlines():
+                rows.append([int(i) for i in line.split(" ")])
+        return np.array(rows)
 
     def _out(self, t):
         return t[0] if self._squeeze else t

@@ -152,3 +152,27 @@ def rk4_step(cfg, state, act, dt, rk4_steps=1, mode="f64"):
     fn = getattr(lib(), "qo_%s_rk4_step" % mode)
     fn(ctypes.byref(cfg), ctypes.c_int(n), _ptr(state, ctypes.c_double), _ptr(act, ctypes.c_float),
        ctypes.c_double(dt), ctypes.c_int(rk4_steps))
+
+
+_map_keepalive = None
+
+
+def set_map(map_matrix):
+    """Obstacle map for the following env_step calls (None = flat).  map_matrix as Quadrotor.load_map returns it (one
+    cell == -1 marks the start); returns (x_offset, y_offset)."""
+    global _map_keepalive
+    if map_matrix is None:
+        lib().qo_set_map(None, 0, 0, 0, 0)
+        _map_keepalive = None
+        return 0, 0
+    m = np.array(map_matrix, dtype=np.int64)
+    ys, xs = np.where(m == -1)
+    assert len(ys) == 1
+    m[ys[0], xs[0]] = 0
+    sat = np.zeros((m.shape[0] + 1, m.shape[1] + 1), dtype=np.int32)
+    sat[1:, 1:] = np.cumsum(np.cumsum((m != 0).astype(np.int32), axis=0), axis=1)
+    sat = np.ascontiguousarray(sat)
+    _map_keepalive = sat
+    lib().qo_set_map(_ptr(sat, ctypes.c_int), ctypes.c_int(m.shape[0]), ctypes.c_int(m.shape[1]),
+                     ctypes.c_int(int(xs[0])), ctypes.c_int(int(ys[0])))
+    return int(xs[0]), int(ys[0])

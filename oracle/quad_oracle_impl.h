@@ -181,6 +181,7 @@ void QO_NAME(env_step)(const qo_cfg *c, int n, double *state, int *ct, const flo
         ct[e] += 1;                                                  /* env.py:128 */
         const double zoff = task == 2 ? 0.0 : 5.0;                   /* env.py:97,112: z_offset only with a map */
         const T z_old = p[2] + KT(zoff);                             /* env.py:131-133 */
+        const double x_old = (double)p[0] + qo_xoff, y_old = (double)p[1] + qo_yoff;
         T vclamp[4];
         for (int k = 0; k < 4; ++k) {                                /* quadrotorsim.py:130-134 */
             double a = (double)act[4 * (long)e + k];
@@ -226,7 +227,12 @@ void QO_NAME(env_step)(const qo_cfg *c, int n, double *state, int *ct, const flo
         /* reward / done, env.py:144-161,211-260 */
         const T z_new = p[2] + KT(zoff);
         const T zmin = z_old < z_new ? z_old : z_new;
-        const int collision = (task != 2) && (zmin < KT(0.0));       /* flat map, see DESIGN.md "collision quirk" */
+        int collision = (task != 2) && (zmin < KT(0.0));             /* flat map: z < np.any(zeros) == z < False */
+        if (task != 2 && qo_sat) {                                   /* env.py:248-260 with an obstacle map */
+            const T zmax = z_old > z_new ? z_old : z_new;
+            const int any = qo_any_obstacle(x_old, y_old, (double)p[0] + qo_xoff, (double)p[1] + qo_yoff);
+            collision = ((int)QO_FLOORT(zmin) < any) || ((int)QO_CEILT(zmax) < any);
+        }
         T e_cost = KT(dt) * pwr;
         double r = -(double)(e_cost < KT(healthy) ? e_cost : KT(healthy));
         int dn = 0;

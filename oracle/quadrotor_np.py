@@ -149,7 +149,7 @@ def velocity_table(q, dt, nt, seed):
 class NumpyQuadrotorEnv(object):
     """gym-style env over the functions above (reset/step like the reference's Quadrotor)."""
 
-    def __init__(self, dt=0.01, nt=1000, seed=0, task="no_collision", healthy_reward=1.0, params=None):
+    def __init__(self, dt=0.01, nt=1000, seed=0, task="no_collision", healthy_reward=1.0, params=None, map_matrix=None):
         assert task in ("velocity_control", "no_collision", "hovering_control"), "Invalid task setting"
         self.q = SimParams(params)
         self.dt, self.nt, self.task, self.healthy = dt, nt, task, healthy_reward
@@ -161,6 +161,14 @@ class NumpyQuadrotorEnv(object):
             self.targets = velocity_table(self.q, dt, nt, seed)
         else:
             self.z_off = 5.0
+            m = np.zeros([100, 100], dtype=np.int32) if map_matrix is None else np.array(map_matrix)
+            if map_matrix is None:
+                m[50, 50] = -1
+            ys, xs = np.where(m == -1)
+            assert len(ys) == 1
+            self.y_off, self.x_off = ys[0], xs[0]
+            m[self.y_off, self.x_off] = 0
+            self.map = m
 
     def _observe(self):
         st = self.st
@@ -186,6 +194,8 @@ class NumpyQuadrotorEnv(object):
         self.ct += 1
         cmd = np.asarray(action, np.float32)
         z_before = self.st.p[2] + self.z_off
+        if self.task != "velocity_control":
+            xy_before = (self.st.p[0] + self.x_off, self.st.p[1] + self.y_off)
         advance(self.st, self.q, cmd.tolist(), self.dt)
         obs = self._observe()
         z_after = self.st.p[2] + self.z_off
@@ -198,7 +208,11 @@ class NumpyQuadrotorEnv(object):
         else:
             z_lo = int(floor(min(z_before, z_after)))
             z_hi = int(ceil(max(z_before, z_after)))
-            hit = z_lo < False or z_hi < False          # flat map: the reference compares against np.any(all-zero map)
+            xy_after = (st.p[0] + self.x_off, st.p[1] + self.y_off)
+            x_lo, x_hi = int(floor(min(xy_before[0], xy_after[0]))), int(ceil(max(xy_before[0], xy_after[0])))
+            y_lo, y_hi = int(floor(min(xy_before[1], xy_after[1]))), int(ceil(max(xy_before[1], xy_after[1])))
+            swept = self.map[y_lo:y_hi + 1, x_lo:x_hi + 1]
+            hit = z_lo < np.any(swept) or z_hi < np.any(swept)      # integer altitude against a BOOL (reference quirk)
             bonus = 0.0 if hit else self.healthy
             if self.task == "hovering_control":
                 bonus -= 1.0 * np.linalg.norm(st.v) + 1.0 * np.linalg.norm(st.w)

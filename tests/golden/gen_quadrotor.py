@@ -23,9 +23,9 @@ def sim_state(sim):
         np.asarray(sim.rotation_matrix, dtype=np.float64).reshape(-1)])
 
 
-def record_episode(ns, task, dt, nt, seed, np_seed, T, action_fn, n_episodes=1):
+def record_episode(ns, task, dt, nt, seed, np_seed, T, action_fn, n_episodes=1, map_file=None):
     """Run n_episodes (each ends on done or after T steps) on ONE env object, like a user would."""
-    env = ns.Quadrotor(task=task, dt=dt, nt=nt, seed=seed)
+    env = ns.Quadrotor(task=task, dt=dt, nt=nt, seed=seed, map_file=map_file)
     rng = np.random.RandomState(np_seed + 1000)
     rec = dict(pre_state=[], pre_ct=[], act=[], post_state=[], post_ct=[], obs=[], rew=[], done=[], power=[],
                ep=[], reset_noise=[], reset_obs=[], reset_ct=[])
@@ -98,6 +98,29 @@ def main():
         out["%s.meta" % name] = np.array([{"hovering_control": 1, "no_collision": 0, "velocity_control": 2}[task],
                                           dt, nt, seed], dtype=np.float64)
         print(name, task, "steps", len(rec["rew"]), "dones", int(rec["done"].sum()))
+
+    # --- obstacle map (env.py:248-260,293-305): a 12x12 map whose start cell is ringed by obstacle cells, so the window
+    # swept by a step almost always contains one and the collision threshold becomes z + 5 < 1 instead of < 0
+    import tempfile
+    obst = np.zeros((12, 12), dtype=np.int64)
+    obst[3:8, 3:8] = 10
+    obst[5, 5] = -1
+    obst[5, 4] = 0
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        for row in obst:
+            f.write(" ".join(str(int(v)).zfill(2) for v in row) + "\n")
+        map_path = f.name
+    out["map_obst"] = obst.astype(np.int32)
+    glide = lambda rng, t: np.array([4.4, 4.6, 4.4, 4.6], dtype=np.float32) + rng.uniform(-0.3, 0.3, 4).astype(np.float32)  # noqa: E731
+    for name, (task, np_seed, fn, neps) in {"map_hover": ("hovering_control", 11, glide, 3),
+                                            "map_nocol": ("no_collision", 12, fall, 2)}.items():
+        rec = record_episode(ns, task, 0.01, 1000, 0, np_seed, 400, fn, neps, map_file=map_path)
+        for k, v in rec.items():
+            out["%s.%s" % (name, k)] = v
+        out["%s.meta" % name] = np.array([{"hovering_control": 1, "no_collision": 0}[task], 0.01, 1000, 0], dtype=np.float64)
+        zs = rec["obs"][:, 15]
+        print(name, "steps", len(rec["rew"]), "dones", int(rec["done"].sum()), "z at done", zs[rec["done"]])
+    os.unlink(map_path)
 
     # --- velocity-task generator alone (quadrotorsim.py:306-319): seeds 0..5, nt=40, dt=0.005
     tabs = []

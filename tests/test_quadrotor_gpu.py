@@ -10,7 +10,7 @@ f32-vs-f64 drift at 7e-6 after 100 steps).
 import numpy as np
 import pytest
 
-from util import OBS_GROUPS, QUAD_RUNS, STATE_GROUPS, golden_run, group_rel_err, scalar_rel_err
+from util import OBS_GROUPS, QUAD_MAP_RUNS, QUAD_RUNS, STATE_GROUPS, golden_run, group_rel_err, scalar_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -399,3 +399,30 @@ def test_wide_kernel_equals_tile_kernel(torch_mod, monkeypatch, N):
     assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("name", QUAD_MAP_RUNS)
+def test_obstacle_map_vs_reference(torch_mod, quad_golden, name, tmp_path):
+    """map_file=: teacher-forced steps of reference episodes flown over an obstacle map; the
+    collision / done pattern (episodes end at z + 5 < 1 over obstacle cells) must be reproduced exactly."""
+    torch = torch_mod
+    r = golden_run(quad_golden, name)
+    path = tmp_path / "map.txt"
+    path.write_text("".join(" ".join(str(int(v)).zfill(2) for v in row) + "\n" for row in quad_golden["map_obst"]))
+    n = r["pre_state"].shape[0]
+    env = make_env(n, r["task"], dt=r["dt"], nt=r["nt"], map_file=str(path))
+    assert (env.x_offset, env.y_offset) == (5, 5)
+    set_state(env, r["pre_state"], r["pre_ct"])
+    obs, rew, done, _ = env.step(torch.as_tensor(r["act"]).cuda())
+    assert np.array_equal(done.cpu().numpy(), r["done"]) and r["done"].sum() >= 2
+    assert scalar_rel_err(rew.cpu().numpy(), r["rew"]) < RTOL_STEP
+    assert group_rel_err(obs.cpu().numpy()[:, :16], r["obs"][:, :16], OBS_GROUPS) < RTOL_STEP
+    _, ct = get_state(env)
+    assert np.array_equal(ct, r["post_ct"])
+    env.close()
+    # the same states on the flat default map do NOT collide (z + 5 is ~0.98 > 0)
+    flat = make_env(n, r["task"], dt=r["dt"], nt=r["nt"])
+    set_state(flat, r["pre_state"], r["pre_ct"])
+    _, _, done2, _ = flat.step(torch.as_tensor(r["act"]).cuda())
+    assert int(done2.sum()) < int(r["done"].sum())
+    flat.close()

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import quad_oracle as qo
-from util import OBS_GROUPS, QUAD_RUNS, STATE_GROUPS, golden_run, group_rel_err, scalar_rel_err
+from util import OBS_GROUPS, QUAD_MAP_RUNS, QUAD_RUNS, STATE_GROUPS, golden_run, group_rel_err, scalar_rel_err
 
 
 @pytest.fixture(scope="module")
@@ -146,3 +146,36 @@ def test_rk4_restatement_converges_to_the_reference_model(cfg):
             qo.sim_step(c2, s, acts[t], int(round(dt / h)), "f64")
         gaps.append(group_rel_err(s_rk, s, STATE_GROUPS))
     assert gaps[0] > 5 * gaps[1] > 10 * gaps[2] / 2 and gaps[2] < 5e-4, gaps
+
+
+@pytest.mark.parametrize("name", QUAD_MAP_RUNS)
+def test_obstacle_map_collision_vs_reference(quad_golden, cfg, name):
+    """Quadrotor(map_file=...) (env.py:248-260,293-305): with obstacle cells in the swept window the reference compares
+    the integer altitude against np.any(...) == True, i.e. it ends the episode at z + 5 < 1.  Teacher-forced steps."""
+    r = golden_run(quad_golden, name)
+    qo.set_map(quad_golden["map_obst"])
+    try:
+        state = np.array(r["pre_state"], dtype=np.float64)
+        ct = np.array(r["pre_ct"], dtype=np.int32)
+        obs, rew, done, fail, power = qo.env_step(cfg, state, ct, r["act"], r["task"], r["dt"], r["nt"], mode="mix")
+    finally:
+        qo.set_map(None)
+    assert np.array_equal(done.astype(bool), r["done"]) and r["done"].sum() >= 2
+    assert np.all(r["obs"][r["done"], 15] > 0.9)             # ended above the floor: the obstacle rule fired
+    assert scalar_rel_err(rew, r["rew"]) < 1e-6 and np.array_equal(ct, r["post_ct"])
+    assert group_rel_err(obs[:, :16], r["obs"][:, :16], OBS_GROUPS) < 1e-6
+
+
+@pytest.mark.parametrize("name,np_seed", [("map_hover", 11), ("map_nocol", 12)])
+def test_numpy_port_with_obstacle_map(quad_golden, name, np_seed):
+    from oracle.quadrotor_np import NumpyQuadrotorEnv
+    r = golden_run(quad_golden, name)
+    env = NumpyQuadrotorEnv(dt=r["dt"], nt=r["nt"], seed=r["seed"], task=r["task"], map_matrix=quad_golden["map_obst"])
+    np.random.seed(np_seed)
+    ep = -1
+    for i in range(len(r["rew"])):
+        if r["ep"][i] != ep:
+            ep = int(r["ep"][i])
+            assert np.array_equal(env.reset(), r["reset_obs"][ep])
+        obs, rew, done, _ = env.step(r["act"][i])
+        assert np.array_equal(obs, r["obs"][i]) and float(rew) == r["rew"][i] and bool(done) == bool(r["done"][i])

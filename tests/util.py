@@ -45,6 +45,7 @@ def golden_run(g, name):
 
 
 QUAD_RUNS = ["hover_a", "hover_b", "hover_fall", "nocol_fall", "nocol_a", "vel_a", "vel_b", "vel_c"]
+QUAD_MAP_RUNS = ["map_hover", "map_nocol"]      # recorded with the obstacle map stored as "map_obst"
 
 
 # ---------------------------------------------------------------------------------------------------------------
