@@ -44,8 +44,8 @@ GRAPH_STEPS = 32              # steps per CUDA graph = slots of the rollout buff
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE quad_step_kernel launch at this shape, from the committed
 # `ncu --set full` capture (not measured by this script; ncu flushes caches, so the L2-resident state is read from DRAM
 # once and the 12.5 MB of outputs had not been written back when the kernel ended).  Algorithmic: 65536 x 281 = 18.4 MB.
-NCU_TRAFFIC_BYTES = 7652864
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_quad_step_65k.txt (4M-env launch: 1186.9 MB vs 1178.6 MB algorithmic, r1_ncu_quad_step_4m.txt)"
+NCU_TRAFFIC_BYTES = 7680768
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_quad_step_wide_65k.txt (4M-env launch: 1186.9 MB vs 1178.6 MB algorithmic, r1_ncu_quad_step_4m.txt)"
 WORKLOAD = ("quadrotor velocity_control, %d envs/GPU, dt=0.005 (5 Euler substeps of 1 ms), nt=1000, "
             "64 velocity tasks, U(0.1,15) actions, auto-reset" % N_ENVS_PER_GPU)
 
@@ -386,7 +386,7 @@ def main():
                                      "no reference counterpart (SURVEY.md fact 2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
-                         "peak_source": peak_src, "kernel": "quad_step_kernel<true,true>",
+                         "peak_source": peak_src, "kernel": "quad_step_wide_kernel<true>",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n,
                          "us_per_launch": us_per_launch},
             "gpu_launches": K,
