@@ -315,3 +315,38 @@ def test_continuous_maze_random_batch_vs_oracle(torch_mod, maze_golden, textures
             assert np.array_equal(pos[e], p2) and ori[e] == a2, (t, e)
             assert np.array_equal(obs[e], o2), (t, e, int((obs[e] != o2).sum()))
     env.close()
+
+
+@pytest.mark.parametrize("kind", ["2D", "3D", "C3D"])
+def test_maximum_maze_size_vs_oracle(torch_mod, textures, kind):
+    """n = 31 cells per side (the engine's maximum; the reference's own smoke script grows n from 9 upwards,
+    metamaze/test.py:17-26), dense food, tasks from the host sampler: GPU == oracle, bit for bit."""
+    torch = torch_mod
+    from metagym_b200 import (BatchedMetaMaze2D, BatchedMetaMazeContinuous3D, BatchedMetaMazeDiscrete3D,
+                              MazeTaskSampler)
+    from oracle.maze_oracle import OracleMaze
+    rs = np.random.RandomState(31)
+    task = MazeTaskSampler(n=31, allow_loops=True, crowd_ratio=0.3, food_density=0.03, food_interval=5, rng=rs)
+    n, res = 4, (64, 40)
+    if kind == "2D":
+        env = BatchedMetaMaze2D(max_steps=80, view_grid=3, num_envs=n, squeeze=False)
+    elif kind == "3D":
+        env = BatchedMetaMazeDiscrete3D(resolution=res, max_steps=80, num_envs=n, squeeze=False, textures=textures)
+    else:
+        env = BatchedMetaMazeContinuous3D(resolution=res, max_steps=80, num_envs=n, squeeze=False, textures=textures)
+    ora = OracleMaze(kind, "SURVIVAL", 80, 3, res, textures=textures if kind != "2D" else None)
+    env.set_task(task)
+    ora.set_task(task)
+    assert np.array_equal(env.reset().cpu().numpy()[0], ora.reset())
+    for t in range(40):
+        if kind == "C3D":
+            a = rs.uniform(-1, 1, 2).astype(np.float32)
+            act = torch.as_tensor(np.tile(a, (n, 1))).cuda()
+        else:
+            a = int(rs.randint(4))
+            act = torch.full((n,), a, dtype=torch.int32, device="cuda")
+        obs, rew, done, _ = env.step(act)
+        o2, r2, d2, _ = ora.step(a)
+        assert np.array_equal(obs.cpu().numpy()[n - 1], o2), t
+        assert float(rew[0]) == r2 and bool(done[0]) == d2
+    env.close()

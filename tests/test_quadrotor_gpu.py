@@ -426,3 +426,38 @@ def test_obstacle_map_vs_reference(torch_mod, quad_golden, name, tmp_path):
     _, _, done2, _ = flat.step(torch.as_tensor(r["act"]).cuda())
     assert int(done2.sum()) < int(r["done"].sum())
     flat.close()
+
+
+@pytest.mark.parametrize("task,action", [("no_collision", 1.0), ("hovering_control", 0.1)])
+def test_reference_smoke_episode_to_termination(torch_mod, task, action):
+    """The reference's own tests (quadrotor/tests/test_env.py:20-29) fly constant actions until the env says done.
+    Same here on one env, side by side with the numpy port (bit-identical to the reference): same episode length,
+    observations within the free-run envelope."""
+    torch = torch_mod
+    from oracle.quadrotor_np import NumpyQuadrotorEnv
+    rng = np.random.RandomState(8)
+    noise = rng.random_sample(12)
+    ref = NumpyQuadrotorEnv(task=task)
+    st = np.random.get_state()
+    np.random.seed(0)
+    # feed the port's reset() the same 12 draws the engine replays
+    import unittest.mock as mock
+    draws = iter([noise[0:3], noise[3:6], noise[6:9], noise[9:12]])
+    with mock.patch("numpy.random.random", side_effect=lambda n: next(draws)):
+        o_ref = ref.reset()
+    np.random.set_state(st)
+    env = make_env(1, task)
+    o = env.reset(noise=noise[None]).cpu().numpy()[0]
+    assert group_rel_err(o[None, :16], o_ref[None, :16], OBS_GROUPS) < 1e-6
+    act = np.full(4, action, dtype=np.float32)
+    steps = 0
+    while True:
+        obs, rew, done, _ = env.step(torch.as_tensor(act[None]).cuda())
+        o_ref, r_ref, d_ref, _ = ref.step(act)
+        steps += 1
+        assert bool(done[0]) == bool(d_ref), steps
+        assert group_rel_err(obs.cpu().numpy()[:, :16], o_ref[None, :16], OBS_GROUPS) < 5e-6 * (1 + steps)
+        if d_ref:
+            break
+    assert 50 < steps < 1000          # falls the 5 m to the floor
+    env.close()
