@@ -92,6 +92,10 @@ struct MazeArgs {
     const uint8_t *mask;
     int do_step;                 // 0: observe only (reset), 1: step then observe
     int do_parts;                // compose kernel: image slices per env
+    int T;                       // maze2d rollout: steps per launch
+    uint64_t act_seed;
+    uint32_t t_base;
+    int32_t *act_out;
     int auto_reset;
 };
 
@@ -358,6 +362,90 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_kernel(const __grid_constan
         __syncthreads();
         for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tile2d[i];
     }
+}
+
+
+// T MetaMaze2D steps in one launch: the agent (cell, step counter, life) stays in registers, food stamps stay in their
+// SoA slots, each step's observation tile of the CTA leaves through double-buffered shared memory + one bulk store.
+__global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid_constant__ MazeConst c,
+                                                                    const __grid_constant__ MazeArgs a)
+{
+    extern __shared__ __align__(128) float tile2d[];
+    const int64_t e0 = (int64_t)blockIdx.x * k2dThreads;
+    const int64_t e = e0 + threadIdx.x;
+    const int W = 2 * c.view_grid + 1, D = W * W;
+    const int rows = (int)((a.n - e0) < k2dThreads ? (a.n - e0) : k2dThreads);
+    const bool active = e < a.n;
+    const uint8_t *blob = nullptr;
+    const TaskHdr *th = nullptr;
+    const int8_t *walls = nullptr;
+    Env s = {0, 0, 0, 0, 0.0};
+    int32_t *eaten = a.eaten + e;
+    if (active) {
+        blob = a.blobs + (int64_t)a.env2task[e] * c.blob_bytes;
+        th = blob_hdr(blob);
+        walls = reinterpret_cast<const int8_t *>(blob + c.off_walls);
+        const int4 ag = a.agent[e];
+        s.gx = ag.x; s.gy = ag.y; s.ori = ag.z; s.steps = ag.w; s.life = a.life[e];
+    }
+    const uint2 akey = make_uint2((uint32_t)a.act_seed, (uint32_t)(a.act_seed >> 32));
+    const int64_t genv = a.env_base + e;
+    const int n = c.n, g = c.view_grid;
+    for (int t = 0; t < a.T; ++t) {
+        float *tile = tile2d + (size_t)(t & 1) * k2dThreads * D;
+        if (threadIdx.x == 0) mgb_bulk_wait_read<1>();      // the store issued two steps ago has read this tile
+        __syncthreads();
+        if (active) {
+            int action;
+            if (a.act) action = a.act[(int64_t)t * a.n + e];
+            else {
+                const uint4 r = mgb_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32),
+                                                             a.t_base + (uint32_t)t, MGB_STREAM_ACTION), akey);
+                action = (int)(r.x >> 30);                   // uniform over {0, 1, 2, 3}
+                if (a.act_out) a.act_out[(int64_t)t * a.n + e] = action;
+            }
+            double reward;
+            int done;
+            maze_logic(c, blob, eaten, a.n_pad, s, action, reward, done);
+            if (done && a.auto_reset) env_reset(c, blob, eaten, a.n_pad, s);
+            if (a.rew) a.rew[(int64_t)t * a.n + e] = reward;
+            if (a.done) a.done[(int64_t)t * a.n + e] = (uint8_t)done;
+            if (a.obs) {
+                float *row = tile + threadIdx.x * D;
+                for (int p = 0; p < W; ++p)
+                    for (int q = 0; q < W; ++q) {
+                        const int x = s.gx - g + p, y = s.gy - g + q;
+                        float v = -1.0f;
+                        if (x >= 0 && x < n && y >= 0 && y < n) {
+                            v = (float)(-(int)walls[x * n + y]);
+                            if (c.task_type == MGB_MAZE_SURVIVAL)
+                                v = (float)((double)v + food_now(c, blob, eaten, a.n_pad, s.steps, x * n + y));
+                            else
+                                v = (float)((double)v + ((x == th->goal[0] && y == th->goal[1]) ? 1.0 : 0.0));
+                        }
+                        row[p * W + q] = v;
+                    }
+                if (c.task_type == MGB_MAZE_SURVIVAL) row[g * W + g] = (float)s.life;
+            }
+        }
+        if (a.obs) {
+            float *dst = reinterpret_cast<float *>(a.obs) + ((int64_t)t * a.n + e0) * D;
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+            if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                mgb_fence_proxy_async();
+                __syncthreads();
+                if (threadIdx.x == 0) { mgb_bulk_store(dst, tile, bytes); mgb_bulk_commit(); }
+            } else {
+                __syncthreads();
+                for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tile[i];
+            }
+        }
+    }
+    if (active) {
+        a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+        a.life[e] = s.life;
+    }
+    if (threadIdx.x == 0) mgb_bulk_wait_read<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1116,6 +1204,7 @@ struct mgb_maze {
     size_t smem3d = 0;
     int num_sms = 0;
     int64_t launches = 0;
+    uint32_t t_base = 0;
 };
 
 static size_t maze3d_smem_bytes(const MazeConst &c)
@@ -1602,6 +1691,28 @@ extern "C" int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_de
         a.obs = obs_dev; a.do_step = 0; a.mask = nullptr;
         return launch_observe(h, a, st);
     }
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, uint64_t act_seed, int32_t *act_out_dev,
+                                float *obs_dev, double *rew_dev, uint8_t *done_dev, void *stream)
+{
+    MGB_REQUIRE(h, "null handle");
+    MGB_REQUIRE(T > 0, "T must be positive");
+    MGB_REQUIRE(h->c.kind == MGB_MAZE_2D, "mgb_maze_rollout is the MetaMaze2D fused rollout");
+    int rc = maze_ready(h);
+    if (rc) return rc;
+    MgbDeviceGuard guard(h->device);
+    MazeArgs a = maze_args(h);
+    a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev; a.do_step = 1;
+    a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
+    const int W = 2 * h->c.view_grid + 1;
+    const size_t sm = (size_t)2 * k2dThreads * W * W * 4;
+    if (sm > 48 * 1024) MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    maze2d_rollout_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+    MGB_CUDA(cudaGetLastError());
+    h->t_base += (uint32_t)T;
+    h->launches += 1;
     return MGB_OK;
 }
 

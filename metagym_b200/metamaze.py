@@ -288,6 +288,24 @@ class BatchedMetaMaze2D(_BatchedMazeBase):
         cfg.n_cells, cfg.max_steps, cfg.view_grid = n_cells, self.max_steps, self.view_grid
         return cfg
 
+    def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):
+        """T steps in one launch.  actions: [T,N] int32 CUDA tensor or None (device-drawn uniform {0..3}).
+        Returns dict(obs [T,N,2g+1,2g+1] f32, rew [T,N] f64, done [T,N] u8, act [T,N] i32 or None)."""
+        if self.need_reset:
+            raise Exception("Must \"reset\" before doing any actions")
+        torch = self._torch
+        N, w, dev = self.num_envs, 2 * self.view_grid + 1, self.device
+        if out is None:
+            out = {"obs": torch.empty((T, N, w, w), dtype=torch.float32, device=dev),
+                   "rew": torch.empty((T, N), dtype=torch.float64, device=dev),
+                   "done": torch.empty((T, N), dtype=torch.uint8, device=dev),
+                   "act": torch.empty((T, N), dtype=torch.int32, device=dev) if want_actions else None}
+        a = None if actions is None else actions.to(torch.int32).reshape(T, N).contiguous()
+        _lib.check(self._lib.mgb_maze_rollout(self._h, int(T), _lib.ptr(a), int(act_seed), _lib.ptr(out.get("act")),
+                                              _lib.ptr(out.get("obs")), _lib.ptr(out.get("rew")),
+                                              _lib.ptr(out.get("done")), self._stream()))
+        return out
+
 
 class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
     """MetaMazeDiscrete3D(enable_render, render_scale, resolution, max_steps, task_type) x num_envs

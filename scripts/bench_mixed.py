@@ -26,6 +26,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 N_QUAD = N_MAZE = 16384          # per GPU (131 072 + 131 072 over 8 GPUs)
 T, CHUNKS = 32, 8
+FUSED_MAZE = os.environ.get("MIXED_FUSED_MAZE", "1") != "0"   # mgb_maze_rollout vs T single mgb_maze_step calls
 qbase, _ = shard_range(N_QUAD * world, rank, world)
 mbase, _ = shard_range(N_MAZE * world, rank, world)
 quad = BatchedQuadrotor(task="hovering_control", dt=0.01, nt=1000, num_envs=N_QUAD, device=local, squeeze=False,
@@ -48,9 +49,14 @@ chunk = {
 
 
 def collect():
-    # quadrotor: T fused steps, device-drawn U(0.1, 15) actions; maze: T single steps with uniform {0..3} actions
+    # quadrotor: T fused steps, device-drawn U(0.1, 15) actions; maze: T fused steps, device-drawn uniform {0..3}
+    # actions (MIXED_FUSED_MAZE=0: T single steps with torch-drawn actions)
     quad.rollout(T, actions=None, act_seed=7, out={"obs": chunk["q_obs"], "rew": chunk["q_rew"], "done": chunk["q_done"],
                                                    "act": chunk["q_act"]})
+    if FUSED_MAZE:
+        maze.rollout(T, actions=None, act_seed=9, out={"obs": chunk["m_obs"], "rew": chunk["m_rew"],
+                                                       "done": chunk["m_done"], "act": chunk["m_act"]})
+        return
     chunk["m_act"].copy_(torch.randint(0, 4, (T, N_MAZE), device=dev, generator=g, dtype=torch.int32))
     for t in range(T):
         o, r, d, _ = maze.step(chunk["m_act"][t])
@@ -96,7 +102,7 @@ if rank == 0:
         "env_steps_per_s_with_gather": steps / (ms_both * 1e-3),
         "allgather_ms": ms_gather, "chunk_bytes_per_rank": nbytes,
         "allgather_busbw_GBps": nbytes * (world - 1) / (ms_gather * 1e-3) / 1e9 if world > 1 else None,
-        "gathered_envs": int(gathered["q_obs"].shape[1]) + int(gathered["m_obs"].shape[1]), "n_gpus": world}), flush=True)
+        "fused_maze_rollout": FUSED_MAZE, "gathered_envs": int(gathered["q_obs"].shape[1]) + int(gathered["m_obs"].shape[1]), "n_gpus": world}), flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

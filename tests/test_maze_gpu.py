@@ -350,3 +350,55 @@ def test_maximum_maze_size_vs_oracle(torch_mod, textures, kind):
         assert np.array_equal(obs.cpu().numpy()[n - 1], o2), t
         assert float(rew[0]) == r2 and bool(done[0]) == d2
     env.close()
+
+
+@pytest.mark.parametrize("task_type", ["SURVIVAL", "ESCAPE"])
+@pytest.mark.parametrize("n,view_grid", [(300, 2), (77, 1), (128, 3)])
+def test_fused_2d_rollout_equals_single_steps(torch_mod, maze_golden, task_type, n, view_grid):
+    """mgb_maze_rollout (T steps, one launch) == T mgb_maze_step calls, bit for bit, auto-reset included; with
+    device-drawn actions the drawn actions replayed through step() give the same trajectory; state hand-over between
+    two consecutive rollouts and a following single step is exact."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 10, g["tasks15.scalars"][k]) for k in range(4)]
+    T = 90
+
+    def fresh():
+        env = BatchedMetaMaze2D(max_steps=35, task_type=task_type, view_grid=view_grid, num_envs=n, squeeze=False,
+                                auto_reset=True)
+        env.set_task(tasks)
+        env.reset()
+        return env
+
+    a_env, b_env = fresh(), fresh()
+    rng = np.random.RandomState(n + view_grid)
+    act = torch.as_tensor(rng.randint(0, 4, (T, n)), dtype=torch.int32).cuda()
+    out = a_env.rollout(T, actions=act)
+    n_done = 0
+    for t in range(T):
+        obs, rew, done, _ = b_env.step(act[t])
+        assert torch.equal(out["obs"][t], obs), t
+        assert torch.equal(out["rew"][t], rew), t
+        assert torch.equal(out["done"][t].bool(), done.bool()), t
+        n_done += int(done.sum())
+    assert n_done > 0
+    # device-drawn actions: two chunks, then one ordinary step
+    o1 = a_env.rollout(40, act_seed=11, want_actions=True)
+    o2 = a_env.rollout(25, act_seed=11, want_actions=True)
+    drawn = torch.cat([o1["act"], o2["act"]])
+    assert int(drawn.min()) == 0 and int(drawn.max()) == 3
+    assert not torch.equal(o1["act"][:25], o2["act"])          # the step counter advances the draw
+    counts = torch.bincount(drawn.flatten().long(), minlength=4).double() / drawn.numel()
+    assert float((counts - 0.25).abs().max()) < 0.03
+    ref_obs = torch.cat([o1["obs"], o2["obs"]]); ref_rew = torch.cat([o1["rew"], o2["rew"]])
+    for t in range(65):
+        obs, rew, done, _ = b_env.step(drawn[t])
+        assert torch.equal(ref_obs[t], obs) and torch.equal(ref_rew[t], rew), t
+    last = torch.as_tensor(rng.randint(0, 4, n), dtype=torch.int32).cuda()
+    ra, rb = a_env.step(last), b_env.step(last)
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+    sa, sb = a_env.agent_state(), b_env.agent_state()
+    assert torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])
+    a_env.close(); b_env.close()
