@@ -240,6 +240,21 @@ const char *mgb_version(void);
 /* Number of CUDA devices visible, or <0 when the runtime cannot initialise (no fallback exists). */
 int mgb_device_count(void);
 
+/* ---- peer memory: the rollout kernels as their own all-gather (NVLink stores, no NCCL on the data) -----------------
+ * Replaces the `comm.allgather(trajectories)` a distributed learner would do around N copies of the reference's
+ * env.step loop.  One receive arena per rank, allocated with mgb_peer_alloc, exported as a 64-byte
+ * cudaIpcMemHandle, opened by every other rank of the node; mgb_*_set_mirrors then makes the fused rollout kernels
+ * store each output at `ptr` and at `ptr + byte_delta[i]`, i < count <= MGB_MAX_MIRRORS. */
+#define MGB_MAX_MIRRORS 7
+#define MGB_PEER_HANDLE_BYTES 64
+int mgb_peer_alloc(int device, uint64_t bytes, void **ptr_out);
+int mgb_peer_free(int device, void *ptr);
+int mgb_peer_export(int device, void *ptr, uint8_t handle_out[MGB_PEER_HANDLE_BYTES]);
+int mgb_peer_open(int device, const uint8_t handle[MGB_PEER_HANDLE_BYTES], void **ptr_out);
+int mgb_peer_close(int device, void *ptr);
+int mgb_quad_set_mirrors(mgb_quad *h, int count, const int64_t *byte_delta);
+int mgb_maze_set_mirrors(mgb_maze *h, int count, const int64_t *byte_delta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,13 @@ SIGNATURES = {
     "mgb_maze_reset": (ctypes.c_int, [vp, vp, vp, vp]),
     "mgb_maze_step": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "mgb_maze_set_options": (ctypes.c_int, [vp, ctypes.c_int]),
+    "mgb_peer_alloc": (ctypes.c_int, [ctypes.c_int, c_u64, ctypes.POINTER(ctypes.c_void_p)]),
+    "mgb_peer_free": (ctypes.c_int, [ctypes.c_int, vp]),
+    "mgb_peer_export": (ctypes.c_int, [ctypes.c_int, vp, vp]),
+    "mgb_peer_open": (ctypes.c_int, [ctypes.c_int, vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "mgb_peer_close": (ctypes.c_int, [ctypes.c_int, vp]),
+    "mgb_quad_set_mirrors": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "mgb_maze_set_mirrors": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "mgb_maze_rollout": (ctypes.c_int, [vp, c_i32, vp, c_u64, vp, vp, vp, vp, vp]),
     "mgb_maze_step_continuous": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "mgb_maze_pose": (ctypes.c_int, [vp, vp, vp, vp]),

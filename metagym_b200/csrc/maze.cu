@@ -96,6 +96,7 @@ struct MazeArgs {
     uint64_t act_seed;
     uint32_t t_base;
     int32_t *act_out;
+    MgbMirrors mir;              // maze2d rollout: every output is also stored at ptr + mir.delta[i]
     int auto_reset;
 };
 
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_kernel(const __grid_constan
 
 // T MetaMaze2D steps in one launch: the agent (cell, step counter, life) stays in registers, food stamps stay in their
 // SoA slots, each step's observation tile of the CTA leaves through double-buffered shared memory + one bulk store.
+template <bool MIRROR>
 __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid_constant__ MazeConst c,
                                                                     const __grid_constant__ MazeArgs a)
 {
@@ -402,14 +404,23 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
                 const uint4 r = mgb_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32),
                                                              a.t_base + (uint32_t)t, MGB_STREAM_ACTION), akey);
                 action = (int)(r.x >> 30);                   // uniform over {0, 1, 2, 3}
-                if (a.act_out) a.act_out[(int64_t)t * a.n + e] = action;
+                if (a.act_out) {
+                    a.act_out[(int64_t)t * a.n + e] = action;
+                    if (MIRROR) mgb_mirror_store(a.mir, a.act_out + (int64_t)t * a.n + e, (int32_t)action);
+                }
             }
             double reward;
             int done;
             maze_logic(c, blob, eaten, a.n_pad, s, action, reward, done);
             if (done && a.auto_reset) env_reset(c, blob, eaten, a.n_pad, s);
-            if (a.rew) a.rew[(int64_t)t * a.n + e] = reward;
-            if (a.done) a.done[(int64_t)t * a.n + e] = (uint8_t)done;
+            if (a.rew) {
+                a.rew[(int64_t)t * a.n + e] = reward;
+                if (MIRROR) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
+            }
+            if (a.done) {
+                a.done[(int64_t)t * a.n + e] = (uint8_t)done;
+                if (MIRROR) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
+            }
             if (a.obs) {
                 float *row = tile + threadIdx.x * D;
                 for (int p = 0; p < W; ++p)
@@ -434,10 +445,17 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
             if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
                 mgb_fence_proxy_async();
                 __syncthreads();
-                if (threadIdx.x == 0) { mgb_bulk_store(dst, tile, bytes); mgb_bulk_commit(); }
+                if (threadIdx.x == 0) {
+                    mgb_bulk_store(dst, tile, bytes);
+                    if (MIRROR) mgb_mirror_bulk_store(a.mir, dst, tile, bytes);
+                    mgb_bulk_commit();
+                }
             } else {
                 __syncthreads();
-                for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tile[i];
+                for (int i = threadIdx.x; i < rows * D; i += blockDim.x) {
+                    dst[i] = tile[i];
+                    if (MIRROR) mgb_mirror_store(a.mir, dst + i, tile[i]);
+                }
             }
         }
     }
@@ -1205,6 +1223,7 @@ struct mgb_maze {
     int num_sms = 0;
     int64_t launches = 0;
     uint32_t t_base = 0;
+    MgbMirrors mir = {};         // mgb_maze_set_mirrors
 };
 
 static size_t maze3d_smem_bytes(const MazeConst &c)
@@ -1708,11 +1727,31 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
     const int W = 2 * h->c.view_grid + 1;
     const size_t sm = (size_t)2 * k2dThreads * W * W * 4;
-    if (sm > 48 * 1024) MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    maze2d_rollout_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+    a.mir = h->mir;
+    const unsigned blocks = (unsigned)((h->n + k2dThreads - 1) / k2dThreads);
+    if (sm > 48 * 1024) {
+        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    if (h->mir.count > 0) maze2d_rollout_kernel<true><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+    else maze2d_rollout_kernel<false><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
     MGB_CUDA(cudaGetLastError());
     h->t_base += (uint32_t)T;
     h->launches += 1;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_set_mirrors(mgb_maze *h, int count, const int64_t *byte_delta)
+{
+    MGB_REQUIRE(h, "null handle");
+    MGB_REQUIRE(count >= 0 && count <= MGB_MAX_MIRRORS && (count == 0 || byte_delta), "count out of range");
+    MgbMirrors m = {};
+    for (int i = 0; i < count; ++i) {
+        MGB_REQUIRE((byte_delta[i] & 15) == 0, "mirror deltas must be multiples of 16 bytes");
+        m.delta[i] = byte_delta[i];
+    }
+    m.count = count;
+    h->mir = m;
     return MGB_OK;
 }
 

@@ -101,6 +101,26 @@ template <int N> __device__ __forceinline__ void mgb_bulk_wait()
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Output mirrors: a rollout kernel can store every trajectory output a second, third, ... time at `pointer + delta[i]`.
+// With the outputs placed in this rank's slot of a receive arena and delta[i] = (peer i's arena base - local arena base)
+// over NVLink peer mappings (mgb_peer_open), the kernel itself performs the all-gather of the trajectory chunk:
+// the remote stores drain through NVLink/NVSwitch while the next env-step integrates.
+// ---------------------------------------------------------------------------------------------------------------
+struct MgbMirrors {
+    int count;
+    int64_t delta[MGB_MAX_MIRRORS];   // bytes
+};
+template <typename T> __device__ __forceinline__ void mgb_mirror_store(const MgbMirrors &m, T *p, const T v)
+{
+    for (int i = 0; i < m.count; ++i) *reinterpret_cast<T *>(reinterpret_cast<char *>(p) + m.delta[i]) = v;
+}
+// issued by ONE thread, before mgb_bulk_commit(): the same smem tile to every mirror of gdst
+__device__ __forceinline__ void mgb_mirror_bulk_store(const MgbMirrors &m, void *gdst, const void *ssrc, uint32_t bytes)
+{
+    for (int i = 0; i < m.count; ++i) mgb_bulk_store(reinterpret_cast<char *>(gdst) + m.delta[i], ssrc, bytes);
+}
+
 // mbarrier + global -> smem bulk load
 __device__ __forceinline__ void mgb_mbar_init(uint64_t *bar, uint32_t count)
 {

@@ -82,6 +82,7 @@ struct QuadArgs {
     uint64_t act_seed;
     uint32_t t_base;
     float *act_out;
+    MgbMirrors mir;            // rollout only: every output is also stored at ptr + mir.delta[i]
 };
 
 struct QState {
@@ -644,6 +645,28 @@ __device__ __forceinline__ void publish_tile(float *gobs, const float *tile, int
     }
 }
 
+__device__ __forceinline__ void publish_tile_mirrored(const MgbMirrors &m, float *gobs, const float *tile, int64_t e0,
+                                                      int rows, int D)
+{
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+    float *dst = gobs + e0 * D;
+    if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        mgb_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mgb_bulk_store(dst, tile, bytes);
+            mgb_mirror_bulk_store(m, dst, tile, bytes);     // deltas are 16-byte multiples (checked on the host)
+            mgb_bulk_commit();
+        }
+    } else {
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * D; i += blockDim.x) {
+            dst[i] = tile[i];
+            mgb_mirror_store(m, dst + i, tile[i]);
+        }
+    }
+}
+
 // One env.step() on register state: integrate, task logic, state / reward / done stores, observation row into the CTA's
 // shared-memory tile (trow); frow receives the terminal observation when auto-reset replaced it.
 template <bool SIMPLE, bool EARLY>
@@ -852,7 +875,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __
 // T env.step()s in one launch: the state never leaves registers; per step the kernel reads 16 B of action (or draws
 // it) and writes obs/reward/done.  Observation tiles are double-buffered so the bulk store of step t overlaps the
 // arithmetic of step t+1.
-template <bool SIMPLE>
+template <bool SIMPLE, bool MIRROR>
 __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_constant__ QuadConst c,
                                                                 const __grid_constant__ QuadArgs a)
 {
@@ -892,7 +915,11 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                 const float span = c.vmax - c.vmin;
                 act = make_float4(fmaf(span, mgb_u01(r.x), c.vmin), fmaf(span, mgb_u01(r.y), c.vmin),
                                   fmaf(span, mgb_u01(r.z), c.vmin), fmaf(span, mgb_u01(r.w), c.vmin));
-                if (a.act_out) reinterpret_cast<float4 *>(a.act_out)[(int64_t)t * a.n + e] = act;
+                if (a.act_out) {
+                    float4 *ap = reinterpret_cast<float4 *>(a.act_out) + (int64_t)t * a.n + e;
+                    *ap = act;
+                    if (MIRROR) mgb_mirror_store(a.mir, ap, act);
+                }
             }
             s.ct += 1;
             TargetRows tr;
@@ -909,8 +936,14 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                 observe_reset(c, a, e, s, o);
                 adjugate(s.R, adj, id);
             }
-            if (a.rew) a.rew[(int64_t)t * a.n + e] = reward;
-            if (a.done) a.done[(int64_t)t * a.n + e] = (uint8_t)done;
+            if (a.rew) {
+                a.rew[(int64_t)t * a.n + e] = reward;
+                if (MIRROR) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
+            }
+            if (a.done) {
+                a.done[(int64_t)t * a.n + e] = (uint8_t)done;
+                if (MIRROR) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
+            }
             if (a.obs) {
                 float *trow = tile + threadIdx.x * D;
 #pragma unroll
@@ -918,7 +951,10 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                 if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
             }
         }
-        if (a.obs) publish_tile(a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
+        if (a.obs) {
+            if (MIRROR) publish_tile_mirrored(a.mir, a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
+            else publish_tile(a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
+        }
     }
     if (active) store_state(a, e, s);
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
@@ -1052,6 +1088,7 @@ struct mgb_quad {
     uint64_t seed = 0;
     uint32_t t_base = 0;
     int64_t launches = 0;
+    MgbMirrors mir = {};       // mgb_quad_set_mirrors
     // host staging for *_host entry points
     float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
     uint8_t *h_done = nullptr;
@@ -1378,11 +1415,31 @@ extern "C" int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, ui
     a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev;
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
     const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
-    if (h->c.simple) quad_rollout_kernel<true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
-    else quad_rollout_kernel<false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    a.mir = h->mir;
+    if (h->mir.count > 0) {
+        if (h->c.simple) quad_rollout_kernel<true, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+        else quad_rollout_kernel<false, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    } else {
+        if (h->c.simple) quad_rollout_kernel<true, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+        else quad_rollout_kernel<false, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    }
     MGB_CUDA(cudaGetLastError());
     h->t_base += (uint32_t)T;
     h->launches += 1;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_set_mirrors(mgb_quad *h, int count, const int64_t *byte_delta)
+{
+    MGB_REQUIRE(h, "null handle");
+    MGB_REQUIRE(count >= 0 && count <= MGB_MAX_MIRRORS && (count == 0 || byte_delta), "count out of range");
+    MgbMirrors m = {};
+    for (int i = 0; i < count; ++i) {
+        MGB_REQUIRE((byte_delta[i] & 15) == 0, "mirror deltas must be multiples of 16 bytes");
+        m.delta[i] = byte_delta[i];
+    }
+    m.count = count;
+    h->mir = m;
     return MGB_OK;
 }
 

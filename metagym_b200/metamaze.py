@@ -288,6 +288,11 @@ class BatchedMetaMaze2D(_BatchedMazeBase):
         cfg.n_cells, cfg.max_steps, cfg.view_grid = n_cells, self.max_steps, self.view_grid
         return cfg
 
+    def set_mirrors(self, byte_deltas):
+        """Every output of rollout() is also stored at `pointer + delta` (see rollout.PeerArena)."""
+        d = np.ascontiguousarray(np.asarray(list(byte_deltas), dtype=np.int64))
+        _lib.check(self._lib.mgb_maze_set_mirrors(self._h, int(d.size), _lib.ptr(d) if d.size else None))
+
     def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):
         """T steps in one launch.  actions: [T,N] int32 CUDA tensor or None (device-drawn uniform {0..3}).
         Returns dict(obs [T,N,2g+1,2g+1] f32, rew [T,N] f64, done [T,N] u8, act [T,N] i32 or None)."""

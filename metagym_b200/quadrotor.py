@@ -297,6 +297,12 @@ class BatchedQuadrotor(object):
                                               _lib.ptr(out.get("done")), self._stream()))
         return out
 
+    def set_mirrors(self, byte_deltas):
+        """Every output of rollout() is also stored at `pointer + delta` for each delta (rollout.PeerArena.mirrors:
+        the kernel then writes the trajectory straight into the other ranks' receive arenas over NVLink)."""
+        d = np.ascontiguousarray(np.asarray(list(byte_deltas), dtype=np.int64))
+        _lib.check(self._lib.mgb_quad_set_mirrors(self._h, int(d.size), _lib.ptr(d) if d.size else None))
+
     @property
     def fail_code(self):
         """[N] int32: MGB_FAIL_* of the last step (the reference raises instead, quadrotorsim.py:212-221)."""

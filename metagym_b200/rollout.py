@@ -23,9 +23,10 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
-def all_gather_rollout(chunk, group=None):
+def all_gather_rollout(chunk, group=None, scratch=None):
     """chunk: dict name -> tensor [T, n_local, ...] (same n_local on every rank).  Returns dict name -> tensor
-    [T, world*n_local, ...] ordered by global env index.  One all_gather_into_tensor per field."""
+    [T, world*n_local, ...] ordered by global env index.  One all_gather_into_tensor per field.
+    scratch: optional dict the receive buffers are kept in between calls (no allocator traffic in steady state)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -42,11 +43,165 @@ def all_gather_rollout(chunk, group=None):
         src = src.contiguous()
         # gather along a new leading rank axis, then fold it into the env axis: [W, T, n, ...] -> [T, W*n, ...]
         T, n = src.shape[0], src.shape[1]
-        buf = torch.empty((world * T,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        shape = (world * T,) + tuple(src.shape[1:])
+        buf = None if scratch is None else scratch.get(k)
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != src.dtype or buf.device != src.device:
+            buf = torch.empty(shape, dtype=src.dtype, device=src.device)
+            if scratch is not None:
+                scratch[k] = buf
         dist.all_gather_into_tensor(buf, src, group=group)        # rank-major concatenation along dim 0
         g = buf.view((world, T) + tuple(src.shape[1:])).movedim(0, 1).reshape((T, world * n) + tuple(src.shape[2:]))
         out[k] = g.to(torch.bool) if v.dtype == torch.bool else g
     return out
+
+
+class RolloutArena:
+    """All fields of a T-step rollout chunk carved out of ONE byte allocation, so that the engine's rollout kernels write
+    straight into it (the C ABI takes plain pointers) and the learner-side collation is ONE all_gather_into_tensor
+    instead of one per field.
+
+        arena = RolloutArena({"obs": ((T, n, 19), torch.float32), "rew": ((T, n), torch.float32), ...}, device)
+        env.rollout(T, out={"obs": arena["obs"], ...})
+        views, work = arena.all_gather(async_op=True)      # views[name]: [world, T, n, ...], zero-copy
+    Rank r's block is the global env range shard_range(...) gives it, so `views[name][r, t, i]` is global env
+    `r*n + i`; `ordered(views)` copies into [T, world*n, ...] when one flat env axis is wanted."""
+
+    ALIGN = 256
+
+    def _layout(self, fields):
+        import torch
+        self.fields, self.offsets, off = {}, {}, 0
+        for k, (shape, dtype) in fields.items():
+            nbytes = int(torch.empty((), dtype=dtype).element_size())
+            for d in shape:
+                nbytes *= int(d)
+            self.fields[k], self.offsets[k] = (tuple(int(d) for d in shape), dtype, nbytes), off
+            off += -(-nbytes // self.ALIGN) * self.ALIGN
+        self.nbytes = off
+
+    def __init__(self, fields, device):
+        import torch
+        self._layout(fields)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.views = {k: self.buf[self.offsets[k]:self.offsets[k] + nb].view(dt).view(shape)
+                      for k, (shape, dt, nb) in self.fields.items()}
+        self._recv = None
+
+    def __getitem__(self, k):
+        return self.views[k]
+
+    def payload_bytes(self):
+        return sum(nb for _, _, nb in self.fields.values())
+
+    def all_gather(self, group=None, async_op=False):
+        """-> (dict name -> [world, *field shape] views of the receive arena, work handle or None)."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return {k: v.unsqueeze(0) for k, v in self.views.items()}, None
+        if self._recv is None or self._recv.numel() != world * self.nbytes:
+            self._recv = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.buf.device)
+        work = dist.all_gather_into_tensor(self._recv, self.buf, group=group, async_op=async_op)
+        recv = self._recv.view(world, self.nbytes)
+        out = {}
+        for k, (shape, dt, nb) in self.fields.items():
+            o = self.offsets[k]
+            out[k] = recv[:, o:o + nb].view(dt).view((world,) + shape)
+        return out, (work if async_op else None)
+
+    @staticmethod
+    def ordered(views):
+        """[world, T, n, ...] -> [T, world*n, ...] (global env order; this one copies)."""
+        return {k: v.movedim(0, 1).reshape((v.shape[1], v.shape[0] * v.shape[2]) + tuple(v.shape[3:]))
+                for k, v in views.items()}
+
+
+class _RawDeviceMemory:
+    """__cuda_array_interface__ carrier: lets torch view memory this library allocated (mgb_peer_alloc / mgb_peer_open)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerArena(RolloutArena):
+    """RolloutArena whose all-gather is done by the rollout kernels themselves.
+
+    Every rank allocates a receive arena [world][arena bytes] with mgb_peer_alloc, the 64-byte cudaIpc handles are
+    exchanged once, and each rank maps the others' arenas (NVLink peer mappings).  `views` (what the env's rollout()
+    writes) is slot `rank` of the LOCAL receive arena; `env.set_mirrors(arena.mirrors)` makes the fused rollout kernel
+    store every output also into slot `rank` of each peer's arena.  After `sync()` (a stream-ordered one-element
+    all-reduce: all kernels of the chunk have completed on every rank) `gathered[name]` is [world, T, n, ...], no copy,
+    no data-path NCCL call.  Use two arenas alternately: rank r may already write chunk k+1 into arena B while the
+    learner of rank s still reads chunk k from arena A; the sync of chunk k+1 orders the reuse of A for chunk k+2."""
+
+    def __init__(self, fields, device, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self._lib, self._libmod = _lib.load(), _lib
+        dev = torch.device(device)
+        self.device_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world - 1 > 7:
+            raise ValueError("PeerArena: at most 8 ranks (MGB_MAX_MIRRORS = 7)")
+        self._layout(fields)
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.mgb_peer_alloc(self.device_index, self.world * self.nbytes, ctypes.byref(p)))
+        self._base = int(p.value)
+        self._peer_ptrs = {}
+        self.mirrors = []
+        if self.world > 1:
+            handle = (ctypes.c_uint8 * 64)()
+            _lib.check(self._lib.mgb_peer_export(self.device_index, self._base, handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().numpy().reshape(self.world, 64)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                q = ctypes.c_void_p()
+                hb = (ctypes.c_uint8 * 64)(*[int(x) for x in every[r]])
+                _lib.check(self._lib.mgb_peer_open(self.device_index, hb, ctypes.byref(q)))
+                self._peer_ptrs[r] = int(q.value)
+                self.mirrors.append(int(q.value) - self._base)
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._recv = torch.as_tensor(_RawDeviceMemory(self._base, self.world * self.nbytes), device=dev)
+        recv = self._recv.view(self.world, self.nbytes)
+        self.buf = recv[self.rank]
+        self.views, self.gathered = {}, {}
+        for k, (shape, dt, nb) in self.fields.items():
+            o = self.offsets[k]
+            self.views[k] = self.buf[o:o + nb].view(dt).view(shape)
+            self.gathered[k] = recv[:, o:o + nb].view(dt).view((self.world,) + shape)
+
+    def sync(self):
+        """Stream-ordered rendezvous: returns (on the stream) once every rank's kernels enqueued so far have finished,
+        i.e. all peer stores of this chunk have landed here.  The data never goes through NCCL."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, group=self.group)
+        return self.gathered
+
+    def close(self):
+        if self._base is None:
+            return
+        import torch
+        torch.cuda.synchronize(self.device_index)
+        self.views = self.gathered = self.buf = self._recv = None
+        for q in self._peer_ptrs.values():
+            self._lib.mgb_peer_close(self.device_index, q)
+        self._peer_ptrs = {}
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)        # nobody frees memory a peer still has mapped
+        self._lib.mgb_peer_free(self.device_index, self._base)
+        self._base = None
 
 
 def rollout_bytes(chunk):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from metagym_b200 import BatchedMetaMaze2D, BatchedQuadrotor, MazeTaskSampler
-from metagym_b200.rollout import all_gather_rollout, rollout_bytes, shard_range
+from metagym_b200.rollout import PeerArena, RolloutArena, all_gather_rollout, rollout_bytes, shard_range
 
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
 torch.cuda.set_device(local)
@@ -39,16 +39,17 @@ maze.set_task(tasks)
 quad.reset()
 maze.reset()
 g = torch.Generator(device=dev).manual_seed(rank)
-chunk = {
-    "q_obs": torch.empty((T, N_QUAD, 16), device=dev), "q_act": torch.empty((T, N_QUAD, 4), device=dev),
-    "q_rew": torch.empty((T, N_QUAD), device=dev), "q_done": torch.empty((T, N_QUAD), dtype=torch.uint8, device=dev),
-    "m_obs": torch.empty((T, N_MAZE, 3, 3), device=dev), "m_act": torch.empty((T, N_MAZE), dtype=torch.int32, device=dev),
-    "m_rew": torch.empty((T, N_MAZE), dtype=torch.float64, device=dev),
-    "m_done": torch.empty((T, N_MAZE), dtype=torch.uint8, device=dev),
+FIELDS = {
+    "q_obs": ((T, N_QUAD, 16), torch.float32), "q_act": ((T, N_QUAD, 4), torch.float32),
+    "q_rew": ((T, N_QUAD), torch.float32), "q_done": ((T, N_QUAD), torch.uint8),
+    "m_obs": ((T, N_MAZE, 3, 3), torch.float32), "m_act": ((T, N_MAZE), torch.int32),
+    "m_rew": ((T, N_MAZE), torch.float64), "m_done": ((T, N_MAZE), torch.uint8),
 }
+arenas = [RolloutArena(FIELDS, dev), RolloutArena(FIELDS, dev)]     # double buffer: collect k+1 while k is gathered
+chunk = arenas[0].views
 
 
-def collect():
+def collect(chunk=chunk):
     # quadrotor: T fused steps, device-drawn U(0.1, 15) actions; maze: T fused steps, device-drawn uniform {0..3}
     # actions (MIXED_FUSED_MAZE=0: T single steps with torch-drawn actions)
     quad.rollout(T, actions=None, act_seed=7, out={"obs": chunk["q_obs"], "rew": chunk["q_rew"], "done": chunk["q_done"],
@@ -81,17 +82,76 @@ def timed(fn, reps):
 
 collect()
 ms_collect = timed(collect, CHUNKS)
-gathered = {}
+gathered, scratch = {}, {}
 
 
 def collect_and_gather():
     collect()
-    gathered.update(all_gather_rollout(chunk))
+    gathered.update(all_gather_rollout(chunk, scratch=scratch))
 
 
-collect_and_gather()
+for _ in range(3):
+    collect_and_gather()
 ms_both = timed(collect_and_gather, CHUNKS)
-ms_gather = timed(lambda: all_gather_rollout(chunk), CHUNKS)
+
+
+def collect_and_gather_arena():
+    collect(arenas[0].views)
+    gathered.update(arenas[0].all_gather()[0])
+
+
+pending = [None]
+tick = [0]
+
+
+def pipelined():
+    ar = arenas[tick[0] & 1]
+    tick[0] += 1
+    collect(ar.views)                     # overlaps the previous chunk's gather (other arena, NCCL's stream)
+    if pending[0] is not None:
+        pending[0].wait()
+    views, pending[0] = ar.all_gather(async_op=True)
+    gathered.update(views)
+
+
+for _ in range(3):
+    collect_and_gather_arena()
+ms_arena = timed(collect_and_gather_arena, CHUNKS)
+ms_arena_gather = timed(lambda: arenas[0].all_gather(), CHUNKS)
+for _ in range(4):
+    pipelined()
+ms_pipe = timed(pipelined, CHUNKS * 2)
+if pending[0] is not None:
+    pending[0].wait()
+# ---- kernel-side gather: the rollout kernels store every output into all ranks' receive arenas (NVLink peer stores)
+peers = [PeerArena(FIELDS, dev), PeerArena(FIELDS, dev)]
+ptick = [0]
+
+
+def collect_peer():
+    ar = peers[ptick[0] & 1]
+    ptick[0] += 1
+    quad.set_mirrors(ar.mirrors)
+    maze.set_mirrors(ar.mirrors)
+    collect(ar.views)
+    gathered.update(ar.sync())
+    return ar
+
+
+ar = collect_peer()
+torch.cuda.synchronize(dev)
+peer_ok = True
+if world > 1:
+    check = torch.empty(world * ar.nbytes, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(check, ar.buf.contiguous())
+    peer_ok = bool(torch.equal(check, ar._recv))          # peer-written arena == NCCL all-gather of the same chunk
+    assert peer_ok, "peer-written arena differs from the NCCL all-gather"
+for _ in range(3):
+    collect_peer()
+ms_peer = timed(collect_peer, CHUNKS * 2)
+quad.set_mirrors([])
+maze.set_mirrors([])
+ms_gather = timed(lambda: all_gather_rollout(chunk, scratch=scratch), CHUNKS)
 steps = (N_QUAD + N_MAZE) * world * T
 nbytes = rollout_bytes(chunk)
 if rank == 0:
@@ -100,9 +160,16 @@ if rank == 0:
                   ((N_QUAD + N_MAZE) * world, world, T),
         "env_steps_per_s_no_gather": steps / (ms_collect * 1e-3),
         "env_steps_per_s_with_gather": steps / (ms_both * 1e-3),
+        "env_steps_per_s_with_arena_gather": steps / (ms_arena * 1e-3),
+        "env_steps_per_s_pipelined_arena_gather": steps / (ms_pipe * 1e-3),
+        "env_steps_per_s_kernel_side_gather": steps / (ms_peer * 1e-3), "kernel_side_gather_equals_nccl": peer_ok,
+        "arena_allgather_ms": ms_arena_gather,
+        "arena_allgather_busbw_GBps": arenas[0].nbytes * (world - 1) / (ms_arena_gather * 1e-3) / 1e9 if world > 1 else None,
         "allgather_ms": ms_gather, "chunk_bytes_per_rank": nbytes,
         "allgather_busbw_GBps": nbytes * (world - 1) / (ms_gather * 1e-3) / 1e9 if world > 1 else None,
-        "fused_maze_rollout": FUSED_MAZE, "gathered_envs": int(gathered["q_obs"].shape[1]) + int(gathered["m_obs"].shape[1]), "n_gpus": world}), flush=True)
+        "fused_maze_rollout": FUSED_MAZE, "gathered_envs": int(gathered["q_obs"].shape[0] * gathered["q_obs"].shape[2]) + int(gathered["m_obs"].shape[0] * gathered["m_obs"].shape[2]), "n_gpus": world}), flush=True)
+for a_ in peers:
+    a_.close()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from metagym_b200.rollout import all_gather_rollout, shard_range
+from metagym_b200.rollout import RolloutArena, all_gather_rollout, shard_range
 
 
 def test_shard_range_partitions_everything():
@@ -42,6 +42,22 @@ def _worker(rank, world, port, q):
     want = (torch.arange(T).view(T, 1, 1) * 1000 + ids.view(1, -1, 1) * 10 + torch.arange(D).view(1, 1, D)).float()
     ok = torch.equal(g["obs"], want) and torch.equal(g["rew"], want[..., 0].double())
     ok = ok and torch.equal(g["done"], want[..., 0] % 20 == 0) and g["done"].dtype == torch.bool and "act" not in g
+    # the same chunk through the single-allocation arena: one collective, zero-copy [world, T, n, ...] views
+    arena = RolloutArena({"obs": ((T, n_local, D), torch.float32), "rew": ((T, n_local), torch.float64),
+                          "done": ((T, n_local), torch.uint8), "act": ((T, n_local), torch.int32)}, "cpu")
+    arena["obs"].copy_(obs); arena["rew"].copy_(obs[..., 0].double()); arena["done"].copy_(chunk["done"])
+    arena["act"].copy_(env_ids.view(1, -1).expand(T, -1))
+    for async_op in (False, True):
+        views, work = arena.all_gather(async_op=async_op)
+        if work is not None:
+            work.wait()
+        ok = ok and tuple(views["obs"].shape) == (world, T, n_local, D)
+        ok = ok and views["obs"].untyped_storage().data_ptr() == views["act"].untyped_storage().data_ptr()
+        flat = RolloutArena.ordered(views)
+        ok = ok and torch.equal(flat["obs"], want) and torch.equal(flat["rew"], want[..., 0].double())
+        ok = ok and torch.equal(flat["done"].bool(), want[..., 0] % 20 == 0)
+        ok = ok and torch.equal(flat["act"], ids.view(1, -1).expand(T, -1).int())
+    ok = ok and arena.nbytes % 256 == 0 and arena.payload_bytes() == T * n_local * (D * 4 + 8 + 1 + 4)
     # max-over-ranks timing reduction used by bench.py
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

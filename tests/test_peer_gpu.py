@@ -1,0 +1,138 @@
+"""GPU tests of the kernel-side trajectory all-gather: output mirrors of the fused rollout kernels and the peer-memory
+(cudaIpc) entry points of the C ABI.  One GPU is enough: a mirror is just `pointer + delta`, here a second arena on the
+same device; the cross-process mapping is exercised with a child process on the same GPU.  The 2-GPU run over NVLink
+is scripts/bench_mixed.py (it asserts the peer-written arenas equal an NCCL all-gather of the same chunk)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def torch_mod(cuda_device):
+    import torch
+    return torch
+
+
+def _arenas(torch, fields, k):
+    from metagym_b200.rollout import RolloutArena
+    return [RolloutArena(fields, "cuda:0") for _ in range(k)]
+
+
+@pytest.mark.parametrize("n,task", [(1000, "velocity_control"), (77, "hovering_control")])
+def test_quad_rollout_mirrors_equal_primary(torch_mod, n, task):
+    torch = torch_mod
+    from metagym_b200 import BatchedQuadrotor
+    T = 12
+    D = 19 if task == "velocity_control" else 16
+    fields = {"obs": ((T, n, D), torch.float32), "act": ((T, n, 4), torch.float32), "rew": ((T, n), torch.float32),
+              "done": ((T, n), torch.uint8)}
+    a0, a1, a2, ref = _arenas(torch, fields, 4)
+
+    def run(arena, mirrors):
+        env = BatchedQuadrotor(task=task, num_envs=n, device=0, squeeze=False, auto_reset=True, nt=40, dt=0.01)
+        env.reset()
+        env.set_mirrors(mirrors)
+        for _ in range(2):                       # two chunks: the second overwrites, the state hand-over is the usual one
+            env.rollout(T, act_seed=5, out={"obs": arena["obs"], "rew": arena["rew"], "done": arena["done"],
+                                            "act": arena["act"]})
+        torch.cuda.synchronize()
+        env.close()
+
+    run(ref, [])
+    run(a0, [a1.buf.data_ptr() - a0.buf.data_ptr(), a2.buf.data_ptr() - a0.buf.data_ptr()])
+    assert torch.equal(a0.buf, ref.buf)          # mirroring does not change the primary outputs (bit-exact)
+    assert torch.equal(a1.buf, a0.buf) and torch.equal(a2.buf, a0.buf)
+    assert float(ref["obs"].abs().sum()) > 0
+
+
+@pytest.mark.parametrize("n,view_grid,task_type", [(300, 2, "SURVIVAL"), (77, 1, "ESCAPE")])
+def test_maze_rollout_mirrors_equal_primary(torch_mod, n, view_grid, task_type):
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, MazeTaskSampler
+    T, w = 40, 2 * view_grid + 1
+    fields = {"obs": ((T, n, w, w), torch.float32), "act": ((T, n), torch.int32), "rew": ((T, n), torch.float64),
+              "done": ((T, n), torch.uint8)}
+    a0, a1, ref = _arenas(torch, fields, 3)
+    rs = np.random.RandomState(3)
+    tasks = [MazeTaskSampler(n=9, allow_loops=True, crowd_ratio=0.3, rng=rs) for _ in range(5)]
+
+    def run(arena, mirrors):
+        env = BatchedMetaMaze2D(max_steps=25, task_type=task_type, view_grid=view_grid, num_envs=n, squeeze=False,
+                                auto_reset=True)
+        env.set_task(tasks)
+        env.reset()
+        env.set_mirrors(mirrors)
+        env.rollout(T, act_seed=2, out={"obs": arena["obs"], "rew": arena["rew"], "done": arena["done"],
+                                        "act": arena["act"]})
+        torch.cuda.synchronize()
+        env.close()
+
+    run(ref, [])
+    run(a0, [a1.buf.data_ptr() - a0.buf.data_ptr()])
+    assert torch.equal(a0.buf, ref.buf) and torch.equal(a1.buf, a0.buf)
+    assert int(ref["done"].sum()) > 0
+
+
+def test_mirror_argument_checks(torch_mod):
+    from metagym_b200 import BatchedQuadrotor, _lib
+    env = BatchedQuadrotor(num_envs=4, device=0, squeeze=False)
+    with pytest.raises(_lib.MgbError):
+        env.set_mirrors([8])                     # not a multiple of 16 bytes
+    with pytest.raises(_lib.MgbError):
+        env.set_mirrors([16] * 8)                # more than MGB_MAX_MIRRORS
+    env.set_mirrors([])
+    env.close()
+
+
+CHILD = r"""
+import ctypes, sys
+sys.path.insert(0, %r)
+import torch
+from metagym_b200 import _lib
+from metagym_b200.rollout import _RawDeviceMemory
+lib = _lib.load()
+handle = (ctypes.c_uint8 * 64)(*bytes.fromhex(sys.argv[1]))
+nbytes = int(sys.argv[2])
+torch.cuda.set_device(0)
+torch.zeros(1, device="cuda")
+q = ctypes.c_void_p()
+_lib.check(lib.mgb_peer_open(0, handle, ctypes.byref(q)))
+t = torch.as_tensor(_RawDeviceMemory(q.value, nbytes), device="cuda:0")
+assert int(t[:16].sum()) == 16 * 7, "parent's content not visible"
+t.copy_((torch.arange(nbytes, device="cuda") %% 251).to(torch.uint8))
+torch.cuda.synchronize()
+del t
+_lib.check(lib.mgb_peer_close(0, q))
+print("child ok")
+"""
+
+
+def test_peer_memory_export_open_across_processes(torch_mod):
+    """mgb_peer_alloc/export here, mgb_peer_open/close in a child process: the child sees our bytes and we see its."""
+    torch = torch_mod
+    from metagym_b200 import _lib
+    from metagym_b200.rollout import _RawDeviceMemory
+    lib = _lib.load()
+    nbytes = 1 << 20
+    p = ctypes.c_void_p()
+    _lib.check(lib.mgb_peer_alloc(0, nbytes, ctypes.byref(p)))
+    t = torch.as_tensor(_RawDeviceMemory(p.value, nbytes), device="cuda:0")
+    assert int(t.sum()) == 0                     # mgb_peer_alloc zero-fills
+    t.fill_(7)
+    torch.cuda.synchronize()
+    handle = (ctypes.c_uint8 * 64)()
+    _lib.check(lib.mgb_peer_export(0, p, handle))
+    r = subprocess.run([sys.executable, "-c", CHILD % ROOT, bytes(handle).hex(), str(nbytes)], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "child ok" in r.stdout, r.stdout + r.stderr
+    want = (torch.arange(nbytes, device="cuda") % 251).to(torch.uint8)
+    assert torch.equal(t, want)
+    del t
+    _lib.check(lib.mgb_peer_free(0, p))
