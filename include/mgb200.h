@@ -254,6 +254,12 @@ int mgb_peer_open(int device, const uint8_t handle[MGB_PEER_HANDLE_BYTES], void 
 int mgb_peer_close(int device, void *ptr);
 int mgb_quad_set_mirrors(mgb_quad *h, int count, const int64_t *byte_delta);
 int mgb_maze_set_mirrors(mgb_maze *h, int count, const int64_t *byte_delta);
+/* NVSwitch multicast variant: the rollout outputs are stored ONLY at `ptr + byte_delta` with multimem.st, where
+ * byte_delta = (multicast mapping base - local arena base) of a multicast object every rank has bound its arena to
+ * (cuMulticast*; torch.distributed._symmetric_memory does that plumbing).  The switch replicates each store into every
+ * rank's arena, this rank's included.  0 switches it off.  Needs num_envs % 4 == 0. */
+int mgb_quad_set_multicast(mgb_quad *h, int64_t byte_delta);
+int mgb_maze_set_multicast(mgb_maze *h, int64_t byte_delta);
 
 #ifdef __cplusplus
 }

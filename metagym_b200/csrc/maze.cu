@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_kernel(const __grid_constan
 
 // T MetaMaze2D steps in one launch: the agent (cell, step counter, life) stays in registers, food stamps stay in their
 // SoA slots, each step's observation tile of the CTA leaves through double-buffered shared memory + one bulk store.
-template <bool MIRROR>
+template <int XM>   // 0 plain, 1 peer mirrors, 2 multicast-only stores (see quad_rollout_kernel)
 __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid_constant__ MazeConst c,
                                                                     const __grid_constant__ MazeArgs a)
 {
@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
         float *tile = tile2d + (size_t)(t & 1) * k2dThreads * D;
         if (threadIdx.x == 0) mgb_bulk_wait_read<1>();      // the store issued two steps ago has read this tile
         __syncthreads();
+        uint32_t done_byte = 0;
         if (active) {
             int action;
             if (a.act) action = a.act[(int64_t)t * a.n + e];
@@ -405,8 +406,9 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
                                                              a.t_base + (uint32_t)t, MGB_STREAM_ACTION), akey);
                 action = (int)(r.x >> 30);                   // uniform over {0, 1, 2, 3}
                 if (a.act_out) {
-                    a.act_out[(int64_t)t * a.n + e] = action;
-                    if (MIRROR) mgb_mirror_store(a.mir, a.act_out + (int64_t)t * a.n + e, (int32_t)action);
+                    if (XM == 2) mgb_mc_st(mgb_shift(a.act_out + (int64_t)t * a.n + e, a.mir.delta[0]), (int32_t)action);
+                    else a.act_out[(int64_t)t * a.n + e] = action;
+                    if (XM == 1) mgb_mirror_store(a.mir, a.act_out + (int64_t)t * a.n + e, (int32_t)action);
                 }
             }
             double reward;
@@ -414,12 +416,14 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
             maze_logic(c, blob, eaten, a.n_pad, s, action, reward, done);
             if (done && a.auto_reset) env_reset(c, blob, eaten, a.n_pad, s);
             if (a.rew) {
-                a.rew[(int64_t)t * a.n + e] = reward;
-                if (MIRROR) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
+                if (XM == 2) mgb_mc_st(mgb_shift(a.rew + (int64_t)t * a.n + e, a.mir.delta[0]), reward);
+                else a.rew[(int64_t)t * a.n + e] = reward;
+                if (XM == 1) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
             }
-            if (a.done) {
+            done_byte = (uint32_t)done;
+            if (a.done && XM != 2) {
                 a.done[(int64_t)t * a.n + e] = (uint8_t)done;
-                if (MIRROR) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
+                if (XM == 1) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
             }
             if (a.obs) {
                 float *row = tile + threadIdx.x * D;
@@ -439,7 +443,14 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
                 if (c.task_type == MGB_MAZE_SURVIVAL) row[g * W + g] = (float)s.life;
             }
         }
-        if (a.obs) {
+        if (XM == 2) {
+            if (a.done) mgb_mc_st_bytes(mgb_shift(a.done + (int64_t)t * a.n + e, a.mir.delta[0]), done_byte, active);
+            if (a.obs) {
+                __syncthreads();
+                mgb_mc_copy_tile(mgb_shift(reinterpret_cast<float *>(a.obs) + ((int64_t)t * a.n + e0) * D, a.mir.delta[0]),
+                                 tile, (uint32_t)rows * (uint32_t)D * 4u);
+            }
+        } else if (a.obs) {
             float *dst = reinterpret_cast<float *>(a.obs) + ((int64_t)t * a.n + e0) * D;
             const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
             if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
@@ -447,14 +458,14 @@ __global__ void __launch_bounds__(k2dThreads) maze2d_rollout_kernel(const __grid
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     mgb_bulk_store(dst, tile, bytes);
-                    if (MIRROR) mgb_mirror_bulk_store(a.mir, dst, tile, bytes);
+                    if (XM == 1) mgb_mirror_bulk_store(a.mir, dst, tile, bytes);
                     mgb_bulk_commit();
                 }
             } else {
                 __syncthreads();
                 for (int i = threadIdx.x; i < rows * D; i += blockDim.x) {
                     dst[i] = tile[i];
-                    if (MIRROR) mgb_mirror_store(a.mir, dst + i, tile[i]);
+                    if (XM == 1) mgb_mirror_store(a.mir, dst + i, tile[i]);
                 }
             }
         }
@@ -1730,11 +1741,17 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
     a.mir = h->mir;
     const unsigned blocks = (unsigned)((h->n + k2dThreads - 1) / k2dThreads);
     if (sm > 48 * 1024) {
-        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
-    if (h->mir.count > 0) maze2d_rollout_kernel<true><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
-    else maze2d_rollout_kernel<false><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+    if (h->mir.count == MGB_MIRROR_MULTICAST) {
+        MGB_REQUIRE(h->n % 4 == 0, "multicast outputs need num_envs % 4 == 0");
+        MGB_REQUIRE((((uintptr_t)done_dev | (uintptr_t)obs_dev | (uintptr_t)act_out_dev) & 3) == 0 && ((uintptr_t)rew_dev & 7) == 0,
+                    "multicast outputs must be 4-byte (rewards: 8-byte) aligned");
+        maze2d_rollout_kernel<2><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+    } else if (h->mir.count > 0) maze2d_rollout_kernel<1><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+    else maze2d_rollout_kernel<0><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
     MGB_CUDA(cudaGetLastError());
     h->t_base += (uint32_t)T;
     h->launches += 1;
@@ -1751,6 +1768,16 @@ extern "C" int mgb_maze_set_mirrors(mgb_maze *h, int count, const int64_t *byte_
         m.delta[i] = byte_delta[i];
     }
     m.count = count;
+    h->mir = m;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_set_multicast(mgb_maze *h, int64_t byte_delta)
+{
+    MGB_REQUIRE(h, "null handle");
+    MGB_REQUIRE((byte_delta & 15) == 0, "multicast delta must be a multiple of 16 bytes");
+    MgbMirrors m = {};
+    if (byte_delta != 0) { m.count = MGB_MIRROR_MULTICAST; m.delta[0] = byte_delta; }
     h->mir = m;
     return MGB_OK;
 }

@@ -108,7 +108,8 @@ template <int N> __device__ __forceinline__ void mgb_bulk_wait()
 // the remote stores drain through NVLink/NVSwitch while the next env-step integrates.
 // ---------------------------------------------------------------------------------------------------------------
 struct MgbMirrors {
-    int count;
+    int count;                        // > 0: peer mirrors; MGB_MIRROR_MULTICAST: delta[0] = multicast base - local base
+#define MGB_MIRROR_MULTICAST (-1)
     int64_t delta[MGB_MAX_MIRRORS];   // bytes
 };
 template <typename T> __device__ __forceinline__ void mgb_mirror_store(const MgbMirrors &m, T *p, const T v)
@@ -119,6 +120,45 @@ template <typename T> __device__ __forceinline__ void mgb_mirror_store(const Mgb
 __device__ __forceinline__ void mgb_mirror_bulk_store(const MgbMirrors &m, void *gdst, const void *ssrc, uint32_t bytes)
 {
     for (int i = 0; i < m.count; ++i) mgb_bulk_store(reinterpret_cast<char *>(gdst) + m.delta[i], ssrc, bytes);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NVSwitch multicast stores (NVLS): ONE store to a multicast address is replicated by the switch into the bound memory of
+// every GPU of the group, so an all-gather costs each GPU its own bytes once instead of (world-1) times.  The address
+// must come from a multicast mapping (cuMulticast*; torch's symmetric memory does that plumbing) and may only be touched
+// with multimem.* instructions.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mgb_mc_st(float *p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void mgb_mc_st(double *p, double v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void mgb_mc_st(uint32_t *p, uint32_t v) { asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void mgb_mc_st(int32_t *p, int32_t v) { asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void mgb_mc_st(float4 *p, float4 v)
+{
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+template <typename T> __device__ __forceinline__ T *mgb_shift(T *p, int64_t bytes)
+{
+    return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + bytes);
+}
+// whole-CTA copy of a shared-memory tile to a multicast address (call after __syncthreads())
+__device__ __forceinline__ void mgb_mc_copy_tile(float *mc_dst, const float *tile, uint32_t bytes)
+{
+    if ((bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(mc_dst) & 15u) == 0)) {
+        const float4 *src = reinterpret_cast<const float4 *>(tile);
+        float4 *dst = reinterpret_cast<float4 *>(mc_dst);
+        for (uint32_t i = threadIdx.x; i < bytes / 16u; i += blockDim.x) mgb_mc_st(dst + i, src[i]);
+    } else {
+        for (uint32_t i = threadIdx.x; i < bytes / 4u; i += blockDim.x) mgb_mc_st(mc_dst + i, tile[i]);
+    }
+}
+// one byte per lane -> 32-bit multicast stores by every fourth lane (all 32 lanes must call; idx % 4 == lane % 4)
+__device__ __forceinline__ void mgb_mc_st_bytes(uint8_t *mc_p, uint32_t byte, bool valid)
+{
+    const uint32_t b1 = __shfl_down_sync(0xffffffffu, byte, 1), b2 = __shfl_down_sync(0xffffffffu, byte, 2),
+                   b3 = __shfl_down_sync(0xffffffffu, byte, 3);
+    if (valid && (threadIdx.x & 3) == 0)
+        mgb_mc_st(reinterpret_cast<uint32_t *>(mc_p), byte | (b1 << 8) | (b2 << 16) | (b3 << 24));
 }
 
 // mbarrier + global -> smem bulk load

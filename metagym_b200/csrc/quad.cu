@@ -875,7 +875,9 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __
 // T env.step()s in one launch: the state never leaves registers; per step the kernel reads 16 B of action (or draws
 // it) and writes obs/reward/done.  Observation tiles are double-buffered so the bulk store of step t overlaps the
 // arithmetic of step t+1.
-template <bool SIMPLE, bool MIRROR>
+// XM: 0 = outputs stored once; 1 = also at every peer mirror (NVLink P2P); 2 = stored ONLY through the multicast
+// mapping (multimem.st: the switch replicates them into every rank's arena, this rank's included)
+template <bool SIMPLE, int XM>
 __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_constant__ QuadConst c,
                                                                 const __grid_constant__ QuadArgs a)
 {
@@ -903,6 +905,7 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
         // the bulk store issued two steps ago must have finished READING this tile before we overwrite it
         if (threadIdx.x == 0) mgb_bulk_wait_read<1>();
         __syncthreads();
+        uint32_t done_byte = 0;
         if (active) {
             float4 act;
             if (a.act) {
@@ -917,8 +920,9 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                                   fmaf(span, mgb_u01(r.z), c.vmin), fmaf(span, mgb_u01(r.w), c.vmin));
                 if (a.act_out) {
                     float4 *ap = reinterpret_cast<float4 *>(a.act_out) + (int64_t)t * a.n + e;
-                    *ap = act;
-                    if (MIRROR) mgb_mirror_store(a.mir, ap, act);
+                    if (XM == 2) mgb_mc_st(mgb_shift(ap, a.mir.delta[0]), act);
+                    else *ap = act;
+                    if (XM == 1) mgb_mirror_store(a.mir, ap, act);
                 }
             }
             s.ct += 1;
@@ -937,12 +941,14 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                 adjugate(s.R, adj, id);
             }
             if (a.rew) {
-                a.rew[(int64_t)t * a.n + e] = reward;
-                if (MIRROR) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
+                if (XM == 2) mgb_mc_st(mgb_shift(a.rew + (int64_t)t * a.n + e, a.mir.delta[0]), reward);
+                else a.rew[(int64_t)t * a.n + e] = reward;
+                if (XM == 1) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
             }
-            if (a.done) {
+            done_byte = (uint32_t)done;
+            if (a.done && XM != 2) {
                 a.done[(int64_t)t * a.n + e] = (uint8_t)done;
-                if (MIRROR) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
+                if (XM == 1) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
             }
             if (a.obs) {
                 float *trow = tile + threadIdx.x * D;
@@ -951,8 +957,16 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                 if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
             }
         }
-        if (a.obs) {
-            if (MIRROR) publish_tile_mirrored(a.mir, a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
+        if (XM == 2) {
+            // n % 4 == 0 (checked on the host): the four done bytes of lanes 4k..4k+3 are all valid or all not
+            if (a.done) mgb_mc_st_bytes(mgb_shift(a.done + (int64_t)t * a.n + e, a.mir.delta[0]), done_byte, active);
+            if (a.obs) {
+                __syncthreads();
+                mgb_mc_copy_tile(mgb_shift(a.obs + ((int64_t)t * a.n + e0) * D, a.mir.delta[0]), tile,
+                                 (uint32_t)rows * (uint32_t)D * 4u);
+            }
+        } else if (a.obs) {
+            if (XM == 1) publish_tile_mirrored(a.mir, a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
             else publish_tile(a.obs + (int64_t)t * a.n * D, tile, e0, rows, D);
         }
     }
@@ -1416,12 +1430,18 @@ extern "C" int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, ui
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
     const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
     a.mir = h->mir;
-    if (h->mir.count > 0) {
-        if (h->c.simple) quad_rollout_kernel<true, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
-        else quad_rollout_kernel<false, true><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    if (h->mir.count == MGB_MIRROR_MULTICAST) {
+        MGB_REQUIRE(h->n % 4 == 0, "multicast outputs need num_envs % 4 == 0");
+        MGB_REQUIRE((((uintptr_t)done_dev | (uintptr_t)rew_dev | (uintptr_t)obs_dev) & 3) == 0 && ((uintptr_t)act_out_dev & 15) == 0,
+                    "multicast outputs must be 4-byte (actions: 16-byte) aligned");
+        if (h->c.simple) quad_rollout_kernel<true, 2><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+        else quad_rollout_kernel<false, 2><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+    } else if (h->mir.count > 0) {
+        if (h->c.simple) quad_rollout_kernel<true, 1><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+        else quad_rollout_kernel<false, 1><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
     } else {
-        if (h->c.simple) quad_rollout_kernel<true, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
-        else quad_rollout_kernel<false, false><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+        if (h->c.simple) quad_rollout_kernel<true, 0><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
+        else quad_rollout_kernel<false, 0><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(h->c, a);
     }
     MGB_CUDA(cudaGetLastError());
     h->t_base += (uint32_t)T;
@@ -1439,6 +1459,16 @@ extern "C" int mgb_quad_set_mirrors(mgb_quad *h, int count, const int64_t *byte_
         m.delta[i] = byte_delta[i];
     }
     m.count = count;
+    h->mir = m;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_set_multicast(mgb_quad *h, int64_t byte_delta)
+{
+    MGB_REQUIRE(h, "null handle");
+    MGB_REQUIRE((byte_delta & 15) == 0, "multicast delta must be a multiple of 16 bytes");
+    MgbMirrors m = {};
+    if (byte_delta != 0) { m.count = MGB_MIRROR_MULTICAST; m.delta[0] = byte_delta; }
     h->mir = m;
     return MGB_OK;
 }

@@ -293,6 +293,10 @@ class BatchedMetaMaze2D(_BatchedMazeBase):
         d = np.ascontiguousarray(np.asarray(list(byte_deltas), dtype=np.int64))
         _lib.check(self._lib.mgb_maze_set_mirrors(self._h, int(d.size), _lib.ptr(d) if d.size else None))
 
+    def set_multicast(self, byte_delta):
+        """rollout() outputs go through an NVSwitch multicast mapping at `pointer + byte_delta` (rollout.MulticastArena)."""
+        _lib.check(self._lib.mgb_maze_set_multicast(self._h, int(byte_delta)))
+
     def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):
         """T steps in one launch.  actions: [T,N] int32 CUDA tensor or None (device-drawn uniform {0..3}).
         Returns dict(obs [T,N,2g+1,2g+1] f32, rew [T,N] f64, done [T,N] u8, act [T,N] i32 or None)."""

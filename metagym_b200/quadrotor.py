@@ -303,6 +303,11 @@ class BatchedQuadrotor(object):
         d = np.ascontiguousarray(np.asarray(list(byte_deltas), dtype=np.int64))
         _lib.check(self._lib.mgb_quad_set_mirrors(self._h, int(d.size), _lib.ptr(d) if d.size else None))
 
+    def set_multicast(self, byte_delta):
+        """rollout() outputs are stored through an NVSwitch multicast mapping at `pointer + byte_delta`
+        (rollout.MulticastArena.multicast_delta); 0 switches it off."""
+        _lib.check(self._lib.mgb_quad_set_multicast(self._h, int(byte_delta)))
+
     @property
     def fail_code(self):
         """[N] int32: MGB_FAIL_* of the last step (the reference raises instead, quadrotorsim.py:212-221)."""

@@ -180,13 +180,16 @@ class PeerArena(RolloutArena):
             self.views[k] = self.buf[o:o + nb].view(dt).view(shape)
             self.gathered[k] = recv[:, o:o + nb].view(dt).view((self.world,) + shape)
 
-    def sync(self):
-        """Stream-ordered rendezvous: returns (on the stream) once every rank's kernels enqueued so far have finished,
-        i.e. all peer stores of this chunk have landed here.  The data never goes through NCCL."""
+    def sync(self, async_op=False):
+        """Stream-ordered rendezvous: complete (on the stream) once every rank's kernels enqueued so far have finished,
+        i.e. all peer stores of this chunk have landed here.  The data never goes through NCCL.
+        async_op=True returns (gathered, work): the rendezvous runs beside the next chunk's rollout; call work.wait()
+        before reading `gathered`; rotate >= 4 arenas then (scripts/bench_mixed.py spells out the ordering argument)."""
+        work = None
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self._flag, group=self.group)
-        return self.gathered
+            work = dist.all_reduce(self._flag, group=self.group, async_op=async_op)
+        return (self.gathered, work) if async_op else self.gathered
 
     def close(self):
         if self._base is None:
@@ -202,6 +205,47 @@ class PeerArena(RolloutArena):
             dist.barrier(group=self.group)        # nobody frees memory a peer still has mapped
         self._lib.mgb_peer_free(self.device_index, self._base)
         self._base = None
+
+
+class MulticastArena(RolloutArena):
+    """PeerArena's sibling for NVSwitch multicast (NVLS): the receive arena [world][arena] of every rank is bound to ONE
+    multicast object, and the rollout kernels store each output once, with multimem.st, at
+    `pointer + multicast_delta`; the switch replicates the store into all ranks' arenas (this rank's included), so the
+    all-gather costs every GPU its own chunk bytes of NVLink egress instead of (world-1) times that.
+
+    Allocation, handle exchange and the cuMulticast* binding are torch.distributed._symmetric_memory's (plumbing);
+    `env.set_multicast(arena.multicast_delta)`, `env.rollout(T, out=arena.views...)`, `arena.sync()` as for PeerArena."""
+
+    def __init__(self, fields, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        dev = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self._layout(fields)
+        self._recv = symm.empty(self.world * self.nbytes, dtype=torch.uint8, device=dev)
+        self._recv.zero_()
+        self._handle = symm.rendezvous(self._recv, self.group)
+        mc = int(self._handle.multicast_ptr)
+        if mc == 0:
+            raise RuntimeError("MulticastArena: this GPU group has no NVSwitch multicast support")
+        self.multicast_delta = mc - int(self._recv.data_ptr())
+        recv = self._recv.view(self.world, self.nbytes)
+        self.buf = recv[self.rank]
+        self.views, self.gathered = {}, {}
+        for k, (shape, dt, nb) in self.fields.items():
+            o = self.offsets[k]
+            self.views[k] = self.buf[o:o + nb].view(dt).view(shape)
+            self.gathered[k] = recv[:, o:o + nb].view(dt).view((self.world,) + shape)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+
+    def sync(self, async_op=False):
+        import torch.distributed as dist
+        work = dist.all_reduce(self._flag, group=self.group, async_op=async_op)
+        return (self.gathered, work) if async_op else self.gathered
 
 
 def rollout_bytes(chunk):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from metagym_b200 import BatchedMetaMaze2D, BatchedQuadrotor, MazeTaskSampler
-from metagym_b200.rollout import PeerArena, RolloutArena, all_gather_rollout, rollout_bytes, shard_range
+from metagym_b200.rollout import MulticastArena, PeerArena, RolloutArena, all_gather_rollout, rollout_bytes, shard_range
 
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
 torch.cuda.set_device(local)
@@ -149,8 +149,80 @@ if world > 1:
 for _ in range(3):
     collect_peer()
 ms_peer = timed(collect_peer, CHUNKS * 2)
+# four arenas in rotation, rendezvous asynchronous: chunk k+1 rolls out while the rendezvous of chunk k completes.
+# Stream order per rank: rollout(k), [rendezvous(k) on NCCL's stream], wait rendezvous(k-1), consume(k-1), rollout(k+1)...
+# rendezvous(k-1) complete  =>  every rank has consumed chunk k-3  =>  rollout(k+1) may overwrite the arena of chunk k-3.
+while len(peers) < 4:
+    peers.append(PeerArena(FIELDS, dev))
+works = [None] * 4
+
+
+def collect_peer_async():
+    i = ptick[0] % 4
+    ptick[0] += 1
+    ar = peers[i]
+    quad.set_mirrors(ar.mirrors)
+    maze.set_mirrors(ar.mirrors)
+    collect(ar.views)
+    _, works[i] = ar.sync(async_op=True)
+    j = (i - 1) % 4
+    if works[j] is not None:
+        works[j].wait()
+        works[j] = None
+        gathered.update(peers[j].gathered)      # the learner would read chunk k-1 here
+
+
+for _ in range(6):
+    collect_peer_async()
+ms_peer_async = timed(collect_peer_async, CHUNKS * 3)
+for w_ in works:
+    if w_ is not None:
+        w_.wait()
+torch.cuda.synchronize(dev)
 quad.set_mirrors([])
 maze.set_mirrors([])
+# ---- NVSwitch multicast: each output stored once with multimem.st, replicated by the switch into every rank's arena
+ms_mc, mc_ok, mc_err = None, None, None
+if world > 1 and os.environ.get("MIXED_MULTICAST", "1") != "0":
+    try:
+        mcs = [MulticastArena(FIELDS, dev) for _ in range(4)]
+    except Exception as e:                       # no NVLS on this box: report, do not fail the other measurements
+        mcs, mc_err = None, repr(e)[:200]
+    if mcs:
+        mtick = [0]
+        mworks = [None] * 4
+
+        def collect_mc():
+            i = mtick[0] % 4
+            mtick[0] += 1
+            ar = mcs[i]
+            quad.set_multicast(ar.multicast_delta)
+            maze.set_multicast(ar.multicast_delta)
+            collect(ar.views)
+            _, mworks[i] = ar.sync(async_op=True)
+            j = (i - 1) % 4
+            if mworks[j] is not None:
+                mworks[j].wait()
+                mworks[j] = None
+                gathered.update(mcs[j].gathered)
+
+        collect_mc()
+        mworks[0].wait()
+        mworks[0] = None
+        torch.cuda.synchronize(dev)
+        check = torch.empty(world * mcs[0].nbytes, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(check, mcs[0].buf.contiguous())
+        mc_ok = bool(torch.equal(check, mcs[0]._recv)) and float(mcs[0].gathered["q_obs"].abs().sum()) > 0
+        assert mc_ok, "multicast-written arena differs from the NCCL all-gather"
+        for _ in range(7):
+            collect_mc()
+        ms_mc = timed(collect_mc, CHUNKS * 3)
+        for w_ in mworks:
+            if w_ is not None:
+                w_.wait()
+        torch.cuda.synchronize(dev)
+        quad.set_multicast(0)
+        maze.set_multicast(0)
 ms_gather = timed(lambda: all_gather_rollout(chunk, scratch=scratch), CHUNKS)
 steps = (N_QUAD + N_MAZE) * world * T
 nbytes = rollout_bytes(chunk)
@@ -163,6 +235,9 @@ if rank == 0:
         "env_steps_per_s_with_arena_gather": steps / (ms_arena * 1e-3),
         "env_steps_per_s_pipelined_arena_gather": steps / (ms_pipe * 1e-3),
         "env_steps_per_s_kernel_side_gather": steps / (ms_peer * 1e-3), "kernel_side_gather_equals_nccl": peer_ok,
+        "env_steps_per_s_kernel_side_gather_async_rendezvous": steps / (ms_peer_async * 1e-3),
+        "env_steps_per_s_multicast_gather": steps / (ms_mc * 1e-3) if ms_mc else None,
+        "multicast_gather_equals_nccl": mc_ok, "multicast_error": mc_err,
         "arena_allgather_ms": ms_arena_gather,
         "arena_allgather_busbw_GBps": arenas[0].nbytes * (world - 1) / (ms_arena_gather * 1e-3) / 1e9 if world > 1 else None,
         "allgather_ms": ms_gather, "chunk_bytes_per_rank": nbytes,
