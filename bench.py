@@ -176,6 +176,20 @@ def maze_extras(torch, dev, peak):
         out[name] = {"value": n / us * 1e6, "unit": "env-steps/s", "us_per_step": us,
                      "algorithmic_bytes_per_env_step": nbytes, "frac_of_measured_hbm": n * nbytes / us * 1e-3 / peak,
                      "parity": "bit-exact vs reference golden episodes (tests/test_maze_gpu.py)"}
+        if hasattr(env, "rollout"):          # MetaMaze2D: T steps per launch, device-drawn uniform actions
+            T = 32
+            bufs = env.rollout(T, act_seed=3, want_actions=True)
+            for _ in range(2):
+                env.rollout(T, act_seed=3, out=bufs)
+            e0.record()
+            for _ in range(8):
+                env.rollout(T, act_seed=3, out=bufs)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / (8 * T)
+            out[name + "_fused_rollout"] = {"value": n / us * 1e6, "unit": "env-steps/s", "us_per_step": us, "T": T,
+                                            "frac_of_measured_hbm": n * nbytes / us * 1e-3 / peak,
+                                            "parity": "bit-exact vs T single steps (tests/test_maze_gpu.py)"}
         env.close()
     return out
 
@@ -339,6 +353,50 @@ def main():
             extras["rollout_allgather"] = {"ms": msg, "bytes_per_rank": nbytes,
                                            "busbw_GBps": nbytes * (world - 1) / (msg * 1e-3) / 1e9,
                                            "gathered_envs": int(gathered["obs"].shape[1])}
+            # ---- the same exchange done by the rollout kernel itself: every output is also stored into the other ranks'
+            # receive arenas over NVLink (PeerArena); the only cross-rank call left is a one-element rendezvous
+            arenas = []
+            try:
+                from metagym_b200.rollout import PeerArena
+                fields = {"obs": ((G, n, D), torch.float32), "act": ((G, n, 4), torch.float32),
+                          "rew": ((G, n), torch.float32), "done": ((G, n), torch.uint8)}
+                arenas = [PeerArena(fields, dev) for _ in range(2)]
+                tick = [0]
+
+                def chunk_peer():
+                    ar = arenas[tick[0] & 1]
+                    tick[0] += 1
+                    env.set_mirrors(ar.mirrors)
+                    env.rollout(G, actions=None, act_seed=3, out=ar.views)
+                    return ar.sync()
+
+                for _ in range(3):
+                    views = chunk_peer()
+                barrier()
+                reps = max(4, K // G)
+                e0.record()
+                for _ in range(reps):
+                    views = chunk_peer()
+                e1.record()
+                barrier()
+                msp = max_over_ranks(e0.elapsed_time(e1))
+                own = bool(torch.equal(views["obs"][rank], arenas[(tick[0] - 1) & 1]["obs"]))
+                extras["fused_rollout_peer_gather"] = {
+                    "value": n * world * reps * G / (msp * 1e-3), "unit": "env-steps/s", "T": G,
+                    "chunk_bytes_per_rank": arenas[0].payload_bytes(),
+                    "ingress_GBps_per_gpu": arenas[0].payload_bytes() * (world - 1) * reps / (msp * 1e-3) / 1e9,
+                    "gathered_shape": list(views["obs"].shape), "own_slot_ok": own,
+                    "note": "quad_rollout_kernel<.,1>: outputs stored into every rank's arena by the kernel (NVLink "
+                            "peer stores), rendezvous = 1-element all-reduce; no NCCL on the data"}
+            except Exception as ex:            # reported, never fatal for the headline numbers
+                extras["fused_rollout_peer_gather"] = {"error": repr(ex)[:300]}
+            finally:
+                env.set_mirrors([])
+                for ar in arenas:
+                    try:
+                        ar.close()
+                    except Exception:
+                        pass
         env.close()
         del env, obs, rew, done, acts
         torch.cuda.empty_cache()
