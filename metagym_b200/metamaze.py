@@ -41,21 +41,112 @@ class _DSU(object):
         return True
 
 
+def _carve_like_reference(n, allow_loops, crowd_ratio, py):
+    """The wall-removal process of maze_task.py:84-151, restated on arrays, consuming `py` (a `random.Random` or the
+    `random` module) call for call like the reference: one `shuffle` of the walls still standing per round (in their
+    row-major order of creation), then walls are examined in shuffled order until one (a) joins different regions
+    without closing a loop, (b) joins regions and closes a loop (only with allow_loops), or (c) once a single region is
+    left, wins a `random() < 0.2` draw.  A round that runs out of walls takes the last one examined (reference quirk:
+    the loop variables simply survive the for statement); a chosen wall with no open neighbour is skipped.
+    Rounds continue while more than one region exists or (allow_loops and interior walls exceed crowd_ratio)."""
+    walls = np.ones((n, n), dtype=np.int32)
+    walls[1:n:2, 1:n:2] = 0
+    region = np.full((n, n), -1, dtype=np.int64)
+    rooms = [(i, j) for i in range(1, n - 1) for j in range(1, n - 1) if walls[i, j] == 0]
+    for k, (i, j) in enumerate(rooms):
+        region[i, j] = k
+    members = {k: [c] for k, c in enumerate(rooms)}
+    standing = [(i, j) for i in range(1, n - 1) for j in range(1, n - 1) if walls[i, j] > 0]
+    limit = (n - 2) * (n - 2) * crowd_ratio
+    while len(members) > 1 or (allow_loops and len(standing) > limit):
+        order = list(standing)
+        py.shuffle(order)
+        if not order:
+            raise RuntimeError("maze sampler: no wall left to remove")
+        for i, j in order:
+            ids = [int(region[a, b]) for a, b in ((i - 1, j), (i + 1, j), (i, j - 1), (i, j + 1)) if walls[a, b] < 1]
+            keep = min(ids) if ids else -1
+            others = set(ids) - {keep}
+            repeats = max([ids.count(v) for v in ids] + [1])
+            if others and repeats < 2:
+                break
+            if others and repeats > 1 and allow_loops:
+                break
+            if allow_loops and len(members) < 2 and py.random() < 0.2:
+                break
+        if keep < 0:
+            continue
+        walls[i, j] = 0
+        region[i, j] = keep
+        members[keep].append((i, j))
+        standing.remove((i, j))
+        for o in others:
+            for a, b in members[o]:
+                region[a, b] = keep
+            members[keep].extend(members.pop(o))
+    return walls
+
+
+def _sample_task_reference_streams(n, allow_loops, cell_size, wall_height, agent_height, step_reward, goal_reward,
+                                   food_reward, initial_life, max_life, food_density, food_interval, crowd_ratio,
+                                   n_texts, py, npr):
+    """maze_task.py:41-190 with the reference's exact random-stream usage: with py = `random` and npr = `numpy.random`
+    after `random.seed(s); numpy.random.seed(s)` (or `random.Random(s)` / `numpy.random.RandomState(s)`) the task is
+    the reference's task for that seed, array for array (tests/test_maze_sampler.py, fixtures recorded from the
+    unmodified reference)."""
+    texts = npr.randint(1, n_texts, size=(n, n))
+    m = (n - 1) // 2
+    sx = py.randint(0, m - 1) * 2 + 1
+    sy = py.randint(0, m - 1) * 2 + 1
+    goal = (n - 2, n - 2)
+    for _ in range(m):                 # the reference's `break` leaves the inner loop only: m rows of up to m draws,
+        for _ in range(m):             # the LAST far-enough candidate of a row that found one wins
+            ex = py.randint(0, m - 1) * 2 + 1
+            ey = py.randint(0, m - 1) * 2 + 1
+            if np.sqrt((ex - sx) ** 2 + (ey - sy) ** 2) > 0.45 * n:
+                goal = (ex, ey)
+                break
+    walls = _carve_like_reference(n, allow_loops, crowd_ratio, py)
+    inner = texts[1:-1, 1:-1]
+    inner[walls[1:-1, 1:-1] < 1] = 0
+    def_goal_reward = -np.sqrt(n) * n * step_reward if goal_reward is None else goal_reward
+    assert def_goal_reward > 0, "goal reward must be > 0"
+    food = np.clip(npr.rand(n, n) * food_reward, 0.10, food_reward)
+    food *= 1.0 - walls
+    expected = (n - 1) * (n - 1) * food_density
+    while np.sum(food) > expected:
+        food *= (npr.rand(n, n) < 0.90).astype("float32")
+    interval = food_interval * (food > 1.0e-3).astype("int32")
+    return TaskConfig(start=(sx, sy), goal=goal, cell_walls=walls, cell_texts=texts, cell_size=cell_size,
+                      step_reward=step_reward, goal_reward=def_goal_reward, wall_height=wall_height,
+                      agent_height=agent_height, initial_life=initial_life, max_life=max_life, food_rewards=food,
+                      food_interval=interval)
+
+
 def MazeTaskSampler(n=15, allow_loops=True, cell_size=2.0, wall_height=3.2, agent_height=1.6, step_reward=-0.01,
                     goal_reward=None, food_reward=0.50, initial_life=1.0, max_life=2.0, food_density=0.010,
-                    food_interval=100, crowd_ratio=0.0, n_texts=7, rng=None):
+                    food_interval=100, crowd_ratio=0.0, n_texts=7, rng=None, seed=None, py_random=None, np_random=None):
     """Random maze task with the reference sampler's schema, defaults and constraints (maze_task.py:41-190).
 
-    Host-side and once per task, so it is written for clarity: rooms sit on odd coordinates, a random spanning tree
-    (Kruskal over the room lattice) connects them, and with `allow_loops` further interior walls are knocked out
-    until at most `crowd_ratio` of the interior is wall.  It draws from its own RandomState, so it reproduces the
-    reference's DISTRIBUTION of mazes (size, connectivity, wall density, food statistics), not its exact samples;
-    feed tasks from the reference sampler through `set_task` when sample-level identity matters.
+    Default (no `rng`): the reference's procedure replayed on the reference's random streams - the global `random` and
+    `numpy.random` modules, or `py_random` / `np_random` instances, or both seeded from `seed` - so that
+    `random.seed(s); numpy.random.seed(s); MazeTaskSampler(...)` returns exactly the task the reference returns.
+
+    With `rng` (a numpy RandomState): a faster sampler of the same DISTRIBUTION family (rooms on odd coordinates, a
+    random spanning tree by Kruskal over the room lattice, then with `allow_loops` interior walls are knocked out until
+    at most `crowd_ratio` of the interior is wall); not sample-identical to the reference.
     """
     assert n > 6, "Minimum required cells are 7"
     assert n % 2 != 0, "Cell Numbers can only be odd"
     assert step_reward < 0, "step_reward must be < 0"
-    rs = rng if rng is not None else np.random.RandomState()
+    if rng is None:
+        import random as _pyrandom
+        py = py_random if py_random is not None else (_pyrandom.Random(seed) if seed is not None else _pyrandom)
+        npr = np_random if np_random is not None else (np.random.RandomState(seed) if seed is not None else np.random)
+        return _sample_task_reference_streams(n, allow_loops, cell_size, wall_height, agent_height, step_reward,
+                                              goal_reward, food_reward, initial_life, max_life, food_density,
+                                              food_interval, crowd_ratio, n_texts, py, npr)
+    rs = rng
     walls = np.ones((n, n), dtype=np.int32)
     walls[1:n:2, 1:n:2] = 0
     m = (n - 1) // 2
