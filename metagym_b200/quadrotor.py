@@ -189,6 +189,7 @@ class BatchedQuadrotor(object):
             self.map_matrix = self.map_matrix.copy()
             self.map_matrix[self.y_offset, self.x_offset] = 0         # env.py:113
         self.velocity_targets = None
+        self.env_index_base = int(env_index_base)
         if task == "velocity_control":
             seeds = [seed] if np.isscalar(seed) else list(seed)
             self.set_velocity_tasks(seeds, env2task=env2task, env_index_base=env_index_base)
@@ -213,6 +214,23 @@ class BatchedQuadrotor(object):
         _lib.check(self._lib.mgb_quad_set_targets(self._h, tbl.data_ptr(), len(seeds), e2t.data_ptr()))
         self.velocity_targets = tbl
         self.env2task = e2t
+
+    def sample_task(self, seed):
+        """[nt, 3] velocity-target table of `seed` (what the reference builds in its constructor for `seed`,
+        quadrotorsim.py:306-319), integrated on the GPU; the env's current tasks are left untouched.  Use
+        set_velocity_tasks(seeds) to install tables."""
+        torch = self._torch
+        acts = velocity_task_actions(self.conf, self.nt, seed)[None]
+        act_dev = torch.from_numpy(np.ascontiguousarray(acts)).to(self.device)
+        tbl = torch.empty((1, self.nt, 3), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.mgb_quad_make_targets(self._h, act_dev.data_ptr(), 1, tbl.data_ptr(), self._stream()))
+        torch.cuda.synchronize(self.device)
+        return tbl[0]
+
+    def set_task(self, seeds, env2task=None):
+        """Install velocity-target tasks by seed (one seed or a list; env e gets seeds[e % len] unless env2task)."""
+        seeds = [int(seeds)] if np.isscalar(seeds) else [int(x) for x in seeds]
+        self.set_velocity_tasks(seeds, env2task=env2task, env_index_base=self.env_index_base)
 
     @staticmethod
     def load_map(map_file):

@@ -193,6 +193,12 @@ def test_velocity_task_generator_vs_reference(torch_mod, quad_golden):
     ref = quad_golden["veltask_tables"]
     scale = np.maximum(np.abs(ref).max(axis=2, keepdims=True), 1e-3)
     assert (np.abs(tbl - ref) / scale).max() < 2e-5
+    # sample_task(seed) returns one table without touching the installed ones; set_task(seeds) installs new ones
+    one = env.sample_task(3).cpu().numpy()
+    assert np.array_equal(one, tbl[3]) and np.array_equal(env.velocity_targets.cpu().numpy(), tbl)
+    env.set_task([5, 4])
+    assert np.array_equal(env.velocity_targets.cpu().numpy(), tbl[[5, 4]])
+    assert env.env2task.cpu().numpy().tolist() == [0, 1, 0, 1, 0, 1]
     env.close()
 
 
