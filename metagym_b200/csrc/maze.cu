@@ -75,8 +75,11 @@ struct MazeArgs {
     const int32_t *pose_index;   // [n_tasks][n*n*4] -> slot or -1
     uint32_t *c_px;              // [n_slots][H*V]   10-bit R | G<<10 | B<<20 | in_wall<<30
     uint8_t *c_fid;              // [n_slots][H*V]   food slot of the floor/ceiling cell under the pixel, 0xFF none
-    uint8_t *c_rgb8;             // [n_slots][H*V*3] min(colour, 255): the finished uint8 pixel when nothing is tinted
-    uint32_t *c_gmask;           // [n_slots][ceil(H*V/128)] bit per 4-pixel group: group may be tinted (slow path)
+    uint8_t *c_rgb8;             // [n_slots][H*V*3] finished uint8 pixel with EVERY food of the task present (baked)
+    uint32_t *c_px_all;          // int32 mode: [n_slots][H*V] packed like c_px, every food present (baked)
+    uint64_t *c_fmask;           // [n_slots][2] food slots that can change this pose's image at all
+    int bake;                    // compose kernel: items are pose slots, output goes to c_rgb8 / c_px_all
+    uint8_t *c_gsig;             // [n_slots][H*V/4] per 4-pixel group: signature of the foods that can tint it
     uint8_t *c_colhits;          // [n_slots][H]     transparent crossings recorded for the column
     void *c_hits;                // [n_slots][H][max_hits] HitRec
     void *dyn;                   // [n] EnvDyn, written by the logic kernel, read by the compose kernel
@@ -848,19 +851,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 g8[0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
                 g8[1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
                 g8[2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
-                // 4-pixel groups (q / 4) that can ever be tinted: a food cell under a pixel or a crossing span over it
-                bool tintable = fid != 0xFF;
-                if (!tintable && cr.n_hits > 0) {
-                    const HitRec *hh = s_hit + (size_t)d_h * c.max_hits;
-                    for (int k = 0; k < cr.n_hits; ++k) tintable = tintable || (d_v >= hh[k].v_s && d_v < hh[k].v_e);
-                }
-                const unsigned dyn_px = __ballot_sync(__activemask(), tintable);
-                if ((tid & 31) == 0 && dyn_px) {
-                    unsigned gbits = 0;                       // lanes 4g..4g+3 -> group bit g of this warp's 8 groups
-                    for (int g = 0; g < 8; ++g) gbits |= ((dyn_px >> (4 * g)) & 0xFu) ? (1u << g) : 0u;
-                    const int group0 = q >> 2;                // q is the warp's first pixel here (lane 0), a multiple of 32
-                    atomicOr(a.c_gmask + (size_t)e * ((total_px + 127) / 128) + (group0 >> 5), gbits << (group0 & 31));
-                }
             }
         } else {
         // ---- pixels.  Each WARP owns runs of whole screen columns (c.run_px / V of them, 768 B of output): the column
@@ -1026,7 +1016,51 @@ __global__ void maze3d_logic_kernel(const __grid_constant__ MazeConst c, const _
         d.present[0] = 1ull;             // the goal cell is pseudo food slot 0, always present (maze_base.py:59-60)
         d.bar_end = 0;
     }
+    // 8-bit signature of the foods that can show in this pose but are currently missing; 0 -> the whole frame is the
+    // baked "all present" frame + life bar
+    const uint64_t *fm = a.c_fmask + (size_t)d.slot * 2;
+    uint64_t miss = ((~d.present[0]) & fm[0]) | ((~d.present[1]) & fm[1]);      // fold 128 slots to (f & 7)
+    miss |= miss >> 32; miss |= miss >> 16; miss |= miss >> 8;
+    d.pad = (int32_t)(miss & 0xFFu);
     reinterpret_cast<EnvDyn *>(a.dyn)[e] = d;
+}
+
+// per pose slot, after the FILL render: (1) c_fmask = the food slots that can change this pose's image at all (under a
+// pixel or in a crossing record); (2) c_gsig = one byte per 4-pixel group, OR of 1 << (f & 7) over the food slots f that
+// can tint a pixel of the group (floor/ceiling cell under it, or a crossing span over it).  0 = never tinted.  An env
+// whose missing foods have the 8-bit signature S needs the float64 path only for groups with (gsig & S) != 0.
+__global__ void __launch_bounds__(256) maze3d_sig_kernel(const __grid_constant__ MazeConst c,
+                                                         const __grid_constant__ MazeArgs a)
+{
+    const int64_t slot = blockIdx.x;
+    const int V = c.res_v, total_px = c.res_h * V;
+    const uint8_t *gfid = a.c_fid + (size_t)slot * total_px;
+    const uint8_t *colhits = a.c_colhits + (size_t)slot * c.res_h;
+    const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)slot * c.res_h * c.max_hits;
+    uint8_t *gsig = a.c_gsig + (size_t)slot * (total_px / 4);
+    uint64_t m0 = 0, m1 = 0;
+    auto note = [&](int f, uint32_t &sig) {
+        if (f < 0 || f >= 128) return;
+        sig |= 1u << (f & 7);
+        if (f < 64) m0 |= 1ull << f; else m1 |= 1ull << (f - 64);
+    };
+    for (int g = threadIdx.x; g < total_px / 4; g += blockDim.x) {
+        uint32_t sig = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int q = 4 * g + k, d_h = q / V, d_v = q - d_h * V;
+            const int f = gfid[q];
+            if (f != 0xFF) note(f, sig);
+            const HitRec *hh = ghits + (size_t)d_h * c.max_hits;
+            for (int j = 0; j < colhits[d_h]; ++j)
+                if (d_v >= hh[j].v_s && d_v < hh[j].v_e) note(hh[j].fid, sig);
+        }
+        gsig[g] = (uint8_t)sig;
+    }
+    for (int o = 16; o > 0; o >>= 1) { m0 |= __shfl_xor_sync(0xffffffffu, m0, o); m1 |= __shfl_xor_sync(0xffffffffu, m1, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (m0) atomicOr(reinterpret_cast<unsigned long long *>(a.c_fmask + slot * 2), (unsigned long long)m0);
+        if (m1) atomicOr(reinterpret_cast<unsigned long long *>(a.c_fmask + slot * 2 + 1), (unsigned long long)m1);
+    }
 }
 
 constexpr int kComposeThreads = 256;
@@ -1035,7 +1069,7 @@ constexpr int kComposeThreads = 256;
 // under the pixel) of the cached pose, the env's 128-bit food presence mask, and -- only for pixels that really are
 // tinted -- the reference's float64 blend on the integer colour.  Everything else is integer work; the traffic is
 // 5 B read + 3 B written per pixel (uint8 mode), i.e. the renderer has become an HBM-bound gather/scatter.
-__global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
+__global__ void __launch_bounds__(kComposeThreads, 6) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
                                                                          const __grid_constant__ MazeArgs a)
 {
     // persistent CTAs: work item = (env, one of kParts slices of its image); grid = resident CTA count, so there is
@@ -1049,8 +1083,15 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
     const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     const int part_px = ((total_px / kParts) + 127) / 128 * 128;          // slice boundaries stay 128-pixel aligned
   const int64_t n_items = a.n * kParts;
+  // bake mode (pose-cache build): item = pose slot, every food present, no life bar, tintable groups only
+  auto fetch = [&](int64_t idx) -> EnvDyn {
+      if (!a.bake) return reinterpret_cast<const EnvDyn *>(a.dyn)[idx];
+      EnvDyn b;
+      b.slot = (int32_t)idx; b.bar_end = 0; b.present[0] = b.present[1] = ~0ull; b.task = a.poses[idx].x; b.pad = 0xFF;
+      return b;
+  };
   EnvDyn d_next;
-  if ((int64_t)blockIdx.x < n_items) d_next = reinterpret_cast<const EnvDyn *>(a.dyn)[blockIdx.x / kParts];
+  if ((int64_t)blockIdx.x < n_items) d_next = fetch(blockIdx.x / kParts);
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int64_t e = item / kParts;
     const int part = (int)(item - e * kParts);
@@ -1058,7 +1099,7 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
     // software pipeline: the next item's EnvDyn (-> pose slot -> every address below) is requested now, so the
     // dependent-load bubble at the start of an item overlaps this item's pixels
     const EnvDyn d = d_next;
-    if (item + gridDim.x < n_items) d_next = reinterpret_cast<const EnvDyn *>(a.dyn)[(item + gridDim.x) / kParts];
+    if (item + gridDim.x < n_items) d_next = fetch((item + gridDim.x) / kParts);
     if (q_begin >= total_px) continue;
     const uint8_t *blob = a.blobs + (int64_t)d.task * c.blob_bytes;
     const double *fval = reinterpret_cast<const double *>(blob + c.off_fval);
@@ -1068,6 +1109,9 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
     const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)d.slot * H * c.max_hits;
     const int lb_ex = d.bar_end;
     uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
+    if (a.bake) gobs = c.obs_dtype == MGB_OBS_U8 ? a.c_rgb8 + (size_t)e * total_px * 3 : nullptr;
+    uint32_t *bake_px = a.bake && c.obs_dtype != MGB_OBS_U8 ? a.c_px_all + (size_t)e * total_px : nullptr;
+    const uint32_t miss_sig = (uint32_t)d.pad & 0xFFu;
 
     auto present = [&](int f) -> bool { return (d.present[f >> 6] >> (f & 63)) & 1ull; };
     auto food_value = [&](int f) -> double { return survival ? __ldg(fval + f) : 1.0; };
@@ -1093,33 +1137,47 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
         if (survival && d_h >= lb_sx && d_h < lb_ex && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
     };
 
-    if ((V & 3) == 0 && (total_px & 127) == 0 && (reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) {
-        // four consecutive rows of one column per thread.  FAST PATH (the cached group can never be tinted and the life
-        // bar does not cross it): uint8 -> copy 12 finished bytes; int32 -> unpack.  Otherwise: 16 B + 4 B in, finish().
-        // (forcing a 4x unroll was measured slower: 87 vs 80 us at 1024 envs)
-        const uint32_t *gmask = a.c_gmask + (size_t)d.slot * (total_px / 128);
+    if ((V & 3) == 0 && (total_px & 127) == 0 && (reinterpret_cast<uintptr_t>(a.bake ? (void *)a.c_rgb8 : (void *)gobs) & 15u) == 0) {
+        // G consecutive 4-row groups of one column per thread and iteration (G = 4 when V % 16 == 0, else 1).
+        // FAST PATH: no food that could tint the group(s) is missing -> the baked all-present pixels are final, up to the
+        // life bar, which is drawn last (maze_discrete_3d.py:118-126) and simply overwrites them: uint8 copies G x 12
+        // finished bytes (three 16-byte words when G = 4), int32 unpacks.  Otherwise: 16 B + 4 B in, finish().
+        const uint8_t *gsig = a.c_gsig + (size_t)d.slot * (total_px / 4);
         const uint8_t *g8 = a.c_rgb8 + (size_t)d.slot * total_px * 3;
+        const uint32_t *gall = a.c_px_all + (size_t)d.slot * total_px;
         const int v_shift = (V & (V - 1)) == 0 ? 31 - __clz(V) : -1;
-        for (int q = q_begin + threadIdx.x * 4; q < q_end; q += kComposeThreads * 4) {
-            const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
-            const int d_v0 = q - d_h * V;
-            const int group = q >> 2;
-            const bool tintable = (__ldg(gmask + (group >> 5)) >> (group & 31)) & 1u;
-            const bool bar = survival && d_h >= lb_sx && d_h < lb_ex && d_v0 + 3 >= lb_sy && d_v0 < lb_ey;
-            if (!tintable && !bar) {
+        auto one_group = [&](int q, int d_h, int d_v0, bool slow) {
+            if (a.bake && !slow) return;                     // bake: untinted groups already hold their final value
+            if (!slow) {
+                const bool bar = survival && d_h >= lb_sx && d_h < lb_ex && d_v0 + 3 >= lb_sy && d_v0 < lb_ey;
                 if (c.obs_dtype == MGB_OBS_U8) {
                     const uint32_t *src = reinterpret_cast<const uint32_t *>(g8 + (size_t)q * 3);
                     uint32_t *dst = reinterpret_cast<uint32_t *>(gobs + (size_t)q * 3);
-                    const uint32_t b0 = __ldg(src), b1 = __ldg(src + 1), b2 = __ldg(src + 2);
-                    dst[0] = b0; dst[1] = b1; dst[2] = b2;
+                    uint32_t b[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+                    if (bar) {
+                        uint8_t px[12];
+                        memcpy(px, b, 12);
+                        for (int k = 0; k < 4; ++k)
+                            if (d_v0 + k >= lb_sy && d_v0 + k < lb_ey) { px[3 * k] = 255; px[3 * k + 1] = 0; px[3 * k + 2] = 0; }
+                        memcpy(b, px, 12);
+                    }
+                    dst[0] = b[0]; dst[1] = b[1]; dst[2] = b[2];
                 } else {
-                    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gall + q));
+                    int o[12] = {(int)(w4.x & 1023u), (int)((w4.x >> 10) & 1023u), (int)((w4.x >> 20) & 1023u),
+                                 (int)(w4.y & 1023u), (int)((w4.y >> 10) & 1023u), (int)((w4.y >> 20) & 1023u),
+                                 (int)(w4.z & 1023u), (int)((w4.z >> 10) & 1023u), (int)((w4.z >> 20) & 1023u),
+                                 (int)(w4.w & 1023u), (int)((w4.w >> 10) & 1023u), (int)((w4.w >> 20) & 1023u)};
+                    if (bar) {
+                        for (int k = 0; k < 4; ++k)
+                            if (d_v0 + k >= lb_sy && d_v0 + k < lb_ey) { o[3 * k] = 255; o[3 * k + 1] = 0; o[3 * k + 2] = 0; }
+                    }
                     int4 *dst = reinterpret_cast<int4 *>(gobs + (size_t)q * 12);
-                    dst[0] = make_int4(w4.x & 1023u, (w4.x >> 10) & 1023u, (w4.x >> 20) & 1023u, w4.y & 1023u);
-                    dst[1] = make_int4((w4.y >> 10) & 1023u, (w4.y >> 20) & 1023u, w4.z & 1023u, (w4.z >> 10) & 1023u);
-                    dst[2] = make_int4((w4.z >> 20) & 1023u, w4.w & 1023u, (w4.w >> 10) & 1023u, (w4.w >> 20) & 1023u);
+                    dst[0] = make_int4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_int4(o[4], o[5], o[6], o[7]);
+                    dst[2] = make_int4(o[8], o[9], o[10], o[11]);
                 }
-                continue;
+                return;
             }
             const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
             const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t *>(gfid + q));
@@ -1134,11 +1192,45 @@ __global__ void __launch_bounds__(kComposeThreads) maze3d_compose_kernel(const _
                 for (int b = 0; b < 12; ++b) pk[b >> 2] |= (uint32_t)(out[b] > 255 ? 255 : out[b]) << (8 * (b & 3));
                 uint32_t *dst = reinterpret_cast<uint32_t *>(gobs + (size_t)q * 3);
                 dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
+            } else if (bake_px) {
+                uint4 pw;
+                pw.x = (uint32_t)out[0] | ((uint32_t)out[1] << 10) | ((uint32_t)out[2] << 20);
+                pw.y = (uint32_t)out[3] | ((uint32_t)out[4] << 10) | ((uint32_t)out[5] << 20);
+                pw.z = (uint32_t)out[6] | ((uint32_t)out[7] << 10) | ((uint32_t)out[8] << 20);
+                pw.w = (uint32_t)out[9] | ((uint32_t)out[10] << 10) | ((uint32_t)out[11] << 20);
+                *reinterpret_cast<uint4 *>(bake_px + q) = pw;
             } else {
                 int4 *dst = reinterpret_cast<int4 *>(gobs + (size_t)q * 12);
                 dst[0] = make_int4(out[0], out[1], out[2], out[3]);
                 dst[1] = make_int4(out[4], out[5], out[6], out[7]);
                 dst[2] = make_int4(out[8], out[9], out[10], out[11]);
+            }
+        };
+        if ((V & 15) == 0 && c.obs_dtype == MGB_OBS_U8) {      // int32: the 4-pixel loop measured faster (81 vs 143 us)
+            const uint32_t miss4 = miss_sig * 0x01010101u;
+            for (int q = q_begin + threadIdx.x * 16; q < q_end; q += kComposeThreads * 16) {
+                const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
+                const int d_v0 = q - d_h * V;
+                uint32_t hit = 0;
+                if (miss_sig) hit = __ldg(reinterpret_cast<const uint32_t *>(gsig + (q >> 2))) & miss4;
+                const bool bar = survival && d_h >= lb_sx && d_h < lb_ex && d_v0 + 15 >= lb_sy && d_v0 < lb_ey;
+                if (!hit && !bar && !a.bake && c.obs_dtype == MGB_OBS_U8) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(g8 + (size_t)q * 3);
+                    uint4 *dst = reinterpret_cast<uint4 *>(gobs + (size_t)q * 3);
+                    const uint4 x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
+                    dst[0] = x0; dst[1] = x1; dst[2] = x2;
+                    continue;
+                }
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) one_group(q + 4 * g, d_h, d_v0 + 4 * g, ((hit >> (8 * g)) & 0xFFu) != 0);
+            }
+        } else {
+            for (int q = q_begin + threadIdx.x * 4; q < q_end; q += kComposeThreads * 4) {
+                const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
+                const int d_v0 = q - d_h * V;
+                bool slow = false;
+                if (miss_sig) slow = (__ldg(gsig + (q >> 2)) & miss_sig) != 0;
+                one_group(q, d_h, d_v0, slow);
             }
         }
     } else {
@@ -1220,7 +1312,9 @@ struct mgb_maze {
     int32_t *pose_index = nullptr;
     uint32_t *c_px = nullptr;
     uint8_t *c_fid = nullptr, *c_colhits = nullptr, *c_rgb8 = nullptr;
-    uint32_t *c_gmask = nullptr;
+    uint32_t *c_px_all = nullptr;
+    uint64_t *c_fmask = nullptr;
+    uint8_t *c_gsig = nullptr;
     HitRec *c_hits = nullptr;
     EnvDyn *dyn = nullptr;
     void *hit_scratch = nullptr;
@@ -1262,7 +1356,8 @@ static MazeArgs maze_args(const mgb_maze *h)
     a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.auto_reset = h->auto_reset;
     a.cpos = h->cpos; a.cori = h->cori; a.coltab_d = h->coltab_d;
     a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
-    a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gmask = h->c_gmask;
+    a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
+    a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
     return a;
 }
 
@@ -1363,7 +1458,8 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
     cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab); cudaFree(h->cpos); cudaFree(h->cori); cudaFree(h->coltab_d);
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
-    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask); cudaFree(h->hit_scratch);
+    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig); cudaFree(h->hit_scratch);
+    cudaFree(h->c_px_all); cudaFree(h->c_fmask);
     delete h;
 }
 
@@ -1622,7 +1718,8 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     MazeConst &c = h->c;
     if (!h->cache_enabled || c.kind != MGB_MAZE_DISCRETE_3D || h->host_poses.empty()) return MGB_OK;
     const size_t slots = h->host_poses.size(), px = (size_t)c.res_h * c.res_v;
-    const double bytes = (double)slots * (px * 8.0 + px / 32.0 + c.res_h * (1.0 + (double)c.max_hits * sizeof(HitRec)));
+    const double bytes = (double)slots * (px * (c.obs_dtype == MGB_OBS_U8 ? 8.0 : 12.0) + px / 4.0 + 16.0 +
+                                          c.res_h * (1.0 + (double)c.max_hits * sizeof(HitRec)));
     if (bytes > h->cache_budget_gb * 1e9) return MGB_OK;
     // cudaMalloc/cudaFree synchronise; a capture in progress cannot build the cache
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1631,9 +1728,11 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
         return MGB_ERR_STATE;
     }
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
-    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gmask);
+    cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig);
+    cudaFree(h->c_px_all); cudaFree(h->c_fmask);
+    h->c_px_all = nullptr; h->c_fmask = nullptr;
     h->poses = nullptr; h->pose_index = nullptr; h->c_px = nullptr; h->c_fid = nullptr; h->c_colhits = nullptr;
-    h->c_hits = nullptr; h->dyn = nullptr; h->c_rgb8 = nullptr; h->c_gmask = nullptr;
+    h->c_hits = nullptr; h->dyn = nullptr; h->c_rgb8 = nullptr; h->c_gsig = nullptr;
     MGB_CUDA(cudaMalloc(&h->poses, slots * sizeof(int4)));
     MGB_CUDA(cudaMalloc(&h->pose_index, h->host_pose_index.size() * sizeof(int32_t)));
     MGB_CUDA(cudaMalloc(&h->c_px, slots * px * sizeof(uint32_t)));
@@ -1641,10 +1740,11 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     MGB_CUDA(cudaMalloc(&h->c_colhits, slots * c.res_h));
     MGB_CUDA(cudaMalloc(&h->c_hits, slots * c.res_h * c.max_hits * sizeof(HitRec)));
     MGB_CUDA(cudaMalloc(&h->dyn, (size_t)h->n_pad * sizeof(EnvDyn)));
-    const size_t mask_words = (px + 127) / 128;
     MGB_CUDA(cudaMalloc(&h->c_rgb8, slots * px * 3));
-    MGB_CUDA(cudaMalloc(&h->c_gmask, slots * mask_words * sizeof(uint32_t)));
-    MGB_CUDA(cudaMemsetAsync(h->c_gmask, 0, slots * mask_words * sizeof(uint32_t), st));
+    MGB_CUDA(cudaMalloc(&h->c_gsig, slots * ((px + 3) / 4)));
+    MGB_CUDA(cudaMemsetAsync(h->c_gsig, 0xFF, slots * ((px + 3) / 4), st));
+    MGB_CUDA(cudaMalloc(&h->c_fmask, slots * 2 * sizeof(uint64_t)));
+    if (c.obs_dtype != MGB_OBS_U8) MGB_CUDA(cudaMalloc(&h->c_px_all, slots * px * sizeof(uint32_t)));
     MGB_CUDA(cudaMemcpy(h->poses, h->host_poses.data(), slots * sizeof(int4), cudaMemcpyHostToDevice));
     MGB_CUDA(cudaMemcpy(h->pose_index, h->host_pose_index.data(), h->host_pose_index.size() * sizeof(int32_t),
                         cudaMemcpyHostToDevice));
@@ -1653,6 +1753,24 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     a.do_step = 0;
     int rc = launch_render<true>(h, a, (unsigned)(slots < (size_t)h->num_sms ? slots : (size_t)h->num_sms), st);
     if (rc) return rc;
+    // "all present" frames: which foods can change a pose's image at all, and the finished pixels with all of them
+    // present (the compose kernel itself, fed one synthetic env per pose slot).  Screens the 4-pixel-group path cannot
+    // take keep an all-ones mask, i.e. never use the baked frame.
+    a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
+    if ((c.res_v & 3) == 0 && (px & 127) == 0) {
+        MGB_CUDA(cudaMemsetAsync(h->c_fmask, 0, slots * 2 * sizeof(uint64_t), st));
+        maze3d_sig_kernel<<<(unsigned)slots, 256, 0, st>>>(c, a);
+        MGB_CUDA(cudaGetLastError());
+        if (h->c_px_all) MGB_CUDA(cudaMemcpyAsync(h->c_px_all, h->c_px, slots * px * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        a.bake = 1;
+        a.do_parts = 1;
+        maze3d_compose_kernel<<<(unsigned)slots, kComposeThreads, 0, st>>>(c, a);
+        MGB_CUDA(cudaGetLastError());
+        a.bake = 0;
+        h->launches += 2;
+    } else {
+        MGB_CUDA(cudaMemsetAsync(h->c_fmask, 0xFF, slots * 2 * sizeof(uint64_t), st));
+    }
     MGB_CUDA(cudaStreamSynchronize(st));
     h->n_poses = (int64_t)slots;
     h->cache_ready = true;
@@ -1673,7 +1791,8 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
         if (h->cache_ready) {
             // memoised path: integer step logic, then compose static pose layers with the current food state
             a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
-            a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gmask = h->c_gmask;
+            a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
+    a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
             maze3d_logic_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
             MGB_CUDA(cudaGetLastError());
             {
