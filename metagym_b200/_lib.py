@@ -109,6 +109,14 @@ def check(rc):
         raise MgbError("libmgb200: %s (code %d)" % (load().mgb_last_error().decode(), rc))
 
 
+def current_stream(torch, device):
+    """Raw cudaStream_t of torch's current stream on `device` (torch.device with an index)."""
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if get is not None:
+        return get(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def ptr(t):
     """Device/host address of a torch tensor or numpy array (None -> NULL)."""
     if t is None:

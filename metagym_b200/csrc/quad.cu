@@ -1202,7 +1202,7 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
     }
-    if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev);   // 0 copies, 1 zero-copy, 2 hybrid
     if (const char *ev = getenv("MGB_STREAM_KERNEL")) h->stream_kernel = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_WIDE_KERNEL")) h->wide_kernel = atoi(ev) != 0;
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
@@ -1520,6 +1520,11 @@ extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs
     if (h->zerocopy && da && dob && dr && dd && (reinterpret_cast<uintptr_t>(da) & 15u) == 0) {
         QuadArgs a = base_args(h);
         a.act = (const float *)da; a.obs = (float *)dob; a.rew = (float *)dr; a.done = (uint8_t *)dd;
+        if (h->zerocopy == 2) {
+            // hybrid: actions by DMA (copy engine), outputs written to host memory by the kernel
+            MGB_CUDA(cudaMemcpyAsync(h->d_act, act_host, n * 16, cudaMemcpyHostToDevice, st));
+            a.act = h->d_act;
+        }
         rc = launch_step(h, a, st);
         if (rc) return rc;
         MGB_CUDA(cudaStreamSynchronize(st));

@@ -220,9 +220,10 @@ class _BatchedMazeBase(object):
         self.need_set_task = True
         self._rew = torch.empty((self.num_envs,), dtype=torch.float64, device=self.device)
         self._done = torch.empty((self.num_envs,), dtype=torch.uint8, device=self.device)
+        self._own_ptrs = None
 
     def _stream(self):
-        return self._torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.current_stream(self._torch, self.device)
 
     def _make_cfg(self, n_cells):
         raise NotImplementedError
@@ -305,11 +306,18 @@ class _BatchedMazeBase(object):
         torch = self._torch
         if not (hasattr(action, "is_cuda") and action.is_cuda):
             action = torch.as_tensor(np.asarray(action).reshape(self.num_envs), device=self.device)
-        act = action.to(torch.int32).reshape(self.num_envs).contiguous()
-        _lib.check(self._lib.mgb_maze_step(self._h, act.data_ptr(), self._obs.data_ptr(), self._rew.data_ptr(),
-                                           self._done.data_ptr(), self._stream()))
+        act = action
+        if act.dtype is not torch.int32 or not act.is_contiguous() or act.numel() != self.num_envs:
+            act = action.to(torch.int32).reshape(self.num_envs).contiguous()
+        if self._own_ptrs is None or self._own_ptrs[0] != self._obs.data_ptr():
+            self._own_ptrs = (self._obs.data_ptr(), self._rew.data_ptr(), self._done.data_ptr())
+            self._done_bool = self._done.view(torch.bool)
+        p = self._own_ptrs
+        rc = self._lib.mgb_maze_step(self._h, act.data_ptr(), p[0], p[1], p[2], self._stream())
+        if rc:
+            _lib.check(rc)
         info = _LazySteps(self)
-        return self._out(self._obs), self._out(self._rew), self._out(self._done.view(torch.bool)), info
+        return self._out(self._obs), self._out(self._rew), self._out(self._done_bool), info
 
     def agent_state(self):
         """-> (agent [N,4] int32 = grid_x, grid_y, ori_index, steps ; life [N] float64)."""

@@ -181,6 +181,7 @@ class BatchedQuadrotor(object):
         self._rew = torch.empty((N,), dtype=torch.float32, device=dev)
         self._done = torch.empty((N,), dtype=torch.uint8, device=dev)
         self._fail = torch.zeros((N,), dtype=torch.int32, device=dev)
+        self._own_ptrs = None
         self._final_obs = torch.zeros((N, D), dtype=torch.float32, device=dev) if self.auto_reset else None
         if self.map_matrix is not None and map_file is not None:
             m = np.ascontiguousarray(self.map_matrix, dtype=np.int32)
@@ -196,7 +197,7 @@ class BatchedQuadrotor(object):
 
     # ------------------------------------------------------------------------------------------------------
     def _stream(self):
-        return self._torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.current_stream(self._torch, self.device)
 
     def set_velocity_tasks(self, seeds, env2task=None, env_index_base=0):
         """define_velocity_control_task (quadrotorsim.py:306-319) for every seed, integrated on the GPU."""
@@ -274,13 +275,27 @@ class BatchedQuadrotor(object):
         torch = self._torch
         if not (hasattr(action, "is_cuda") and action.is_cuda):
             return self._step_host(action)
-        act = action.to(torch.float32).reshape(self.num_envs, 4).contiguous()
-        obs, rew, done = (self._obs, self._rew, self._done) if out is None else out
-        _lib.check(self._lib.mgb_quad_step(self._h, act.data_ptr(), obs.data_ptr(), rew.data_ptr(),
-                                           done.data_ptr(), self._fail.data_ptr(), _lib.ptr(self._final_obs),
-                                           self._stream()))
+        act = action
+        if act.dtype is not torch.float32 or not act.is_contiguous() or act.numel() != self.num_envs * 4:
+            act = action.to(torch.float32).reshape(self.num_envs, 4).contiguous()
+        if out is None:                       # the env's own output tensors: addresses and views are fixed
+            if self._own_ptrs is None:
+                self._own_ptrs = (self._obs.data_ptr(), self._rew.data_ptr(), self._done.data_ptr(),
+                                  self._fail.data_ptr(), _lib.ptr(self._final_obs))
+                self._done_bool = self._done.view(torch.bool)
+            p = self._own_ptrs
+            rc = self._lib.mgb_quad_step(self._h, act.data_ptr(), p[0], p[1], p[2], p[3], p[4], self._stream())
+            if rc:
+                _lib.check(rc)
+            obs, rew, done_b = self._obs, self._rew, self._done_bool
+        else:
+            obs, rew, done = out
+            _lib.check(self._lib.mgb_quad_step(self._h, act.data_ptr(), obs.data_ptr(), rew.data_ptr(),
+                                               done.data_ptr(), self._fail.data_ptr(), _lib.ptr(self._final_obs),
+                                               self._stream()))
+            done_b = done.view(torch.bool)
         info = QuadInfo(obs, self.obs_keys)
-        return self._out(obs), self._out(rew), self._out(done.view(torch.bool)), info
+        return self._out(obs), self._out(rew), self._out(done_b), info
 
     def _step_host(self, action):
         act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(self.num_envs, 4))
