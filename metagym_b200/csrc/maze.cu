@@ -1065,10 +1065,9 @@ __global__ void __launch_bounds__(256) maze3d_sig_kernel(const __grid_constant__
 
 constexpr int kComposeThreads = 256;
 
-// One CTA per env.  Per pixel: one packed word (colour before transparency + in-wall flag) and one byte (food slot
-// under the pixel) of the cached pose, the env's 128-bit food presence mask, and -- only for pixels that really are
-// tinted -- the reference's float64 blend on the integer colour.  Everything else is integer work; the traffic is
-// 5 B read + 3 B written per pixel (uint8 mode), i.e. the renderer has become an HBM-bound gather/scatter.
+// Work item = (env, image slice).  Pixels no missing food can tint are copied from the pose's baked all-present frame;
+// the others take the cached static layers (packed colour + in-wall flag, food slot under the pixel, crossing records
+// of the column) through the reference's float64 blend with the env's 128-bit food presence mask.
 __global__ void __launch_bounds__(kComposeThreads, 6) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
                                                                          const __grid_constant__ MazeArgs a)
 {

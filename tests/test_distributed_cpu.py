@@ -19,6 +19,25 @@ def test_shard_range_partitions_everything():
         assert seen == list(range(n))
 
 
+def test_rollout_arena_layout_single_process():
+    """Fields are carved out of one allocation at 256-byte offsets; without a process group the gather is the identity."""
+    fields = {"obs": ((3, 5, 19), torch.float32), "done": ((3, 5), torch.uint8), "rew": ((3, 5), torch.float64),
+              "act": ((3, 5), torch.int32)}
+    ar = RolloutArena(fields, "cpu")
+    base = ar.buf.data_ptr()
+    offs = [ar[k].data_ptr() - base for k in fields]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert ar.payload_bytes() == 3 * 5 * (19 * 4 + 1 + 8 + 4) and ar.nbytes >= ar.payload_bytes()
+    for k, (shape, dt) in fields.items():
+        assert tuple(ar[k].shape) == shape and ar[k].dtype == dt and ar[k].is_contiguous()
+    ar["obs"].fill_(2.5); ar["done"].fill_(1)
+    views, work = ar.all_gather()
+    assert work is None and tuple(views["obs"].shape) == (1, 3, 5, 19)
+    assert views["obs"].data_ptr() == ar["obs"].data_ptr() and float(views["obs"].sum()) == 2.5 * 3 * 5 * 19
+    flat = RolloutArena.ordered(views)
+    assert tuple(flat["done"].shape) == (3, 5) and int(flat["done"].sum()) == 15
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
