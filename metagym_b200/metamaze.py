@@ -501,23 +501,3 @@ MetaMaze2D = BatchedMetaMaze2D
 MetaMazeDiscrete3D = BatchedMetaMazeDiscrete3D
 MetaMazeContinuous3D = BatchedMetaMazeContinuous3D
 
-
-def smoke():
-    """Tiny 3-D + 2-D maze episode on cuda:0 checked bit for bit against the CPU oracle (called by smoke())."""
-    import torch
-    from oracle.maze_oracle import OracleMaze
-    rs = np.random.RandomState(3)
-    task = MazeTaskSampler(n=9, food_density=0.05, food_interval=4, rng=rs)
-    tex = synthetic_textures(seed=0)
-    env = BatchedMetaMazeDiscrete3D(resolution=(32, 24), max_steps=30, num_envs=2, squeeze=False, textures=tex)
-    ora = OracleMaze("3D", "SURVIVAL", 30, 1, (32, 24), textures=tex)
-    env.set_task(task)
-    ora.set_task(task)
-    assert np.array_equal(env.reset().cpu().numpy()[0], ora.reset())
-    for t in range(12):
-        a = int(rs.randint(4))
-        obs, rew, done, _ = env.step(torch.full((2,), a, device="cuda", dtype=torch.int32))
-        o2, r2, d2, _ = ora.step(a)
-        assert np.array_equal(obs.cpu().numpy()[1], o2) and float(rew[0]) == r2 and bool(done[0]) == d2
-    env.close()
-    print("smoke ok: maze3d 32x24 render bit-exact vs oracle")

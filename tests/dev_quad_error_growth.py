@@ -1,14 +1,14 @@
-"""Development aid: per-step max error of the GPU quadrotor against the CPU oracle (mix) and the f64 arbiter."""
+"""Development aid (test infrastructure, not collected by pytest): per-step max error of the GPU quadrotor against the CPU oracle (mix) and the f64 arbiter."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 from metagym_b200 import BatchedQuadrotor
 from oracle import quad_oracle as qo
 from util import OBS_GROUPS, STATE_GROUPS, group_rel_err
 
 cfg = qo.make_cfg()
-g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "quadrotor_golden.npz"))
+g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quadrotor_golden.npz"))
 # KAT 200
 env = BatchedQuadrotor(task="velocity_control", nt=1000, seed=0, num_envs=1, squeeze=False)
 act = torch.full((1, 4), 5.0, device="cuda")
