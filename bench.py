@@ -176,8 +176,8 @@ def maze_extras(torch, dev, peak):
         out[name] = {"value": n / us * 1e6, "unit": "env-steps/s", "us_per_step": us,
                      "algorithmic_bytes_per_env_step": nbytes, "frac_of_measured_hbm": n * nbytes / us * 1e-3 / peak,
                      "parity": "bit-exact vs reference golden episodes (tests/test_maze_gpu.py)"}
-        if hasattr(env, "rollout"):          # MetaMaze2D: T steps per launch, device-drawn uniform actions
-            T = 32
+        if hasattr(env, "rollout"):          # T steps per launch, device-drawn uniform actions
+            T = 32 if nbytes < 1000 else 16
             bufs = env.rollout(T, act_seed=3, want_actions=True)
             for _ in range(2):
                 env.rollout(T, act_seed=3, out=bufs)

@@ -214,12 +214,14 @@ int mgb_maze_step(mgb_maze *h, const int32_t *act_dev, void *obs_dev, double *re
                   void *stream);
 int mgb_maze_set_options(mgb_maze *h, int auto_reset);
 
-/* MetaMaze2D: T consecutive steps in ONE launch (agent state in registers; auto-reset semantics as configured).
+/* MetaMaze2D and MetaMazeDiscrete3D: T consecutive steps in ONE launch (agent state in registers; auto-reset semantics
+ * as configured; the 3-D form runs on the pose cache: one CTA per env, step logic by one thread, frame by the CTA).
  *   act_dev [T][n] int32 or NULL: NULL draws uniform {0..3} actions from the counter-based generator (stream id
  *   act_seed, keyed by the global env index), written to act_out_dev [T][n] if not NULL.
- *   obs_dev [T][n][2g+1][2g+1] float32, rew_dev [T][n] float64, done_dev [T][n] uint8 (any may be NULL). */
+ *   obs_dev [T][n][obs of one env] (2-D: float32 [2g+1][2g+1]; 3-D: uint8 or int32 [res_h][res_v][3]),
+ *   rew_dev [T][n] float64, done_dev [T][n] uint8 (any may be NULL). */
 int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, uint64_t act_seed, int32_t *act_out_dev,
-                     float *obs_dev, double *rew_dev, uint8_t *done_dev, void *stream);
+                     void *obs_dev, double *rew_dev, uint8_t *done_dev, void *stream);
 
 /* MetaMazeContinuous3D.step (maze_env.py:129-146 -> maze_continuous_3d.py:47-56, dynamics.py:58-92): act_dev [n][2]
  * float32 = (turn_rate, walk_speed), clipped to [-1, 1] like the reference; ten 10 ms sub-steps of turn/walk with the

@@ -975,6 +975,51 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     if ((tid & 31) == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copies; the kernel boundary flushes the writes
 }
 
+// What the compose step needs from an env after its step logic: pose slot, life bar, food presence, and the 8-bit
+// signature of the foods that can show in this pose but are currently missing.
+__device__ __forceinline__ EnvDyn make_dyn(const MazeConst &c, const MazeArgs &a, const uint8_t *blob, int task, const Env &s,
+                                           const int32_t *eaten)
+{
+    const TaskHdr *th = blob_hdr(blob);
+    EnvDyn d;
+    d.slot = a.pose_index[(size_t)task * c.n * c.n * 4 + (s.gx * c.n + s.gy) * 4 + s.ori];
+    d.task = task; d.pad = 0;
+    d.present[0] = d.present[1] = 0;
+    if (c.task_type == MGB_MAZE_SURVIVAL) {
+        const int32_t *fint = reinterpret_cast<const int32_t *>(blob + c.off_fint);
+        // batches of 8 foods: the 16 loads of a batch are issued together (one memory latency per batch, not per food)
+        const int n_food = th->n_food;
+        for (int f0 = 0; f0 < n_food; f0 += 8) {
+            int ea[8], fi[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int f = f0 + k < n_food ? f0 + k : n_food - 1;
+                ea[k] = eaten[f * a.n_pad];
+                fi[k] = fint[f];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int f = f0 + k;
+                if (f < n_food && ((ea[k] == kNever) || (s.steps >= ea[k] + fi[k]))) d.present[f >> 6] |= 1ull << (f & 63);
+            }
+        }
+        int ex = trunc_i(c.lb_sx + s.life / th->max_life * c.lb_l);      // maze_discrete_3d.py:118-126
+        if (ex < 0) { ex += c.res_h; if (ex < 0) ex = 0; }
+        if (ex > c.res_h) ex = c.res_h;
+        d.bar_end = ex;
+    } else {
+        d.present[0] = 1ull;             // the goal cell is pseudo food slot 0, always present (maze_base.py:59-60)
+        d.bar_end = 0;
+    }
+    // 8-bit signature of the foods that can show in this pose but are currently missing; 0 -> the whole frame is the
+    // baked "all present" frame + life bar
+    const uint64_t *fm = a.c_fmask + (size_t)d.slot * 2;
+    uint64_t miss = ((~d.present[0]) & fm[0]) | ((~d.present[1]) & fm[1]);      // fold 128 slots to (f & 7)
+    miss |= miss >> 32; miss |= miss >> 16; miss |= miss >> 8;
+    d.pad = (int32_t)(miss & 0xFFu);
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Pose cache path: step logic (one thread per env) + compose (static pose layers x current food state -> observation)
 // ---------------------------------------------------------------------------------------------------------------
@@ -998,30 +1043,7 @@ __global__ void maze3d_logic_kernel(const __grid_constant__ MazeConst c, const _
         a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
         a.life[e] = s.life;
     }
-    EnvDyn d;
-    d.slot = a.pose_index[(size_t)task * c.n * c.n * 4 + (s.gx * c.n + s.gy) * 4 + s.ori];
-    d.task = task; d.pad = 0;
-    d.present[0] = d.present[1] = 0;
-    if (c.task_type == MGB_MAZE_SURVIVAL) {
-        const int32_t *fint = reinterpret_cast<const int32_t *>(blob + c.off_fint);
-        for (int f = 0; f < th->n_food; ++f) {
-            const int ea = eaten[f * a.n_pad];
-            if ((ea == kNever) || (s.steps >= ea + fint[f])) d.present[f >> 6] |= 1ull << (f & 63);
-        }
-        int ex = trunc_i(c.lb_sx + s.life / th->max_life * c.lb_l);      // maze_discrete_3d.py:118-126
-        if (ex < 0) { ex += c.res_h; if (ex < 0) ex = 0; }
-        if (ex > c.res_h) ex = c.res_h;
-        d.bar_end = ex;
-    } else {
-        d.present[0] = 1ull;             // the goal cell is pseudo food slot 0, always present (maze_base.py:59-60)
-        d.bar_end = 0;
-    }
-    // 8-bit signature of the foods that can show in this pose but are currently missing; 0 -> the whole frame is the
-    // baked "all present" frame + life bar
-    const uint64_t *fm = a.c_fmask + (size_t)d.slot * 2;
-    uint64_t miss = ((~d.present[0]) & fm[0]) | ((~d.present[1]) & fm[1]);      // fold 128 slots to (f & 7)
-    miss |= miss >> 32; miss |= miss >> 16; miss |= miss >> 8;
-    d.pad = (int32_t)(miss & 0xFFu);
+    const EnvDyn d = make_dyn(c, a, blob, task, s, eaten);
     reinterpret_cast<EnvDyn *>(a.dyn)[e] = d;
 }
 
@@ -1100,152 +1122,72 @@ __global__ void __launch_bounds__(kComposeThreads, 6) maze3d_compose_kernel(cons
     const EnvDyn d = d_next;
     if (item + gridDim.x < n_items) d_next = fetch((item + gridDim.x) / kParts);
     if (q_begin >= total_px) continue;
-    const uint8_t *blob = a.blobs + (int64_t)d.task * c.blob_bytes;
-    const double *fval = reinterpret_cast<const double *>(blob + c.off_fval);
-    const uint32_t *gpx = a.c_px + (size_t)d.slot * total_px;
-    const uint8_t *gfid = a.c_fid + (size_t)d.slot * total_px;
-    const uint8_t *colhits = a.c_colhits + (size_t)d.slot * H;
-    const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)d.slot * H * c.max_hits;
-    const int lb_ex = d.bar_end;
-    uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * total_px * px_bytes;
-    if (a.bake) gobs = c.obs_dtype == MGB_OBS_U8 ? a.c_rgb8 + (size_t)e * total_px * 3 : nullptr;
-    uint32_t *bake_px = a.bake && c.obs_dtype != MGB_OBS_U8 ? a.c_px_all + (size_t)e * total_px : nullptr;
-    const uint32_t miss_sig = (uint32_t)d.pad & 0xFFu;
+#include "maze_compose_body.inc"
+  }
+}
 
-    auto present = [&](int f) -> bool { return (d.present[f >> 6] >> (f & 63)) & 1ull; };
-    auto food_value = [&](int f) -> double { return survival ? __ldg(fval + f) : 1.0; };
-    // one pixel: static colour -> floor/ceiling tint -> crossings of the column -> life bar (ray_caster_utils.py:118-205)
-    auto finish = [&](uint32_t w, int f, int d_h, int d_v, int n_hits, int rgb[3]) {
-        rgb[0] = (int)(w & 1023u); rgb[1] = (int)((w >> 10) & 1023u); rgb[2] = (int)((w >> 20) & 1023u);
-        const bool in_wall = (w >> 30) & 1u;
-        bool mark = false;
-        if (f != 0xFF && present(f)) {
-            const double tv = food_value(f);
-            if (d_v > V / 2 ? tv > 0.01 : tv > 0) {          // floor tests > 0.01 (:119), ceiling > 0 (:150)
-                if (!in_wall) blend(rgb, tv * 0.50 + 0.10);
-                mark = true;
-            }
+// T MetaMazeDiscrete3D steps in one launch (pose-cache path): one CTA per env; thread 0 runs the step logic and leaves the
+// env's EnvDyn in shared memory, then the whole CTA composes frame t straight into obs[t][env].  No logic launch, no
+// EnvDyn round trip through global memory, and the logic of one env overlaps the pixels of the others on the SM.
+__global__ void __launch_bounds__(kComposeThreads, 5) maze3d_rollout_kernel(const __grid_constant__ MazeConst c,
+                                                                            const __grid_constant__ MazeArgs a)
+{
+    __shared__ EnvDyn s_dyn;
+    __shared__ int s_nslow;
+    extern __shared__ int s_slow[];                     // total_px / 4 entries: queued tinted groups of the current frame
+    bool deferred_pass = false;
+    const int H = c.res_h, V = c.res_v, total_px = H * V;
+    const bool survival = c.task_type == MGB_MAZE_SURVIVAL;
+    const int lb_sx = trunc_i(c.lb_sx), lb_sy = trunc_i(c.lb_sy);
+    int lb_ey = trunc_i(c.lb_sy + c.lb_w);
+    if (lb_ey > V) lb_ey = V;
+    const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
+    const uint2 akey = make_uint2((uint32_t)a.act_seed, (uint32_t)(a.act_seed >> 32));
+    for (int64_t env = blockIdx.x; env < a.n; env += gridDim.x) {
+        const int task = a.env2task[env];
+        const uint8_t *eblob = a.blobs + (int64_t)task * c.blob_bytes;
+        int32_t *eaten = a.eaten + env;
+        Env s = {0, 0, 0, 0, 0.0};
+        if (threadIdx.x == 0) {
+            const int4 ag = a.agent[env];
+            s.gx = ag.x; s.gy = ag.y; s.ori = ag.z; s.steps = ag.w; s.life = a.life[env];
         }
-        if (n_hits > 0 && !mark) {
-            const HitRec *hits = ghits + (size_t)d_h * c.max_hits;
-            for (int k = 0; k < n_hits; ++k) {
-                const HitRec hr = hits[k];
-                if (present(hr.fid) && d_v >= hr.v_s && d_v < hr.v_e) blend(rgb, hr.tf);
-            }
-        }
-        if (survival && d_h >= lb_sx && d_h < lb_ex && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
-    };
-
-    if ((V & 3) == 0 && (total_px & 127) == 0 && (reinterpret_cast<uintptr_t>(a.bake ? (void *)a.c_rgb8 : (void *)gobs) & 15u) == 0) {
-        // G consecutive 4-row groups of one column per thread and iteration (G = 4 when V % 16 == 0, else 1).
-        // FAST PATH: no food that could tint the group(s) is missing -> the baked all-present pixels are final, up to the
-        // life bar, which is drawn last (maze_discrete_3d.py:118-126) and simply overwrites them: uint8 copies G x 12
-        // finished bytes (three 16-byte words when G = 4), int32 unpacks.  Otherwise: 16 B + 4 B in, finish().
-        const uint8_t *gsig = a.c_gsig + (size_t)d.slot * (total_px / 4);
-        const uint8_t *g8 = a.c_rgb8 + (size_t)d.slot * total_px * 3;
-        const uint32_t *gall = a.c_px_all + (size_t)d.slot * total_px;
-        const int v_shift = (V & (V - 1)) == 0 ? 31 - __clz(V) : -1;
-        auto one_group = [&](int q, int d_h, int d_v0, bool slow) {
-            if (a.bake && !slow) return;                     // bake: untinted groups already hold their final value
-            if (!slow) {
-                const bool bar = survival && d_h >= lb_sx && d_h < lb_ex && d_v0 + 3 >= lb_sy && d_v0 < lb_ey;
-                if (c.obs_dtype == MGB_OBS_U8) {
-                    const uint32_t *src = reinterpret_cast<const uint32_t *>(g8 + (size_t)q * 3);
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(gobs + (size_t)q * 3);
-                    uint32_t b[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
-                    if (bar) {
-                        uint8_t px[12];
-                        memcpy(px, b, 12);
-                        for (int k = 0; k < 4; ++k)
-                            if (d_v0 + k >= lb_sy && d_v0 + k < lb_ey) { px[3 * k] = 255; px[3 * k + 1] = 0; px[3 * k + 2] = 0; }
-                        memcpy(b, px, 12);
-                    }
-                    dst[0] = b[0]; dst[1] = b[1]; dst[2] = b[2];
-                } else {
-                    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gall + q));
-                    int o[12] = {(int)(w4.x & 1023u), (int)((w4.x >> 10) & 1023u), (int)((w4.x >> 20) & 1023u),
-                                 (int)(w4.y & 1023u), (int)((w4.y >> 10) & 1023u), (int)((w4.y >> 20) & 1023u),
-                                 (int)(w4.z & 1023u), (int)((w4.z >> 10) & 1023u), (int)((w4.z >> 20) & 1023u),
-                                 (int)(w4.w & 1023u), (int)((w4.w >> 10) & 1023u), (int)((w4.w >> 20) & 1023u)};
-                    if (bar) {
-                        for (int k = 0; k < 4; ++k)
-                            if (d_v0 + k >= lb_sy && d_v0 + k < lb_ey) { o[3 * k] = 255; o[3 * k + 1] = 0; o[3 * k + 2] = 0; }
-                    }
-                    int4 *dst = reinterpret_cast<int4 *>(gobs + (size_t)q * 12);
-                    dst[0] = make_int4(o[0], o[1], o[2], o[3]);
-                    dst[1] = make_int4(o[4], o[5], o[6], o[7]);
-                    dst[2] = make_int4(o[8], o[9], o[10], o[11]);
+        const int64_t genv = a.env_base + env;
+        for (int t = 0; t < a.T; ++t) {
+            if (threadIdx.x == 0) {
+                int action;
+                if (a.act) action = a.act[(int64_t)t * a.n + env];
+                else {
+                    const uint4 r = mgb_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32),
+                                                                 a.t_base + (uint32_t)t, MGB_STREAM_ACTION), akey);
+                    action = (int)(r.x >> 30);
+                    if (a.act_out) a.act_out[(int64_t)t * a.n + env] = action;
                 }
-                return;
+                double reward;
+                int done;
+                maze_logic(c, eblob, eaten, a.n_pad, s, action, reward, done);
+                if (done && a.auto_reset) env_reset(c, eblob, eaten, a.n_pad, s);
+                if (a.rew) a.rew[(int64_t)t * a.n + env] = reward;
+                if (a.done) a.done[(int64_t)t * a.n + env] = (uint8_t)done;
+                s_dyn = make_dyn(c, a, eblob, task, s, eaten);
+                s_nslow = 0;
             }
-            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
-            const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t *>(gfid + q));
-            const int n_hits = colhits[d_h];
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-            int out[12];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) finish(w[k], (int)((f4 >> (8 * k)) & 0xFFu), d_h, d_v0 + k, n_hits, out + 3 * k);
-            if (c.obs_dtype == MGB_OBS_U8) {
-                uint32_t pk[3] = {0u, 0u, 0u};
-#pragma unroll
-                for (int b = 0; b < 12; ++b) pk[b >> 2] |= (uint32_t)(out[b] > 255 ? 255 : out[b]) << (8 * (b & 3));
-                uint32_t *dst = reinterpret_cast<uint32_t *>(gobs + (size_t)q * 3);
-                dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
-            } else if (bake_px) {
-                uint4 pw;
-                pw.x = (uint32_t)out[0] | ((uint32_t)out[1] << 10) | ((uint32_t)out[2] << 20);
-                pw.y = (uint32_t)out[3] | ((uint32_t)out[4] << 10) | ((uint32_t)out[5] << 20);
-                pw.z = (uint32_t)out[6] | ((uint32_t)out[7] << 10) | ((uint32_t)out[8] << 20);
-                pw.w = (uint32_t)out[9] | ((uint32_t)out[10] << 10) | ((uint32_t)out[11] << 20);
-                *reinterpret_cast<uint4 *>(bake_px + q) = pw;
-            } else {
-                int4 *dst = reinterpret_cast<int4 *>(gobs + (size_t)q * 12);
-                dst[0] = make_int4(out[0], out[1], out[2], out[3]);
-                dst[1] = make_int4(out[4], out[5], out[6], out[7]);
-                dst[2] = make_int4(out[8], out[9], out[10], out[11]);
+            __syncthreads();
+            if (a.obs) {
+                const EnvDyn d = s_dyn;
+                const int64_t e = (int64_t)t * a.n + env;             // frame index of the included body
+                const int q_begin = 0, q_end = total_px;
+#define MGB_COMPOSE_DEFER_SLOW 1
+#include "maze_compose_body.inc"
+#undef MGB_COMPOSE_DEFER_SLOW
             }
-        };
-        if ((V & 15) == 0 && c.obs_dtype == MGB_OBS_U8) {      // int32: the 4-pixel loop measured faster (81 vs 143 us)
-            const uint32_t miss4 = miss_sig * 0x01010101u;
-            for (int q = q_begin + threadIdx.x * 16; q < q_end; q += kComposeThreads * 16) {
-                const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
-                const int d_v0 = q - d_h * V;
-                uint32_t hit = 0;
-                if (miss_sig) hit = __ldg(reinterpret_cast<const uint32_t *>(gsig + (q >> 2))) & miss4;
-                const bool bar = survival && d_h >= lb_sx && d_h < lb_ex && d_v0 + 15 >= lb_sy && d_v0 < lb_ey;
-                if (!hit && !bar && !a.bake && c.obs_dtype == MGB_OBS_U8) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(g8 + (size_t)q * 3);
-                    uint4 *dst = reinterpret_cast<uint4 *>(gobs + (size_t)q * 3);
-                    const uint4 x0 = __ldg(src), x1 = __ldg(src + 1), x2 = __ldg(src + 2);
-                    dst[0] = x0; dst[1] = x1; dst[2] = x2;
-                    continue;
-                }
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) one_group(q + 4 * g, d_h, d_v0 + 4 * g, ((hit >> (8 * g)) & 0xFFu) != 0);
-            }
-        } else {
-            for (int q = q_begin + threadIdx.x * 4; q < q_end; q += kComposeThreads * 4) {
-                const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
-                const int d_v0 = q - d_h * V;
-                bool slow = false;
-                if (miss_sig) slow = (__ldg(gsig + (q >> 2)) & miss_sig) != 0;
-                one_group(q, d_h, d_v0, slow);
-            }
+            __syncthreads();                                          // s_dyn is rewritten by the next step
         }
-    } else {
-        for (int q = q_begin + threadIdx.x; q < q_end; q += kComposeThreads) {
-            const int d_h = q / V, d_v = q - d_h * V;
-            int rgb[3];
-            finish(__ldg(gpx + q), (int)gfid[q], d_h, d_v, colhits[d_h], rgb);
-            if (c.obs_dtype == MGB_OBS_U8) {
-                for (int k = 0; k < 3; ++k) gobs[(size_t)q * 3 + k] = (uint8_t)(rgb[k] > 255 ? 255 : rgb[k]);
-            } else {
-                int32_t *o = reinterpret_cast<int32_t *>(gobs) + (size_t)q * 3;
-                o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
-            }
+        if (threadIdx.x == 0) {
+            a.agent[env] = make_int4(s.gx, s.gy, s.ori, s.steps);
+            a.life[env] = s.life;
         }
     }
-  }
 }
 
 // Pose-independent part of the floor/ceiling geometry: eff(d_h, d_v) = distance(d_v) / cos_hp(d_h)
@@ -1843,20 +1785,42 @@ extern "C" int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_de
 }
 
 extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, uint64_t act_seed, int32_t *act_out_dev,
-                                float *obs_dev, double *rew_dev, uint8_t *done_dev, void *stream)
+                                void *obs_dev, double *rew_dev, uint8_t *done_dev, void *stream)
 {
     MGB_REQUIRE(h, "null handle");
     MGB_REQUIRE(T > 0, "T must be positive");
-    MGB_REQUIRE(h->c.kind == MGB_MAZE_2D, "mgb_maze_rollout is the MetaMaze2D fused rollout");
+    MGB_REQUIRE(h->c.kind == MGB_MAZE_2D || h->c.kind == MGB_MAZE_DISCRETE_3D,
+                "mgb_maze_rollout serves MetaMaze2D and MetaMazeDiscrete3D");
     int rc = maze_ready(h);
     if (rc) return rc;
     MgbDeviceGuard guard(h->device);
     MazeArgs a = maze_args(h);
     a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev; a.do_step = 1;
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
+    a.mir = h->mir;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->c.kind == MGB_MAZE_DISCRETE_3D) {
+        MGB_REQUIRE(h->mir.count == 0, "output mirrors are implemented for the MetaMaze2D rollout only");
+        rc = ensure_pose_cache(h, st);
+        if (rc) return rc;
+        MGB_REQUIRE(h->cache_ready, "the fused 3-D rollout runs on the pose cache (MGB_MAZE_CACHE=0 or cache budget too small)");
+        a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
+        a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
+        a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
+        a.bake = 0;
+        const int64_t resident = (int64_t)h->num_sms * 5;          // __launch_bounds__(256, 5): 48 registers, no spills
+        const size_t qbytes = ((size_t)h->c.res_h * h->c.res_v / 4 + 1) * sizeof(int);
+        MGB_REQUIRE(qbytes <= 200 * 1024, "screen too large for the fused rollout's group queue");
+        if (qbytes > 40 * 1024)
+            MGB_CUDA(cudaFuncSetAttribute(maze3d_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qbytes));
+        maze3d_rollout_kernel<<<(unsigned)(h->n < resident ? h->n : resident), kComposeThreads, qbytes, st>>>(h->c, a);
+        MGB_CUDA(cudaGetLastError());
+        h->t_base += (uint32_t)T;
+        h->launches += 1;
+        return MGB_OK;
+    }
     const int W = 2 * h->c.view_grid + 1;
     const size_t sm = (size_t)2 * k2dThreads * W * W * 4;
-    a.mir = h->mir;
     const unsigned blocks = (unsigned)((h->n + k2dThreads - 1) / k2dThreads);
     if (sm > 48 * 1024) {
         MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -1867,9 +1831,9 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
         MGB_REQUIRE(h->n % 4 == 0, "multicast outputs need num_envs % 4 == 0");
         MGB_REQUIRE((((uintptr_t)done_dev | (uintptr_t)obs_dev | (uintptr_t)act_out_dev) & 3) == 0 && ((uintptr_t)rew_dev & 7) == 0,
                     "multicast outputs must be 4-byte (rewards: 8-byte) aligned");
-        maze2d_rollout_kernel<2><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
-    } else if (h->mir.count > 0) maze2d_rollout_kernel<1><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
-    else maze2d_rollout_kernel<0><<<blocks, k2dThreads, sm, (cudaStream_t)stream>>>(h->c, a);
+        maze2d_rollout_kernel<2><<<blocks, k2dThreads, sm, st>>>(h->c, a);
+    } else if (h->mir.count > 0) maze2d_rollout_kernel<1><<<blocks, k2dThreads, sm, st>>>(h->c, a);
+    else maze2d_rollout_kernel<0><<<blocks, k2dThreads, sm, st>>>(h->c, a);
     MGB_CUDA(cudaGetLastError());
     h->t_base += (uint32_t)T;
     h->launches += 1;

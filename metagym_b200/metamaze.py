@@ -319,6 +319,22 @@ class _BatchedMazeBase(object):
         info = _LazySteps(self)
         return self._out(self._obs), self._out(self._rew), self._out(self._done_bool), info
 
+    def _rollout(self, T, actions, act_seed, want_actions, out):
+        if self.need_reset:
+            raise Exception("Must \"reset\" before doing any actions")
+        torch = self._torch
+        N, dev = self.num_envs, self.device
+        if out is None:
+            out = {"obs": torch.empty((T, N) + tuple(self._obs.shape[1:]), dtype=self._obs.dtype, device=dev),
+                   "rew": torch.empty((T, N), dtype=torch.float64, device=dev),
+                   "done": torch.empty((T, N), dtype=torch.uint8, device=dev),
+                   "act": torch.empty((T, N), dtype=torch.int32, device=dev) if want_actions else None}
+        a = None if actions is None else actions.to(torch.int32).reshape(T, N).contiguous()
+        _lib.check(self._lib.mgb_maze_rollout(self._h, int(T), _lib.ptr(a), int(act_seed), _lib.ptr(out.get("act")),
+                                              _lib.ptr(out.get("obs")), _lib.ptr(out.get("rew")),
+                                              _lib.ptr(out.get("done")), self._stream()))
+        return out
+
     def agent_state(self):
         """-> (agent [N,4] int32 = grid_x, grid_y, ori_index, steps ; life [N] float64)."""
         torch = self._torch
@@ -397,22 +413,9 @@ class BatchedMetaMaze2D(_BatchedMazeBase):
         _lib.check(self._lib.mgb_maze_set_multicast(self._h, int(byte_delta)))
 
     def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):
-        """T steps in one launch.  actions: [T,N] int32 CUDA tensor or None (device-drawn uniform {0..3}).
-        Returns dict(obs [T,N,2g+1,2g+1] f32, rew [T,N] f64, done [T,N] u8, act [T,N] i32 or None)."""
-        if self.need_reset:
-            raise Exception("Must \"reset\" before doing any actions")
-        torch = self._torch
-        N, w, dev = self.num_envs, 2 * self.view_grid + 1, self.device
-        if out is None:
-            out = {"obs": torch.empty((T, N, w, w), dtype=torch.float32, device=dev),
-                   "rew": torch.empty((T, N), dtype=torch.float64, device=dev),
-                   "done": torch.empty((T, N), dtype=torch.uint8, device=dev),
-                   "act": torch.empty((T, N), dtype=torch.int32, device=dev) if want_actions else None}
-        a = None if actions is None else actions.to(torch.int32).reshape(T, N).contiguous()
-        _lib.check(self._lib.mgb_maze_rollout(self._h, int(T), _lib.ptr(a), int(act_seed), _lib.ptr(out.get("act")),
-                                              _lib.ptr(out.get("obs")), _lib.ptr(out.get("rew")),
-                                              _lib.ptr(out.get("done")), self._stream()))
-        return out
+        """T steps in one launch (mgb_maze_rollout).  actions: [T,N] int32 CUDA tensor or None (device-drawn uniform
+        {0..3}).  Returns dict(obs [T,N,<obs of one env>], rew [T,N] f64, done [T,N] u8, act [T,N] i32 or None)."""
+        return self._rollout(T, actions, act_seed, want_actions, out)
 
 
 class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
@@ -448,6 +451,13 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
         cfg.max_vision, cfg.fov = self.max_vision_range, self.fol_angle       # maze_discrete_3d.py:22-23
         cfg.l_focal, cfg.text_size = 0.20, 1.0                                # maze_discrete_3d.py:116
         return cfg
+
+    def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):
+        """T steps in one launch on the pose cache: obs [T,N,res_h,res_v,3] (uint8 or int32), rew, done, act as for
+        BatchedMetaMaze2D.rollout."""
+        if self.KIND != 1:
+            raise NotImplementedError("fused rollout: MetaMaze2D and MetaMazeDiscrete3D")
+        return self._rollout(T, actions, act_seed, want_actions, out)
 
     def _after_create(self):
         grounds = np.ascontiguousarray(self.textures[0], dtype=np.uint8)

@@ -66,6 +66,18 @@ def main():
         print(json.dumps({"case": name, "envs": n, "us_per_step": us, "env_steps_per_s": n / us * 1e6,
                           "algorithmic_bytes_per_env_step": bytes_per_step, "achieved_GBps": gbps,
                           "frac_of_measured_hbm": gbps / peak()}), flush=True)
+        if kind == "3D" and dt == "uint8":
+            T = 16 if n <= 1024 else 4
+
+            def roll3():
+                env.rollout(T, act_seed=3, out=bufs3)
+            bufs3 = env.rollout(T, act_seed=3, want_actions=True)
+            roll3()
+            us_r = timeit(roll3, 4) / T
+            print(json.dumps({"case": name + "_fused_rollout", "envs": n, "T": T, "us_per_step": us_r,
+                              "env_steps_per_s": n / us_r * 1e6, "achieved_GBps": n * bytes_per_step / us_r * 1e-3,
+                              "frac_of_measured_hbm": n * bytes_per_step / us_r * 1e-3 / peak()}), flush=True)
+            del bufs3
         if kind == "2D":
             T = 32 if n <= 65536 else 8
 

@@ -402,3 +402,47 @@ def test_fused_2d_rollout_equals_single_steps(torch_mod, maze_golden, task_type,
     sa, sb = a_env.agent_state(), b_env.agent_state()
     assert torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])
     a_env.close(); b_env.close()
+
+
+@pytest.mark.parametrize("task_type,obs_dtype,res,n", [("SURVIVAL", "uint8", (64, 48), 37), ("SURVIVAL", "int32", (32, 32), 20),
+                                                       ("ESCAPE", "uint8", (40, 24), 9), ("SURVIVAL", "uint8", (128, 128), 800)])
+def test_fused_3d_rollout_equals_single_steps(torch_mod, maze_golden, textures, task_type, obs_dtype, res, n):
+    """mgb_maze_rollout on MetaMazeDiscrete3D (one CTA per env, logic + compose per step, one launch) == T mgb_maze_step
+    calls bit for bit: frames, rewards, dones, final agent state; given actions and device-drawn ones; more envs than
+    resident CTAs (800 > 148 x 5) exercises the env loop of a CTA."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 10, g["tasks15.scalars"][k]) for k in range(4)]
+    T = 12 if n > 100 else 45
+
+    def fresh():
+        env = BatchedMetaMazeDiscrete3D(resolution=res, max_steps=20, task_type=task_type, num_envs=n, squeeze=False,
+                                        auto_reset=True, obs_dtype=obs_dtype, textures=textures)
+        env.set_task(tasks)
+        env.reset()
+        return env
+
+    a_env, b_env = fresh(), fresh()
+    rng = np.random.RandomState(n)
+    act = torch.as_tensor(rng.randint(0, 4, (T, n)), dtype=torch.int32).cuda()
+    out = a_env.rollout(T, actions=act)
+    assert out["obs"].dtype == (torch.uint8 if obs_dtype == "uint8" else torch.int32)
+    n_done = 0
+    for t in range(T):
+        obs, rew, done, _ = b_env.step(act[t])
+        assert torch.equal(out["obs"][t], obs), t
+        assert torch.equal(out["rew"][t], rew) and torch.equal(out["done"][t].bool(), done.bool()), t
+        n_done += int(done.sum())
+    assert n_done > 0 or n > 100
+    o2 = a_env.rollout(7, act_seed=4, want_actions=True)
+    for t in range(7):
+        obs, rew, done, _ = b_env.step(o2["act"][t])
+        assert torch.equal(o2["obs"][t], obs) and torch.equal(o2["rew"][t], rew), t
+    sa, sb = a_env.agent_state(), b_env.agent_state()
+    assert torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])
+    last = torch.as_tensor(rng.randint(0, 4, n), dtype=torch.int32).cuda()
+    ra, rb = a_env.step(last), b_env.step(last)
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+    a_env.close(); b_env.close()
