@@ -467,3 +467,43 @@ def test_reference_smoke_episode_to_termination(torch_mod, task, action):
             break
     assert 50 < steps < 1000          # falls the 5 m to the floor
     env.close()
+
+
+@pytest.mark.parametrize("name", ["c_hover", "c_nocol", "c_vel", "c_spin"])
+def test_custom_simulator_config_vs_reference(torch_mod, name, tmp_path):
+    """Reference episodes recorded with a NON-default config (off-diagonal inertia, centre-of-gravity offset, CT[2],
+    out-of-plane rotor, initial velocities, other voltage range, healthy_reward = 2; tests/golden/gen_quadrotor_conf.py):
+    the terms config.json zeroes are exercised.  Teacher-forced steps at 1e-5, reset with replayed draws, and the
+    velocity-task table built from this config."""
+    import json
+    import os
+    torch = torch_mod
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quadrotor_conf_golden.npz"))
+    conf = tmp_path / "conf.json"
+    conf.write_text(str(g["conf_json"]))
+    assert json.loads(conf.read_text())["quality"] == 0.8
+    r = golden_run(g, name)
+    n = r["pre_state"].shape[0]
+    kw = dict(dt=r["dt"], nt=r["nt"], simulator_conf=str(conf), healthy_reward=float(g["healthy_reward"]))
+    if r["task"] == "velocity_control":
+        kw["seed"] = r["seed"]
+    env = make_env(n, r["task"], **kw)
+    if r["task"] == "velocity_control":
+        tbl = env.velocity_targets.cpu().numpy()[0]
+        assert np.abs(tbl - r["targets"]).max() < 2e-5 * max(1.0, np.abs(r["targets"]).max())
+        env._lib.mgb_quad_set_targets(env._h, torch.as_tensor(r["targets"][None]).cuda().contiguous().data_ptr(), 1,
+                                      env.env2task.data_ptr())
+    # reset with the recorded draws reproduces the recorded first observation
+    noise = np.tile(r["reset_noise"][:1], (n, 1))
+    o0 = env.reset(noise=noise).cpu().numpy()
+    assert group_rel_err(o0[:1, :16], r["reset_obs"][:1, :16].astype(np.float64), OBS_GROUPS) < RTOL_STEP
+    set_state(env, r["pre_state"], r["pre_ct"])
+    obs, rew, done, info = env.step(torch.as_tensor(r["act"]).cuda())
+    st, ct = get_state(env)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    assert group_rel_err(st, r["post_state"], STATE_GROUPS) < RTOL_STEP
+    assert group_rel_err(obs[:, :16], r["obs"][:, :16], OBS_GROUPS) < RTOL_STEP
+    assert scalar_rel_err(rew, r["rew"]) < RTOL_STEP
+    assert np.array_equal(done, r["done"]) and np.array_equal(ct, r["post_ct"])
+    assert not env.fail_code.cpu().numpy().any()
+    env.close()

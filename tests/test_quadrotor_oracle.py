@@ -179,3 +179,62 @@ def test_numpy_port_with_obstacle_map(quad_golden, name, np_seed):
             assert np.array_equal(env.reset(), r["reset_obs"][ep])
         obs, rew, done, _ = env.step(r["act"][i])
         assert np.array_equal(obs, r["obs"][i]) and float(rew) == r["rew"][i] and bool(done) == bool(r["done"][i])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# non-default simulator config (tests/golden/gen_quadrotor_conf.py): off-diagonal inertia, centre-of-gravity offset,
+# CT[2] != 0, an out-of-plane rotor, initial velocities, other voltage range, healthy_reward = 2
+# ---------------------------------------------------------------------------------------------------------------
+CONF_RUNS = ["c_hover", "c_nocol", "c_vel", "c_spin"]
+
+
+@pytest.fixture(scope="module")
+def conf_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quadrotor_conf_golden.npz"))
+
+
+@pytest.mark.parametrize("name", CONF_RUNS)
+def test_custom_config_teacher_forced(conf_golden, name):
+    import json
+    params = json.loads(str(conf_golden["conf_json"]))
+    ccfg = qo.make_cfg(params)
+    r = golden_run(conf_golden, name)
+    state = np.array(r["pre_state"], dtype=np.float64)
+    ct = np.array(r["pre_ct"], dtype=np.int32)
+    n = state.shape[0]
+    kw = {}
+    if r["task"] == "velocity_control":
+        kw = dict(targets=r["targets"][None], env2task=np.zeros(n, np.int32))
+    obs, rew, done, fail, power = qo.env_step(ccfg, state, ct, r["act"], r["task"], r["dt"], r["nt"],
+                                              healthy=float(conf_golden["healthy_reward"]), mode="mix", **kw)
+    assert group_rel_err(state, r["post_state"], STATE_GROUPS) < 1e-6
+    assert group_rel_err(obs[:, :16], r["obs"][:, :16], OBS_GROUPS) < 1e-6
+    assert scalar_rel_err(rew, r["rew"]) < 1e-6
+    assert np.array_equal(done.astype(bool), r["done"]) and np.array_equal(ct, r["post_ct"])
+    assert scalar_rel_err(power, r["power"]) < 1e-6 and not fail.any()
+    # reset(): the recorded draws through the oracle's reset give the recorded first pre-step state
+    s0 = qo.reset_state(params, r["reset_noise"][:1])
+    assert group_rel_err(s0, r["pre_state"][:1], STATE_GROUPS) < 1e-7
+
+
+@pytest.mark.parametrize("name,np_seed", [("c_hover", 21), ("c_nocol", 22), ("c_vel", 23)])
+def test_numpy_port_with_custom_config(conf_golden, name, np_seed):
+    """The numpy port (CPU baseline) stays bit-identical to the reference under the non-default config."""
+    import json
+    from oracle.quadrotor_np import NumpyQuadrotorEnv
+    params = json.loads(str(conf_golden["conf_json"]))
+    r = golden_run(conf_golden, name)
+    env = NumpyQuadrotorEnv(dt=r["dt"], nt=r["nt"], seed=r["seed"], task=r["task"], params=params,
+                            healthy_reward=float(conf_golden["healthy_reward"]))
+    if r["task"] == "velocity_control":
+        assert np.array_equal(np.asarray(env.targets, dtype=np.float32), r["targets"])
+    np.random.seed(np_seed)
+    ep = -1
+    for i in range(len(r["rew"])):
+        if r["ep"][i] != ep:
+            ep = int(r["ep"][i])
+            assert np.array_equal(env.reset(), r["reset_obs"][ep])
+        obs, rew, done, _ = env.step(r["act"][i])
+        assert np.array_equal(obs, r["obs"][i]) and float(rew) == r["rew"][i] and bool(done) == bool(r["done"][i])
+        assert np.array_equal(env.st.as_row(), r["post_state"][i])
