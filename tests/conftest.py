@@ -35,6 +35,12 @@ def maze_golden():
 
 
 @pytest.fixture(scope="session")
+def geom_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "maze_geom_golden.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
 def cont_golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "maze_continuous_golden.npz"), allow_pickle=False)

@@ -39,12 +39,15 @@ def render_path(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("name", MAZE_CASES)
+GEOM_CASES = ["g3d_surv", "g3d_esc"]      # non-default cell / wall / eye heights (tests/golden/gen_maze_geom.py)
+
+
+@pytest.mark.parametrize("name", MAZE_CASES + GEOM_CASES)
 @pytest.mark.parametrize("n", [1, 3])
-def test_reference_episode(torch_mod, maze_golden, textures, name, n, render_path):
+def test_reference_episode(torch_mod, maze_golden, geom_golden, textures, name, n, render_path):
     """Replay the recorded reference episode on n identical envs (manual reset after done, like the reference user)."""
     torch = torch_mod
-    c = maze_case(maze_golden, name)
+    c = maze_case(geom_golden if name in GEOM_CASES else maze_golden, name)
     if c["kind"] == "2D" and render_path == "direct_render":
         pytest.skip("2-D has a single path")
     env = make_env(c, n, textures)
@@ -244,14 +247,14 @@ def test_reference_default_resolutions_vs_oracle(torch_mod, maze_golden, texture
     env.close()
 
 
-@pytest.mark.parametrize("name", ["c3d_surv", "c3d_esc"])
-def test_continuous_maze_reference_episode(torch_mod, cont_golden, textures, name):
+@pytest.mark.parametrize("name", ["c3d_surv", "c3d_esc", "gc3d"])
+def test_continuous_maze_reference_episode(torch_mod, cont_golden, geom_golden, textures, name):
     """MetaMazeContinuous3D: reference episodes replayed on the GPU -- float32 positions, float64
     headings, cells, rewards, dones, life and every recorded frame bit for bit."""
     torch = torch_mod
     from metagym_b200 import BatchedMetaMazeContinuous3D
     from util import cont_case
-    c = cont_case(cont_golden, name)
+    c = cont_case(geom_golden if name == "gc3d" else cont_golden, name)
     n = 3
     env = BatchedMetaMazeContinuous3D(resolution=c["resolution"], max_steps=c["max_steps"], task_type=c["task_type"],
                                       num_envs=n, squeeze=False, textures=textures)

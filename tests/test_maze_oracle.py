@@ -22,9 +22,18 @@ def replay(case, make_env):
             env.reset()
 
 
-@pytest.mark.parametrize("name", MAZE_CASES)
-def test_oracle_matches_reference_episode(maze_golden, name):
-    c = maze_case(maze_golden, name)
+@pytest.fixture(scope="module")
+def geom_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "maze_geom_golden.npz"))
+
+
+GEOM_CASES = ["g3d_surv", "g3d_esc"]      # non-default cell / wall / eye heights (tests/golden/gen_maze_geom.py)
+
+
+@pytest.mark.parametrize("name", MAZE_CASES + GEOM_CASES)
+def test_oracle_matches_reference_episode(maze_golden, geom_golden, name):
+    c = maze_case(geom_golden if name in GEOM_CASES else maze_golden, name)
     tex = synthetic_textures(seed=0)
 
     def make():
@@ -66,12 +75,12 @@ def test_values_can_exceed_uint8(maze_golden):
     assert 300 < int(obs.max()) < 400
 
 
-@pytest.mark.parametrize("name", ["c3d_surv", "c3d_esc"])
-def test_continuous_maze_oracle_matches_reference(cont_golden, name):
+@pytest.mark.parametrize("name", ["c3d_surv", "c3d_esc", "gc3d"])
+def test_continuous_maze_oracle_matches_reference(cont_golden, geom_golden, name):
     """MetaMazeContinuous3D: float32 positions, float64 headings, rewards, dones and every
     recorded frame of the reference episodes, bit for bit (numba/numpy typing of dynamics.py reproduced in C)."""
     from util import cont_case
-    c = cont_case(cont_golden, name)
+    c = cont_case(geom_golden if name == "gc3d" else cont_golden, name)
     tex = synthetic_textures(seed=0)
     env = OracleMaze("C3D", c["task_type"], c["max_steps"], 1, c["resolution"], textures=tex)
     env.set_task(c["task"])
