@@ -366,7 +366,7 @@ def main():
                 def chunk_peer():
                     ar = arenas[tick[0] & 1]
                     tick[0] += 1
-                    env.set_mirrors(ar.mirrors)
+                    ar.attach(env)
                     env.rollout(G, actions=None, act_seed=3, out=ar.views)
                     return ar.sync()
 

@@ -256,6 +256,11 @@ int mgb_peer_open(int device, const uint8_t handle[MGB_PEER_HANDLE_BYTES], void 
 int mgb_peer_close(int device, void *ptr);
 int mgb_quad_set_mirrors(mgb_quad *h, int count, const int64_t *byte_delta);
 int mgb_maze_set_mirrors(mgb_maze *h, int count, const int64_t *byte_delta);
+/* Guard: while mirrors (or multicast) are on, a rollout whose obs/rew/done/act_out pointers are not all inside
+ * [base, base + bytes) -- this rank's slot of the arena the deltas were computed for -- is refused with MGB_ERR_ARG
+ * instead of storing to `pointer + delta` somewhere else.  bytes = 0 removes the guard. */
+int mgb_quad_set_mirror_window(mgb_quad *h, const void *base, uint64_t bytes);
+int mgb_maze_set_mirror_window(mgb_maze *h, const void *base, uint64_t bytes);
 /* NVSwitch multicast variant: the rollout outputs are stored ONLY at `ptr + byte_delta` with multimem.st, where
  * byte_delta = (multicast mapping base - local arena base) of a multicast object every rank has bound its arena to
  * (cuMulticast*; torch.distributed._symmetric_memory does that plumbing).  The switch replicates each store into every

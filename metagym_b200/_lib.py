@@ -72,6 +72,8 @@ SIGNATURES = {
     "mgb_peer_close": (ctypes.c_int, [ctypes.c_int, vp]),
     "mgb_quad_set_mirrors": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "mgb_maze_set_mirrors": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "mgb_quad_set_mirror_window": (ctypes.c_int, [vp, vp, c_u64]),
+    "mgb_maze_set_mirror_window": (ctypes.c_int, [vp, vp, c_u64]),
     "mgb_quad_set_multicast": (ctypes.c_int, [vp, ctypes.c_int64]),
     "mgb_maze_set_multicast": (ctypes.c_int, [vp, ctypes.c_int64]),
     "mgb_maze_rollout": (ctypes.c_int, [vp, c_i32, vp, c_u64, vp, vp, vp, vp, vp]),

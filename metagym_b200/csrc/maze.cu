@@ -1270,6 +1270,7 @@ struct mgb_maze {
     int64_t launches = 0;
     uint32_t t_base = 0;
     MgbMirrors mir = {};         // mgb_maze_set_mirrors
+    MgbMirrorWindow mir_win;     // mgb_maze_set_mirror_window
 };
 
 static size_t maze3d_smem_bytes(const MazeConst &c)
@@ -1798,6 +1799,10 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
     a.act = act_dev; a.obs = obs_dev; a.rew = rew_dev; a.done = done_dev; a.do_step = 1;
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
     a.mir = h->mir;
+    if (h->mir.count != 0)
+        MGB_REQUIRE(h->mir_win.holds(obs_dev) && h->mir_win.holds(rew_dev) && h->mir_win.holds(done_dev) &&
+                        h->mir_win.holds(act_out_dev),
+                    "mirrors are on but an output lies outside the mirrored arena (set_mirrors([]) first)");
     cudaStream_t st = (cudaStream_t)stream;
     if (h->c.kind == MGB_MAZE_DISCRETE_3D) {
         MGB_REQUIRE(h->mir.count == 0, "output mirrors are implemented for the MetaMaze2D rollout only");
@@ -1851,6 +1856,14 @@ extern "C" int mgb_maze_set_mirrors(mgb_maze *h, int count, const int64_t *byte_
     }
     m.count = count;
     h->mir = m;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_set_mirror_window(mgb_maze *h, const void *base, uint64_t bytes)
+{
+    MGB_REQUIRE(h, "null handle");
+    h->mir_win.base = reinterpret_cast<uintptr_t>(base);
+    h->mir_win.bytes = bytes;
     return MGB_OK;
 }
 

@@ -112,6 +112,15 @@ struct MgbMirrors {
 #define MGB_MIRROR_MULTICAST (-1)
     int64_t delta[MGB_MAX_MIRRORS];   // bytes
 };
+struct MgbMirrorWindow {             // host side: where mirrored outputs must lie (0 bytes = unchecked)
+    uintptr_t base = 0;
+    uint64_t bytes = 0;
+    bool holds(const void *p) const
+    {
+        return p == nullptr || bytes == 0 ||
+               (reinterpret_cast<uintptr_t>(p) >= base && reinterpret_cast<uintptr_t>(p) < base + bytes);
+    }
+};
 template <typename T> __device__ __forceinline__ void mgb_mirror_store(const MgbMirrors &m, T *p, const T v)
 {
     for (int i = 0; i < m.count; ++i) *reinterpret_cast<T *>(reinterpret_cast<char *>(p) + m.delta[i]) = v;

@@ -1103,6 +1103,7 @@ struct mgb_quad {
     uint32_t t_base = 0;
     int64_t launches = 0;
     MgbMirrors mir = {};       // mgb_quad_set_mirrors
+    MgbMirrorWindow mir_win;   // mgb_quad_set_mirror_window
     // host staging for *_host entry points
     float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
     uint8_t *h_done = nullptr;
@@ -1430,6 +1431,10 @@ extern "C" int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, ui
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
     const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
     a.mir = h->mir;
+    if (h->mir.count != 0)
+        MGB_REQUIRE(h->mir_win.holds(obs_dev) && h->mir_win.holds(rew_dev) && h->mir_win.holds(done_dev) &&
+                        h->mir_win.holds(act_out_dev),
+                    "mirrors are on but an output lies outside the mirrored arena (set_mirrors([]) first)");
     if (h->mir.count == MGB_MIRROR_MULTICAST) {
         MGB_REQUIRE(h->n % 4 == 0, "multicast outputs need num_envs % 4 == 0");
         MGB_REQUIRE((((uintptr_t)done_dev | (uintptr_t)rew_dev | (uintptr_t)obs_dev) & 3) == 0 && ((uintptr_t)act_out_dev & 15) == 0,
@@ -1460,6 +1465,14 @@ extern "C" int mgb_quad_set_mirrors(mgb_quad *h, int count, const int64_t *byte_
     }
     m.count = count;
     h->mir = m;
+    return MGB_OK;
+}
+
+extern "C" int mgb_quad_set_mirror_window(mgb_quad *h, const void *base, uint64_t bytes)
+{
+    MGB_REQUIRE(h, "null handle");
+    h->mir_win.base = reinterpret_cast<uintptr_t>(base);
+    h->mir_win.bytes = bytes;
     return MGB_OK;
 }
 

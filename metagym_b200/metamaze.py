@@ -403,13 +403,21 @@ class BatchedMetaMaze2D(_BatchedMazeBase):
         cfg.n_cells, cfg.max_steps, cfg.view_grid = n_cells, self.max_steps, self.view_grid
         return cfg
 
-    def set_mirrors(self, byte_deltas):
+    def _set_window(self, window):
+        """window = (base address, bytes) of this rank's arena slot: rollouts writing elsewhere are refused while
+        mirrors are on (arena.attach(env) passes it)."""
+        base, nbytes = (0, 0) if window is None else (int(window[0]), int(window[1]))
+        _lib.check(self._lib.mgb_maze_set_mirror_window(self._h, base, nbytes))
+
+    def set_mirrors(self, byte_deltas, window=None):
         """Every output of rollout() is also stored at `pointer + delta` (see rollout.PeerArena)."""
+        self._set_window(window)
         d = np.ascontiguousarray(np.asarray(list(byte_deltas), dtype=np.int64))
         _lib.check(self._lib.mgb_maze_set_mirrors(self._h, int(d.size), _lib.ptr(d) if d.size else None))
 
-    def set_multicast(self, byte_delta):
+    def set_multicast(self, byte_delta, window=None):
         """rollout() outputs go through an NVSwitch multicast mapping at `pointer + byte_delta` (rollout.MulticastArena)."""
+        self._set_window(window)
         _lib.check(self._lib.mgb_maze_set_multicast(self._h, int(byte_delta)))
 
     def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):

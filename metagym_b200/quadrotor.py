@@ -330,15 +330,23 @@ class BatchedQuadrotor(object):
                                               _lib.ptr(out.get("done")), self._stream()))
         return out
 
-    def set_mirrors(self, byte_deltas):
+    def _set_window(self, window):
+        """window = (base address, bytes) of this rank's arena slot: rollouts writing elsewhere are refused while
+        mirrors are on (arena.attach(env) passes it)."""
+        base, nbytes = (0, 0) if window is None else (int(window[0]), int(window[1]))
+        _lib.check(self._lib.mgb_quad_set_mirror_window(self._h, base, nbytes))
+
+    def set_mirrors(self, byte_deltas, window=None):
         """Every output of rollout() is also stored at `pointer + delta` for each delta (rollout.PeerArena.mirrors:
         the kernel then writes the trajectory straight into the other ranks' receive arenas over NVLink)."""
+        self._set_window(window)
         d = np.ascontiguousarray(np.asarray(list(byte_deltas), dtype=np.int64))
         _lib.check(self._lib.mgb_quad_set_mirrors(self._h, int(d.size), _lib.ptr(d) if d.size else None))
 
-    def set_multicast(self, byte_delta):
+    def set_multicast(self, byte_delta, window=None):
         """rollout() outputs are stored through an NVSwitch multicast mapping at `pointer + byte_delta`
         (rollout.MulticastArena.multicast_delta); 0 switches it off."""
+        self._set_window(window)
         _lib.check(self._lib.mgb_quad_set_multicast(self._h, int(byte_delta)))
 
     @property

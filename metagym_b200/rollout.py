@@ -180,6 +180,16 @@ class PeerArena(RolloutArena):
             self.views[k] = self.buf[o:o + nb].view(dt).view(shape)
             self.gathered[k] = recv[:, o:o + nb].view(dt).view((self.world,) + shape)
 
+    def attach(self, *envs):
+        """Point the envs' fused rollouts at this arena: mirrors on, and only outputs inside this rank's slot accepted."""
+        for env in envs:
+            env.set_mirrors(self.mirrors, window=(self.buf.data_ptr(), self.nbytes))
+
+    @staticmethod
+    def detach(*envs):
+        for env in envs:
+            env.set_mirrors([])
+
     def sync(self, async_op=False):
         """Stream-ordered rendezvous: complete (on the stream) once every rank's kernels enqueued so far have finished,
         i.e. all peer stores of this chunk have landed here.  The data never goes through NCCL.
@@ -241,6 +251,15 @@ class MulticastArena(RolloutArena):
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)
+
+    def attach(self, *envs):
+        for env in envs:
+            env.set_multicast(self.multicast_delta, window=(self.buf.data_ptr(), self.nbytes))
+
+    @staticmethod
+    def detach(*envs):
+        for env in envs:
+            env.set_multicast(0)
 
     def sync(self, async_op=False):
         import torch.distributed as dist

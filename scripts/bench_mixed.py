@@ -131,8 +131,7 @@ ptick = [0]
 def collect_peer():
     ar = peers[ptick[0] & 1]
     ptick[0] += 1
-    quad.set_mirrors(ar.mirrors)
-    maze.set_mirrors(ar.mirrors)
+    ar.attach(quad, maze)
     collect(ar.views)
     gathered.update(ar.sync())
     return ar
@@ -161,8 +160,7 @@ def collect_peer_async():
     i = ptick[0] % 4
     ptick[0] += 1
     ar = peers[i]
-    quad.set_mirrors(ar.mirrors)
-    maze.set_mirrors(ar.mirrors)
+    ar.attach(quad, maze)
     collect(ar.views)
     _, works[i] = ar.sync(async_op=True)
     j = (i - 1) % 4
@@ -196,8 +194,7 @@ if world > 1 and os.environ.get("MIXED_MULTICAST", "1") != "0":
             i = mtick[0] % 4
             mtick[0] += 1
             ar = mcs[i]
-            quad.set_multicast(ar.multicast_delta)
-            maze.set_multicast(ar.multicast_delta)
+            ar.attach(quad, maze)
             collect(ar.views)
             _, mworks[i] = ar.sync(async_op=True)
             j = (i - 1) % 4

@@ -200,3 +200,43 @@ def test_multicast_rollout_outputs_equal_plain(torch_mod):
     if "NO_MULTICAST" in r.stdout:
         pytest.skip("no multicast support here: " + r.stdout.strip()[-200:])
     assert r.returncode == 0 and "MC_OK" in r.stdout and "MISSING_CHECK" not in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_mirror_window_refuses_outputs_outside_the_arena(torch_mod):
+    """With mirrors on and the arena window registered (arena.attach), a rollout into any other buffer is refused
+    instead of storing to `pointer + delta` at a meaningless address; detaching restores plain rollouts."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, BatchedQuadrotor, MazeTaskSampler, _lib
+    T, n = 4, 64
+    qf = {"obs": ((T, n, 16), torch.float32), "act": ((T, n, 4), torch.float32), "rew": ((T, n), torch.float32),
+          "done": ((T, n), torch.uint8)}
+    a0, a1 = _arenas(torch, qf, 2)
+    env = BatchedQuadrotor(num_envs=n, device=0, squeeze=False, auto_reset=True)
+    env.reset()
+    delta = a1.buf.data_ptr() - a0.buf.data_ptr()
+    env.set_mirrors([delta], window=(a0.buf.data_ptr(), a0.nbytes))
+    env.rollout(T, act_seed=1, out=a0.views)                          # inside the window: fine, and mirrored
+    torch.cuda.synchronize()
+    assert torch.equal(a0.buf, a1.buf)
+    with pytest.raises(_lib.MgbError):
+        env.rollout(T, act_seed=1)                                    # own buffers: outside -> refused
+    with pytest.raises(_lib.MgbError):
+        env.rollout(T, act_seed=1, out=a1.views)                      # the other arena: outside -> refused
+    env.set_mirrors([])
+    env.rollout(T, act_seed=1)                                        # plain rollout works again
+    env.close()
+    mf = {"obs": ((T, n, 3, 3), torch.float32), "act": ((T, n), torch.int32), "rew": ((T, n), torch.float64),
+          "done": ((T, n), torch.uint8)}
+    m0, m1 = _arenas(torch, mf, 2)
+    maze = BatchedMetaMaze2D(max_steps=20, task_type="ESCAPE", view_grid=1, num_envs=n, squeeze=False, auto_reset=True)
+    maze.set_task(MazeTaskSampler(n=9, rng=np.random.RandomState(0)))
+    maze.reset()
+    maze.set_mirrors([m1.buf.data_ptr() - m0.buf.data_ptr()], window=(m0.buf.data_ptr(), m0.nbytes))
+    maze.rollout(T, act_seed=2, out=m0.views)
+    torch.cuda.synchronize()
+    assert torch.equal(m0.buf, m1.buf)
+    with pytest.raises(_lib.MgbError):
+        maze.rollout(T, act_seed=2, want_actions=True)
+    maze.set_mirrors([])
+    maze.rollout(T, act_seed=2)
+    maze.close()
