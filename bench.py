@@ -39,6 +39,7 @@ METRIC = "env-steps/sec (quadrotor 6-DoF, 65k envs)"
 N_ENVS_PER_GPU = 65536
 DT, NT, N_TASKS = 0.005, 1000, 64
 TASK = "velocity_control"
+FLOPS_PER_STEP = 350 * 5 + 60   # dt 0.005 = 5 substeps
 BYTES_PER_STEP = 281          # read state 88 + ct 4 + action 16; write state 88 + ct 4 + obs 76 + rew 4 + done 1
 GRAPH_STEPS = 32              # steps per CUDA graph = slots of the rollout buffer
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE quad_step_kernel launch at this shape, from the committed
@@ -446,7 +447,11 @@ def main():
                          "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
                          "peak_source": peak_src, "kernel": "quad_step_wide_kernel<true>",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n,
-                         "us_per_launch": us_per_launch},
+                         "us_per_launch": us_per_launch,
+                         # secondary figure SURVEY.md 8d asks for: ~350 flop per substep + ~60 per step (hand count)
+                         "flops_per_env_step": FLOPS_PER_STEP,
+                         "achieved_fp32_tflops": n / (us_per_launch * 1e-6) * FLOPS_PER_STEP / 1e12,
+                         "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12},
             "gpu_launches": K,
             "clocks": clocks,
             "finite_outputs": finite,
