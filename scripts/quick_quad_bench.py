@@ -10,8 +10,12 @@ def timeit(fn, iters):
     e0.record(); fn(iters); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3  # us per iter
 
-for task, dt, N in [("velocity_control", 0.005, 65536), ("hovering_control", 0.01, 4096),
-                    ("velocity_control", 0.005, 4194304), ("hovering_control", 0.01, 65536)]:
+CASES = [("velocity_control", 0.005, 65536), ("hovering_control", 0.01, 4096),
+         ("velocity_control", 0.005, 4194304), ("hovering_control", 0.01, 65536)]
+ONLY = int(sys.argv[1]) if len(sys.argv) > 1 else None      # e.g. `quick_quad_bench.py 4096`: that batch size only
+if ONLY is not None:
+    CASES = [c for c in CASES if c[2] == ONLY]
+for task, dt, N in CASES:
     env = BatchedQuadrotor(task=task, dt=dt, nt=1000, seed=list(range(64)), num_envs=N, squeeze=False,
                            auto_reset=True)
     env.reset()
@@ -56,6 +60,8 @@ for task, dt, N in [("velocity_control", 0.005, 65536), ("hovering_control", 0.0
     torch.cuda.empty_cache()
 
 # RK4 variant of the bench shape (config 3 wording)
+if ONLY is not None:
+    sys.exit(0)
 env = BatchedQuadrotor(task="velocity_control", dt=0.005, nt=1000, seed=list(range(64)), num_envs=65536, squeeze=False,
                        auto_reset=True, integrator="rk4")
 env.reset()
