@@ -64,3 +64,32 @@ def test_product_never_imports_the_oracle():
                 continue
             src = open(os.path.join(d, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), (sub, fn)
+
+
+def test_host_config_parsing_agrees_with_the_oracle():
+    """metagym_b200.quadrotor.build_cfg (what the product hands to mgb_quad_create) and oracle.quad_oracle.make_cfg are
+    written independently from QuadrotorSim._parse_cfg (quadrotorsim.py:50-109): same derived numbers for the default
+    config and for the non-default one of tests/golden/gen_quadrotor_conf.py; malformed configs raise RuntimeError with
+    the reference's prefix."""
+    import json
+    import numpy as np
+    from metagym_b200.quadrotor import build_cfg, velocity_task_actions
+    from oracle import quad_oracle as qo
+    g = np.load(os.path.join(ROOT, "tests", "golden", "quadrotor_conf_golden.npz"))
+    for params in (qo.DEFAULT_PARAMS, json.loads(str(g["conf_json"]))):
+        c = build_cfg(params, 0.005, 40, "velocity_control", 2.0)
+        o = qo.make_cfg(params)
+        f32 = lambda xs: [float(np.float32(x)) for x in xs]      # noqa: E731
+        assert f32(c.inv_inertia) == f32(o.Iinv) and f32(c.drag_m) == f32(o.Dm) and f32(c.drag_f) == f32(o.Df)
+        assert f32(c.gravity_center) == f32(o.cg) and f32(c.propeller) == f32(o.prop) and f32(c.propeller_norm) == f32(o.lm)
+        assert f32(c.ct) == f32([o.ct0, o.ct1, o.ct2]) and (c.mm, c.jm, c.phi, c.ra) == (o.mm, o.jm, o.phi, o.ra)
+        assert (c.precision, c.quality) == (o.h, o.m) and (c.min_voltage, c.max_voltage) == (o.vmin, o.vmax)
+        assert (c.fail_velocity, c.fail_range, c.fail_w) == (o.fail_v, o.fail_r, o.fail_w)
+        assert c.z_offset == 0.0 and c.healthy_reward == 2.0 and c.nt == 40
+        a = velocity_task_actions(params, 7, 3)
+        assert a.dtype == np.float32 and a.shape == (7, 4) and a.min() >= o.vmin and a.max() <= o.vmax
+    assert build_cfg(qo.DEFAULT_PARAMS, 0.01, 10, "hovering_control", 1.0).z_offset == 5.0
+    bad = dict(qo.DEFAULT_PARAMS)
+    del bad["thrust"]
+    with pytest.raises(RuntimeError, match="Error in loading configuration"):
+        build_cfg(bad, 0.01, 10, "hovering_control", 1.0)
