@@ -108,7 +108,7 @@ int mgb_quad_set_map(mgb_quad *h, const int32_t *map_host, int32_t rows, int32_t
  * task row of every local env, env2task [n_envs] int32.  Both are COPIED into the handle (synchronous). */
 int mgb_quad_set_targets(mgb_quad *h, const float *tbl_dev, int32_t n_tasks, const int32_t *env2task_dev);
 
-/* Runs define_velocity_control_task on the device for n_tasks seeds: act_host [n_tasks][nt][4] float32 are the
+/* Runs define_velocity_control_task (quadrotorsim.py:306-319) on the device for n_tasks seeds: act_host [n_tasks][nt][4] float32 are the
  * np.random.uniform draws (host-replayed for RNG parity); tbl_dev [n_tasks][nt][3] receives global_velocity after
  * every step from the zero state.  Independent of the handle's env state. */
 int mgb_quad_make_targets(mgb_quad *h, const float *act_dev, int32_t n_tasks, float *tbl_dev, void *stream);
@@ -127,14 +127,16 @@ int mgb_quad_reset(mgb_quad *h, const uint8_t *mask_dev, const double *noise_dev
 int mgb_quad_step(mgb_quad *h, const float *act_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev,
                   int32_t *fail_dev, float *final_obs_dev, void *stream);
 
-/* T consecutive steps in ONE launch with the state held in registers (auto-reset semantics as configured).
+/* T consecutive Quadrotor.step calls (env.py:127-165; the rollout loop of quadrotor/tests/test_env.py:22-28) in ONE launch
+ * with the state held in registers (auto-reset semantics as configured).
  *   act_dev [T][n][4] or NULL: NULL draws U(min_voltage, max_voltage) actions from the counter-based generator
  *   (stream id `act_seed`), written to act_out_dev [T][n][4] if not NULL.
  *   obs_dev [T][n][obs_dim], rew_dev [T][n], done_dev [T][n]; any of them may be NULL to skip that output. */
 int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, uint64_t act_seed, float *act_out_dev,
                      float *obs_dev, float *rew_dev, uint8_t *done_dev, void *stream);
 
-/* Same as mgb_quad_step with HOST buffers: stages through pinned memory, copies inside the call, returns when the
+/* Quadrotor.step as the reference's numpy users call it (env.py:127-165: ndarray in, ndarray out).
+ * Same as mgb_quad_step with HOST buffers: stages through pinned memory, copies inside the call, returns when the
  * outputs are on the host (synchronous).  This is the call a numpy user of the reference API makes. */
 int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host, uint8_t *done_host);
 
@@ -214,7 +216,8 @@ int mgb_maze_step(mgb_maze *h, const int32_t *act_dev, void *obs_dev, double *re
                   void *stream);
 int mgb_maze_set_options(mgb_maze *h, int auto_reset);
 
-/* MetaMaze2D and MetaMazeDiscrete3D: T consecutive steps in ONE launch (agent state in registers; auto-reset semantics
+/* MetaMaze2D and MetaMazeDiscrete3D: T consecutive step() calls (maze_env.py:59-75,189-206; the random-action loops of
+ * metamaze/test.py:9-47) in ONE launch (agent state in registers; auto-reset semantics
  * as configured; the 3-D form runs on the pose cache: one CTA per env, step logic by one thread, frame by the CTA).
  *   act_dev [T][n] int32 or NULL: NULL draws uniform {0..3} actions from the counter-based generator (stream id
  *   act_seed, keyed by the global env index), written to act_out_dev [T][n] if not NULL.
@@ -229,10 +232,12 @@ int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, uint64_t ac
  * what the reference computes for float32 actions (its action_space.sample()): float32 position, float64 heading. */
 int mgb_maze_step_continuous(mgb_maze *h, const float *act_dev, void *obs_dev, double *rew_dev, uint8_t *done_dev,
                              void *stream);
-/* Continuous pose: pos_dev [n][2] float32 (_agent_loc), ori_dev [n] float64 (_agent_ori). */
+/* Continuous pose (maze_continuous_3d.py:47-56, dynamics.py:71-92): pos_dev [n][2] float32 (_agent_loc), ori_dev [n]
+ * float64 (_agent_ori). */
 int mgb_maze_pose(mgb_maze *h, float *pos_dev, double *ori_dev, void *stream);
 
-/* Inspection: agent [n][4] int32 = grid_x, grid_y, ori_index, steps; life [n] float64. */
+/* Inspection (info["steps"] maze_env.py:73; _agent_grid, _agent_ori_index, _life of maze_base.py:40-63): agent [n][4]
+ * int32 = grid_x, grid_y, ori_index, steps; life [n] float64. */
 int mgb_maze_state(mgb_maze *h, int32_t *agent_dev, double *life_dev, void *stream);
 int64_t mgb_maze_launch_count(const mgb_maze *h);
 
