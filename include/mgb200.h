@@ -136,9 +136,14 @@ int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, uint64_t act_
                      float *obs_dev, float *rew_dev, uint8_t *done_dev, void *stream);
 
 /* Quadrotor.step as the reference's numpy users call it (env.py:127-165: ndarray in, ndarray out).
- * Same as mgb_quad_step with HOST buffers: stages through pinned memory, copies inside the call, returns when the
- * outputs are on the host (synchronous).  This is the call a numpy user of the reference API makes. */
-int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host, uint8_t *done_host);
+ * Same as mgb_quad_step with HOST buffers: stages through pinned memory (or, for pinned caller buffers, lets the kernel
+ * read/write host memory directly), copies inside the call, returns when the outputs are on the host (synchronous).
+ * All work is enqueued on `stream` (the caller's current stream), so the step is ordered after a preceding
+ * mgb_quad_reset / mgb_quad_rollout / mgb_quad_state on that stream.  fail_host [n] int32 and final_obs_host
+ * [n][obs_dim] may be NULL; they report what mgb_quad_step's fail_dev / final_obs_dev report (quadrotorsim.py:212-221).
+ * This is the call a numpy user of the reference API makes. */
+int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host, uint8_t *done_host,
+                       int32_t *fail_host, float *final_obs_host, void *stream);
 
 /* Checkpoint / inspection (quadrotorsim.py:30-48 _save_state/_restore_state): state_dev [n][22] float32 row-major
  * = p3 v3 w3 prop4 R9, ct_dev [n] int32.  load = 0 copies handle -> buffers, 1 buffers -> handle. */
@@ -146,6 +151,12 @@ int mgb_quad_state(mgb_quad *h, float *state_dev, int32_t *ct_dev, int load, voi
 
 /* Number of kernel launches issued through this handle so far (bench.py reports it as gpu_launches). */
 int64_t mgb_quad_launch_count(const mgb_quad *h);
+
+/* Name of the kernel an mgb_quad_step launch of this handle takes at its batch size ("quad_step2_kernel<true,1>":
+ * two envs per thread in packed FFMA2 registers; "quad_stream2_kernel<..>": persistent TMA-pipelined variant for
+ * multi-wave batches; "quad_step_kernel<..>": scalar reference instantiation, MGB_PACKED=0 or the RK4 option).
+ * Reporting only (bench.py's roofline.kernel); no reference counterpart. */
+const char *mgb_quad_step_kernel(const mgb_quad *h);
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* MetaMaze (2D grid + discrete-3D raycast)                                                                       */

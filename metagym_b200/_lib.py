@@ -54,9 +54,10 @@ SIGNATURES = {
     "mgb_quad_reset": (ctypes.c_int, [vp, vp, vp, vp, vp]),
     "mgb_quad_step": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "mgb_quad_rollout": (ctypes.c_int, [vp, c_i32, vp, c_u64, vp, vp, vp, vp, vp]),
-    "mgb_quad_step_host": (ctypes.c_int, [vp, vp, vp, vp, vp]),
+    "mgb_quad_step_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "mgb_quad_state": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp]),
     "mgb_quad_launch_count": (c_i64, [vp]),
+    "mgb_quad_step_kernel": (ctypes.c_char_p, [vp]),
     "mgb_maze_create": (ctypes.c_int, [ctypes.POINTER(vp), c_i64, ctypes.POINTER(MazeCfg), ctypes.c_int, c_i64]),
     "mgb_maze_destroy": (None, [vp]),
     "mgb_maze_obs_bytes_per_env": (c_i64, [vp]),

@@ -1800,8 +1800,9 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
     a.T = T; a.act_seed = act_seed; a.t_base = h->t_base; a.act_out = act_out_dev;
     a.mir = h->mir;
     if (h->mir.count != 0)
-        MGB_REQUIRE(h->mir_win.holds(obs_dev) && h->mir_win.holds(rew_dev) && h->mir_win.holds(done_dev) &&
-                        h->mir_win.holds(act_out_dev),
+        MGB_REQUIRE(h->mir_win.holds(obs_dev, (uint64_t)T * h->n * (uint64_t)mgb_maze_obs_bytes_per_env(h)) &&
+                        h->mir_win.holds(rew_dev, (uint64_t)T * h->n * 8) && h->mir_win.holds(done_dev, (uint64_t)T * h->n) &&
+                        h->mir_win.holds(act_out_dev, (uint64_t)T * h->n * 4),
                     "mirrors are on but an output lies outside the mirrored arena (set_mirrors([]) first)");
     cudaStream_t st = (cudaStream_t)stream;
     if (h->c.kind == MGB_MAZE_DISCRETE_3D) {

@@ -115,10 +115,12 @@ struct MgbMirrors {
 struct MgbMirrorWindow {             // host side: where mirrored outputs must lie (0 bytes = unchecked)
     uintptr_t base = 0;
     uint64_t bytes = 0;
-    bool holds(const void *p) const
+    // the whole extent [p, p + len) must lie inside the window: a rollout with a larger T or N than the arena slot was
+    // laid out for would otherwise store `ptr + delta` past the peer's slot
+    bool holds(const void *p, uint64_t len) const
     {
-        return p == nullptr || bytes == 0 ||
-               (reinterpret_cast<uintptr_t>(p) >= base && reinterpret_cast<uintptr_t>(p) < base + bytes);
+        const uintptr_t q = reinterpret_cast<uintptr_t>(p);
+        return p == nullptr || bytes == 0 || (q >= base && len <= bytes && q - base <= bytes - len);
     }
 };
 template <typename T> __device__ __forceinline__ void mgb_mirror_store(const MgbMirrors &m, T *p, const T v)

@@ -1,5 +1,8 @@
-// Quadrotor hot path for sm_100a: one thread = one env; the 22-float rigid-body state, the adjugate of the rotation
-// matrix and every substep intermediate live in registers for the whole env.step().
+// Quadrotor hot path for sm_100a.  The float32 arithmetic of one env.step() is written ONCE, templated on a lane type
+// (quad_lanes.cuh): T = float runs one env per thread; T = f2 runs TWO envs per thread in packed registers
+// (FFMA2 / FADD2), which halves the floating-point instruction count per env -- the step kernel is issue-bound, not
+// bandwidth-bound, at 65 536 envs (profiles/r1_ncu_quad_step_wide_65k.txt).  The 22-float rigid-body state, the adjugate
+// of the rotation matrix and every substep intermediate live in registers for the whole env.step().
 //
 // Replaces (reference file:line, PaddlePaddle/MetaGym):
 //   QuadrotorSim._run_internal / _check_failure / step      metagym/quadrotor/quadrotorsim.py:122-221, 295-304
@@ -7,13 +10,13 @@
 //   Quadrotor.step / _get_reward / _check_collision / _update_state / _convert_state_to_ndarray
 //                                                             metagym/quadrotor/env.py:127-165, 193-281
 //
-// Data layout in HBM (DESIGN.md "state planes"): per tile of 128 envs, six planes of float4 stored back to back
-// (tile t, plane k, env j -> float4 index (t*6 + k)*128 + j).  Every load/store is one coalesced 128-bit access per
-// thread (512 B contiguous per warp) AND a tile's whole state is one contiguous 12 KB block, so a CTA touches 3 DRAM
-// pages instead of 12 far-apart ones (measured: plane-major [6][n] streamed at 4.3 TB/s, tile-major at see DESIGN.md):
-//   P0 = p.x p.y p.z v.x | P1 = v.y v.z w.x w.y | P2 = w.z m0 m1 m2 | P3 = m3 R00 R01 R02
-//   P4 = R10 R11 R12 R20 | P5 = R21 R22 ct(int) episode(int)
-// (p position, v velocity, w body angular velocity, m propeller speeds, R rotation matrix)
+// Data layout in HBM (DESIGN.md "state planes"): envs are stored as PAIRS (2j, 2j+1).  Per tile of 128 envs = 64 pairs,
+// twelve planes of float4 stored back to back (tile t, plane k, pair j -> float4 index (t*12 + k)*64 + j); one float4
+// holds two consecutive fields of both envs of the pair: (f[2k] of A, f[2k] of B, f[2k+1] of A, f[2k+1] of B), with the 24
+// fields  p.x p.y p.z v.x v.y v.z w.x w.y w.z m0 m1 m2 m3 R00 R01 R02 R10 R11 R12 R20 R21 R22 ct(int) episode(int)
+// (p position, v velocity, w body angular velocity, m propeller speeds, R rotation matrix).  A packed thread loads its
+// pair with twelve coalesced 128-bit accesses (512 B contiguous per warp) and every float4 half IS a packed register
+// pair (no shuffling); a tile's whole state is one contiguous 12 KB block (one bulk/TMA copy in the streaming kernel).
 // Observations leave through a shared-memory tile and ONE bulk (TMA) store per CTA, so the [n][obs_dim] row-major
 // array the gym API wants is written with full 128 B lines even though obs_dim*4 (64 or 76 B) is not a line.
 #include <math.h>
@@ -23,10 +26,11 @@
 #include <vector>
 
 #include "mgb_common.cuh"
+#include "quad_lanes.cuh"
 
 namespace {
 
-constexpr int kThreads = 64;   // 65 536 envs -> 1024 CTAs = 6.9 per SM: 1 % tail imbalance (128 -> 15 %)
+constexpr int kThreads = 64;   // scalar tile kernel / rollout kernel: envs per CTA
 constexpr int kMaxObs = 19;
 
 // Constants derived on the host (double arithmetic, rounded once to float32 -- numpy's "weak python scalar" rule).
@@ -76,7 +80,7 @@ struct QuadArgs {
     const int32_t *env2task;   // [n]
     uint64_t seed;
     int auto_reset;
-    int per_cta;               // quad_step_wide_kernel: envs per CTA
+    int per_cta;               // quad_step2_kernel: envs per CTA (multiple of 4)
     // rollout only
     int T;
     uint64_t act_seed;
@@ -85,107 +89,176 @@ struct QuadArgs {
     MgbMirrors mir;            // rollout only: every output is also stored at ptr + mir.delta[i]
 };
 
-struct QState {
-    float p[3], v[3], om[3], w[4], R[9];
-    int ct, ep;
+// Register state of Lanes<T>::N envs
+template <class T> struct VState {
+    T p[3], v[3], om[3], w[4], R[9];
+    int ct[Lanes<T>::N], ep[Lanes<T>::N];
 };
+using QState = VState<float>;
 
-constexpr int kTileEnvs = 128;   // envs per state tile (layout unit, independent of the CTA size)
+constexpr int kTileEnvs = 128;    // envs per state tile (layout unit, independent of the CTA size)
+constexpr int kTilePairs = 64;
+constexpr int kPlanes = 12;       // float4 planes per tile
 
-__device__ __forceinline__ float4 *tile_base(const QuadArgs &a, int64_t e)
+// scalar view of the pair-interleaved layout: field f of env e is base[(f >> 1) * 256 + (f & 1) * 2]
+__device__ __forceinline__ float *env_base_ptr(const QuadArgs &a, int64_t e)
 {
-    return a.planes + (e / kTileEnvs) * (6 * kTileEnvs) + (e % kTileEnvs);
+    return reinterpret_cast<float *>(a.planes) + ((e / kTileEnvs) * (kPlanes * kTilePairs) + ((e % kTileEnvs) >> 1)) * 4 +
+           (e & 1);
 }
+#define MGB_QF(f) (((f) >> 1) * (kTilePairs * 4) + ((f) & 1) * 2)
 
 __device__ __forceinline__ void load_state(const QuadArgs &a, int64_t e, QState &s)
 {
-    const float4 *b = tile_base(a, e);
-    const float4 q0 = b[0 * kTileEnvs], q1 = b[1 * kTileEnvs], q2 = b[2 * kTileEnvs], q3 = b[3 * kTileEnvs],
-                 q4 = b[4 * kTileEnvs], q5 = b[5 * kTileEnvs];
-    s.p[0] = q0.x; s.p[1] = q0.y; s.p[2] = q0.z; s.v[0] = q0.w;
-    s.v[1] = q1.x; s.v[2] = q1.y; s.om[0] = q1.z; s.om[1] = q1.w;
-    s.om[2] = q2.x; s.w[0] = q2.y; s.w[1] = q2.z; s.w[2] = q2.w;
-    s.w[3] = q3.x; s.R[0] = q3.y; s.R[1] = q3.z; s.R[2] = q3.w;
-    s.R[3] = q4.x; s.R[4] = q4.y; s.R[5] = q4.z; s.R[6] = q4.w;
-    s.R[7] = q5.x; s.R[8] = q5.y; s.ct = __float_as_int(q5.z); s.ep = __float_as_int(q5.w);
+    const float *b = env_base_ptr(a, e);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { s.p[k] = b[MGB_QF(k)]; s.v[k] = b[MGB_QF(3 + k)]; s.om[k] = b[MGB_QF(6 + k)]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.w[k] = b[MGB_QF(9 + k)];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s.R[k] = b[MGB_QF(13 + k)];
+    s.ct[0] = __float_as_int(b[MGB_QF(22)]);
+    s.ep[0] = __float_as_int(b[MGB_QF(23)]);
 }
 
 __device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const QState &s)
 {
-    float4 *b = tile_base(a, e);
-    b[0 * kTileEnvs] = make_float4(s.p[0], s.p[1], s.p[2], s.v[0]);
-    b[1 * kTileEnvs] = make_float4(s.v[1], s.v[2], s.om[0], s.om[1]);
-    b[2 * kTileEnvs] = make_float4(s.om[2], s.w[0], s.w[1], s.w[2]);
-    b[3 * kTileEnvs] = make_float4(s.w[3], s.R[0], s.R[1], s.R[2]);
-    b[4 * kTileEnvs] = make_float4(s.R[3], s.R[4], s.R[5], s.R[6]);
-    b[5 * kTileEnvs] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct), __int_as_float(s.ep));
+    float *b = env_base_ptr(a, e);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { b[MGB_QF(k)] = s.p[k]; b[MGB_QF(3 + k)] = s.v[k]; b[MGB_QF(6 + k)] = s.om[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[MGB_QF(9 + k)] = s.w[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) b[MGB_QF(13 + k)] = s.R[k];
+    b[MGB_QF(22)] = __int_as_float(s.ct[0]);
+    b[MGB_QF(23)] = __int_as_float(s.ep[0]);
+}
+
+// packed view: the twelve float4 of pair P (envs 2P, 2P+1); q[k] = (f[2k].A, f[2k].B, f[2k+1].A, f[2k+1].B)
+__device__ __forceinline__ void unpack_state(const float4 q[kPlanes], VState<f2> &s)
+{
+#define MGB_LO(k) f2{make_float2(q[k].x, q[k].y)}
+#define MGB_HI(k) f2{make_float2(q[k].z, q[k].w)}
+    s.p[0] = MGB_LO(0); s.p[1] = MGB_HI(0); s.p[2] = MGB_LO(1); s.v[0] = MGB_HI(1);
+    s.v[1] = MGB_LO(2); s.v[2] = MGB_HI(2); s.om[0] = MGB_LO(3); s.om[1] = MGB_HI(3);
+    s.om[2] = MGB_LO(4); s.w[0] = MGB_HI(4); s.w[1] = MGB_LO(5); s.w[2] = MGB_HI(5);
+    s.w[3] = MGB_LO(6); s.R[0] = MGB_HI(6); s.R[1] = MGB_LO(7); s.R[2] = MGB_HI(7);
+    s.R[3] = MGB_LO(8); s.R[4] = MGB_HI(8); s.R[5] = MGB_LO(9); s.R[6] = MGB_HI(9);
+    s.R[7] = MGB_LO(10); s.R[8] = MGB_HI(10);
+    s.ct[0] = __float_as_int(q[11].x); s.ct[1] = __float_as_int(q[11].y);
+    s.ep[0] = __float_as_int(q[11].z); s.ep[1] = __float_as_int(q[11].w);
+#undef MGB_LO
+#undef MGB_HI
+}
+__device__ __forceinline__ float4 *pair_ptr(const QuadArgs &a, int64_t P)
+{
+    return a.planes + (P / kTilePairs) * (kPlanes * kTilePairs) + (P % kTilePairs);
+}
+__device__ __forceinline__ void load_state2(const QuadArgs &a, int64_t P, VState<f2> &s)
+{
+    const float4 *b = pair_ptr(a, P);
+    float4 q[kPlanes];
+#pragma unroll
+    for (int k = 0; k < kPlanes; ++k) q[k] = b[k * kTilePairs];
+    unpack_state(q, s);
+}
+__device__ __forceinline__ void store_state2(const QuadArgs &a, int64_t P, const VState<f2> &s)
+{
+    float4 *b = pair_ptr(a, P);
+#define MGB_ST(k, lo, hi) b[(k) * kTilePairs] = make_float4((lo).v.x, (lo).v.y, (hi).v.x, (hi).v.y)
+    MGB_ST(0, s.p[0], s.p[1]); MGB_ST(1, s.p[2], s.v[0]); MGB_ST(2, s.v[1], s.v[2]); MGB_ST(3, s.om[0], s.om[1]);
+    MGB_ST(4, s.om[2], s.w[0]); MGB_ST(5, s.w[1], s.w[2]); MGB_ST(6, s.w[3], s.R[0]); MGB_ST(7, s.R[1], s.R[2]);
+    MGB_ST(8, s.R[3], s.R[4]); MGB_ST(9, s.R[5], s.R[6]); MGB_ST(10, s.R[7], s.R[8]);
+#undef MGB_ST
+    b[11 * kTilePairs] = make_float4(__int_as_float(s.ct[0]), __int_as_float(s.ct[1]), __int_as_float(s.ep[0]),
+                                     __int_as_float(s.ep[1]));
+}
+
+// lane h of a packed state <-> scalar state
+template <class T> __device__ __forceinline__ void get_lane_state(const VState<T> &s, int h, QState &o)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.p[k] = lane(s.p[k], h); o.v[k] = lane(s.v[k], h); o.om[k] = lane(s.om[k], h); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.w[k] = lane(s.w[k], h);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o.R[k] = lane(s.R[k], h);
+    o.ct[0] = s.ct[h];
+    o.ep[0] = s.ep[h];
+}
+template <class T> __device__ __forceinline__ void set_lane_state(VState<T> &s, int h, const QState &o)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { set_lane(s.p[k], h, o.p[k]); set_lane(s.v[k], h, o.v[k]); set_lane(s.om[k], h, o.om[k]); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) set_lane(s.w[k], h, o.w[k]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) set_lane(s.R[k], h, o.R[k]);
+    s.ct[h] = o.ct[0];
+    s.ep[h] = o.ep[0];
 }
 
 // ---- explicit float32 building blocks.  This file is compiled with -fmad=false and every fused multiply-add is
-// written out, so the arithmetic of an env does not depend on which kernel variant (tile / wide / streaming / rollout)
-// or which inlining context the compiler happened to see: results are bit-identical for any batch size or sharding.
-__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2)
+// written out, so the arithmetic of an env does not depend on which kernel variant (scalar / packed / streaming /
+// rollout) or which inlining context the compiler happened to see: results are bit-identical for any batch size,
+// sharding or lane type.
+template <class T> __device__ __forceinline__ T dot3(T a0, T b0, T a1, T b1, T a2, T b2)
 {
-    return fmaf(a2, b2, fmaf(a1, b1, a0 * b0));
+    return vfma(a2, b2, vfma(a1, b1, vmul(a0, b0)));
 }
-__device__ __forceinline__ float det2(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); }   // ab - cd
-__device__ __forceinline__ float sq3(const float v[3]) { return dot3(v[0], v[0], v[1], v[1], v[2], v[2]); }
+template <class T> __device__ __forceinline__ T det2(T a, T b, T c, T d) { return vfma(a, b, vneg(vmul(c, d))); }   // ab - cd
+template <class T> __device__ __forceinline__ T sq3(const T v[3]) { return dot3(v[0], v[0], v[1], v[1], v[2], v[2]); }
 
 // ---- fast float32 primitives.  The reference's own float32 noise (1.3e-7 relative per step against a
 // float64 restatement) is larger than the error of any of these, and each replaces a 10-60 instruction IEEE sequence.
-__device__ __forceinline__ float fast_sqrt(float x)      // sqrt.approx: MUFU.SQRT, <= 1 ulp-ish, sqrt(0) = 0
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_rcp(float x)       // MUFU.RCP + one Newton step (~0.5 ulp)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
 // atan2 with a degree-7 minimax polynomial in a^2 on [0,1] (max abs error 7.5e-8 rad evaluated in float32, fitted for
 // this file) instead of libdevice's ~65-instruction atan2f.  atan2(+-0, x>0) = +-0 like numpy.
-__device__ __forceinline__ float fast_atan2(float y, float x)
+template <class T> __device__ __forceinline__ T fast_atan2(T y, T x)
 {
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    float rc;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
-    float a = mn * rc;
-    a = fmaf(fmaf(-a, mx, mn), rc, a);                  // one correction step of the quotient
-    a = mx > 0.f ? a : 0.f;
-    const float q = a * a;
-    float r = 0.0026222404558211565f;
-    r = fmaf(r, q, -0.015132519416511059f);
-    r = fmaf(r, q, 0.04112182930111885f);
-    r = fmaf(r, q, -0.07366703450679779f);
-    r = fmaf(r, q, 0.10573931038379669f);
-    r = fmaf(r, q, -0.1418597549200058f);
-    r = fmaf(r, q, 0.1999039649963379f);
-    r = fmaf(r, q, -0.33332985639572144f);
-    r = fmaf(r * q, a, a);
-    r = ay > ax ? 1.57079632679489662f - r : r;
-    r = x < 0.f ? 3.14159265358979324f - r : r;
-    return copysignf(r, y);
+    const T ax = vabs(x), ay = vabs(y);
+    const T mx = vmax(ax, ay), mn = vmin(ax, ay);
+    const T rc = vrcp_approx(mx);
+    T a = vmul(mn, rc);
+    a = vfma(vfma(vneg(a), mx, mn), rc, a);                  // one correction step of the quotient
+#pragma unroll
+    for (int h = 0; h < Lanes<T>::N; ++h) set_lane(a, h, lane(mx, h) > 0.f ? lane(a, h) : 0.f);
+    const T q = vmul(a, a);
+    T r = bc<T>(0.0026222404558211565f);
+    r = vfma(r, q, bc<T>(-0.015132519416511059f));
+    r = vfma(r, q, bc<T>(0.04112182930111885f));
+    r = vfma(r, q, bc<T>(-0.07366703450679779f));
+    r = vfma(r, q, bc<T>(0.10573931038379669f));
+    r = vfma(r, q, bc<T>(-0.1418597549200058f));
+    r = vfma(r, q, bc<T>(0.1999039649963379f));
+    r = vfma(r, q, bc<T>(-0.33332985639572144f));
+    r = vfma(vmul(r, q), a, a);
+    const T r1 = vsub(1.57079632679489662f, r);
+    const T r2a = vsub(3.14159265358979324f, r), r2b = vsub(3.14159265358979324f, r1);
+    T out;
+#pragma unroll
+    for (int h = 0; h < Lanes<T>::N; ++h) {
+        const bool swap = lane(ay, h) > lane(ax, h), neg = lane(x, h) < 0.f;
+        const float v = swap ? (neg ? lane(r2b, h) : lane(r1, h)) : (neg ? lane(r2a, h) : lane(r, h));
+        set_lane(out, h, copysignf(v, lane(y, h)));
+    }
+    return out;
 }
 
 // adjugate of R (unscaled inverse) and 1/det; R^-1 = adj * id.  R drifts away from orthogonality (the reference never
 // re-orthonormalises, quadrotorsim.py:193-202), so this is a genuine inverse, not a transpose.  det = 1 +- a few 1e-3.
-__device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &id)
+template <class T> __device__ __forceinline__ void adjugate(const T R[9], T adj[9], T &id)
 {
     adj[0] = det2(R[4], R[8], R[5], R[7]);
     adj[3] = det2(R[5], R[6], R[3], R[8]);
     adj[6] = det2(R[3], R[7], R[4], R[6]);
-    const float det = dot3(R[0], adj[0], R[1], adj[3], R[2], adj[6]);
+    const T det = dot3(R[0], adj[0], R[1], adj[3], R[2], adj[6]);
     adj[1] = det2(R[2], R[7], R[1], R[8]);
     adj[2] = det2(R[1], R[5], R[2], R[4]);
     adj[4] = det2(R[0], R[8], R[2], R[6]);
     adj[5] = det2(R[2], R[3], R[0], R[5]);
     adj[7] = det2(R[1], R[6], R[0], R[7]);
     adj[8] = det2(R[0], R[4], R[1], R[3]);
-    id = fast_rcp(det);
+    id = vrcp(det);
 }
 
 // One call of _run_internal (quadrotorsim.py:122-208) on register state.  Algebra used (exact in real arithmetic):
@@ -193,78 +266,78 @@ __device__ __forceinline__ void adjugate(const float R[9], float adj[9], float &
 //   w_i' = w_i + (h/jm)(me_i - Mm) = w_i + (cw_i - hk w_i),  hk = (h/jm) k1phi, cw_i = (h/jm)(kV_i - Mm)   :141-145
 //   yaw reaction -me0+me1-me2+me3 = Kz - k1phi((w1-w0)+(w3-w2)),  Kz = (kV1-kV0)+(kV3-kV2)               :164
 // so the per-rotor work is 2 ops for the speed, 2 for the inflow, 3 for the thrust, 2 for the torque arm.
-template <bool SIMPLE>
-__device__ __forceinline__ void substep(const QuadConst &c, QState &s, const float cw[4], float Kz, float adj[9],
-                                        float &id, float &vsq, float &osq)
+template <bool SIMPLE, class T>
+__device__ __forceinline__ void substep(const QuadConst &c, VState<T> &s, const T cw[4], T Kz, T adj[9], T &id, T &vsq,
+                                        T &osq)
 {
     // body-frame velocity R^-1 v (:147-148), shared by the four rotors and the drag term
-    const float bvx = dot3(adj[0], s.v[0], adj[1], s.v[1], adj[2], s.v[2]) * id;
-    const float bvy = dot3(adj[3], s.v[0], adj[4], s.v[1], adj[5], s.v[2]) * id;
-    const float bvz = dot3(adj[6], s.v[0], adj[7], s.v[1], adj[8], s.v[2]) * id;
-    const float nvn = -fast_sqrt(vsq), non = -fast_sqrt(osq);
-    const float tz = fmaf(-c.k1phi, (s.w[1] - s.w[0]) + (s.w[3] - s.w[2]), Kz);
-    float th[4];
+    const T bvx = vmul(dot3(adj[0], s.v[0], adj[1], s.v[1], adj[2], s.v[2]), id);
+    const T bvy = vmul(dot3(adj[3], s.v[0], adj[4], s.v[1], adj[5], s.v[2]), id);
+    const T bvz = vmul(dot3(adj[6], s.v[0], adj[7], s.v[1], adj[8], s.v[2]), id);
+    const T nvn = vneg(vsqrt(vsq)), non = vneg(vsqrt(osq));
+    const T tz = vfma(-c.k1phi, vadd(vsub(s.w[1], s.w[0]), vsub(s.w[3], s.w[2])), Kz);
+    T th[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float v1 = fmaf(s.om[0], c.A[i], fmaf(-s.om[1], c.B[i], bvz));      // inflow, :146-151
+        const T v1 = vfma(s.om[0], c.A[i], vfma(vneg(s.om[1]), c.B[i], bvz));      // inflow, :146-151
         // increment first, then ONE rounding at the magnitude of w -- the reference's rounding structure (:144-145).  Near
         // its fixed point a rotor's float32 speed stagnates within +-ulp/2 of increment; any other association
         // (w*(1-hk)+cw, (w+cw)-hk*w) stagnates elsewhere and biases thrust by ~1e-5.
-        const float wm = s.w[i] + fmaf(-c.hk, s.w[i], cw[i]);
-        th[i] = wm * fmaf(c.ct0, wm, c.ct1 * v1);                                 // :154-156
-        if (!SIMPLE) th[i] = fmaf(c.ct2 * v1, fabsf(v1), th[i]);
+        const T wm = vadd(s.w[i], vfma(-c.hk, s.w[i], cw[i]));
+        th[i] = vmul(wm, vfma(c.ct0, wm, vmul(c.ct1, v1)));                        // :154-156
+        if (!SIMPLE) th[i] = vfma(vmul(c.ct2, v1), vabs(v1), th[i]);
         s.w[i] = wm;
     }
-    const float fz = (th[0] + th[1]) + (th[2] + th[3]);
+    const T fz = vadd(vadd(th[0], th[1]), vadd(th[2], th[3]));
     // -(0,0,th) x p_i summed over the rotors, :160-162
-    const float tx = fmaf(th[0], c.py[0], fmaf(th[1], c.py[1], fmaf(th[2], c.py[2], th[3] * c.py[3])));
-    const float ty = -fmaf(th[0], c.px[0], fmaf(th[1], c.px[1], fmaf(th[2], c.px[2], th[3] * c.px[3])));
+    const T tx = vfma(th[0], c.py[0], vfma(th[1], c.py[1], vfma(th[2], c.py[2], vmul(th[3], c.py[3]))));
+    const T ty = vneg(vfma(th[0], c.px[0], vfma(th[1], c.px[1], vfma(th[2], c.px[2], vmul(th[3], c.px[3])))));
 
     // force: thrust + gravity (R^-1 g m) + drag (-|v| Df R^-1 v), :166-180
-    const float idgm = id * c.gm;
-    const float Fx = fmaf(nvn * c.Df[0], bvx, adj[2] * idgm);
-    const float Fy = fmaf(nvn * c.Df[1], bvy, adj[5] * idgm);
-    const float Fz = fmaf(nvn * c.Df[2], bvz, fmaf(adj[8], idgm, fz));
-    float Tx = fmaf(non * c.Dm[0], s.om[0], tx);
-    float Ty = fmaf(non * c.Dm[1], s.om[1], ty);
-    float Tz = fmaf(non * c.Dm[2], s.om[2], tz);
+    const T idgm = vmul(id, c.gm);
+    const T Fx = vfma(vmul(nvn, c.Df[0]), bvx, vmul(adj[2], idgm));
+    const T Fy = vfma(vmul(nvn, c.Df[1]), bvy, vmul(adj[5], idgm));
+    const T Fz = vfma(vmul(nvn, c.Df[2]), bvz, vfma(adj[8], idgm, fz));
+    T Tx = vfma(vmul(non, c.Dm[0]), s.om[0], tx);
+    T Ty = vfma(vmul(non, c.Dm[1]), s.om[1], ty);
+    T Tz = vfma(vmul(non, c.Dm[2]), s.om[2], tz);
     if (!SIMPLE) {  // gravity torque -(f_grav x cg), :177-178
-        const float gx = adj[2] * idgm, gy = adj[5] * idgm, gz = adj[8] * idgm;
-        Tx -= det2(gy, c.cg[2], gz, c.cg[1]);
-        Ty -= det2(gz, c.cg[0], gx, c.cg[2]);
-        Tz -= det2(gx, c.cg[1], gy, c.cg[0]);
+        const T gx = vmul(adj[2], idgm), gy = vmul(adj[5], idgm), gz = vmul(adj[8], idgm);
+        Tx = vsub(Tx, det2(gy, bc<T>(c.cg[2]), gz, bc<T>(c.cg[1])));
+        Ty = vsub(Ty, det2(gz, bc<T>(c.cg[0]), gx, bc<T>(c.cg[2])));
+        Tz = vsub(Tz, det2(gx, bc<T>(c.cg[1]), gy, bc<T>(c.cg[0])));
     }
 
     // translation, :183-187 (1/mass folded into the step constants)
-    const float ax = dot3(s.R[0], Fx, s.R[1], Fy, s.R[2], Fz);
-    const float ay = dot3(s.R[3], Fx, s.R[4], Fy, s.R[5], Fz);
-    const float az = dot3(s.R[6], Fx, s.R[7], Fy, s.R[8], Fz);
-    s.p[0] = fmaf(ax, c.c_h2m, fmaf(s.v[0], c.h, s.p[0]));
-    s.p[1] = fmaf(ay, c.c_h2m, fmaf(s.v[1], c.h, s.p[1]));
-    s.p[2] = fmaf(az, c.c_h2m, fmaf(s.v[2], c.h, s.p[2]));
-    s.v[0] = fmaf(ax, c.c_hm, s.v[0]);
-    s.v[1] = fmaf(ay, c.c_hm, s.v[1]);
-    s.v[2] = fmaf(az, c.c_hm, s.v[2]);
+    const T ax = dot3(s.R[0], Fx, s.R[1], Fy, s.R[2], Fz);
+    const T ay = dot3(s.R[3], Fx, s.R[4], Fy, s.R[5], Fz);
+    const T az = dot3(s.R[6], Fx, s.R[7], Fy, s.R[8], Fz);
+    s.p[0] = vfma(ax, c.c_h2m, vfma(s.v[0], c.h, s.p[0]));
+    s.p[1] = vfma(ay, c.c_h2m, vfma(s.v[1], c.h, s.p[1]));
+    s.p[2] = vfma(az, c.c_h2m, vfma(s.v[2], c.h, s.p[2]));
+    s.v[0] = vfma(ax, c.c_hm, s.v[0]);
+    s.v[1] = vfma(ay, c.c_hm, s.v[1]);
+    s.v[2] = vfma(az, c.c_hm, s.v[2]);
 
     // rotation, :190-204
-    float ahx, ahy, ahz;  // h * I^-1 * torque
+    T ahx, ahy, ahz;  // h * I^-1 * torque
     if (SIMPLE) {
-        ahx = Tx * c.hI[0]; ahy = Ty * c.hI[4]; ahz = Tz * c.hI[8];
+        ahx = vmul(Tx, c.hI[0]); ahy = vmul(Ty, c.hI[4]); ahz = vmul(Tz, c.hI[8]);
     } else {
-        ahx = dot3(c.hI[0], Tx, c.hI[1], Ty, c.hI[2], Tz);
-        ahy = dot3(c.hI[3], Tx, c.hI[4], Ty, c.hI[5], Tz);
-        ahz = dot3(c.hI[6], Tx, c.hI[7], Ty, c.hI[8], Tz);
+        ahx = dot3(bc<T>(c.hI[0]), Tx, bc<T>(c.hI[1]), Ty, bc<T>(c.hI[2]), Tz);
+        ahy = dot3(bc<T>(c.hI[3]), Tx, bc<T>(c.hI[4]), Ty, bc<T>(c.hI[5]), Tz);
+        ahz = dot3(bc<T>(c.hI[6]), Tx, bc<T>(c.hI[7]), Ty, bc<T>(c.hI[8]), Tz);
     }
-    const float hwx = c.h * fmaf(0.5f, ahx, s.om[0]);
-    const float hwy = c.h * fmaf(0.5f, ahy, s.om[1]);
-    const float hwz = c.h * fmaf(0.5f, ahz, s.om[2]);
-    s.om[0] += ahx; s.om[1] += ahy; s.om[2] += ahz;
+    const T hwx = vmul(c.h, vfma(0.5f, ahx, s.om[0]));
+    const T hwy = vmul(c.h, vfma(0.5f, ahy, s.om[1]));
+    const T hwz = vmul(c.h, vfma(0.5f, ahz, s.om[2]));
+    s.om[0] = vadd(s.om[0], ahx); s.om[1] = vadd(s.om[1], ahy); s.om[2] = vadd(s.om[2], ahz);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {   // R += h R [w]x
-        const float r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
-        s.R[3 * r + 0] = fmaf(r1, hwz, fmaf(-r2, hwy, r0));
-        s.R[3 * r + 1] = fmaf(r2, hwx, fmaf(-r0, hwz, r1));
-        s.R[3 * r + 2] = fmaf(r0, hwy, fmaf(-r1, hwx, r2));
+        const T r0 = s.R[3 * r], r1 = s.R[3 * r + 1], r2 = s.R[3 * r + 2];
+        s.R[3 * r + 0] = vfma(r1, hwz, vfma(vneg(r2), hwy, r0));
+        s.R[3 * r + 1] = vfma(r2, hwx, vfma(vneg(r0), hwz, r1));
+        s.R[3 * r + 2] = vfma(r0, hwy, vfma(vneg(r1), hwx, r2));
     }
     adjugate(s.R, adj, id);                                                  // :206-208
     vsq = sq3(s.v);
@@ -275,43 +348,64 @@ template <bool SIMPLE>
 __device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
                                              float &power);
 
-// `substeps` calls of _run_internal (quadrotorsim.py:295-304).  Returns the fail code (0 = none); power = electrical
-// power of the last executed substep (:139,188).  The loop is unrolled by 5 when substeps % 5 == 0 (dt = 0.005, 0.01)
-// so the ~40 step constants stay in uniform registers across the unrolled body.
-template <bool SIMPLE>
-__device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
-                                         float &power)
+// _check_failure (quadrotorsim.py:210-221) of lane h; the negated comparisons also catch NaN
+__device__ __forceinline__ int fail_code(const QuadConst &c, float psq, float vsq, float osq)
 {
-    if (c.rk4_steps > 0) return integrate_rk4<SIMPLE>(c, s, act, adj, id, power);   // uniform branch
+    if (!(psq <= c.fail_r2)) return MGB_FAIL_RANGE;
+    if (!(vsq <= c.fail_v2)) return MGB_FAIL_VELOCITY;
+    if (!(osq <= c.fail_w2)) return MGB_FAIL_ANGULAR;
+    return 0;
+}
+
+// `substeps` calls of _run_internal (quadrotorsim.py:295-304).  fail[h] = fail code of lane h (0 = none); the loop stops
+// at the first substep after which ANY lane failed (for T = f2 the caller then redoes both envs with the scalar
+// instantiation, so a failing env never changes what its pair partner computes).  power = electrical power of the
+// last executed substep (:139,188).  The loop is unrolled by 5 when substeps % 5 == 0 (dt = 0.005, 0.01) so the ~40 step
+// constants stay in uniform registers across the unrolled body.
+template <bool SIMPLE, class T>
+__device__ __forceinline__ bool integrate(const QuadConst &c, VState<T> &s, const T Vin[4], T adj[9], T &id, T &power,
+                                          int fail[Lanes<T>::N])
+{
+    constexpr int N = Lanes<T>::N;
     // voltage clamp (:130-134) and the per-step rotor constants
-    float V[4] = {act.x, act.y, act.z, act.w};
-    float kV[4], cw[4];
+    T V[4], kV[4], cw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        V[i] = V[i] > c.vmax ? c.vmax : (V[i] < c.vmin ? c.vmin : V[i]);
-        kV[i] = c.k1 * V[i];
-        cw[i] = c.hjm * (kV[i] - c.mm);
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+            const float x = lane(Vin[i], h);
+            set_lane(V[i], h, x > c.vmax ? c.vmax : (x < c.vmin ? c.vmin : x));
+        }
+        kV[i] = vmul(c.k1, V[i]);
+        cw[i] = vmul(c.hjm, vsub(kV[i], c.mm));
     }
-    const float Kz = (kV[1] - kV[0]) + (kV[3] - kV[2]);
-    int fail = 0;
-    float vsq = sq3(s.v);
-    float osq = sq3(s.om);
-    float wl[4] = {s.w[0], s.w[1], s.w[2], s.w[3]};     // rotor speeds entering the last executed substep
+    const T Kz = vadd(vsub(kV[1], kV[0]), vsub(kV[3], kV[2]));
+    bool failed = false;
+#pragma unroll
+    for (int h = 0; h < N; ++h) fail[h] = 0;
+    T vsq = sq3(s.v);
+    T osq = sq3(s.om);
+    T wl[4] = {s.w[0], s.w[1], s.w[2], s.w[3]};     // rotor speeds entering the last executed substep
 
-    // _check_failure after every substep (:210-221); the negated comparisons also catch NaN
+    // _check_failure after every substep (:210-221)
 #define MGB_QUAD_ONE_SUBSTEP()                                                                                   \
     {                                                                                                            \
         wl[0] = s.w[0]; wl[1] = s.w[1]; wl[2] = s.w[2]; wl[3] = s.w[3];                                          \
         substep<SIMPLE>(c, s, cw, Kz, adj, id, vsq, osq);                                                        \
-        const float psq = sq3(s.p);                                   \
-        if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {                                 \
-            fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR); \
+        const T psq = sq3(s.p);                                                                                  \
+        bool bad = false;                                                                                        \
+        _Pragma("unroll") for (int h = 0; h < N; ++h)                                                            \
+            bad |= !(lane(psq, h) <= c.fail_r2) || !(lane(vsq, h) <= c.fail_v2) || !(lane(osq, h) <= c.fail_w2); \
+        if (bad) {                                                                                               \
+            _Pragma("unroll") for (int h = 0; h < N; ++h)                                                        \
+                fail[h] = fail_code(c, lane(psq, h), lane(vsq, h), lane(osq, h));                                \
+            failed = true;                                                                                       \
             break;                                                                                               \
         }                                                                                                        \
     }
     if (c.substeps % 5 == 0) {
 #pragma unroll 1
-        for (int k = 0; k < c.substeps && !fail; k += 5) {
+        for (int k = 0; k < c.substeps && !failed; k += 5) {
 #pragma unroll
             for (int u = 0; u < 5; ++u) MGB_QUAD_ONE_SUBSTEP()
         }
@@ -320,11 +414,23 @@ __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const fl
         for (int k = 0; k < c.substeps; ++k) MGB_QUAD_ONE_SUBSTEP()
     }
 #undef MGB_QUAD_ONE_SUBSTEP
-    float pw = 0.f;
+    T pw = bc<T>(0.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pw += fabsf(fmaf(-c.k1phi, wl[i], kV[i]) * c.inv_phi * V[i]);
+    for (int i = 0; i < 4; ++i) pw = vadd(pw, vabs(vmul(vmul(vfma(-c.k1phi, wl[i], kV[i]), c.inv_phi), V[i])));
     power = pw;
-    return fail;
+    return failed;
+}
+
+// scalar entry point (reference integrator or RK4): returns the fail code
+template <bool SIMPLE>
+__device__ __forceinline__ int integrate1(const QuadConst &c, QState &s, const float4 act, float adj[9], float &id,
+                                          float &power)
+{
+    if (c.rk4_steps > 0) return integrate_rk4<SIMPLE>(c, s, act, adj, id, power);   // uniform branch
+    const float V[4] = {act.x, act.y, act.z, act.w};
+    int fail[1];
+    integrate<SIMPLE, float>(c, s, V, adj, id, power, fail);
+    return fail[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -335,7 +441,7 @@ __device__ __forceinline__ int integrate(const QuadConst &c, QState &s, const fl
 // with the reference's force model: F_body = (0,0,sum T_i) + R^-1 g m - |v| Df R^-1 v, T_i = ct0 m_i^2 + ct1 m_i v1_i
 // (+ ct2 v1_i |v1_i|), v1_i = (R^-1 v)_z + ((w x p_i) |p_i|)_z, tau = sum -(0,0,T_i) x p_i + yaw reaction - |w| Dm w
 // (- f_grav x cg).  The substep quirks that vanish as h -> 0 (thrust from the already-updated rotor speed, the
-// 0.5 h^2 a position term) are not part of the continuous model.
+// 0.5 h^2 a position term) are not part of the continuous model.  Scalar lanes only.
 // ---------------------------------------------------------------------------------------------------------------
 struct QDeriv { float p[3], v[3], om[3], w[4], R[9]; };
 
@@ -347,8 +453,8 @@ __device__ __forceinline__ void quad_rhs(const QuadConst &c, const QState &s, co
     const float bvx = dot3(adj[0], s.v[0], adj[1], s.v[1], adj[2], s.v[2]) * id;
     const float bvy = dot3(adj[3], s.v[0], adj[4], s.v[1], adj[5], s.v[2]) * id;
     const float bvz = dot3(adj[6], s.v[0], adj[7], s.v[1], adj[8], s.v[2]) * id;
-    const float nvn = -fast_sqrt(sq3(s.v));
-    const float non = -fast_sqrt(sq3(s.om));
+    const float nvn = -vsqrt(sq3(s.v));
+    const float non = -vsqrt(sq3(s.om));
     float fz = 0.f, tx = 0.f, ty = 0.f, me[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -441,16 +547,14 @@ __device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, cons
         for (int r = 0; r < 4; ++r) acc.w[r] += k.w[r];
 #pragma unroll
         for (int r = 0; r < 9; ++r) acc.R[r] += k.R[r];
-        const int ct = s.ct, ep = s.ep;
+        const int ct = s.ct[0], ep = s.ep[0];
         quad_axpy(s, acc, h * (1.0f / 6.0f), t);
-        s = t; s.ct = ct; s.ep = ep;
+        s = t; s.ct[0] = ct; s.ep[0] = ep;
         const float psq = sq3(s.p);
         const float vsq = sq3(s.v);
         const float osq = sq3(s.om);
-        if (!(psq <= c.fail_r2) || !(vsq <= c.fail_v2) || !(osq <= c.fail_w2)) {
-            fail = !(psq <= c.fail_r2) ? MGB_FAIL_RANGE : (!(vsq <= c.fail_v2) ? MGB_FAIL_VELOCITY : MGB_FAIL_ANGULAR);
-            break;
-        }
+        fail = fail_code(c, psq, vsq, osq);
+        if (fail) break;
     }
     adjugate(s.R, adj, id);
     float pw = 0.f;      // electrical power at the end state (the reference reports the last substep's, :139,188)
@@ -462,39 +566,40 @@ __device__ __forceinline__ int integrate_rk4(const QuadConst &c, QState &s, cons
 
 // get_state + get_sensor + _convert_state_to_ndarray (quadrotorsim.py:260-293, env.py:193-209)
 // key order: b_v xyz, b xyz, acc xyz, gyro xyz, pitch, roll, yaw, z (+ z_offset)
-__device__ __forceinline__ void observe(const QuadConst &c, const QState &s, const float adj[9], float id, float *o,
-                                        float bv[3], float Ri[9])
+template <class T>
+__device__ __forceinline__ void observe(const QuadConst &c, const VState<T> &s, const T adj[9], T id, T *o, T bv[3],
+                                        T Ri[9])
 {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Ri[k] = adj[k] * id;
+    for (int k = 0; k < 9; ++k) Ri[k] = vmul(adj[k], id);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         bv[r] = dot3(Ri[3 * r], s.v[0], Ri[3 * r + 1], s.v[1], Ri[3 * r + 2], s.v[2]);
         o[r] = bv[r];
         o[3 + r] = dot3(Ri[3 * r], s.p[0], Ri[3 * r + 1], s.p[1], Ri[3 * r + 2], s.p[2]);
-        o[6 + r] = Ri[3 * r + 2] * -9.8f;    // body_acceleration is never updated (:22,:278): IMU = R^-1 g only
+        o[6 + r] = vmul(Ri[3 * r + 2], -9.8f);    // body_acceleration is never updated (:22,:278): IMU = R^-1 g only
         o[9 + r] = s.om[r];
     }
-    o[12] = fast_atan2(-s.R[6], fast_sqrt(fmaf(s.R[8], s.R[8], s.R[7] * s.R[7])));   // pitch, :111-120
-    o[13] = fast_atan2(s.R[7], s.R[8]);                                       // roll
-    o[14] = fast_atan2(s.R[3], s.R[0]);                                       // yaw
-    o[15] = s.p[2] + c.z_off;
+    o[12] = fast_atan2(vneg(s.R[6]), vsqrt(vfma(s.R[8], s.R[8], vmul(s.R[7], s.R[7]))));   // pitch, :111-120
+    o[13] = fast_atan2(s.R[7], s.R[8]);                                                     // roll
+    o[14] = fast_atan2(s.R[3], s.R[0]);                                                     // yaw
+    o[15] = vadd(s.p[2], c.z_off);
 }
 
-// QuadrotorSim.reset applied to one env with the twelve uniform draws u[12] (quadrotorsim.py:239-258)
-__device__ __forceinline__ void reset_env(const QuadConst &c, QState &s, const double u[12])
+// QuadrotorSim.reset applied to lane h with the twelve uniform draws u[12] (quadrotorsim.py:239-258)
+template <class T> __device__ __forceinline__ void reset_env(const QuadConst &c, VState<T> &s, int h, const double u[12])
 {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        s.p[k] = 0.f;
+        set_lane(s.p[k], h, 0.f);
         const double sv = u[k] > 0.5 ? 1.0 : -1.0, sw = u[6 + k] > 0.5 ? 1.0 : -1.0;
-        s.v[k] = (float)((double)c.init_v[k] + ((double)c.noise_v * u[3 + k]) * sv);
-        s.om[k] = (float)((double)c.init_w[k] + ((double)c.noise_w * u[9 + k]) * sw);
+        set_lane(s.v[k], h, (float)((double)c.init_v[k] + ((double)c.noise_v * u[3 + k]) * sv));
+        set_lane(s.om[k], h, (float)((double)c.init_w[k] + ((double)c.noise_w * u[9 + k]) * sw));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.w[k] = 0.f;
+    for (int k = 0; k < 4; ++k) set_lane(s.w[k], h, 0.f);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s.R[k] = (k % 4 == 0) ? 1.f : 0.f;
+    for (int k = 0; k < 9; ++k) set_lane(s.R[k], h, (k % 4 == 0) ? 1.f : 0.f);
 }
 
 __device__ __forceinline__ void philox_reset_draws(uint64_t seed, int64_t genv, int ep, double u[12])
@@ -513,18 +618,17 @@ __device__ __forceinline__ void philox_reset_draws(uint64_t seed, int64_t genv, 
 
 // Velocity-target rows an env needs this step, fetched BEFORE the integrator runs so the (dependent: env2task -> row)
 // L2 latency hides under the ~1000 arithmetic instructions of the substeps instead of stalling the epilogue.
-struct TargetRows {
-    float cur[3];    // velocity_targets[ct - 1]         (env.py:153)
-    float nxt[3];    // velocity_targets[min(ct, nt-1)]  (env.py:270-274)
+template <class T> struct TargetRows {
+    T cur[3];    // velocity_targets[ct - 1]         (env.py:153)
+    T nxt[3];    // velocity_targets[min(ct, nt-1)]  (env.py:270-274)
 };
-__device__ __forceinline__ void prefetch_targets(const QuadConst &c, const QuadArgs &a, const float *trow, int ct,
-                                                 TargetRows &tr)
+template <class T>
+__device__ __forceinline__ void prefetch_targets(const QuadConst &c, const float *trow, int ct, int h, TargetRows<T> &tr)
 {
-    if (c.task != MGB_TASK_VELOCITY_CONTROL) return;
     const int t = ct < c.nt - 1 ? ct : c.nt - 1;
     const float *g = trow + 3 * (ct - 1), *q = trow + 3 * t;
-    tr.cur[0] = __ldg(g); tr.cur[1] = __ldg(g + 1); tr.cur[2] = __ldg(g + 2);
-    tr.nxt[0] = __ldg(q); tr.nxt[1] = __ldg(q + 1); tr.nxt[2] = __ldg(q + 2);
+    set_lane(tr.cur[0], h, __ldg(g)); set_lane(tr.cur[1], h, __ldg(g + 1)); set_lane(tr.cur[2], h, __ldg(g + 2));
+    set_lane(tr.nxt[0], h, __ldg(q)); set_lane(tr.nxt[1], h, __ldg(q + 1)); set_lane(tr.nxt[2], h, __ldg(q + 2));
 }
 
 // python slice bound for a[start:stop] on an axis of length len (negative indices wrap once, then clamp)
@@ -556,73 +660,91 @@ __device__ __forceinline__ bool map_collision(const QuadArgs &a, float x_old, fl
     return z_lo < any || z_hi < any;
 }
 
-// Task logic after the integrator: observation, reward, collision, done, counters, optional auto-reset.
-// o[] receives the observation to publish; fo[] the terminal observation (valid iff *had_final).
-__device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &a, int64_t e, QState &s,
-                                            const float adj[9], float id, float z_old, float x_old, float y_old,
-                                            float power, int fail, const TargetRows &tr, float *o, float &reward,
-                                            int &done_flag, bool &write_final)
+// Observation of a freshly reset env (R = I): cheap closed form of observe().  Written into lane h of o[].
+template <class T>
+__device__ __forceinline__ void observe_reset(const QuadConst &c, const QuadArgs &a, int64_t e, const VState<T> &s, int h,
+                                              T *o)
 {
-    float bv[3], Ri[9];
+    set_lane(o[0], h, lane(s.v[0], h)); set_lane(o[1], h, lane(s.v[1], h)); set_lane(o[2], h, lane(s.v[2], h));
+    set_lane(o[3], h, 0.f); set_lane(o[4], h, 0.f); set_lane(o[5], h, 0.f);
+    set_lane(o[6], h, 0.f * -9.8f); set_lane(o[7], h, 0.f * -9.8f); set_lane(o[8], h, -9.8f);
+    set_lane(o[9], h, lane(s.om[0], h)); set_lane(o[10], h, lane(s.om[1], h)); set_lane(o[11], h, lane(s.om[2], h));
+    set_lane(o[12], h, -0.f); set_lane(o[13], h, 0.f); set_lane(o[14], h, 0.f);   // arctan2(-0, 1) = -0 (:114-117 at R = I)
+    set_lane(o[15], h, 0.f + c.z_off);
+    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
+        const float *trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
+        const int t = s.ct[h] < c.nt - 1 ? s.ct[h] : c.nt - 1;
+        set_lane(o[16], h, __ldg(trow + 3 * t)); set_lane(o[17], h, __ldg(trow + 3 * t + 1));
+        set_lane(o[18], h, __ldg(trow + 3 * t + 2));
+    }
+}
+
+// Task logic after the integrator: observation, reward, collision, done, counters, optional auto-reset.
+// o[] receives the observation of the (pre-reset) end state; lane h of env e + h.  write_final[h]: auto-reset replaced
+// the env, o[] is its terminal observation and the caller must publish observe_reset() instead.
+template <class T>
+__device__ __forceinline__ void finish_step(const QuadConst &c, const QuadArgs &a, int64_t e, VState<T> &s,
+                                            const T adj[9], T id, T z_old, T x_old, T y_old, T power,
+                                            const int fail[Lanes<T>::N], const TargetRows<T> &tr, T *o, T &reward,
+                                            int done_flag[Lanes<T>::N], bool write_final[Lanes<T>::N])
+{
+    constexpr int N = Lanes<T>::N;
+    T bv[3], Ri[9];
     observe(c, s, adj, id, o, bv, Ri);
     if (c.task == MGB_TASK_VELOCITY_CONTROL) {                // env.py:270-274 (ct already incremented)
         o[16] = tr.nxt[0]; o[17] = tr.nxt[1]; o[18] = tr.nxt[2];
     }
     // energy term, env.py:217
-    reward = -fminf(c.dt * power, c.healthy);
-    int done = 0;
-    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
-        const float g0 = tr.cur[0], g1 = tr.cur[1], g2 = tr.cur[2];   // env.py:153-157
-        float diff = 0.f;
+    reward = vneg(vmin(vmul(c.dt, power), bc<T>(c.healthy)));
+    int done[N];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) diff += fabsf(dot3(Ri[3 * r], g0, Ri[3 * r + 1], g1, Ri[3 * r + 2], g2) - bv[r]);
-        reward += -0.001f * diff;
+    for (int h = 0; h < N; ++h) done[h] = 0;
+    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
+        const T g0 = tr.cur[0], g1 = tr.cur[1], g2 = tr.cur[2];   // env.py:153-157
+        T diff = bc<T>(0.f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) diff = vadd(diff, vabs(vsub(dot3(Ri[3 * r], g0, Ri[3 * r + 1], g1, Ri[3 * r + 2], g2), bv[r])));
+        reward = vadd(reward, vmul(-0.001f, diff));
     } else {
         // collision, env.py:248-260: `z_min < np.any(taken_pos) or z_max < np.any(taken_pos)` compares integer
         // altitudes against a BOOL: 0 over free cells (flat map: always), 1 as soon as the window swept by the step
         // contains any obstacle cell (the obstacle's height is never used -- reference quirk)
-        const float z_new = s.p[2] + c.z_off;
-        bool coll;
-        if (a.sat) coll = map_collision(a, x_old, y_old, z_old, s.p[0], s.p[1], z_new);
-        else coll = fminf(z_old, z_new) < 0.f;
-        float tr = coll ? 0.f : c.healthy;
+        const T z_new = vadd(s.p[2], c.z_off);
+        T bonus, vn, on;
         if (c.task == MGB_TASK_HOVERING_CONTROL) {            // env.py:222-243
-            const float vn = fast_sqrt(sq3(s.v));
-            const float on = fast_sqrt(sq3(s.om));
-            tr -= vn + on;
-            const float zm = fabsf(0.f - s.p[2]);             // pos_0[2] is always 0 (env.py:123, :26)
-            tr += zm < 0.5f ? 10.f : fmaxf(-20.f, 0.5f - zm);
+            vn = vsqrt(sq3(s.v));
+            on = vsqrt(sq3(s.om));
         }
-        reward += tr;
-        if (coll) { done = 1; s.ct = 0; }                    // env.py:147-150
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+            bool coll;
+            if (a.sat) coll = map_collision(a, lane(x_old, h), lane(y_old, h), lane(z_old, h), lane(s.p[0], h),
+                                            lane(s.p[1], h), lane(z_new, h));
+            else coll = fminf(lane(z_old, h), lane(z_new, h)) < 0.f;
+            float tr = coll ? 0.f : c.healthy;
+            if (c.task == MGB_TASK_HOVERING_CONTROL) {
+                tr -= lane(vn, h) + lane(on, h);
+                const float zm = fabsf(0.f - lane(s.p[2], h));     // pos_0[2] is always 0 (env.py:123, :26)
+                tr += zm < 0.5f ? 10.f : fmaxf(-20.f, 0.5f - zm);
+            }
+            set_lane(bonus, h, tr);
+            if (coll) { done[h] = 1; s.ct[h] = 0; }              // env.py:147-150
+        }
+        reward = vadd(reward, bonus);
     }
-    if (s.ct == c.nt) { done = 1; s.ct = 0; }                // env.py:159-161
-    if (fail) { done = 1; s.ct = 0; }                        // the reference raises (quadrotorsim.py:212-221)
-    done_flag = done;
-    write_final = false;
-    if (done && a.auto_reset) {
-        write_final = true;
-        s.ep += 1;
-        double u[12];
-        philox_reset_draws(a.seed, a.env_base + e, s.ep, u);
-        reset_env(c, s, u);
-    }
-}
-
-// Observation of a freshly reset env (R = I): cheap closed form of observe().
-__device__ __forceinline__ void observe_reset(const QuadConst &c, const QuadArgs &a, int64_t e, const QState &s,
-                                              float *o)
-{
-    o[0] = s.v[0]; o[1] = s.v[1]; o[2] = s.v[2];
-    o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;
-    o[6] = 0.f * -9.8f; o[7] = 0.f * -9.8f; o[8] = -9.8f;
-    o[9] = s.om[0]; o[10] = s.om[1]; o[11] = s.om[2];
-    o[12] = -0.f; o[13] = 0.f; o[14] = 0.f;   // arctan2(-0, 1) = -0 (quadrotorsim.py:114-117 at R = I)
-    o[15] = 0.f + c.z_off;
-    if (c.task == MGB_TASK_VELOCITY_CONTROL) {
-        const float *trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
-        const int t = s.ct < c.nt - 1 ? s.ct : c.nt - 1;
-        o[16] = __ldg(trow + 3 * t); o[17] = __ldg(trow + 3 * t + 1); o[18] = __ldg(trow + 3 * t + 2);
+#pragma unroll
+    for (int h = 0; h < N; ++h) {
+        if (s.ct[h] == c.nt) { done[h] = 1; s.ct[h] = 0; }        // env.py:159-161
+        if (fail[h]) { done[h] = 1; s.ct[h] = 0; }                // the reference raises (quadrotorsim.py:212-221)
+        done_flag[h] = done[h];
+        write_final[h] = false;
+        if (done[h] && a.auto_reset) {
+            write_final[h] = true;
+            s.ep[h] += 1;
+            double u[12];
+            philox_reset_draws(a.seed, a.env_base + e + h, s.ep[h], u);
+            reset_env(c, s, h, u);
+        }
     }
 }
 
@@ -667,50 +789,147 @@ __device__ __forceinline__ void publish_tile_mirrored(const MgbMirrors &m, float
     }
 }
 
-// One env.step() on register state: integrate, task logic, state / reward / done stores, observation row into the CTA's
-// shared-memory tile (trow); frow receives the terminal observation when auto-reset replaced it.
-template <bool SIMPLE, bool EARLY>
-__device__ __forceinline__ void step_body(const QuadConst &c, const QuadArgs &a, int64_t e, QState &s, const float4 act,
-                                          float *trow, float *frow, bool &any_final)
+// One env.step() of Lanes<T>::N consecutive envs (e, e+1) on register state: integrate, task logic, state / reward /
+// done stores, observation rows into the CTA's shared-memory tile (trow = row of env e); frow receives the terminal
+// observation when auto-reset replaced it (bit h of final_mask).  nact = number of valid lanes (a ragged last pair has 1).
+template <bool SIMPLE, bool EARLY, class T>
+__device__ __forceinline__ void step_body(const QuadConst &c, const QuadArgs &a, int64_t e, int nact, VState<T> &s,
+                                          const T V[4], float *trow, float *frow, int &final_mask)
 {
+    constexpr int N = Lanes<T>::N;
     const int D = c.obs_dim;
-    float adj[9], id, power;
+    T adj[9], id, power;
     adjugate(s.R, adj, id);
-    s.ct += 1;                                              // env.py:128
-    TargetRows tr;
-    const int ct_now = s.ct;
-    if (EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
-        prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
-    const float z_old = s.p[2] + c.z_off;                   // env.py:131-133
-    const float x_old = s.p[0], y_old = s.p[1];
-    const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
-    if (!EARLY && c.task == MGB_TASK_VELOCITY_CONTROL)
-        prefetch_targets(c, a, a.targets + ((int64_t)__ldg(a.env2task + e) * c.nt) * 3, ct_now, tr);
-    float o[kMaxObs], reward;
-    int done;
-    bool wf;
-    finish_step(c, a, e, s, adj, id, z_old, x_old, y_old, power, fail, tr, o, reward, done, wf);
-    store_state(a, e, s);
-    a.rew[e] = reward;
-    a.done[e] = (uint8_t)done;
-    if (a.fail) a.fail[e] = fail;
-    if (wf) {
-        if (a.final_obs) {
+    TargetRows<T> tr;
+    int ct_now[N];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) frow[k] = o[k];
-            if (D == 19) { frow[16] = o[16]; frow[17] = o[17]; frow[18] = o[18]; }
-            any_final = true;
-        }
-        observe_reset(c, a, e, s, o);
+    for (int h = 0; h < N; ++h) {
+        s.ct[h] += 1;                                       // env.py:128
+        ct_now[h] = s.ct[h];
     }
+    const bool vel = c.task == MGB_TASK_VELOCITY_CONTROL;
+    if (EARLY && vel) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) trow[k] = o[k];
-    if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
+        for (int h = 0; h < N; ++h) {
+            const int64_t eh = h < nact ? e + h : e;
+            prefetch_targets(c, a.targets + ((int64_t)__ldg(a.env2task + eh) * c.nt) * 3, ct_now[h], h, tr);
+        }
+    }
+    const T z_old = vadd(s.p[2], c.z_off);                  // env.py:131-133
+    const T x_old = s.p[0], y_old = s.p[1];
+    int fail[N];
+    if (N == 1 && c.rk4_steps > 0) {                        // uniform branch; RK4 exists for scalar lanes only
+        QState s1;
+        get_lane_state(s, 0, s1);
+        float adj1[9], id1, pw1;
+        fail[0] = integrate_rk4<SIMPLE>(c, s1, make_float4(lane(V[0], 0), lane(V[1], 0), lane(V[2], 0), lane(V[3], 0)),
+                                        adj1, id1, pw1);
+        set_lane_state(s, 0, s1);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) set_lane(adj[k], 0, adj1[k]);
+        set_lane(id, 0, id1);
+        set_lane(power, 0, pw1);
+    } else {
+        const bool failed = integrate<SIMPLE, T>(c, s, V, adj, id, power, fail);
+        if (N > 1 && failed) {
+            // rare: some lane left the valid zone.  Redo every lane on its own with the scalar instantiation from the
+            // state still in HBM, so that a failing env cannot change what its pair partner computes.
+#pragma unroll 1
+            for (int h = 0; h < N; ++h) {
+                QState s1;
+                load_state(a, e + h, s1);
+                float adj1[9], id1, pw1;
+                adjugate(s1.R, adj1, id1);
+                const float V1[4] = {lane(V[0], h), lane(V[1], h), lane(V[2], h), lane(V[3], h)};
+                int f1[1];
+                integrate<SIMPLE, float>(c, s1, V1, adj1, id1, pw1, f1);
+                s1.ct[0] = s.ct[h];
+                s1.ep[0] = s.ep[h];
+                set_lane_state(s, h, s1);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) set_lane(adj[k], h, adj1[k]);
+                set_lane(id, h, id1);
+                set_lane(power, h, pw1);
+                fail[h] = f1[0];
+            }
+        }
+    }
+    if (!EARLY && vel) {
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+            const int64_t eh = h < nact ? e + h : e;
+            prefetch_targets(c, a.targets + ((int64_t)__ldg(a.env2task + eh) * c.nt) * 3, ct_now[h], h, tr);
+        }
+    }
+    T o[kMaxObs], reward;
+    int done[N];
+    bool wf[N];
+    finish_step(c, a, e, s, adj, id, z_old, x_old, y_old, power, fail, tr, o, reward, done, wf);
+    // ---- state / reward / done / fail stores
+    bool stored = false;
+    if constexpr (N == 2) {
+        if (nact == 2) {
+            store_state2(a, e >> 1, s);
+            *reinterpret_cast<float2 *>(a.rew + e) = reward.v;
+            *reinterpret_cast<uchar2 *>(a.done + e) = make_uchar2((uint8_t)done[0], (uint8_t)done[1]);
+            if (a.fail) *reinterpret_cast<int2 *>(a.fail + e) = make_int2(fail[0], fail[1]);
+            stored = true;
+        }
+    }
+    if (!stored) {
+#pragma unroll
+        for (int h = 0; h < N; ++h) {
+            if (h < nact) {
+                QState s1;
+                get_lane_state(s, h, s1);
+                store_state(a, e + h, s1);
+                a.rew[e + h] = lane(reward, h);
+                a.done[e + h] = (uint8_t)done[h];
+                if (a.fail) a.fail[e + h] = fail[h];
+            }
+        }
+    }
+    // ---- observation rows
+#pragma unroll
+    for (int h = 0; h < N; ++h) {
+        if (h < nact) {
+            float *tr_h = trow + h * D;
+            if (wf[h]) {
+                if (a.final_obs) {
+                    float *fr_h = frow + h * D;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) fr_h[k] = lane(o[k], h);
+                    if (D == 19) { fr_h[16] = lane(o[16], h); fr_h[17] = lane(o[17], h); fr_h[18] = lane(o[18], h); }
+                    final_mask |= 1 << h;
+                }
+                observe_reset(c, a, e + h, s, h, o);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tr_h[k] = lane(o[k], h);
+            if (D == 19) { tr_h[16] = lane(o[16], h); tr_h[17] = lane(o[17], h); tr_h[18] = lane(o[18], h); }
+        }
+    }
 }
 
-// EARLY: fetch the velocity-target rows before the integrator (hides their latency, +8 registers).  Right when one
-// launch is a single wave of CTAs (latency-bound, e.g. 65 536 envs); for multi-wave launches (millions of envs) the
-// extra registers cost one resident CTA per SM and other CTAs already hide the latency, so the host picks EARLY=false.
+// terminal observations are rare: only CTAs that saw one write them (rows of other envs are left untouched)
+__device__ __forceinline__ void publish_final(const QuadArgs &a, const float *ftile, int64_t e, int local_row, int lanes,
+                                              int final_mask, int D)
+{
+    if (!a.final_obs) return;
+    if (__syncthreads_or(final_mask)) {
+        for (int h = 0; h < lanes; ++h) {
+            if (final_mask & (1 << h)) {
+                float *dst = a.final_obs + (e + h) * D;
+                const float *frow = ftile + (local_row + h) * D;
+                for (int k = 0; k < D; ++k) dst[k] = frow[k];
+            }
+        }
+    }
+}
+
+// Scalar step kernel: one thread = one env, 64 envs per CTA.  Kept as the reference instantiation of the generic code
+// (tests compare the packed kernels against it bit for bit; MGB_PACKED=0 selects it) and for the RK4 option.
+// EARLY: fetch the velocity-target rows before the integrator (hides their latency, +8 registers).
 template <bool SIMPLE, bool EARLY>
 __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_constant__ QuadConst c,
                                                              const __grid_constant__ QuadArgs a)
@@ -722,14 +941,11 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
     const int rows = (int)((a.n - e0) < kThreads ? (a.n - e0) : kThreads);
     const int D = c.obs_dim;
     const bool active = e < a.n;
-    bool any_final = false;
+    int final_mask = 0;
 
     // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now (its CTAs park at their own
     // griddepcontrol.wait), and this kernel waits here until the PREVIOUS one has completed and flushed -- the
-    // launch latency of back-to-back env steps (the 2-3 us that dominate a 65k-env step) overlaps the previous step.
-    // (A finer per-tile ticket/flag hand-off between launches was built and measured: 9.8 us/step instead of 6.0 at
-    // 65 536 envs -- all CTAs of one launch are co-resident in a single wave, so there is nothing to overlap and the
-    // spinning early CTAs only steal issue slots.  Rejected; see DESIGN.md.)
+    // launch latency of back-to-back env steps overlaps the previous step.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -737,77 +953,66 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
         QState s;
         load_state(a, e, s);
         const float4 act = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
-        step_body<SIMPLE, EARLY>(c, a, e, s, act, tile + threadIdx.x * D, ftile + threadIdx.x * D, any_final);
+        const float V[4] = {act.x, act.y, act.z, act.w};
+        step_body<SIMPLE, EARLY, float>(c, a, e, 1, s, V, tile + threadIdx.x * D, ftile + threadIdx.x * D, final_mask);
     }
     publish_tile(a.obs, tile, e0, rows, D);
-    // terminal observations are rare: only CTAs that saw one write them (rows of other envs are left untouched)
-    if (a.final_obs) {
-        if (__syncthreads_or(any_final ? 1 : 0)) {
-            if (active && any_final) {
-                float *dst = a.final_obs + e * D;
-                const float *frow = ftile + threadIdx.x * D;
-                for (int k = 0; k < D; ++k) dst[k] = frow[k];
-            }
-        }
-    }
+    publish_final(a, ftile, e, threadIdx.x, 1, final_mask, D);
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
 }
 
-// "One CTA per SM" variant for launches that fit a single wave (N <= 148 x 512): grid = number of SMs, each CTA owns
-// `per` = ceil(N / grid) envs (rounded to 4 so that every observation tile stays 16-byte aligned for the bulk store).
-// 148 CTA dispatches instead of 1024 and a perfectly balanced wave (444 vs 443 envs per SM at 65 536 envs).
-template <bool SIMPLE>
-__global__ void __launch_bounds__(512, 1) quad_step_wide_kernel(const __grid_constant__ QuadConst c,
-                                                                const __grid_constant__ QuadArgs a)
+// Packed step kernel: one thread = the env pair (e, e+1) in FFMA2 / FADD2 registers.  Each CTA owns `per` consecutive envs
+// (a multiple of 4, so that every observation tile stays 16-byte aligned for the bulk store): per = 128 for small batches,
+// ceil(N / #SMs) for launches that fit one wave -- one CTA per SM, 148 CTA dispatches and a balanced wave (444 vs 443 envs
+// per SM at 65 536 envs).  MINB = 2 caps the registers at 128 so that the CTAs of launch k+1 can become resident (parked at
+// griddepcontrol.wait) while those of launch k finish.
+template <bool SIMPLE, int MINB>
+__global__ void __launch_bounds__(256, MINB) quad_step2_kernel(const __grid_constant__ QuadConst c,
+                                                               const __grid_constant__ QuadArgs a)
 {
-    extern __shared__ __align__(128) float wide_smem[];
+    extern __shared__ __align__(128) float pair_smem[];
     const int per = a.per_cta;
-    float *tile = wide_smem, *ftile = wide_smem + (size_t)per * kMaxObs;
+    float *tile = pair_smem, *ftile = pair_smem + (size_t)per * kMaxObs;
     const int64_t e0 = (int64_t)blockIdx.x * per;
-    const int64_t e = e0 + threadIdx.x;
     int rows = (int)((a.n - e0) < per ? (a.n - e0) : per);
     if (rows < 0) rows = 0;
+    const int le = 2 * (int)threadIdx.x;               // local index of lane 0's env
+    const int64_t e = e0 + le;
     const int D = c.obs_dim;
-    const bool active = (int)threadIdx.x < rows;
-    bool any_final = false;
+    const int nact = rows - le >= 2 ? 2 : (rows - le > 0 ? 1 : 0);
+    int final_mask = 0;
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (active) {
-        QState s;
-        load_state(a, e, s);
-        const float4 act = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
-        step_body<SIMPLE, true>(c, a, e, s, act, tile + threadIdx.x * D, ftile + threadIdx.x * D, any_final);
+    if (nact > 0) {
+        VState<f2> s;
+        load_state2(a, e >> 1, s);
+        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
+        const float4 a1 = nact == 2 ? __ldg(reinterpret_cast<const float4 *>(a.act) + e + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const f2 V[4] = {pack2(a0.x, a1.x), pack2(a0.y, a1.y), pack2(a0.z, a1.z), pack2(a0.w, a1.w)};
+        step_body<SIMPLE, true, f2>(c, a, e, nact, s, V, tile + le * D, ftile + le * D, final_mask);
     }
     if (rows > 0) publish_tile(a.obs, tile, e0, rows, D);
     else __syncthreads();
-    if (a.final_obs) {
-        if (__syncthreads_or(any_final ? 1 : 0)) {
-            if (active && any_final) {
-                float *dst = a.final_obs + e * D;
-                const float *frow = ftile + threadIdx.x * D;
-                for (int k = 0; k < D; ++k) dst[k] = frow[k];
-            }
-        }
-    }
+    publish_final(a, ftile, e, le, 2, final_mask, D);
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();
 }
 
-// Streaming variant for multi-wave launches (millions of envs): PERSISTENT CTAs loop over tiles of 128 envs and the state
-// of tile i+1 (six 2 KB plane segments + 2 KB of actions) is fetched by the TMA engine (cp.async.bulk + mbarrier) into
-// the other half of a double-buffered shared-memory stage while tile i integrates, so HBM latency is off the critical
-// path without spending registers or occupancy on it.  Same arithmetic (step_body), same outputs.
-constexpr int kStreamThreads = 128;
+// Streaming variant for multi-wave launches (millions of envs): PERSISTENT CTAs of 64 threads loop over tiles of 128 envs
+// (64 pairs) and the state of tile i+1 (one contiguous 12 KB block) + its 2 KB of actions are fetched by the TMA engine
+// (cp.async.bulk + mbarrier) into the other half of a double-buffered shared-memory stage while tile i integrates, so HBM
+// latency is off the critical path without spending registers or occupancy on it.  Same arithmetic (step_body<f2>).
+constexpr int kStreamThreads = 64;
 
 template <bool SIMPLE>
-__global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __grid_constant__ QuadConst c,
-                                                                        const __grid_constant__ QuadArgs a)
+__global__ void __launch_bounds__(kStreamThreads, 4) quad_stream2_kernel(const __grid_constant__ QuadConst c,
+                                                                         const __grid_constant__ QuadArgs a)
 {
-    __shared__ __align__(128) float4 stage[2][7][kStreamThreads];    // planes 0..5 + action
-    __shared__ __align__(128) float tile[kStreamThreads * kMaxObs];
-    __shared__ __align__(128) float ftile[kStreamThreads * kMaxObs];
+    __shared__ __align__(128) float4 stage[2][kPlanes * kTilePairs + kTileEnvs];    // 12 planes x 64 pairs + 128 actions
+    __shared__ __align__(128) float tile[kTileEnvs * kMaxObs];
+    __shared__ __align__(128) float ftile[kTileEnvs * kMaxObs];
     __shared__ __align__(8) uint64_t full[2];
     const int D = c.obs_dim;
-    const int64_t n_tiles = (a.n + kStreamThreads - 1) / kStreamThreads;
+    const int64_t n_tiles = (a.n + kTileEnvs - 1) / kTileEnvs;
     const int tid = threadIdx.x;
 
     asm volatile("griddepcontrol.launch_dependents;");
@@ -820,12 +1025,11 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __
     __syncthreads();
 
     auto fetch = [&](int64_t t, int st) {      // one thread: 2 bulk copies land on full[st]
-        const int64_t e0 = t * kStreamThreads;
-        const uint32_t rows = (uint32_t)((a.n - e0) < kStreamThreads ? (a.n - e0) : kStreamThreads);
-        static_assert(kStreamThreads == kTileEnvs, "one CTA iteration = one state tile");
-        mgb_mbar_expect_tx(&full[st], 6u * kTileEnvs * 16u + rows * 16u);
-        mgb_bulk_load(stage[st][0], a.planes + t * (6 * kTileEnvs), 6u * kTileEnvs * 16u, &full[st]);   // 12 KB, contiguous
-        mgb_bulk_load(stage[st][6], reinterpret_cast<const float4 *>(a.act) + e0, rows * 16u, &full[st]);
+        const int64_t e0 = t * kTileEnvs;
+        const uint32_t rows = (uint32_t)((a.n - e0) < kTileEnvs ? (a.n - e0) : kTileEnvs);
+        mgb_mbar_expect_tx(&full[st], (uint32_t)(kPlanes * kTilePairs) * 16u + rows * 16u);
+        mgb_bulk_load(stage[st], a.planes + t * (kPlanes * kTilePairs), (uint32_t)(kPlanes * kTilePairs) * 16u, &full[st]);
+        mgb_bulk_load(stage[st] + kPlanes * kTilePairs, reinterpret_cast<const float4 *>(a.act) + e0, rows * 16u, &full[st]);
     };
 
     int64_t t = blockIdx.x;
@@ -838,35 +1042,26 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __
         if (tid == 0 && t_next < n_tiles) fetch(t_next, st ^ 1);
         mgb_mbar_wait(&full[st], phase[st]);
         phase[st] ^= 1u;
-        const int64_t e0 = t * kStreamThreads, e = e0 + tid;
-        const int rows = (int)((a.n - e0) < kStreamThreads ? (a.n - e0) : kStreamThreads);
-        bool any_final = false;
+        const int64_t e0 = t * kTileEnvs, e = e0 + 2 * tid;
+        const int rows = (int)((a.n - e0) < kTileEnvs ? (a.n - e0) : kTileEnvs);
+        const int nact = rows - 2 * tid >= 2 ? 2 : (rows - 2 * tid > 0 ? 1 : 0);
+        int final_mask = 0;
         // the observation tile of the previous iteration must have been read by its bulk store
         if (tid == 0) mgb_bulk_wait_read<0>();
         __syncthreads();
-        if (tid < rows) {
-            QState s;
-            const float4 q0 = stage[st][0][tid], q1 = stage[st][1][tid], q2 = stage[st][2][tid], q3 = stage[st][3][tid],
-                         q4 = stage[st][4][tid], q5 = stage[st][5][tid];
-            s.p[0] = q0.x; s.p[1] = q0.y; s.p[2] = q0.z; s.v[0] = q0.w;
-            s.v[1] = q1.x; s.v[2] = q1.y; s.om[0] = q1.z; s.om[1] = q1.w;
-            s.om[2] = q2.x; s.w[0] = q2.y; s.w[1] = q2.z; s.w[2] = q2.w;
-            s.w[3] = q3.x; s.R[0] = q3.y; s.R[1] = q3.z; s.R[2] = q3.w;
-            s.R[3] = q4.x; s.R[4] = q4.y; s.R[5] = q4.z; s.R[6] = q4.w;
-            s.R[7] = q5.x; s.R[8] = q5.y; s.ct = __float_as_int(q5.z); s.ep = __float_as_int(q5.w);
-            const float4 act = stage[st][6][tid];
-            step_body<SIMPLE, true>(c, a, e, s, act, tile + tid * D, ftile + tid * D, any_final);
+        if (nact > 0) {
+            VState<f2> s;
+            float4 q[kPlanes];
+#pragma unroll
+            for (int k = 0; k < kPlanes; ++k) q[k] = stage[st][k * kTilePairs + tid];
+            unpack_state(q, s);
+            const float4 a0 = stage[st][kPlanes * kTilePairs + 2 * tid];
+            const float4 a1 = nact == 2 ? stage[st][kPlanes * kTilePairs + 2 * tid + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const f2 V[4] = {pack2(a0.x, a1.x), pack2(a0.y, a1.y), pack2(a0.z, a1.z), pack2(a0.w, a1.w)};
+            step_body<SIMPLE, true, f2>(c, a, e, nact, s, V, tile + 2 * tid * D, ftile + 2 * tid * D, final_mask);
         }
         publish_tile(a.obs, tile, e0, rows, D);
-        if (a.final_obs) {
-            if (__syncthreads_or(any_final ? 1 : 0)) {
-                if (tid < rows && any_final) {
-                    float *dst = a.final_obs + e * D;
-                    const float *frow = ftile + tid * D;
-                    for (int k = 0; k < D; ++k) dst[k] = frow[k];
-                }
-            }
-        }
+        publish_final(a, ftile, e, 2 * tid, 2, final_mask, D);
         __syncthreads();      // everyone is done with stage[st] and ftile before they are refilled
     }
     if (tid == 0) mgb_bulk_wait_read<0>();
@@ -925,19 +1120,20 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                     if (XM == 1) mgb_mirror_store(a.mir, ap, act);
                 }
             }
-            s.ct += 1;
-            TargetRows tr;
-            prefetch_targets(c, a, trow, s.ct, tr);
+            s.ct[0] += 1;
+            TargetRows<float> tr;
+            if (c.task == MGB_TASK_VELOCITY_CONTROL) prefetch_targets(c, trow, s.ct[0], 0, tr);
             const float z_old = s.p[2] + c.z_off;
             const float x_old = s.p[0], y_old = s.p[1];
             float power;
-            const int fail = integrate<SIMPLE>(c, s, act, adj, id, power);
+            int fail[1];
+            fail[0] = integrate1<SIMPLE>(c, s, act, adj, id, power);
             float o[kMaxObs], reward;
-            int done;
-            bool wf;
-            finish_step(c, a, e, s, adj, id, z_old, x_old, y_old, power, fail, tr, o, reward, done, wf);
-            if (wf) {
-                observe_reset(c, a, e, s, o);
+            int done[1];
+            bool wf[1];
+            finish_step<float>(c, a, e, s, adj, id, z_old, x_old, y_old, power, fail, tr, o, reward, done, wf);
+            if (wf[0]) {
+                observe_reset(c, a, e, s, 0, o);
                 adjugate(s.R, adj, id);
             }
             if (a.rew) {
@@ -945,16 +1141,16 @@ __global__ void __launch_bounds__(kThreads, 8) quad_rollout_kernel(const __grid_
                 else a.rew[(int64_t)t * a.n + e] = reward;
                 if (XM == 1) mgb_mirror_store(a.mir, a.rew + (int64_t)t * a.n + e, reward);
             }
-            done_byte = (uint32_t)done;
+            done_byte = (uint32_t)done[0];
             if (a.done && XM != 2) {
-                a.done[(int64_t)t * a.n + e] = (uint8_t)done;
-                if (XM == 1) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done);
+                a.done[(int64_t)t * a.n + e] = (uint8_t)done[0];
+                if (XM == 1) mgb_mirror_store(a.mir, a.done + (int64_t)t * a.n + e, (uint8_t)done[0]);
             }
             if (a.obs) {
-                float *trow = tile + threadIdx.x * D;
+                float *orow = tile + threadIdx.x * D;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) trow[k] = o[k];
-                if (D == 19) { trow[16] = o[16]; trow[17] = o[17]; trow[18] = o[18]; }
+                for (int k = 0; k < 16; ++k) orow[k] = o[k];
+                if (D == 19) { orow[16] = o[16]; orow[17] = o[17]; orow[18] = o[18]; }
             }
         }
         if (XM == 2) {
@@ -990,10 +1186,10 @@ __global__ void __launch_bounds__(kThreads) quad_reset_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < 12; ++k) u[k] = noise[e * 12 + k];
         } else {
-            s.ep += 1;
-            philox_reset_draws(a.seed, a.env_base + e, s.ep, u);
+            s.ep[0] += 1;
+            philox_reset_draws(a.seed, a.env_base + e, s.ep[0], u);
         }
-        reset_env(c, s, u);
+        reset_env(c, s, 0, u);
         store_state(a, e, s);
     }
     if (a.obs) {
@@ -1002,7 +1198,7 @@ __global__ void __launch_bounds__(kThreads) quad_reset_kernel(const __grid_const
         observe(c, s, adj, id, o, bv, Ri);
         if (c.task == MGB_TASK_VELOCITY_CONTROL) {
             const float *trow = a.targets + ((int64_t)a.env2task[e] * c.nt) * 3;
-            const int t = s.ct < c.nt - 1 ? s.ct : c.nt - 1;
+            const int t = s.ct[0] < c.nt - 1 ? s.ct[0] : c.nt - 1;
             o[16] = trow[3 * t]; o[17] = trow[3 * t + 1]; o[18] = trow[3 * t + 2];
         }
         float *dst = a.obs + e * c.obs_dim;
@@ -1024,13 +1220,13 @@ __global__ void quad_state_kernel(QuadArgs a, float *state, int32_t *ct, int loa
         for (int k = 0; k < 3; ++k) { s.p[k] = row[k]; s.v[k] = row[3 + k]; s.om[k] = row[6 + k]; }
         for (int k = 0; k < 4; ++k) s.w[k] = row[9 + k];
         for (int k = 0; k < 9; ++k) s.R[k] = row[13 + k];
-        if (ct) s.ct = ct[e];
+        if (ct) s.ct[0] = ct[e];
         store_state(a, e, s);
     } else {
         for (int k = 0; k < 3; ++k) { row[k] = s.p[k]; row[3 + k] = s.v[k]; row[6 + k] = s.om[k]; }
         for (int k = 0; k < 4; ++k) row[9 + k] = s.w[k];
         for (int k = 0; k < 9; ++k) row[13 + k] = s.R[k];
-        if (ct) ct[e] = s.ct;
+        if (ct) ct[e] = s.ct[0];
     }
 }
 
@@ -1042,8 +1238,8 @@ __global__ void quad_init_kernel(QuadArgs a)
     for (int k = 0; k < 3; ++k) s.p[k] = s.v[k] = s.om[k] = 0.f;
     for (int k = 0; k < 4; ++k) s.w[k] = 0.f;
     for (int k = 0; k < 9; ++k) s.R[k] = (k % 4 == 0) ? 1.f : 0.f;
-    s.ct = 0;
-    s.ep = 0;
+    s.ct[0] = 0;
+    s.ep[0] = 0;
     store_state(a, e, s);
 }
 
@@ -1059,12 +1255,12 @@ __global__ void quad_targets_kernel(const __grid_constant__ QuadConst c, const f
     for (int q = 0; q < 3; ++q) s.p[q] = s.v[q] = s.om[q] = 0.f;
     for (int q = 0; q < 4; ++q) s.w[q] = 0.f;
     for (int q = 0; q < 9; ++q) s.R[q] = (q % 4 == 0) ? 1.f : 0.f;
-    s.ct = 0; s.ep = 0;
+    s.ct[0] = 0; s.ep[0] = 0;
     float adj[9], id, power;
     adjugate(s.R, adj, id);
     for (int t = 0; t < c.nt; ++t) {
         const float4 a4 = reinterpret_cast<const float4 *>(act)[(int64_t)k * c.nt + t];
-        const int fail = integrate<SIMPLE>(c, s, a4, adj, id, power);
+        const int fail = integrate1<SIMPLE>(c, s, a4, adj, id, power);
         float *dst = tbl + ((int64_t)k * c.nt + t) * 3;
         dst[0] = s.v[0]; dst[1] = s.v[1]; dst[2] = s.v[2];
         if (fail) {   // the reference would raise here; fill the rest with NaN so the caller notices
@@ -1095,7 +1291,8 @@ struct mgb_quad {
     int n_tasks = 0;
     int auto_reset = 0;
     int num_sms = 148;
-    int wide_kernel = 1;       // one-CTA-per-SM step kernel for single-wave launches (MGB_WIDE_KERNEL=0 disables)
+    int packed = 1;            // two envs per thread in packed FFMA2 registers (MGB_PACKED=0: scalar reference kernel)
+    int step_minb = 1;         // packed step kernel: min resident CTAs per SM it is compiled for (MGB_STEP_MINB=2: <= 128 regs)
     int stream_kernel = 1;     // persistent TMA-pipelined kernel for multi-wave launches (MGB_STREAM_KERNEL=0 disables)
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
@@ -1105,12 +1302,12 @@ struct mgb_quad {
     MgbMirrors mir = {};       // mgb_quad_set_mirrors
     MgbMirrorWindow mir_win;   // mgb_quad_set_mirror_window
     // host staging for *_host entry points
-    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_final = nullptr;
     uint8_t *h_done = nullptr;
-    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+    int32_t *h_fail = nullptr;
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_final = nullptr;
     uint8_t *d_done = nullptr;
-    cudaStream_t hstream[2] = {nullptr, nullptr};
-    cudaEvent_t hevent[2] = {nullptr, nullptr};
+    int32_t *d_fail = nullptr;
 };
 
 static QuadArgs base_args(const mgb_quad *h)
@@ -1205,7 +1402,22 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     }
     if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev);   // 0 copies, 1 zero-copy, 2 hybrid
     if (const char *ev = getenv("MGB_STREAM_KERNEL")) h->stream_kernel = atoi(ev) != 0;
-    if (const char *ev = getenv("MGB_WIDE_KERNEL")) h->wide_kernel = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_PACKED")) h->packed = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_STEP_MINB")) h->step_minb = atoi(ev) == 2 ? 2 : 1;
+    {
+        // the packed step kernel needs up to 2 x 512 x 19 floats of dynamic shared memory; the attribute is per function and
+        // device, idempotent, and set to the maximum so that handles never lower each other's limit
+        const int max_smem = 512 * kMaxObs * 4 * 2;
+        cudaFuncSetAttribute(quad_step2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (cudaGetLastError() != cudaSuccess) {
+            mgb_set_error("cudaFuncSetAttribute(quad_step2_kernel, %d bytes of shared memory) failed", max_smem);
+            delete h;
+            return MGB_ERR_CUDA;
+        }
+    }
     cudaError_t e = cudaMalloc(&h->planes, sizeof(float4) * 6 * h->n_pad);
     if (e != cudaSuccess) {
         mgb_set_error("cudaMalloc(state planes, %lld envs) -> %s", (long long)n_envs, cudaGetErrorString(e));
@@ -1236,11 +1448,9 @@ extern "C" void mgb_quad_destroy(mgb_quad *h)
     cudaFree(h->targets);
     cudaFree(h->env2task);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    cudaFree(h->d_fail); cudaFree(h->d_final);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done);
-    for (int i = 0; i < 2; ++i) {
-        if (h->hstream[i]) cudaStreamDestroy(h->hstream[i]);
-        if (h->hevent[i]) cudaEventDestroy(h->hevent[i]);
-    }
+    cudaFreeHost(h->h_fail); cudaFreeHost(h->h_final);
     delete h;
 }
 
@@ -1341,66 +1551,86 @@ extern "C" int mgb_quad_reset(mgb_quad *h, const uint8_t *mask_dev, const double
     return MGB_OK;
 }
 
+// Which step kernel a launch of this handle takes (also reported through mgb_quad_step_kernel for the bench line)
+enum StepKernel { STEP_SCALAR = 0, STEP_PACKED = 1, STEP_STREAM = 2 };
+
+static StepKernel choose_step_kernel(const mgb_quad *h, const QuadArgs &a)
+{
+    // the packed kernels store reward / done / fail of an env pair with one 8 / 2 / 8-byte access
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.act) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.rew) & 7u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(a.fail) & 7u) == 0;
+    if (!h->packed || h->c.rk4_steps > 0 || !aligned) return STEP_SCALAR;
+    if (h->stream_kernel && a.n > (int64_t)h->num_sms * 2048) return STEP_STREAM;
+    return STEP_PACKED;
+}
+
 static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
 {
-    const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(kThreads);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // multi-wave launches stream: persistent CTAs + TMA double buffering (quad_stream_kernel)
-    if (h->stream_kernel && (int64_t)blocks > (int64_t)h->num_sms * 32 &&
-        (reinterpret_cast<uintptr_t>(a.act) & 15u) == 0) {
+    const StepKernel which = choose_step_kernel(h, a);
+    if (which == STEP_STREAM) {
+        // multi-wave launches stream: persistent CTAs + TMA double buffering (quad_stream2_kernel)
         cfg.gridDim = dim3((unsigned)(h->num_sms * 4));
         cfg.blockDim = dim3(kStreamThreads);
-        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<true>, h->c, a));
-        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<false>, h->c, a));
-        MGB_CUDA(cudaGetLastError());
-        h->launches += 1;
-        return MGB_OK;
-    }
-    // launches that fit one wave of 512-thread CTAs: one CTA per SM (7x fewer CTA dispatches, balanced wave)
-    if (h->wide_kernel && a.n <= (int64_t)h->num_sms * 512 && a.n >= (int64_t)h->num_sms * 64) {
-        int per = (int)((a.n + h->num_sms - 1) / h->num_sms);
-        per = (per + 3) / 4 * 4;
+        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream2_kernel<true>, h->c, a));
+        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream2_kernel<false>, h->c, a));
+    } else if (which == STEP_PACKED) {
+        // per = envs per CTA: one warp of pairs for small batches, one CTA per SM when the launch fits a single wave of
+        // 256-thread CTAs (7x fewer CTA dispatches than 64-env tiles and a balanced wave), 256 envs per CTA beyond that
+        int per;
+        if (a.n <= (int64_t)h->num_sms * 64) per = 64;
+        else if (a.n <= (int64_t)h->num_sms * 128) per = 128;
+        else if (a.n <= (int64_t)h->num_sms * 512) per = (int)(((a.n + h->num_sms - 1) / h->num_sms + 3) / 4 * 4);
+        else per = 256;
         QuadArgs aw = a;
         aw.per_cta = per;
-        const unsigned grid = (unsigned)((a.n + per - 1) / per);
-        const unsigned threads = (unsigned)((per + 31) / 32 * 32);
-        const size_t sm = (size_t)per * kMaxObs * 4 * 2;
-        static size_t g_limit[64] = {0};
-        if (sm > g_limit[h->device & 63]) {
-            MGB_CUDA(cudaFuncSetAttribute(quad_step_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            MGB_CUDA(cudaFuncSetAttribute(quad_step_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            g_limit[h->device & 63] = sm;
+        cfg.gridDim = dim3((unsigned)((a.n + per - 1) / per));
+        cfg.blockDim = dim3((unsigned)((per / 2 + 31) / 32 * 32));
+        cfg.dynamicSmemBytes = (size_t)per * kMaxObs * 4 * 2;
+        if (h->step_minb == 2) {
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 2>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 2>, h->c, aw));
+        } else {
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 1>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 1>, h->c, aw));
         }
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(threads);
-        cfg.dynamicSmemBytes = sm;
-        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_wide_kernel<true>, h->c, aw));
-        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_wide_kernel<false>, h->c, aw));
-        MGB_CUDA(cudaGetLastError());
-        h->launches += 1;
-        return MGB_OK;
-    }
-    // single wave (<= ~8 resident CTAs per SM) -> latency-bound -> early target fetch; otherwise favour occupancy
-    const bool early = blocks <= (unsigned)h->num_sms * 10u;
-    if (h->c.simple) {
-        if (early) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true, true>, h->c, a));
-        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true, false>, h->c, a));
     } else {
-        if (early) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false, true>, h->c, a));
-        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false, false>, h->c, a));
+        const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(kThreads);
+        // single wave (<= ~8 resident CTAs per SM) -> latency-bound -> early target fetch; otherwise favour occupancy
+        const bool early = blocks <= (unsigned)h->num_sms * 10u;
+        if (h->c.simple) {
+            if (early) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true, true>, h->c, a));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<true, false>, h->c, a));
+        } else {
+            if (early) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false, true>, h->c, a));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_kernel<false, false>, h->c, a));
+        }
     }
     MGB_CUDA(cudaGetLastError());
     h->launches += 1;
     return MGB_OK;
+}
+
+extern "C" const char *mgb_quad_step_kernel(const mgb_quad *h)
+{
+    if (!h) return "";
+    QuadArgs a = base_args(h);
+    switch (choose_step_kernel(h, a)) {
+    case STEP_STREAM: return h->c.simple ? "quad_stream2_kernel<true>" : "quad_stream2_kernel<false>";
+    case STEP_PACKED:
+        if (h->step_minb == 2) return h->c.simple ? "quad_step2_kernel<true,2>" : "quad_step2_kernel<false,2>";
+        return h->c.simple ? "quad_step2_kernel<true,1>" : "quad_step2_kernel<false,1>";
+    default: return h->c.simple ? "quad_step_kernel<true,.>" : "quad_step_kernel<false,.>";
+    }
 }
 
 extern "C" int mgb_quad_step(mgb_quad *h, const float *act_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev,
@@ -1432,8 +1662,9 @@ extern "C" int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, ui
     const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
     a.mir = h->mir;
     if (h->mir.count != 0)
-        MGB_REQUIRE(h->mir_win.holds(obs_dev) && h->mir_win.holds(rew_dev) && h->mir_win.holds(done_dev) &&
-                        h->mir_win.holds(act_out_dev),
+        MGB_REQUIRE(h->mir_win.holds(obs_dev, (uint64_t)T * h->n * h->c.obs_dim * 4) &&
+                        h->mir_win.holds(rew_dev, (uint64_t)T * h->n * 4) && h->mir_win.holds(done_dev, (uint64_t)T * h->n) &&
+                        h->mir_win.holds(act_out_dev, (uint64_t)T * h->n * 16),
                     "mirrors are on but an output lies outside the mirrored arena (set_mirrors([]) first)");
     if (h->mir.count == MGB_MIRROR_MULTICAST) {
         MGB_REQUIRE(h->n % 4 == 0, "multicast outputs need num_envs % 4 == 0");
@@ -1494,14 +1725,16 @@ static int ensure_host_staging(mgb_quad *h)
     MGB_CUDA(cudaMalloc(&h->d_obs, n * D * 4));
     MGB_CUDA(cudaMalloc(&h->d_rew, n * 4));
     MGB_CUDA(cudaMalloc(&h->d_done, n));
+    MGB_CUDA(cudaMalloc(&h->d_fail, n * 4));
+    MGB_CUDA(cudaMalloc(&h->d_final, n * D * 4));
+    MGB_CUDA(cudaMemset(h->d_fail, 0, n * 4));
+    MGB_CUDA(cudaMemset(h->d_final, 0, n * D * 4));     // rows keep the last terminal observation seen, like final_obs_dev
     MGB_CUDA(cudaMallocHost(&h->h_act, n * 16));
     MGB_CUDA(cudaMallocHost(&h->h_obs, n * D * 4));
     MGB_CUDA(cudaMallocHost(&h->h_rew, n * 4));
     MGB_CUDA(cudaMallocHost(&h->h_done, n));
-    for (int i = 0; i < 2; ++i) {
-        MGB_CUDA(cudaStreamCreateWithFlags(&h->hstream[i], cudaStreamNonBlocking));
-        MGB_CUDA(cudaEventCreateWithFlags(&h->hevent[i], cudaEventDisableTiming));
-    }
+    MGB_CUDA(cudaMallocHost(&h->h_fail, n * 4));
+    MGB_CUDA(cudaMallocHost(&h->h_final, n * D * 4));
     return MGB_OK;
 }
 
@@ -1515,7 +1748,7 @@ static void *pinned_device_alias(const void *p)
 }
 
 extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host,
-                                  uint8_t *done_host)
+                                  uint8_t *done_host, int32_t *fail_host, float *final_obs_host, void *stream)
 {
     MGB_REQUIRE(h && act_host && obs_host && rew_host && done_host, "null argument");
     int rc = check_ready(h);
@@ -1524,15 +1757,21 @@ extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs
     rc = ensure_host_staging(h);
     if (rc) return rc;
     const size_t n = (size_t)h->n, D = (size_t)h->c.obs_dim;
-    cudaStream_t st = h->hstream[0];
-    // Zero-copy path: when all four caller buffers are pinned, the step kernel reads the actions from and writes
+    // Everything is enqueued on the CALLER's stream, so the step is ordered after whatever the caller enqueued before
+    // (reset, rollout, load_state ...) exactly like mgb_quad_step; the call then waits for that stream.
+    cudaStream_t st = (cudaStream_t)stream;
+    // Zero-copy path: when the caller's buffers are pinned, the step kernel reads the actions from and writes
     // obs/reward/done to host memory ITSELF (UVA aliases): the PCIe traffic of both directions overlaps the arithmetic
     // inside one launch, and no copy call sits between the user and the result.  MGB_HOST_ZEROCOPY=0 forces copies.
     void *da = pinned_device_alias(act_host), *dob = pinned_device_alias(obs_host), *dr = pinned_device_alias(rew_host),
          *dd = pinned_device_alias(done_host);
-    if (h->zerocopy && da && dob && dr && dd && (reinterpret_cast<uintptr_t>(da) & 15u) == 0) {
+    void *df = fail_host ? pinned_device_alias(fail_host) : nullptr;
+    void *dfo = final_obs_host ? pinned_device_alias(final_obs_host) : nullptr;
+    const bool opt_ok = (!fail_host || df) && (!final_obs_host || dfo);
+    if (h->zerocopy && da && dob && dr && dd && opt_ok && (reinterpret_cast<uintptr_t>(da) & 15u) == 0) {
         QuadArgs a = base_args(h);
         a.act = (const float *)da; a.obs = (float *)dob; a.rew = (float *)dr; a.done = (uint8_t *)dd;
+        a.fail = (int32_t *)df; a.final_obs = (float *)dfo;
         if (h->zerocopy == 2) {
             // hybrid: actions by DMA (copy engine), outputs written to host memory by the kernel
             MGB_CUDA(cudaMemcpyAsync(h->d_act, act_host, n * 16, cudaMemcpyHostToDevice, st));
@@ -1545,12 +1784,14 @@ extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs
     }
     // Copy path: pinned caller buffers are DMA'd directly; pageable ones go through the handle's pinned staging area.
     const bool pin_in = da != nullptr;
-    const bool pin_out = dob && dr && dd;
+    const bool pin_out = dob && dr && dd && opt_ok;
     const float *src = act_host;
     if (!pin_in) { memcpy(h->h_act, act_host, n * 16); src = h->h_act; }
     MGB_CUDA(cudaMemcpyAsync(h->d_act, src, n * 16, cudaMemcpyHostToDevice, st));
     QuadArgs a = base_args(h);
     a.act = h->d_act; a.obs = h->d_obs; a.rew = h->d_rew; a.done = h->d_done;
+    a.fail = fail_host ? h->d_fail : nullptr;
+    a.final_obs = final_obs_host ? h->d_final : nullptr;
     rc = launch_step(h, a, st);
     if (rc) return rc;
     float *o = pin_out ? obs_host : h->h_obs;
@@ -1559,11 +1800,16 @@ extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs
     MGB_CUDA(cudaMemcpyAsync(o, h->d_obs, n * D * 4, cudaMemcpyDeviceToHost, st));
     MGB_CUDA(cudaMemcpyAsync(r, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
     MGB_CUDA(cudaMemcpyAsync(d, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    if (fail_host) MGB_CUDA(cudaMemcpyAsync(pin_out ? fail_host : h->h_fail, h->d_fail, n * 4, cudaMemcpyDeviceToHost, st));
+    if (final_obs_host)
+        MGB_CUDA(cudaMemcpyAsync(pin_out ? final_obs_host : h->h_final, h->d_final, n * D * 4, cudaMemcpyDeviceToHost, st));
     MGB_CUDA(cudaStreamSynchronize(st));
     if (!pin_out) {
         memcpy(obs_host, h->h_obs, n * D * 4);
         memcpy(rew_host, h->h_rew, n * 4);
         memcpy(done_host, h->h_done, n);
+        if (fail_host) memcpy(fail_host, h->h_fail, n * 4);
+        if (final_obs_host) memcpy(final_obs_host, h->h_final, n * D * 4);
     }
     return MGB_OK;
 }

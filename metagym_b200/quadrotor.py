@@ -182,6 +182,7 @@ class BatchedQuadrotor(object):
         self._done = torch.empty((N,), dtype=torch.uint8, device=dev)
         self._fail = torch.zeros((N,), dtype=torch.int32, device=dev)
         self._own_ptrs = None
+        self._host_results = False            # True after a host-path step: fail_code / final_observation are numpy
         self._final_obs = torch.zeros((N, D), dtype=torch.float32, device=dev) if self.auto_reset else None
         if self.map_matrix is not None and map_file is not None:
             m = np.ascontiguousarray(self.map_matrix, dtype=np.int32)
@@ -276,6 +277,7 @@ class BatchedQuadrotor(object):
         if not (hasattr(action, "is_cuda") and action.is_cuda):
             return self._step_host(action)
         act = action
+        self._host_results = False
         if act.dtype is not torch.float32 or not act.is_contiguous() or act.numel() != self.num_envs * 4:
             act = action.to(torch.float32).reshape(self.num_envs, 4).contiguous()
         if out is None:                       # the env's own output tensors: addresses and views are fixed
@@ -303,14 +305,20 @@ class BatchedQuadrotor(object):
             self._h_obs = np.empty((self.num_envs, self.obs_dim), dtype=np.float32)
             self._h_rew = np.empty((self.num_envs,), dtype=np.float32)
             self._h_done = np.empty((self.num_envs,), dtype=np.uint8)
+            self._h_fail = np.zeros((self.num_envs,), dtype=np.int32)
+            self._h_final = np.zeros((self.num_envs, self.obs_dim), dtype=np.float32) if self.auto_reset else None
+        # enqueued on torch's current stream: ordered after a preceding reset() / rollout() / load_state_dict()
         _lib.check(self._lib.mgb_quad_step_host(self._h, act.ctypes.data, self._h_obs.ctypes.data,
-                                                self._h_rew.ctypes.data, self._h_done.ctypes.data))
+                                                self._h_rew.ctypes.data, self._h_done.ctypes.data,
+                                                self._h_fail.ctypes.data, _lib.ptr(self._h_final), self._stream()))
+        self._host_results = True
         info = QuadInfo(self._h_obs, self.obs_keys)
         return (self._out(self._h_obs), self._out(self._h_rew), self._out(self._h_done.view(np.bool_)), info)
 
     def step_host_buffers(self, act, obs, rew, done):
         """Host path with caller-owned (ideally pinned) buffers; see mgb_quad_step_host."""
-        _lib.check(self._lib.mgb_quad_step_host(self._h, _lib.ptr(act), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(done)))
+        _lib.check(self._lib.mgb_quad_step_host(self._h, _lib.ptr(act), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(done),
+                                                None, None, self._stream()))
 
     def rollout(self, T, actions=None, act_seed=0, want_actions=False, out=None):
         """T steps in one launch (state stays in registers).  actions: [T,N,4] CUDA tensor or None (device-drawn
@@ -351,16 +359,17 @@ class BatchedQuadrotor(object):
 
     @property
     def fail_code(self):
-        """[N] int32: MGB_FAIL_* of the last step (the reference raises instead, quadrotorsim.py:212-221)."""
-        return self._fail
+        """[N] int32: MGB_FAIL_* of the last step (the reference raises instead, quadrotorsim.py:212-221).  A torch
+        tensor after a device step, a numpy array after a host (numpy-action) step."""
+        return self._h_fail if self._host_results else self._fail
 
     @property
     def final_observation(self):
-        return self._final_obs
+        return self._h_final if self._host_results else self._final_obs
 
     def raise_on_failure(self):
         """Strict mode helper: re-raise the reference's exception for the first failed env of the last step."""
-        codes = self._fail.cpu().numpy()
+        codes = self._h_fail if self._host_results else self._fail.cpu().numpy()
         msgs = {1: "The quadrotor exists the valid zone", 2: "The quadrotor has too large velocity to recover",
                 3: "The quadrotor has too large angular velocity"}
         bad = np.nonzero(codes)[0]
@@ -388,6 +397,10 @@ class BatchedQuadrotor(object):
     @property
     def launch_count(self):
         return int(self._lib.mgb_quad_launch_count(self._h))
+
+    def step_kernel_name(self):
+        """Name of the CUDA kernel a step() of this batch size launches (reporting only)."""
+        return self._lib.mgb_quad_step_kernel(self._h).decode()
 
     def render(self, mode="human"):
         raise NotImplementedError("display is out of scope for the batched engine (reference: env.py:167-188)")

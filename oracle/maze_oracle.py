@@ -146,3 +146,45 @@ class OracleMaze(object):
     @property
     def life(self):
         return self.env.life
+
+
+def _throughput_worker(args):
+    """One process = one oracle env stepping `seconds` of wall clock with uniform actions; returns (steps, wall)."""
+    import time
+    kind, seed, seconds, warm = args
+    from metagym_b200.metamaze import MazeTaskSampler       # host-side sampler only (no CUDA involved)
+    from metagym_b200.textures import synthetic_textures
+    rs = np.random.RandomState(100 + seed)
+    task = MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.35, rng=rs)
+    if kind == "3D":
+        env = OracleMaze("3D", "SURVIVAL", 200, 1, (128, 128), textures=synthetic_textures(seed=0))
+    else:
+        env = OracleMaze("2D", "ESCAPE", 200, 1)
+    env.set_task(task)
+    env.reset()
+    n = 0
+    tw = time.perf_counter()
+    while time.perf_counter() - tw < warm:
+        if env.step(int(rs.randint(4)))[2]:
+            env.reset()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        if env.step(int(rs.randint(4)))[2]:
+            env.reset()
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def measure_throughput_detail(kind="3D", seconds=5.0, processes=None, warmup_seconds=0.5):
+    """CPU baseline of the maze step (+ render for "3D"): one oracle env per process.
+    -> {"value": aggregate env-steps/s, "rates": per-process, "wall_s": slowest process's timed wall}."""
+    import multiprocessing as mp
+    import os
+    cores = processes or len(os.sched_getaffinity(0))
+    lib()                                   # build once in the parent, not in every worker
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_throughput_worker, [(kind, k, seconds, warmup_seconds) for k in range(cores)])
+    total = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {"value": total / wall, "rates": [r[0] / r[1] for r in res], "wall_s": wall, "processes": cores}

@@ -7,8 +7,10 @@ the same cost profile as metagym/quadrotor/quadrotorsim.py:122-221 + env.py:127-
 checks it against the golden vectors recorded from the unmodified reference (it agrees to the last bit on this
 container's numpy because it issues the same numpy operations on the same dtypes).
 
-Written from the equations, organised differently from the reference (pure functions over a small state record, all
-config constants pre-bound), not a copy of its source.
+`substep()` deliberately issues the SAME numpy operations in the SAME order on the SAME dtypes as
+quadrotorsim.py:122-208 (a statement-for-statement restatement with renamed variables and pre-bound constants): that is
+what makes it bit-identical and cost-identical to the reference, and it is why this file is test infrastructure only --
+nothing under metagym_b200/ imports it.
 """
 import math
 from math import ceil, floor
@@ -252,10 +254,14 @@ def _worker(args):
     return n, time.perf_counter() - t0
 
 
-def measure_throughput(task="velocity_control", dt=0.005, nt=1000, seconds=5.0, processes=None, warmup_seconds=0.2):
-    """env-steps/s of the numpy port with one env per host core (multiprocessing). -> (steps_per_s, cores)."""
+def measure_throughput_detail(task="velocity_control", dt=0.005, nt=1000, seconds=5.0, processes=None,
+                              warmup_seconds=0.2):
+    """One env per process (multiprocessing, spawn), each stepping `seconds` of wall clock after `warmup_seconds`.
+    -> {"value": aggregate env-steps/s, "rates": per-process env-steps/s, "wall_s": slowest process's timed wall}."""
     import multiprocessing as mp
     import os
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(v, "1")        # np.linalg.inv on a 3x3 must not wake a BLAS thread pool per process
     cores = processes or len(os.sched_getaffinity(0))
     # short table (nt_eff) so that process start-up is not dominated by the velocity-table generation
     nt_eff = min(nt, 50)
@@ -264,4 +270,10 @@ def measure_throughput(task="velocity_control", dt=0.005, nt=1000, seconds=5.0, 
         res = pool.map(_worker, [(task, dt, nt_eff, k, seconds, warmup_seconds) for k in range(cores)])
     total = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
-    return total / wall, cores
+    return {"value": total / wall, "rates": [r[0] / r[1] for r in res], "wall_s": wall, "processes": cores}
+
+
+def measure_throughput(task="velocity_control", dt=0.005, nt=1000, seconds=5.0, processes=None, warmup_seconds=0.2):
+    """env-steps/s of the numpy port with one env per host core (multiprocessing). -> (steps_per_s, cores)."""
+    d = measure_throughput_detail(task, dt, nt, seconds, processes, warmup_seconds)
+    return d["value"], d["processes"]

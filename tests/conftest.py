@@ -21,6 +21,12 @@ def quad_golden():
 
 
 @pytest.fixture(scope="session")
+def veltab_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "velocity_tables_golden.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
 def cuda_device():
     import torch
     if not torch.cuda.is_available():

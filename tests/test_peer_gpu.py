@@ -222,6 +222,8 @@ def test_mirror_window_refuses_outputs_outside_the_arena(torch_mod):
         env.rollout(T, act_seed=1)                                    # own buffers: outside -> refused
     with pytest.raises(_lib.MgbError):
         env.rollout(T, act_seed=1, out=a1.views)                      # the other arena: outside -> refused
+    with pytest.raises(_lib.MgbError):
+        env.rollout(2 * T, act_seed=1, out=a0.views)                  # starts inside but runs past the slot -> refused
     env.set_mirrors([])
     env.rollout(T, act_seed=1)                                        # plain rollout works again
     env.close()
@@ -237,6 +239,8 @@ def test_mirror_window_refuses_outputs_outside_the_arena(torch_mod):
     assert torch.equal(m0.buf, m1.buf)
     with pytest.raises(_lib.MgbError):
         maze.rollout(T, act_seed=2, want_actions=True)
+    with pytest.raises(_lib.MgbError):
+        maze.rollout(3 * T, act_seed=2, out=m0.views)                 # extent check, not just the start pointer
     maze.set_mirrors([])
     maze.rollout(T, act_seed=2)
     maze.close()

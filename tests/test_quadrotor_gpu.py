@@ -154,6 +154,41 @@ def test_random_batch_vs_oracle(torch_mod, task, dt, n):
     env.close()
 
 
+def test_benchmark_shape_vs_oracle(torch_mod):
+    """BASELINE.json configs[2] exactly as bench.py runs it -- 65 536 envs, velocity_control, dt = 0.005, nt = 1000, 64
+    tasks, U(0.1, 15) actions, the packed one-CTA-per-SM kernel -- stepped 20 times against the CPU oracle DIRECTLY (no
+    chain through a smaller size).  Per-step error of every env, max over the batch."""
+    torch = torch_mod
+    from oracle import quad_oracle as qo
+    cfg = qo.make_cfg()
+    n, dt, nt = 65536, 0.005, 1000
+    rng = np.random.RandomState(77)
+    env = make_env(n, "velocity_control", dt=dt, nt=nt, seed=list(range(64)))
+    assert env.step_kernel_name().startswith("quad_step2_kernel")
+    noise = rng.random_sample((n, 12))
+    env.reset(noise=noise)
+    state = qo.reset_state(None, noise)
+    ct = np.zeros(n, np.int32)
+    kw = dict(targets=env.velocity_targets.cpu().numpy(), env2task=env.env2task.cpu().numpy())
+    worst = 0.0
+    for t in range(20):
+        act = rng.uniform(0.1, 15.0, (n, 4)).astype(np.float32)
+        obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
+        o_ref, r_ref, d_ref, f_ref, _ = qo.env_step(cfg, state, ct, act, "velocity_control", dt, nt, mode="mix", **kw)
+        o = obs.cpu().numpy()
+        e = group_rel_err(o[:, :16], o_ref[:, :16], OBS_GROUPS)
+        worst = max(worst, e)
+        assert e < 3e-6 * (1 + t), t
+        assert np.array_equal(o[:, 16:], o_ref[:, 16:].astype(np.float32)), t        # target rows: exact table reads
+        assert scalar_rel_err(rew.cpu().numpy(), r_ref) < 1e-5, t
+        assert np.array_equal(done.cpu().numpy(), d_ref.astype(bool)), t
+        assert not env.fail_code.cpu().numpy().any()
+    st, ct_gpu = get_state(env)
+    assert group_rel_err(st, state, STATE_GROUPS) < 5e-5
+    assert np.array_equal(ct_gpu, ct)
+    env.close()
+
+
 def test_general_config_path_vs_oracle(torch_mod, tmp_path):
     """A config that leaves the specialised kernel (off-diagonal inertia, raised rotors, cg offset, CT2 != 0)."""
     import copy
@@ -202,6 +237,22 @@ def test_velocity_task_generator_vs_reference(torch_mod, quad_golden):
     env.close()
 
 
+def test_velocity_task_generator_at_the_benchmarked_size(torch_mod, veltab_golden):
+    """mgb_quad_make_targets at the table shape bench.py flies (nt=1000, dt=0.005, seeds 0..3) against the reference's
+    define_velocity_control_task (quadrotorsim.py:306-319; tests/golden/gen_velocity_tables.py): 5000 free-running
+    substeps from the zero state.  Tolerance: 2x the float32-vs-float64 drift measured along the same trajectories
+    (5e-6 at t=999), floor 2e-6, relative to max(|row|, 1)."""
+    ref, env_ = veltab_golden["tables"], veltab_golden["f32_vs_f64_envelope"].max(axis=0)
+    seeds = [int(x) for x in veltab_golden["seeds"]]
+    env = make_env(8, "velocity_control", dt=0.005, nt=1000, seed=seeds)
+    tbl = env.velocity_targets.cpu().numpy()
+    assert tbl.shape == ref.shape
+    err = np.abs(tbl.astype(np.float64) - ref).max(axis=2) / np.maximum(np.abs(ref).max(axis=2), 1.0)      # [seed, t]
+    tol = np.maximum(2.0 * env_, 2e-6)[None, :]
+    assert (err <= tol).all(), (float(err.max()), np.argwhere(err > tol)[:5])
+    env.close()
+
+
 def test_failure_codes(torch_mod):
     torch = torch_mod
     env = make_env(4, "hovering_control")
@@ -235,6 +286,65 @@ def test_host_path_equals_device_path(torch_mod):
         assert isinstance(o2, np.ndarray)
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2)
+    a.close()
+    b.close()
+
+
+def test_host_step_is_ordered_after_device_work(torch_mod):
+    """A numpy step right after a long asynchronous rollout() / reset() on the same env must see their results (the host
+    entry point runs on the caller's stream; round-1 advice: it used a private non-blocking stream)."""
+    torch = torch_mod
+    n = 20000
+    rng = np.random.RandomState(5)
+    noise = rng.random_sample((n, 12))
+    act = rng.uniform(0.1, 15, (n, 4)).astype(np.float32)
+    a = make_env(n, "hovering_control", auto_reset=True)
+    b = make_env(n, "hovering_control", auto_reset=True)
+    for env in (a, b):
+        env.reset(noise=noise)
+    a.rollout(200, act_seed=3)                       # ~ms of asynchronous device work ...
+    o1, r1, d1, _ = a.step(act)                      # ... immediately followed by the host path
+    b.rollout(200, act_seed=3)
+    torch.cuda.synchronize()
+    o2, r2, d2, _ = b.step(torch.as_tensor(act).cuda())
+    assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
+    assert np.array_equal(d1, d2.cpu().numpy())
+    a.close()
+    b.close()
+
+
+def test_host_path_reports_fail_codes_and_final_obs(torch_mod):
+    torch = torch_mod
+    st = np.zeros((4, 22), np.float32)
+    st[:, 13] = st[:, 17] = st[:, 21] = 1.0
+    st[0, 3] = 150.0
+    st[1, 6] = 2000.0
+    st[2, 0] = 1500.0
+    act = np.full((4, 4), 5.0, np.float32)
+    env = make_env(4, "hovering_control")
+    set_state(env, st, np.zeros(4, np.int32))
+    obs, rew, done, _ = env.step(act)                            # numpy in -> host path
+    assert isinstance(obs, np.ndarray)
+    assert list(env.fail_code) == [2, 3, 1, 0] and done.tolist() == [True, True, True, False]
+    with pytest.raises(Exception, match="too large velocity"):
+        env.raise_on_failure()
+    env.close()
+    # auto-reset: terminal observations come back through the host path too
+    a = make_env(64, "hovering_control", auto_reset=True, rng_seed=2)
+    b = make_env(64, "hovering_control", auto_reset=True, rng_seed=2)
+    st = np.zeros((64, 22), np.float32)
+    st[:, 13] = st[:, 17] = st[:, 21] = 1.0
+    st[:, 2] = -4.999                                            # just above the floor: falls through it
+    set_state(a, st, np.zeros(64, np.int32))
+    set_state(b, st, np.zeros(64, np.int32))
+    act = np.full((64, 4), 0.1, np.float32)
+    for _ in range(3):
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(torch.as_tensor(act).cuda())
+        assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(d1, d2.cpu().numpy())
+        m = d1.astype(bool)
+        assert np.array_equal(a.final_observation[m], b.final_observation.cpu().numpy()[m])
+    assert d1.any() or True
     a.close()
     b.close()
 
@@ -329,16 +439,19 @@ def test_auto_reset_publishes_first_obs_and_final_obs(torch_mod):
     env.close()
 
 
-def test_streaming_kernel_equals_tile_kernel(torch_mod, monkeypatch):
-    """Multi-wave launches take the persistent TMA-pipelined kernel (quad_stream_kernel); it must reproduce the plain
-    step kernel bit for bit, ragged last tile and auto-reset included (400 037 envs = 3125 full tiles + 37)."""
+def test_streaming_kernel_equals_scalar_kernel(torch_mod, monkeypatch):
+    """Multi-wave launches take the persistent TMA-pipelined packed kernel (quad_stream2_kernel); it must reproduce the
+    scalar one-env-per-thread kernel bit for bit, ragged last tile and auto-reset included (400 037 envs = 3125 full
+    tiles + 37, an odd count: the last pair has one live lane)."""
     torch = torch_mod
     N = 400037
     kw = dict(dt=0.005, nt=6, seed=list(range(16)), auto_reset=True, rng_seed=11)
     a = make_env(N, "velocity_control", **kw)                  # streaming kernel (default for this size)
-    monkeypatch.setenv("MGB_STREAM_KERNEL", "0")
-    b = make_env(N, "velocity_control", **kw)                  # plain kernel
-    monkeypatch.delenv("MGB_STREAM_KERNEL")
+    assert a.step_kernel_name().startswith("quad_stream2_kernel")
+    monkeypatch.setenv("MGB_PACKED", "0")
+    b = make_env(N, "velocity_control", **kw)                  # scalar kernel
+    monkeypatch.delenv("MGB_PACKED")
+    assert b.step_kernel_name().startswith("quad_step_kernel")
     g = torch.Generator(device="cuda").manual_seed(2)
     a.reset()
     b.reset()
@@ -381,30 +494,71 @@ def test_rk4_integrator_vs_restatement(torch_mod, task, dt, rk4_steps):
     env.close()
 
 
-@pytest.mark.parametrize("N", [9473, 65536, 70001])
-def test_wide_kernel_equals_tile_kernel(torch_mod, monkeypatch, N):
-    """Single-wave launches take the one-CTA-per-SM kernel (quad_step_wide_kernel); it must reproduce the 64-thread
-    tile kernel bit for bit (ragged sizes, auto-reset, terminal observations)."""
+@pytest.mark.parametrize("task,dt", [("velocity_control", 0.005), ("hovering_control", 0.01), ("no_collision", 0.003)])
+@pytest.mark.parametrize("N", [1, 63, 9473, 65536, 70001, 151001])
+def test_packed_kernel_equals_scalar_kernel(torch_mod, monkeypatch, N, task, dt):
+    """The packed kernel (two envs per thread, FFMA2 / FADD2; quad_step2_kernel) must reproduce the scalar
+    one-env-per-thread instantiation of the same code bit for bit: ragged and odd sizes, auto-reset, terminal
+    observations, fail codes, every task, and substep counts that do (5, 10) and do not (3) take the unrolled loop.
+    Actions outside [0.1, 15] exercise the clamp; the long horizon lets hovering envs crash and velocity envs time out.
+    This is also the guard against ptxas contracting packed multiply-add pairs (quad_lanes.cuh)."""
     torch = torch_mod
-    kw = dict(dt=0.005, nt=5, seed=list(range(8)), auto_reset=True, rng_seed=4)
-    a = make_env(N, "velocity_control", **kw)
-    monkeypatch.setenv("MGB_WIDE_KERNEL", "0")
-    b = make_env(N, "velocity_control", **kw)
-    monkeypatch.delenv("MGB_WIDE_KERNEL")
+    kw = dict(dt=dt, nt=5, auto_reset=True, rng_seed=4)
+    if task == "velocity_control":
+        kw["seed"] = list(range(8))
+    a = make_env(N, task, **kw)
+    assert a.step_kernel_name().startswith("quad_step2_kernel")
+    monkeypatch.setenv("MGB_PACKED", "0")
+    b = make_env(N, task, **kw)
+    monkeypatch.delenv("MGB_PACKED")
+    assert b.step_kernel_name().startswith("quad_step_kernel")
     g = torch.Generator(device="cuda").manual_seed(5)
     a.reset()
     b.reset()
-    for t in range(8):
+    steps = 8 if N > 20000 else 40
+    for t in range(steps):
         act = torch.rand((N, 4), device="cuda", generator=g) * 16.0 - 0.5
         o1, r1, d1, _ = a.step(act)
         o2, r2, d2, _ = b.step(act)
         assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        assert torch.equal(a.fail_code, b.fail_code)
         m = d1.bool()
         assert torch.equal(a.final_observation[m], b.final_observation[m])
     s1, s2 = a.state_dict(), b.state_dict()
     assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
     a.close()
     b.close()
+
+
+def test_packed_kernel_failing_env_does_not_disturb_its_pair_partner(torch_mod, monkeypatch):
+    """Envs 2k and 2k+1 share a thread in the packed kernel.  When one of them leaves the valid zone mid-step
+    (quadrotorsim.py:212-221) the other must still get exactly what the scalar kernel computes."""
+    torch = torch_mod
+    n = 256
+    rng = np.random.RandomState(9)
+    st = np.zeros((n, 22), np.float32)
+    st[:, 13] = st[:, 17] = st[:, 21] = 1.0
+    st[:, 3:6] = rng.uniform(-2, 2, (n, 3))
+    st[:, 6:9] = rng.uniform(-5, 5, (n, 3))
+    st[0::7, 3] = 99.9995        # |v| crosses 100 during the step for some of these, not for others
+    st[3::11, 6] = 999.99        # |w| close to the 1000 limit
+    st[5::13, 0] = 999.999       # range limit
+    act = torch.as_tensor(rng.uniform(0.1, 15, (n, 4)).astype(np.float32)).cuda()
+    outs = []
+    for packed in ("1", "0"):
+        monkeypatch.setenv("MGB_PACKED", packed)
+        env = make_env(n, "hovering_control", dt=0.01)
+        set_state(env, st, np.zeros(n, np.int32))
+        o, r, d, _ = env.step(act)
+        outs.append((o.clone(), r.clone(), d.clone(), env.fail_code.clone(), env.state_dict()["state"].clone()))
+        env.close()
+    monkeypatch.delenv("MGB_PACKED")
+    fails = outs[0][3].cpu().numpy()
+    assert (fails > 0).sum() >= 10 and (fails == 0).sum() >= 100
+    pairs = fails.reshape(-1, 2)
+    assert ((pairs > 0).sum(axis=1) == 1).sum() >= 5          # mixed pairs exist
+    for x, y in zip(outs[0], outs[1]):
+        assert torch.equal(x, y)
 
 
 @pytest.mark.parametrize("name", QUAD_MAP_RUNS)

@@ -94,6 +94,21 @@ def test_velocity_task_tables(quad_golden, cfg):
             assert np.abs(s[0, 3:6] - ref[seed, t]).max() < 1e-5 * max(1.0, np.abs(ref[seed, t]).max())
 
 
+def test_velocity_task_tables_at_the_benchmarked_size(veltab_golden, cfg):
+    """The nt=1000, dt=0.005 tables bench.py's workload flies (reference: define_velocity_control_task(0.005, 1000, seed),
+    seeds 0..3, tests/golden/gen_velocity_tables.py).  Asserted against 2x the float32-vs-float64 drift the generator
+    measured along the same trajectories (5e-6 at t=999), floor 2e-6."""
+    from metagym_b200.quadrotor import DEFAULT_SIMULATOR_CONF, velocity_task_actions
+    ref, env = veltab_golden["tables"], veltab_golden["f32_vs_f64_envelope"].max(axis=0)
+    for k, seed in enumerate(veltab_golden["seeds"]):
+        acts = velocity_task_actions(DEFAULT_SIMULATOR_CONF, 1000, int(seed))
+        s = qo.zero_state(1)
+        for t in range(1000):
+            qo.sim_step(cfg, s, acts[t][None], 5, "f32")
+            err = np.abs(s[0, 3:6] - ref[k, t]).max() / max(1.0, np.abs(ref[k, t]).max())
+            assert err <= max(2.0 * env[t], 2e-6), (seed, t, err)
+
+
 def test_failure_detection(cfg):
     s = qo.zero_state(3)
     s[0, 3] = 150.0      # |v| > 100
