@@ -81,6 +81,11 @@ struct QuadArgs {
     uint64_t seed;
     int auto_reset;
     int per_cta;               // quad_step2_kernel: envs per CTA (multiple of 4)
+    // chained steps (mgb_quad_set_chaining): per-CTA tickets instead of the grid-wide programmatic wait, see quad_step2_kernel
+    int stagger_ns;            // quad_step2_kernel: CTAs of the second half of the grid start this much later (tuning knob)
+    int trigger_early;         // non-chained kernels: execute griddepcontrol.launch_dependents (never after chaining was used)
+    uint32_t *chain_started;   // [grid] launches of this env block that have STARTED   (null = not chained)
+    uint32_t *chain_done;      // [grid] launches of this env block that have COMPLETED
     // rollout only
     int T;
     uint64_t act_seed;
@@ -112,13 +117,13 @@ __device__ __forceinline__ void load_state(const QuadArgs &a, int64_t e, QState 
 {
     const float *b = env_base_ptr(a, e);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { s.p[k] = b[MGB_QF(k)]; s.v[k] = b[MGB_QF(3 + k)]; s.om[k] = b[MGB_QF(6 + k)]; }
+    for (int k = 0; k < 3; ++k) { s.p[k] = __ldcg(b + MGB_QF(k)); s.v[k] = __ldcg(b + MGB_QF(3 + k)); s.om[k] = __ldcg(b + MGB_QF(6 + k)); }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.w[k] = b[MGB_QF(9 + k)];
+    for (int k = 0; k < 4; ++k) s.w[k] = __ldcg(b + MGB_QF(9 + k));
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s.R[k] = b[MGB_QF(13 + k)];
-    s.ct[0] = __float_as_int(b[MGB_QF(22)]);
-    s.ep[0] = __float_as_int(b[MGB_QF(23)]);
+    for (int k = 0; k < 9; ++k) s.R[k] = __ldcg(b + MGB_QF(13 + k));
+    s.ct[0] = __float_as_int(__ldcg(b + MGB_QF(22)));
+    s.ep[0] = __float_as_int(__ldcg(b + MGB_QF(23)));
 }
 
 __device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const QState &s)
@@ -159,7 +164,7 @@ __device__ __forceinline__ void load_state2(const QuadArgs &a, int64_t P, VState
     const float4 *b = pair_ptr(a, P);
     float4 q[kPlanes];
 #pragma unroll
-    for (int k = 0; k < kPlanes; ++k) q[k] = b[k * kTilePairs];
+    for (int k = 0; k < kPlanes; ++k) q[k] = __ldcg(b + k * kTilePairs);   // L2 (coherence point): launches may overlap
     unpack_state(q, s);
 }
 __device__ __forceinline__ void store_state2(const QuadArgs &a, int64_t P, const VState<f2> &s)
@@ -403,13 +408,18 @@ __device__ __forceinline__ bool integrate(const QuadConst &c, VState<T> &s, cons
             break;                                                                                               \
         }                                                                                                        \
     }
+#ifdef MGB_QUAD_UNROLL5
     if (c.substeps % 5 == 0) {
 #pragma unroll 1
         for (int k = 0; k < c.substeps && !failed; k += 5) {
 #pragma unroll
             for (int u = 0; u < 5; ++u) MGB_QUAD_ONE_SUBSTEP()
         }
-    } else {
+    } else
+#endif
+    {
+        // one rolled loop: the substep body (~190 packed instructions, 3 KB) then stays in the instruction cache, while the
+        // 5x-unrolled form made every warp stream 15 KB of straight-line code once per launch (ncu: 12 % no_instructions)
 #pragma unroll 1
         for (int k = 0; k < c.substeps; ++k) MGB_QUAD_ONE_SUBSTEP()
     }
@@ -945,8 +955,9 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
 
     // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now (its CTAs park at their own
     // griddepcontrol.wait), and this kernel waits here until the PREVIOUS one has completed and flushed -- the
-    // launch latency of back-to-back env steps overlaps the previous step.
-    asm volatile("griddepcontrol.launch_dependents;");
+    // launch latency of back-to-back env steps overlaps the previous step.  (Not on a handle that uses chained steps:
+    // a chained successor does not wait for the whole grid, so only ticket-taking kernels may let it start early.)
+    if (a.trigger_early) asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (active) {
@@ -964,10 +975,52 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
 // Packed step kernel: one thread = the env pair (e, e+1) in FFMA2 / FADD2 registers.  Each CTA owns `per` consecutive envs
 // (a multiple of 4, so that every observation tile stays 16-byte aligned for the bulk store): per = 128 for small batches,
 // ceil(N / #SMs) for launches that fit one wave -- one CTA per SM, 148 CTA dispatches and a balanced wave (444 vs 443 envs
-// per SM at 65 536 envs).  MINB = 2 caps the registers at 128 so that the CTAs of launch k+1 can become resident (parked at
-// griddepcontrol.wait) while those of launch k finish.
-template <bool SIMPLE, int MINB>
-__global__ void __launch_bounds__(256, MINB) quad_step2_kernel(const __grid_constant__ QuadConst c,
+// per SM at 65 536 envs).
+//
+// Chained mode (a.chain_started != null; mgb_quad_set_chaining).  An env's step k+1 depends on ITS OWN step k and on
+// nothing else, so consecutive step launches need no grid-wide barrier: CTA j of launch k+1 only has to wait for CTA j of
+// launch k.  Every CTA takes a ticket (how many launches of its env block started before it), lets the next launch's CTAs
+// be scheduled (griddepcontrol.launch_dependents -- they become resident as soon as a slot frees up, 4 CTAs of 64 threads
+// fit per SM), waits until `ticket` launches of its block have completed (acquire), steps its envs, and publishes
+// completion (release) after its state stores.  It never executes griddepcontrol.wait, so while one CTA of an SM waits for
+// its loads or drains its stores, CTAs of the next launch already integrate on the same SM: load, arithmetic and store
+// phases of consecutive steps overlap instead of adding up (the one-launch-at-a-time kernel spends more time moving 281
+// B/env through L2 than integrating, profiles/r2_launchfloor.txt).  Ordering argument: the runtime starts launch k+1 only
+// after EVERY CTA of launch k has executed launch_dependents, which each does after taking its ticket -- so tickets of a block
+// are taken in launch order, and a CTA only ever waits for a CTA that is already resident or finished (no deadlock).  The
+// spin is bounded and traps instead of hanging the device.
+__device__ __forceinline__ uint32_t chain_enter(const QuadArgs &a)
+{
+    uint32_t ticket = 0;
+    if (threadIdx.x == 0) {
+        ticket = atomicAdd(a.chain_started + blockIdx.x, 1u);
+        if (ticket == 0xffffffffu) asm volatile("griddepcontrol.launch_dependents;");   // (data dependency: the ticket is taken first)
+        asm volatile("griddepcontrol.launch_dependents;");
+        uint32_t spins = 0;
+        for (;;) {
+            uint32_t d;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(a.chain_done + blockIdx.x) : "memory");
+            if ((int32_t)(d - ticket) >= 0) break;
+            if (++spins > (1u << 22)) __trap();        // ~seconds: a lost predecessor must not hang the GPU
+            __nanosleep(20);
+        }
+    }
+    __syncthreads();
+    return ticket;
+}
+__device__ __forceinline__ void chain_exit(const QuadArgs &a, uint32_t ticket)
+{
+    __syncthreads();                                   // every thread's state stores are issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.chain_done + blockIdx.x), "r"(ticket + 1u) : "memory");
+    }
+}
+
+// THREADS / MINB: launch bounds.  <256, 1>: the one-CTA-per-SM form (no register cap: 220).  <64, 6>: chained 128-env CTAs
+// capped at 168 registers so that six of them (768 envs, 1.7 launches of the 65 536-env shape) are resident per SM.
+template <bool SIMPLE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) quad_step2_kernel(const __grid_constant__ QuadConst c,
                                                                const __grid_constant__ QuadArgs a)
 {
     extern __shared__ __align__(128) float pair_smem[];
@@ -981,8 +1034,15 @@ __global__ void __launch_bounds__(256, MINB) quad_step2_kernel(const __grid_cons
     const int D = c.obs_dim;
     const int nact = rows - le >= 2 ? 2 : (rows - le > 0 ? 1 : 0);
     int final_mask = 0;
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t ticket = 0;
+    const bool chained = a.chain_started != nullptr;
+    if (chained) {
+        ticket = chain_enter(a);
+    } else {
+        if (a.trigger_early) asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    if (a.stagger_ns > 0 && blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep(a.stagger_ns);
     if (nact > 0) {
         VState<f2> s;
         load_state2(a, e >> 1, s);
@@ -991,6 +1051,7 @@ __global__ void __launch_bounds__(256, MINB) quad_step2_kernel(const __grid_cons
         const f2 V[4] = {pack2(a0.x, a1.x), pack2(a0.y, a1.y), pack2(a0.z, a1.z), pack2(a0.w, a1.w)};
         step_body<SIMPLE, true, f2>(c, a, e, nact, s, V, tile + le * D, ftile + le * D, final_mask);
     }
+    if (chained) chain_exit(a, ticket);
     if (rows > 0) publish_tile(a.obs, tile, e0, rows, D);
     else __syncthreads();
     publish_final(a, ftile, e, le, 2, final_mask, D);
@@ -1015,7 +1076,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream2_kernel(const _
     const int64_t n_tiles = (a.n + kTileEnvs - 1) / kTileEnvs;
     const int tid = threadIdx.x;
 
-    asm volatile("griddepcontrol.launch_dependents;");
+    if (a.trigger_early) asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         mgb_mbar_init(&full[0], 1);
@@ -1292,7 +1353,13 @@ struct mgb_quad {
     int auto_reset = 0;
     int num_sms = 148;
     int packed = 1;            // two envs per thread in packed FFMA2 registers (MGB_PACKED=0: scalar reference kernel)
-    int step_minb = 1;         // packed step kernel: min resident CTAs per SM it is compiled for (MGB_STEP_MINB=2: <= 128 regs)
+    int chaining_ever = 0;     // chaining was enabled at some point: non-chained kernels of this handle no longer trigger early
+    int chaining = 0;          // mgb_quad_set_chaining: consecutive packed step launches overlap (per-CTA tickets)
+    uint32_t *chain_flags = nullptr;   // [2][max grid]: started, done
+    int chain_grid = 0;
+    int step_per = 0;          // tuning: envs per CTA of the packed step kernel (MGB_STEP_PER; 0 = one CTA per SM)
+    int stagger_ns = 0;        // tuning: MGB_STAGGER_NS
+    int chain_minb = 6;        // chained step kernel: resident CTAs per SM it is compiled for (MGB_CHAIN_MINB=4: no register cap)
     int stream_kernel = 1;     // persistent TMA-pipelined kernel for multi-wave launches (MGB_STREAM_KERNEL=0 disables)
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
@@ -1323,6 +1390,7 @@ static QuadArgs base_args(const mgb_quad *h)
     a.env2task = h->env2task;
     a.seed = h->seed;
     a.auto_reset = h->auto_reset;
+    a.trigger_early = h->chaining_ever ? 0 : 1;
     return a;
 }
 
@@ -1403,15 +1471,15 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev);   // 0 copies, 1 zero-copy, 2 hybrid
     if (const char *ev = getenv("MGB_STREAM_KERNEL")) h->stream_kernel = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_PACKED")) h->packed = atoi(ev) != 0;
-    if (const char *ev = getenv("MGB_STEP_MINB")) h->step_minb = atoi(ev) == 2 ? 2 : 1;
+    if (const char *ev = getenv("MGB_CHAIN_MINB")) h->chain_minb = atoi(ev) == 4 ? 4 : 6;
+    if (const char *ev = getenv("MGB_STEP_PER")) h->step_per = atoi(ev);
+    if (const char *ev = getenv("MGB_STAGGER_NS")) h->stagger_ns = atoi(ev);
     {
         // the packed step kernel needs up to 2 x 512 x 19 floats of dynamic shared memory; the attribute is per function and
         // device, idempotent, and set to the maximum so that handles never lower each other's limit
         const int max_smem = 512 * kMaxObs * 4 * 2;
-        cudaFuncSetAttribute(quad_step2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        cudaFuncSetAttribute(quad_step2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        cudaFuncSetAttribute(quad_step2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        cudaFuncSetAttribute(quad_step2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<true, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<false, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (cudaGetLastError() != cudaSuccess) {
             mgb_set_error("cudaFuncSetAttribute(quad_step2_kernel, %d bytes of shared memory) failed", max_smem);
             delete h;
@@ -1445,6 +1513,7 @@ extern "C" void mgb_quad_destroy(mgb_quad *h)
     cudaDeviceSynchronize();
     cudaFree(h->planes);
     cudaFree(h->sat);
+    cudaFree(h->chain_flags);
     cudaFree(h->targets);
     cudaFree(h->env2task);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
@@ -1585,21 +1654,33 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
         // per = envs per CTA: one warp of pairs for small batches, one CTA per SM when the launch fits a single wave of
         // 256-thread CTAs (7x fewer CTA dispatches than 64-env tiles and a balanced wave), 256 envs per CTA beyond that
         int per;
-        if (a.n <= (int64_t)h->num_sms * 64) per = 64;
+        QuadArgs aw = a;
+        if (h->chaining) {
+            // chained steps: 128-env CTAs (= one state tile, 64 threads, 4 resident per SM) so that CTAs of consecutive
+            // launches share an SM; the block -> env mapping is the same for every launch of the handle
+            per = kTileEnvs;
+            aw.chain_started = h->chain_flags;
+            aw.chain_done = h->chain_flags + h->chain_grid;
+        } else if (a.n <= (int64_t)h->num_sms * 64) per = 64;
         else if (a.n <= (int64_t)h->num_sms * 128) per = 128;
         else if (a.n <= (int64_t)h->num_sms * 512) per = (int)(((a.n + h->num_sms - 1) / h->num_sms + 3) / 4 * 4);
         else per = 256;
-        QuadArgs aw = a;
+        if (!h->chaining && h->step_per > 0 && a.n > (int64_t)h->num_sms * 128) per = (h->step_per + 3) / 4 * 4;
+        if (per > 512) per = 512;
         aw.per_cta = per;
+        aw.stagger_ns = h->stagger_ns;
         cfg.gridDim = dim3((unsigned)((a.n + per - 1) / per));
         cfg.blockDim = dim3((unsigned)((per / 2 + 31) / 32 * 32));
         cfg.dynamicSmemBytes = (size_t)per * kMaxObs * 4 * 2;
-        if (h->step_minb == 2) {
-            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 2>, h->c, aw));
-            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 2>, h->c, aw));
+        if (h->chaining && h->chain_minb == 6) {
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 64, 6>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 64, 6>, h->c, aw));
+        } else if (h->chaining) {
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 64, 4>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 64, 4>, h->c, aw));
         } else {
-            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 1>, h->c, aw));
-            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 1>, h->c, aw));
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 256, 1>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 256, 1>, h->c, aw));
         }
     } else {
         const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
@@ -1620,6 +1701,22 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
     return MGB_OK;
 }
 
+extern "C" int mgb_quad_set_chaining(mgb_quad *h, int on)
+{
+    MGB_REQUIRE(h, "null handle");
+    MgbDeviceGuard guard(h->device);
+    if (on && !h->chain_flags) {
+        h->chain_grid = (int)((h->n + kTileEnvs - 1) / kTileEnvs);
+        MGB_CUDA(cudaDeviceSynchronize());       // earlier launches of this handle may still trigger early: let them finish
+        MGB_CUDA(cudaMalloc(&h->chain_flags, sizeof(uint32_t) * 2 * (size_t)h->chain_grid));
+        MGB_CUDA(cudaMemset(h->chain_flags, 0, sizeof(uint32_t) * 2 * (size_t)h->chain_grid));
+        MGB_CUDA(cudaDeviceSynchronize());
+    }
+    if (on) h->chaining_ever = 1;
+    h->chaining = on ? 1 : 0;
+    return MGB_OK;
+}
+
 extern "C" const char *mgb_quad_step_kernel(const mgb_quad *h)
 {
     if (!h) return "";
@@ -1627,8 +1724,10 @@ extern "C" const char *mgb_quad_step_kernel(const mgb_quad *h)
     switch (choose_step_kernel(h, a)) {
     case STEP_STREAM: return h->c.simple ? "quad_stream2_kernel<true>" : "quad_stream2_kernel<false>";
     case STEP_PACKED:
-        if (h->step_minb == 2) return h->c.simple ? "quad_step2_kernel<true,2>" : "quad_step2_kernel<false,2>";
-        return h->c.simple ? "quad_step2_kernel<true,1>" : "quad_step2_kernel<false,1>";
+        if (h->chaining && h->chain_minb == 6)
+            return h->c.simple ? "quad_step2_kernel<true,64,6> (chained)" : "quad_step2_kernel<false,64,6> (chained)";
+        if (h->chaining) return h->c.simple ? "quad_step2_kernel<true,64,4> (chained)" : "quad_step2_kernel<false,64,4> (chained)";
+        return h->c.simple ? "quad_step2_kernel<true,256,1>" : "quad_step2_kernel<false,256,1>";
     default: return h->c.simple ? "quad_step_kernel<true,.>" : "quad_step_kernel<false,.>";
     }
 }

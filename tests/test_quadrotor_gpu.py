@@ -530,6 +530,63 @@ def test_packed_kernel_equals_scalar_kernel(torch_mod, monkeypatch, N, task, dt)
     b.close()
 
 
+@pytest.mark.parametrize("N,task", [(65536, "velocity_control"), (151001, "velocity_control"), (4096, "hovering_control"),
+                                    (777, "no_collision")])
+def test_chained_steps_equal_unchained_steps(torch_mod, N, task):
+    """set_chaining(True): consecutive step launches overlap on the GPU (per-block tickets instead of the grid-wide wait).
+    Trajectories must be bit-identical to ordinary stepping -- eager back-to-back launches, a CUDA graph replayed several
+    times (tickets are taken on the device, so replays need no host-side epoch), other kernels of the same handle in
+    between (masked reset, state read), and switching chaining off again."""
+    torch = torch_mod
+    T = 48
+    kw = dict(dt=0.005, nt=7, auto_reset=True, rng_seed=6)
+    if task == "velocity_control":
+        kw["seed"] = list(range(5))
+    a = make_env(N, task, **kw)
+    b = make_env(N, task, **kw)
+    a.set_chaining(True)
+    assert "chained" in a.step_kernel_name()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    acts = torch.rand((T, N, 4), device="cuda", generator=g) * 16.0 - 0.5
+    D = a.obs_dim
+    outs = []
+    for env in (a, b):
+        obs = torch.zeros((T, N, D), device="cuda")
+        rew = torch.zeros((T, N), device="cuda")
+        done = torch.zeros((T, N), dtype=torch.uint8, device="cuda")
+        env.reset()
+        for t in range(16):                                   # eager, back to back
+            env.step(acts[t], out=(obs[t], rew[t], done[t]))
+        mask = (torch.arange(N, device="cuda") % 3 == 0)
+        env.reset(mask=mask)                                  # an ordinary kernel of the same handle in between
+        st_mid = env.state_dict()["state"].clone()
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())       # torch side streams do not synchronise with the default one
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            env.step(acts[16], out=(obs[16], rew[16], done[16]))          # warm-up on the capture stream
+            stream.synchronize()
+            with torch.cuda.graph(graph, stream=stream):
+                for t in range(17, 25):
+                    env.step(acts[t], out=(obs[t], rew[t], done[t]))
+        torch.cuda.synchronize()
+        for _ in range(3):                                    # the same 8 launches three times: 24 more steps
+            graph.replay()
+        torch.cuda.synchronize()
+        if env is a:
+            env.set_chaining(False)                           # back to grid-wide waits: still consistent
+        for t in range(25, T):
+            env.step(acts[t], out=(obs[t], rew[t], done[t]))
+        torch.cuda.synchronize()
+        outs.append((obs, rew, done, st_mid, env.state_dict()))
+    for x, y in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(x, y)
+    assert torch.equal(outs[0][4]["state"], outs[1][4]["state"]) and torch.equal(outs[0][4]["ct"], outs[1][4]["ct"])
+    assert int(outs[0][2].sum()) > 0
+    a.close()
+    b.close()
+
+
 def test_packed_kernel_failing_env_does_not_disturb_its_pair_partner(torch_mod, monkeypatch):
     """Envs 2k and 2k+1 share a thread in the packed kernel.  When one of them leaves the valid zone mid-step
     (quadrotorsim.py:212-221) the other must still get exactly what the scalar kernel computes."""
