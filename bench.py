@@ -379,19 +379,6 @@ def run_quadrotor(ctx, sampler):
     def enqueue(t):
         env.step(acts[t % G], out=(obs[t % G], rew[t % G], done[t % G]))
 
-    # unchained reference point first (grid-wide programmatic wait between consecutive launches), then the reported
-    # configuration: chained steps -- the action table is pre-generated, which is exactly the contract of
-    # mgb_quad_set_chaining (include/mgb200.h); per-step results are bit-identical (tests/test_quadrotor_gpu.py)
-    unchained = None
-    if not args.no_chaining:
-        if not args.no_extras:
-            b0 = GraphedBlock(torch, dev, enqueue, K, min(W, G))
-            t0 = ctx.time_block(b0, W)
-            unchained = {"us_per_launch": t0["ms_per_step"] * 1e3, "timed_steps": t0["timed_steps"],
-                         "frac": n * BYTES_PER_STEP / (t0["ms_per_step"] * 1e-3) / 1e9 / ctx.peak,
-                         "note": "same launches with the grid-wide wait between consecutive steps (set_chaining(False))"}
-            del b0
-        env.set_chaining(True)
     block = GraphedBlock(torch, dev, enqueue, K, min(W, G))
     tm = ctx.time_block(block, W)
     us_per_launch = tm["ms_per_step"] * 1e3
@@ -402,9 +389,6 @@ def run_quadrotor(ctx, sampler):
     kernel_name = env.step_kernel_name() if hasattr(env, "step_kernel_name") else "quad_step"
 
     extras, e2e = {}, None
-    if unchained is not None:
-        extras["unchained_steps"] = unchained
-    env.set_chaining(False)
     if not args.no_extras:
         # ---- end to end through the host-buffer C-ABI entry point, pinned buffers, copies inside the timed region
         h_act = torch.empty((n, 4), dtype=torch.float32).pin_memory()
@@ -491,11 +475,7 @@ def run_quadrotor(ctx, sampler):
     cfg = base_config("quadrotor", world)
     info = {}
     info.update({
-        "launch": block.describe("mgb_quad_step") + (
-            " (programmatic dependent launch between consecutive steps)" if args.no_chaining else
-            "; chained steps (mgb_quad_set_chaining): launch k+1 is scheduled while launch k runs and each 128-env block "
-            "waits only for the same block of the previous launch (device-side tickets), actions come from the "
-            "pre-generated [32,n,4] table; us_per_launch = timed time / launches (launches overlap)"),
+        "launch": block.describe("mgb_quad_step") + " (programmatic dependent launch between consecutive steps)",
         "timed_region": "R x K = %d steps in %.1f ms (>= %.0f ms), CUDA events, max over ranks" % (
             tm["timed_steps"], tm["ms"], MIN_TIMED_MS),
         "l2": "rollout buffers obs [32,n,19] f32 = 160 MB > 126 MB L2 (inputs/outputs never L2-hot); "
@@ -916,7 +896,6 @@ def main():
     ap.add_argument("--workload", default="quadrotor", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE shape)")
     ap.add_argument("--no-extras", action="store_true", help="skip streaming / fused / e2e / cpu legs")
-    ap.add_argument("--no-chaining", action="store_true", help="quadrotor: grid-wide wait between consecutive step launches")
     ap.add_argument("--cpu-seconds", type=float, default=0.0, help="length of the CPU arm (default 10 s; reference arm 30 s)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -152,20 +152,9 @@ int mgb_quad_state(mgb_quad *h, float *state_dev, int32_t *ct_dev, int load, voi
 /* Number of kernel launches issued through this handle so far (bench.py reports it as gpu_launches). */
 int64_t mgb_quad_launch_count(const mgb_quad *h);
 
-/* Chained steps.  on = 1: consecutive mgb_quad_step launches on one stream may OVERLAP -- the step kernel replaces the
- * grid-wide wait between launches by per-block tickets (block j of launch k+1 waits for block j of launch k only; an env's
- * step depends on its own previous step and on nothing else), so the load / integrate / store phases of consecutive
- * steps pipeline on every SM.  Results are bit-identical to unchained stepping.  The caller's side of the contract: the
- * `act_dev` buffer of a step must not be written by work enqueued AFTER the previous mgb_quad_step of this handle (e.g.
- * pre-generated action tables, or a policy that runs one step ahead); everything else the step reads belongs to the
- * handle.  A policy kernel enqueued between two steps still works -- it simply serialises them like any stream-ordered
- * kernel.  Rollouts of a fixed-action table (the reference's random-action smoke loop, quadrotor/tests/test_env.py:22-28)
- * are the use case.  No reference counterpart. */
-int mgb_quad_set_chaining(mgb_quad *h, int on);
-
-/* Name of the kernel an mgb_quad_step launch of this handle takes at its batch size ("quad_step2_kernel<true,1>":
- * two envs per thread in packed FFMA2 registers; "quad_stream2_kernel<..>": persistent TMA-pipelined variant for
- * multi-wave batches; "quad_step_kernel<..>": scalar reference instantiation, MGB_PACKED=0 or the RK4 option).
+/* Name of the kernel an mgb_quad_step launch of this handle takes at its batch size ("quad_step_wide_kernel<..>": one
+ * CTA per SM for single-wave batches; "quad_stream_kernel<..>": persistent TMA-pipelined variant for multi-wave batches;
+ * "quad_step_kernel<..>": 64-env CTAs otherwise; "quad_step2_kernel<..>": the packed two-envs-per-thread variant, MGB_PACKED=1).
  * Reporting only (bench.py's roofline.kernel); no reference counterpart. */
 const char *mgb_quad_step_kernel(const mgb_quad *h);
 

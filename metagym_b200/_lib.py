@@ -58,7 +58,6 @@ SIGNATURES = {
     "mgb_quad_state": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp]),
     "mgb_quad_launch_count": (c_i64, [vp]),
     "mgb_quad_step_kernel": (ctypes.c_char_p, [vp]),
-    "mgb_quad_set_chaining": (ctypes.c_int, [vp, ctypes.c_int]),
     "mgb_maze_create": (ctypes.c_int, [ctypes.POINTER(vp), c_i64, ctypes.POINTER(MazeCfg), ctypes.c_int, c_i64]),
     "mgb_maze_destroy": (None, [vp]),
     "mgb_maze_obs_bytes_per_env": (c_i64, [vp]),

@@ -10,13 +10,13 @@
 //   Quadrotor.step / _get_reward / _check_collision / _update_state / _convert_state_to_ndarray
 //                                                             metagym/quadrotor/env.py:127-165, 193-281
 //
-// Data layout in HBM (DESIGN.md "state planes"): envs are stored as PAIRS (2j, 2j+1).  Per tile of 128 envs = 64 pairs,
-// twelve planes of float4 stored back to back (tile t, plane k, pair j -> float4 index (t*12 + k)*64 + j); one float4
-// holds two consecutive fields of both envs of the pair: (f[2k] of A, f[2k] of B, f[2k+1] of A, f[2k+1] of B), with the 24
-// fields  p.x p.y p.z v.x v.y v.z w.x w.y w.z m0 m1 m2 m3 R00 R01 R02 R10 R11 R12 R20 R21 R22 ct(int) episode(int)
-// (p position, v velocity, w body angular velocity, m propeller speeds, R rotation matrix).  A packed thread loads its
-// pair with twelve coalesced 128-bit accesses (512 B contiguous per warp) and every float4 half IS a packed register
-// pair (no shuffling); a tile's whole state is one contiguous 12 KB block (one bulk/TMA copy in the streaming kernel).
+// Data layout in HBM (DESIGN.md "state planes"): per tile of 128 envs, six planes of float4 stored back to back
+// (tile t, plane k, env j -> float4 index (t*6 + k)*128 + j).  Every load/store is one coalesced 128-bit access per
+// thread (512 B contiguous per warp) AND a tile's whole state is one contiguous 12 KB block, so a CTA touches 3 DRAM
+// pages instead of 12 far-apart ones (and the streaming kernel fetches it with one bulk/TMA copy):
+//   P0 = p.x p.y p.z v.x | P1 = v.y v.z w.x w.y | P2 = w.z m0 m1 m2 | P3 = m3 R00 R01 R02
+//   P4 = R10 R11 R12 R20 | P5 = R21 R22 ct(int) episode(int)
+// (p position, v velocity, w body angular velocity, m propeller speeds, R rotation matrix)
 // Observations leave through a shared-memory tile and ONE bulk (TMA) store per CTA, so the [n][obs_dim] row-major
 // array the gym API wants is written with full 128 B lines even though obs_dim*4 (64 or 76 B) is not a line.
 #include <math.h>
@@ -80,12 +80,7 @@ struct QuadArgs {
     const int32_t *env2task;   // [n]
     uint64_t seed;
     int auto_reset;
-    int per_cta;               // quad_step2_kernel: envs per CTA (multiple of 4)
-    // chained steps (mgb_quad_set_chaining): per-CTA tickets instead of the grid-wide programmatic wait, see quad_step2_kernel
-    int stagger_ns;            // quad_step2_kernel: CTAs of the second half of the grid start this much later (tuning knob)
-    int trigger_early;         // non-chained kernels: execute griddepcontrol.launch_dependents (never after chaining was used)
-    uint32_t *chain_started;   // [grid] launches of this env block that have STARTED   (null = not chained)
-    uint32_t *chain_done;      // [grid] launches of this env block that have COMPLETED
+    int per_cta;               // quad_step_wide_kernel / quad_step2_kernel: envs per CTA (multiple of 4)
     // rollout only
     int T;
     uint64_t act_seed;
@@ -101,82 +96,71 @@ template <class T> struct VState {
 };
 using QState = VState<float>;
 
-constexpr int kTileEnvs = 128;    // envs per state tile (layout unit, independent of the CTA size)
-constexpr int kTilePairs = 64;
-constexpr int kPlanes = 12;       // float4 planes per tile
+constexpr int kTileEnvs = 128;   // envs per state tile (layout unit, independent of the CTA size)
+constexpr int kPlanes = 6;       // float4 planes per env
 
-// scalar view of the pair-interleaved layout: field f of env e is base[(f >> 1) * 256 + (f & 1) * 2]
-__device__ __forceinline__ float *env_base_ptr(const QuadArgs &a, int64_t e)
+__device__ __forceinline__ float4 *tile_base(const QuadArgs &a, int64_t e)
 {
-    return reinterpret_cast<float *>(a.planes) + ((e / kTileEnvs) * (kPlanes * kTilePairs) + ((e % kTileEnvs) >> 1)) * 4 +
-           (e & 1);
+    return a.planes + (e / kTileEnvs) * (kPlanes * kTileEnvs) + (e % kTileEnvs);
 }
-#define MGB_QF(f) (((f) >> 1) * (kTilePairs * 4) + ((f) & 1) * 2)
+
+__device__ __forceinline__ void unpack_state(const float4 q[kPlanes], QState &s)
+{
+    s.p[0] = q[0].x; s.p[1] = q[0].y; s.p[2] = q[0].z; s.v[0] = q[0].w;
+    s.v[1] = q[1].x; s.v[2] = q[1].y; s.om[0] = q[1].z; s.om[1] = q[1].w;
+    s.om[2] = q[2].x; s.w[0] = q[2].y; s.w[1] = q[2].z; s.w[2] = q[2].w;
+    s.w[3] = q[3].x; s.R[0] = q[3].y; s.R[1] = q[3].z; s.R[2] = q[3].w;
+    s.R[3] = q[4].x; s.R[4] = q[4].y; s.R[5] = q[4].z; s.R[6] = q[4].w;
+    s.R[7] = q[5].x; s.R[8] = q[5].y; s.ct[0] = __float_as_int(q[5].z); s.ep[0] = __float_as_int(q[5].w);
+}
+__device__ __forceinline__ void pack_state(const QState &s, float4 q[kPlanes])
+{
+    q[0] = make_float4(s.p[0], s.p[1], s.p[2], s.v[0]);
+    q[1] = make_float4(s.v[1], s.v[2], s.om[0], s.om[1]);
+    q[2] = make_float4(s.om[2], s.w[0], s.w[1], s.w[2]);
+    q[3] = make_float4(s.w[3], s.R[0], s.R[1], s.R[2]);
+    q[4] = make_float4(s.R[3], s.R[4], s.R[5], s.R[6]);
+    q[5] = make_float4(s.R[7], s.R[8], __int_as_float(s.ct[0]), __int_as_float(s.ep[0]));
+}
 
 __device__ __forceinline__ void load_state(const QuadArgs &a, int64_t e, QState &s)
 {
-    const float *b = env_base_ptr(a, e);
+    const float4 *b = tile_base(a, e);
+    float4 q[kPlanes];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { s.p[k] = __ldcg(b + MGB_QF(k)); s.v[k] = __ldcg(b + MGB_QF(3 + k)); s.om[k] = __ldcg(b + MGB_QF(6 + k)); }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s.w[k] = __ldcg(b + MGB_QF(9 + k));
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s.R[k] = __ldcg(b + MGB_QF(13 + k));
-    s.ct[0] = __float_as_int(__ldcg(b + MGB_QF(22)));
-    s.ep[0] = __float_as_int(__ldcg(b + MGB_QF(23)));
+    for (int k = 0; k < kPlanes; ++k) q[k] = b[k * kTileEnvs];
+    unpack_state(q, s);
 }
 
 __device__ __forceinline__ void store_state(const QuadArgs &a, int64_t e, const QState &s)
 {
-    float *b = env_base_ptr(a, e);
+    float4 *b = tile_base(a, e);
+    float4 q[kPlanes];
+    pack_state(s, q);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { b[MGB_QF(k)] = s.p[k]; b[MGB_QF(3 + k)] = s.v[k]; b[MGB_QF(6 + k)] = s.om[k]; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) b[MGB_QF(9 + k)] = s.w[k];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) b[MGB_QF(13 + k)] = s.R[k];
-    b[MGB_QF(22)] = __int_as_float(s.ct[0]);
-    b[MGB_QF(23)] = __int_as_float(s.ep[0]);
+    for (int k = 0; k < kPlanes; ++k) b[k * kTileEnvs] = q[k];
 }
 
-// packed view: the twelve float4 of pair P (envs 2P, 2P+1); q[k] = (f[2k].A, f[2k].B, f[2k+1].A, f[2k+1].B)
-__device__ __forceinline__ void unpack_state(const float4 q[kPlanes], VState<f2> &s)
+// lane h of a packed state <-> scalar state (forward declarations used by the packed load/store)
+template <class T> __device__ __forceinline__ void get_lane_state(const VState<T> &s, int h, QState &o);
+template <class T> __device__ __forceinline__ void set_lane_state(VState<T> &s, int h, const QState &o);
+
+// packed threads own the envs (e, e+1), e even: two float4 per plane, adjacent in the plane (one 32-byte stretch)
+__device__ __forceinline__ void load_state2(const QuadArgs &a, int64_t e, VState<f2> &s)
 {
-#define MGB_LO(k) f2{make_float2(q[k].x, q[k].y)}
-#define MGB_HI(k) f2{make_float2(q[k].z, q[k].w)}
-    s.p[0] = MGB_LO(0); s.p[1] = MGB_HI(0); s.p[2] = MGB_LO(1); s.v[0] = MGB_HI(1);
-    s.v[1] = MGB_LO(2); s.v[2] = MGB_HI(2); s.om[0] = MGB_LO(3); s.om[1] = MGB_HI(3);
-    s.om[2] = MGB_LO(4); s.w[0] = MGB_HI(4); s.w[1] = MGB_LO(5); s.w[2] = MGB_HI(5);
-    s.w[3] = MGB_LO(6); s.R[0] = MGB_HI(6); s.R[1] = MGB_LO(7); s.R[2] = MGB_HI(7);
-    s.R[3] = MGB_LO(8); s.R[4] = MGB_HI(8); s.R[5] = MGB_LO(9); s.R[6] = MGB_HI(9);
-    s.R[7] = MGB_LO(10); s.R[8] = MGB_HI(10);
-    s.ct[0] = __float_as_int(q[11].x); s.ct[1] = __float_as_int(q[11].y);
-    s.ep[0] = __float_as_int(q[11].z); s.ep[1] = __float_as_int(q[11].w);
-#undef MGB_LO
-#undef MGB_HI
+    QState s0, s1;
+    load_state(a, e, s0);
+    load_state(a, e + 1, s1);            // e + 1 < n_pad: the planes are padded to whole tiles
+    set_lane_state(s, 0, s0);
+    set_lane_state(s, 1, s1);
 }
-__device__ __forceinline__ float4 *pair_ptr(const QuadArgs &a, int64_t P)
+__device__ __forceinline__ void store_state2(const QuadArgs &a, int64_t e, const VState<f2> &s)
 {
-    return a.planes + (P / kTilePairs) * (kPlanes * kTilePairs) + (P % kTilePairs);
-}
-__device__ __forceinline__ void load_state2(const QuadArgs &a, int64_t P, VState<f2> &s)
-{
-    const float4 *b = pair_ptr(a, P);
-    float4 q[kPlanes];
-#pragma unroll
-    for (int k = 0; k < kPlanes; ++k) q[k] = __ldcg(b + k * kTilePairs);   // L2 (coherence point): launches may overlap
-    unpack_state(q, s);
-}
-__device__ __forceinline__ void store_state2(const QuadArgs &a, int64_t P, const VState<f2> &s)
-{
-    float4 *b = pair_ptr(a, P);
-#define MGB_ST(k, lo, hi) b[(k) * kTilePairs] = make_float4((lo).v.x, (lo).v.y, (hi).v.x, (hi).v.y)
-    MGB_ST(0, s.p[0], s.p[1]); MGB_ST(1, s.p[2], s.v[0]); MGB_ST(2, s.v[1], s.v[2]); MGB_ST(3, s.om[0], s.om[1]);
-    MGB_ST(4, s.om[2], s.w[0]); MGB_ST(5, s.w[1], s.w[2]); MGB_ST(6, s.w[3], s.R[0]); MGB_ST(7, s.R[1], s.R[2]);
-    MGB_ST(8, s.R[3], s.R[4]); MGB_ST(9, s.R[5], s.R[6]); MGB_ST(10, s.R[7], s.R[8]);
-#undef MGB_ST
-    b[11 * kTilePairs] = make_float4(__int_as_float(s.ct[0]), __int_as_float(s.ct[1]), __int_as_float(s.ep[0]),
-                                     __int_as_float(s.ep[1]));
+    QState s0, s1;
+    get_lane_state(s, 0, s0);
+    get_lane_state(s, 1, s1);
+    store_state(a, e, s0);
+    store_state(a, e + 1, s1);
 }
 
 // lane h of a packed state <-> scalar state
@@ -408,18 +392,16 @@ __device__ __forceinline__ bool integrate(const QuadConst &c, VState<T> &s, cons
             break;                                                                                               \
         }                                                                                                        \
     }
-#ifdef MGB_QUAD_UNROLL5
-    if (c.substeps % 5 == 0) {
+    // scalar lanes: unrolled by 5 when substeps % 5 == 0 (dt = 0.005, 0.01), measured 4 % faster than the rolled loop (the ~40
+    // step constants stay in uniform registers across the unrolled body); packed lanes: rolled (half the code, 26 fewer
+    // registers, measured 3 % faster than unrolled)
+    if (N == 1 && c.substeps % 5 == 0) {
 #pragma unroll 1
         for (int k = 0; k < c.substeps && !failed; k += 5) {
 #pragma unroll
             for (int u = 0; u < 5; ++u) MGB_QUAD_ONE_SUBSTEP()
         }
-    } else
-#endif
-    {
-        // one rolled loop: the substep body (~190 packed instructions, 3 KB) then stays in the instruction cache, while the
-        // 5x-unrolled form made every warp stream 15 KB of straight-line code once per launch (ncu: 12 % no_instructions)
+    } else {
 #pragma unroll 1
         for (int k = 0; k < c.substeps; ++k) MGB_QUAD_ONE_SUBSTEP()
     }
@@ -879,7 +861,7 @@ __device__ __forceinline__ void step_body(const QuadConst &c, const QuadArgs &a,
     bool stored = false;
     if constexpr (N == 2) {
         if (nact == 2) {
-            store_state2(a, e >> 1, s);
+            store_state2(a, e, s);
             *reinterpret_cast<float2 *>(a.rew + e) = reward.v;
             *reinterpret_cast<uchar2 *>(a.done + e) = make_uchar2((uint8_t)done[0], (uint8_t)done[1]);
             if (a.fail) *reinterpret_cast<int2 *>(a.fail + e) = make_int2(fail[0], fail[1]);
@@ -937,9 +919,10 @@ __device__ __forceinline__ void publish_final(const QuadArgs &a, const float *ft
     }
 }
 
-// Scalar step kernel: one thread = one env, 64 envs per CTA.  Kept as the reference instantiation of the generic code
-// (tests compare the packed kernels against it bit for bit; MGB_PACKED=0 selects it) and for the RK4 option.
-// EARLY: fetch the velocity-target rows before the integrator (hides their latency, +8 registers).
+// Scalar step kernel, 64 envs per CTA (small batches, and batches between one wave of 512-thread CTAs and the streaming
+// regime).  EARLY: fetch the velocity-target rows before the integrator (hides their latency, +8 registers).  Right when one
+// launch is a single wave of CTAs (latency-bound, e.g. 65 536 envs); for multi-wave launches the extra registers cost one
+// resident CTA per SM and other CTAs already hide the latency, so the host picks EARLY=false.
 template <bool SIMPLE, bool EARLY>
 __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_constant__ QuadConst c,
                                                              const __grid_constant__ QuadArgs a)
@@ -955,9 +938,13 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
 
     // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now (its CTAs park at their own
     // griddepcontrol.wait), and this kernel waits here until the PREVIOUS one has completed and flushed -- the
-    // launch latency of back-to-back env steps overlaps the previous step.  (Not on a handle that uses chained steps:
-    // a chained successor does not wait for the whole grid, so only ticket-taking kernels may let it start early.)
-    if (a.trigger_early) asm volatile("griddepcontrol.launch_dependents;");
+    // launch latency of back-to-back env steps overlaps the previous step.
+    // (Finer hand-offs between consecutive launches were built and measured twice: a per-tile ticket/flag protocol in round
+    // 1, and in round 2 "chained" launches whose CTAs skip the grid-wide wait and wait only for the same env block of the
+    // previous launch.  Both are correct (bit-identical trajectories) and neither is faster: an env block's step k+1 cannot
+    // start before its own step k has stored its state, so the per-block latency chain -- not the grid barrier -- sets the
+    // pace, and the register file holds barely more than one launch's worth of threads.  DESIGN.md section 4.)
+    asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (active) {
@@ -972,56 +959,47 @@ __global__ void __launch_bounds__(kThreads) quad_step_kernel(const __grid_consta
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copy; the kernel boundary flushes the writes
 }
 
-// Packed step kernel: one thread = the env pair (e, e+1) in FFMA2 / FADD2 registers.  Each CTA owns `per` consecutive envs
-// (a multiple of 4, so that every observation tile stays 16-byte aligned for the bulk store): per = 128 for small batches,
-// ceil(N / #SMs) for launches that fit one wave -- one CTA per SM, 148 CTA dispatches and a balanced wave (444 vs 443 envs
-// per SM at 65 536 envs).
-//
-// Chained mode (a.chain_started != null; mgb_quad_set_chaining).  An env's step k+1 depends on ITS OWN step k and on
-// nothing else, so consecutive step launches need no grid-wide barrier: CTA j of launch k+1 only has to wait for CTA j of
-// launch k.  Every CTA takes a ticket (how many launches of its env block started before it), lets the next launch's CTAs
-// be scheduled (griddepcontrol.launch_dependents -- they become resident as soon as a slot frees up, 4 CTAs of 64 threads
-// fit per SM), waits until `ticket` launches of its block have completed (acquire), steps its envs, and publishes
-// completion (release) after its state stores.  It never executes griddepcontrol.wait, so while one CTA of an SM waits for
-// its loads or drains its stores, CTAs of the next launch already integrate on the same SM: load, arithmetic and store
-// phases of consecutive steps overlap instead of adding up (the one-launch-at-a-time kernel spends more time moving 281
-// B/env through L2 than integrating, profiles/r2_launchfloor.txt).  Ordering argument: the runtime starts launch k+1 only
-// after EVERY CTA of launch k has executed launch_dependents, which each does after taking its ticket -- so tickets of a block
-// are taken in launch order, and a CTA only ever waits for a CTA that is already resident or finished (no deadlock).  The
-// spin is bounded and traps instead of hanging the device.
-__device__ __forceinline__ uint32_t chain_enter(const QuadArgs &a)
+// "One CTA per SM" variant for launches that fit a single wave (N <= 148 x 512): grid = number of SMs, each CTA owns
+// `per` = ceil(N / grid) envs (rounded to 4 so that every observation tile stays 16-byte aligned for the bulk store).
+// 148 CTA dispatches instead of 1024 and a perfectly balanced wave (444 vs 443 envs per SM at 65 536 envs).
+template <bool SIMPLE>
+__global__ void __launch_bounds__(512, 1) quad_step_wide_kernel(const __grid_constant__ QuadConst c,
+                                                                const __grid_constant__ QuadArgs a)
 {
-    uint32_t ticket = 0;
-    if (threadIdx.x == 0) {
-        ticket = atomicAdd(a.chain_started + blockIdx.x, 1u);
-        if (ticket == 0xffffffffu) asm volatile("griddepcontrol.launch_dependents;");   // (data dependency: the ticket is taken first)
-        asm volatile("griddepcontrol.launch_dependents;");
-        uint32_t spins = 0;
-        for (;;) {
-            uint32_t d;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(a.chain_done + blockIdx.x) : "memory");
-            if ((int32_t)(d - ticket) >= 0) break;
-            if (++spins > (1u << 22)) __trap();        // ~seconds: a lost predecessor must not hang the GPU
-            __nanosleep(20);
-        }
+    extern __shared__ __align__(128) float wide_smem[];
+    const int per = a.per_cta;
+    float *tile = wide_smem, *ftile = wide_smem + (size_t)per * kMaxObs;
+    const int64_t e0 = (int64_t)blockIdx.x * per;
+    const int64_t e = e0 + threadIdx.x;
+    int rows = (int)((a.n - e0) < per ? (a.n - e0) : per);
+    if (rows < 0) rows = 0;
+    const int D = c.obs_dim;
+    const bool active = (int)threadIdx.x < rows;
+    int final_mask = 0;
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (active) {
+        QState s;
+        load_state(a, e, s);
+        const float4 act = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
+        const float V[4] = {act.x, act.y, act.z, act.w};
+        step_body<SIMPLE, true, float>(c, a, e, 1, s, V, tile + threadIdx.x * D, ftile + threadIdx.x * D, final_mask);
     }
-    __syncthreads();
-    return ticket;
-}
-__device__ __forceinline__ void chain_exit(const QuadArgs &a, uint32_t ticket)
-{
-    __syncthreads();                                   // every thread's state stores are issued
-    if (threadIdx.x == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.chain_done + blockIdx.x), "r"(ticket + 1u) : "memory");
-    }
+    if (rows > 0) publish_tile(a.obs, tile, e0, rows, D);
+    else __syncthreads();
+    publish_final(a, ftile, e, threadIdx.x, 1, final_mask, D);
+    if (threadIdx.x == 0) mgb_bulk_wait_read<0>();
 }
 
-// THREADS / MINB: launch bounds.  <256, 1>: the one-CTA-per-SM form (no register cap: 220).  <64, 6>: chained 128-env CTAs
-// capped at 168 registers so that six of them (768 envs, 1.7 launches of the 65 536-env shape) are resident per SM.
-template <bool SIMPLE, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) quad_step2_kernel(const __grid_constant__ QuadConst c,
-                                                               const __grid_constant__ QuadArgs a)
+// Packed variant (MGB_PACKED=1; not the default): one thread = the env pair (e, e+1) in FFMA2 / FADD2 registers, `per`
+// envs per CTA as in the wide kernel.  Bit-identical to the scalar kernels (tests/test_quadrotor_gpu.py) and 26 % fewer
+// executed warp-instructions per env, but NOT faster on B200: FFMA2 occupies the FP32 pipe for two cycles (same lane-FMA
+// rate as FFMA, scripts/microbench/fma_latency.cu), the step is bound by that pipe and by load/store latency, and halving
+// the warp count halves what hides that latency (6.8-7.3 us vs 6.2 us per 65 536-env step; profiles/r2_variants_a.txt,
+// profiles/r2_ncu_quad_step2_65k.txt).  Kept as the measured answer to "would packed f32x2 help?".
+template <bool SIMPLE>
+__global__ void __launch_bounds__(256, 1) quad_step2_kernel(const __grid_constant__ QuadConst c,
+                                                            const __grid_constant__ QuadArgs a)
 {
     extern __shared__ __align__(128) float pair_smem[];
     const int per = a.per_cta;
@@ -1034,49 +1012,42 @@ __global__ void __launch_bounds__(THREADS, MINB) quad_step2_kernel(const __grid_
     const int D = c.obs_dim;
     const int nact = rows - le >= 2 ? 2 : (rows - le > 0 ? 1 : 0);
     int final_mask = 0;
-    uint32_t ticket = 0;
-    const bool chained = a.chain_started != nullptr;
-    if (chained) {
-        ticket = chain_enter(a);
-    } else {
-        if (a.trigger_early) asm volatile("griddepcontrol.launch_dependents;");
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-    }
-    if (a.stagger_ns > 0 && blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep(a.stagger_ns);
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (nact > 0) {
         VState<f2> s;
-        load_state2(a, e >> 1, s);
+        load_state2(a, e, s);
         const float4 a0 = __ldg(reinterpret_cast<const float4 *>(a.act) + e);
         const float4 a1 = nact == 2 ? __ldg(reinterpret_cast<const float4 *>(a.act) + e + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         const f2 V[4] = {pack2(a0.x, a1.x), pack2(a0.y, a1.y), pack2(a0.z, a1.z), pack2(a0.w, a1.w)};
         step_body<SIMPLE, true, f2>(c, a, e, nact, s, V, tile + le * D, ftile + le * D, final_mask);
     }
-    if (chained) chain_exit(a, ticket);
     if (rows > 0) publish_tile(a.obs, tile, e0, rows, D);
     else __syncthreads();
     publish_final(a, ftile, e, le, 2, final_mask, D);
     if (threadIdx.x == 0) mgb_bulk_wait_read<0>();
 }
 
-// Streaming variant for multi-wave launches (millions of envs): PERSISTENT CTAs of 64 threads loop over tiles of 128 envs
-// (64 pairs) and the state of tile i+1 (one contiguous 12 KB block) + its 2 KB of actions are fetched by the TMA engine
+// Streaming variant for multi-wave launches (millions of envs): PERSISTENT CTAs loop over tiles of 128 envs and the state
+// of tile i+1 (six 2 KB plane segments = one contiguous 12 KB block + 2 KB of actions) is fetched by the TMA engine
 // (cp.async.bulk + mbarrier) into the other half of a double-buffered shared-memory stage while tile i integrates, so HBM
-// latency is off the critical path without spending registers or occupancy on it.  Same arithmetic (step_body<f2>).
-constexpr int kStreamThreads = 64;
+// latency is off the critical path without spending registers or occupancy on it.  Same arithmetic (step_body), same
+// outputs.
+constexpr int kStreamThreads = 128;
 
 template <bool SIMPLE>
-__global__ void __launch_bounds__(kStreamThreads, 4) quad_stream2_kernel(const __grid_constant__ QuadConst c,
-                                                                         const __grid_constant__ QuadArgs a)
+__global__ void __launch_bounds__(kStreamThreads, 4) quad_stream_kernel(const __grid_constant__ QuadConst c,
+                                                                        const __grid_constant__ QuadArgs a)
 {
-    __shared__ __align__(128) float4 stage[2][kPlanes * kTilePairs + kTileEnvs];    // 12 planes x 64 pairs + 128 actions
-    __shared__ __align__(128) float tile[kTileEnvs * kMaxObs];
-    __shared__ __align__(128) float ftile[kTileEnvs * kMaxObs];
+    __shared__ __align__(128) float4 stage[2][7][kStreamThreads];    // planes 0..5 + action
+    __shared__ __align__(128) float tile[kStreamThreads * kMaxObs];
+    __shared__ __align__(128) float ftile[kStreamThreads * kMaxObs];
     __shared__ __align__(8) uint64_t full[2];
     const int D = c.obs_dim;
-    const int64_t n_tiles = (a.n + kTileEnvs - 1) / kTileEnvs;
+    const int64_t n_tiles = (a.n + kStreamThreads - 1) / kStreamThreads;
     const int tid = threadIdx.x;
 
-    if (a.trigger_early) asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         mgb_mbar_init(&full[0], 1);
@@ -1086,11 +1057,12 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream2_kernel(const _
     __syncthreads();
 
     auto fetch = [&](int64_t t, int st) {      // one thread: 2 bulk copies land on full[st]
-        const int64_t e0 = t * kTileEnvs;
-        const uint32_t rows = (uint32_t)((a.n - e0) < kTileEnvs ? (a.n - e0) : kTileEnvs);
-        mgb_mbar_expect_tx(&full[st], (uint32_t)(kPlanes * kTilePairs) * 16u + rows * 16u);
-        mgb_bulk_load(stage[st], a.planes + t * (kPlanes * kTilePairs), (uint32_t)(kPlanes * kTilePairs) * 16u, &full[st]);
-        mgb_bulk_load(stage[st] + kPlanes * kTilePairs, reinterpret_cast<const float4 *>(a.act) + e0, rows * 16u, &full[st]);
+        const int64_t e0 = t * kStreamThreads;
+        const uint32_t rows = (uint32_t)((a.n - e0) < kStreamThreads ? (a.n - e0) : kStreamThreads);
+        static_assert(kStreamThreads == kTileEnvs, "one CTA iteration = one state tile");
+        mgb_mbar_expect_tx(&full[st], 6u * kTileEnvs * 16u + rows * 16u);
+        mgb_bulk_load(stage[st][0], a.planes + t * (6 * kTileEnvs), 6u * kTileEnvs * 16u, &full[st]);   // 12 KB, contiguous
+        mgb_bulk_load(stage[st][6], reinterpret_cast<const float4 *>(a.act) + e0, rows * 16u, &full[st]);
     };
 
     int64_t t = blockIdx.x;
@@ -1103,26 +1075,24 @@ __global__ void __launch_bounds__(kStreamThreads, 4) quad_stream2_kernel(const _
         if (tid == 0 && t_next < n_tiles) fetch(t_next, st ^ 1);
         mgb_mbar_wait(&full[st], phase[st]);
         phase[st] ^= 1u;
-        const int64_t e0 = t * kTileEnvs, e = e0 + 2 * tid;
-        const int rows = (int)((a.n - e0) < kTileEnvs ? (a.n - e0) : kTileEnvs);
-        const int nact = rows - 2 * tid >= 2 ? 2 : (rows - 2 * tid > 0 ? 1 : 0);
+        const int64_t e0 = t * kStreamThreads, e = e0 + tid;
+        const int rows = (int)((a.n - e0) < kStreamThreads ? (a.n - e0) : kStreamThreads);
         int final_mask = 0;
         // the observation tile of the previous iteration must have been read by its bulk store
         if (tid == 0) mgb_bulk_wait_read<0>();
         __syncthreads();
-        if (nact > 0) {
-            VState<f2> s;
+        if (tid < rows) {
+            QState s;
             float4 q[kPlanes];
 #pragma unroll
-            for (int k = 0; k < kPlanes; ++k) q[k] = stage[st][k * kTilePairs + tid];
+            for (int k = 0; k < kPlanes; ++k) q[k] = stage[st][k][tid];
             unpack_state(q, s);
-            const float4 a0 = stage[st][kPlanes * kTilePairs + 2 * tid];
-            const float4 a1 = nact == 2 ? stage[st][kPlanes * kTilePairs + 2 * tid + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const f2 V[4] = {pack2(a0.x, a1.x), pack2(a0.y, a1.y), pack2(a0.z, a1.z), pack2(a0.w, a1.w)};
-            step_body<SIMPLE, true, f2>(c, a, e, nact, s, V, tile + 2 * tid * D, ftile + 2 * tid * D, final_mask);
+            const float4 act = stage[st][6][tid];
+            const float V[4] = {act.x, act.y, act.z, act.w};
+            step_body<SIMPLE, true, float>(c, a, e, 1, s, V, tile + tid * D, ftile + tid * D, final_mask);
         }
         publish_tile(a.obs, tile, e0, rows, D);
-        publish_final(a, ftile, e, 2 * tid, 2, final_mask, D);
+        publish_final(a, ftile, e, tid, 1, final_mask, D);
         __syncthreads();      // everyone is done with stage[st] and ftile before they are refilled
     }
     if (tid == 0) mgb_bulk_wait_read<0>();
@@ -1352,14 +1322,8 @@ struct mgb_quad {
     int n_tasks = 0;
     int auto_reset = 0;
     int num_sms = 148;
-    int packed = 1;            // two envs per thread in packed FFMA2 registers (MGB_PACKED=0: scalar reference kernel)
-    int chaining_ever = 0;     // chaining was enabled at some point: non-chained kernels of this handle no longer trigger early
-    int chaining = 0;          // mgb_quad_set_chaining: consecutive packed step launches overlap (per-CTA tickets)
-    uint32_t *chain_flags = nullptr;   // [2][max grid]: started, done
-    int chain_grid = 0;
-    int step_per = 0;          // tuning: envs per CTA of the packed step kernel (MGB_STEP_PER; 0 = one CTA per SM)
-    int stagger_ns = 0;        // tuning: MGB_STAGGER_NS
-    int chain_minb = 6;        // chained step kernel: resident CTAs per SM it is compiled for (MGB_CHAIN_MINB=4: no register cap)
+    int wide_kernel = 1;       // one-CTA-per-SM step kernel for single-wave launches (MGB_WIDE_KERNEL=0 disables)
+    int packed = 0;            // MGB_PACKED=1: two envs per thread in packed FFMA2 registers (bit-identical, measured slower)
     int stream_kernel = 1;     // persistent TMA-pipelined kernel for multi-wave launches (MGB_STREAM_KERNEL=0 disables)
     int pdl = 1;               // programmatic dependent launch of consecutive step kernels (MGB_PDL=0 disables)
     int zerocopy = 1;          // host entry point: kernel reads/writes pinned host buffers directly (MGB_HOST_ZEROCOPY=0)
@@ -1390,7 +1354,6 @@ static QuadArgs base_args(const mgb_quad *h)
     a.env2task = h->env2task;
     a.seed = h->seed;
     a.auto_reset = h->auto_reset;
-    a.trigger_early = h->chaining_ever ? 0 : 1;
     return a;
 }
 
@@ -1471,17 +1434,18 @@ extern "C" int mgb_quad_create(mgb_quad **out, int64_t n_envs, const mgb_quad_cf
     if (const char *ev = getenv("MGB_HOST_ZEROCOPY")) h->zerocopy = atoi(ev);   // 0 copies, 1 zero-copy, 2 hybrid
     if (const char *ev = getenv("MGB_STREAM_KERNEL")) h->stream_kernel = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_PACKED")) h->packed = atoi(ev) != 0;
-    if (const char *ev = getenv("MGB_CHAIN_MINB")) h->chain_minb = atoi(ev) == 4 ? 4 : 6;
-    if (const char *ev = getenv("MGB_STEP_PER")) h->step_per = atoi(ev);
-    if (const char *ev = getenv("MGB_STAGGER_NS")) h->stagger_ns = atoi(ev);
+    if (const char *ev = getenv("MGB_WIDE_KERNEL")) h->wide_kernel = atoi(ev) != 0;
     {
-        // the packed step kernel needs up to 2 x 512 x 19 floats of dynamic shared memory; the attribute is per function and
-        // device, idempotent, and set to the maximum so that handles never lower each other's limit
+        // the one-CTA-per-SM step kernels need up to 2 x 512 x 19 floats of dynamic shared memory; the attribute is per
+        // function and device, idempotent, and set to the maximum so that handles never lower each other's limit (round-1
+        // advice: the process-global high-water mark it replaces was not thread-safe)
         const int max_smem = 512 * kMaxObs * 4 * 2;
-        cudaFuncSetAttribute(quad_step2_kernel<true, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        cudaFuncSetAttribute(quad_step2_kernel<false, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(quad_step2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (cudaGetLastError() != cudaSuccess) {
-            mgb_set_error("cudaFuncSetAttribute(quad_step2_kernel, %d bytes of shared memory) failed", max_smem);
+            mgb_set_error("cudaFuncSetAttribute(quad_step_wide_kernel, %d bytes of shared memory) failed", max_smem);
             delete h;
             return MGB_ERR_CUDA;
         }
@@ -1513,7 +1477,6 @@ extern "C" void mgb_quad_destroy(mgb_quad *h)
     cudaDeviceSynchronize();
     cudaFree(h->planes);
     cudaFree(h->sat);
-    cudaFree(h->chain_flags);
     cudaFree(h->targets);
     cudaFree(h->env2task);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
@@ -1621,22 +1584,32 @@ extern "C" int mgb_quad_reset(mgb_quad *h, const uint8_t *mask_dev, const double
 }
 
 // Which step kernel a launch of this handle takes (also reported through mgb_quad_step_kernel for the bench line)
-enum StepKernel { STEP_SCALAR = 0, STEP_PACKED = 1, STEP_STREAM = 2 };
+enum StepKernel { STEP_TILE = 0, STEP_WIDE = 1, STEP_STREAM = 2, STEP_PACKED = 3 };
 
 static StepKernel choose_step_kernel(const mgb_quad *h, const QuadArgs &a)
 {
-    // the packed kernels store reward / done / fail of an env pair with one 8 / 2 / 8-byte access
-    const bool aligned = (reinterpret_cast<uintptr_t>(a.act) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.rew) & 7u) == 0 &&
-                         (reinterpret_cast<uintptr_t>(a.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(a.fail) & 7u) == 0;
-    if (!h->packed || h->c.rk4_steps > 0 || !aligned) return STEP_SCALAR;
-    if (h->stream_kernel && a.n > (int64_t)h->num_sms * 2048) return STEP_STREAM;
-    return STEP_PACKED;
+    const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
+    const bool act16 = (reinterpret_cast<uintptr_t>(a.act) & 15u) == 0;
+    // multi-wave launches stream: persistent CTAs + TMA double buffering (quad_stream_kernel)
+    if (h->stream_kernel && (int64_t)blocks > (int64_t)h->num_sms * 32 && act16) return STEP_STREAM;
+    if (h->packed && h->c.rk4_steps == 0 && a.n >= 2) {
+        // the packed kernel stores reward / done / fail of an env pair with one 8 / 2 / 8-byte access
+        const bool aligned = act16 && (reinterpret_cast<uintptr_t>(a.rew) & 7u) == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(a.fail) & 7u) == 0;
+        if (aligned) return STEP_PACKED;
+    }
+    // launches that fit one wave of 512-thread CTAs: one CTA per SM (7x fewer CTA dispatches, balanced wave)
+    if (h->wide_kernel && a.n <= (int64_t)h->num_sms * 512 && a.n >= (int64_t)h->num_sms * 64) return STEP_WIDE;
+    return STEP_TILE;
 }
 
 static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
 {
+    const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kThreads);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1645,47 +1618,30 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
     cfg.numAttrs = 1;
     const StepKernel which = choose_step_kernel(h, a);
     if (which == STEP_STREAM) {
-        // multi-wave launches stream: persistent CTAs + TMA double buffering (quad_stream2_kernel)
         cfg.gridDim = dim3((unsigned)(h->num_sms * 4));
         cfg.blockDim = dim3(kStreamThreads);
-        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream2_kernel<true>, h->c, a));
-        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream2_kernel<false>, h->c, a));
-    } else if (which == STEP_PACKED) {
-        // per = envs per CTA: one warp of pairs for small batches, one CTA per SM when the launch fits a single wave of
-        // 256-thread CTAs (7x fewer CTA dispatches than 64-env tiles and a balanced wave), 256 envs per CTA beyond that
+        if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<true>, h->c, a));
+        else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_stream_kernel<false>, h->c, a));
+    } else if (which == STEP_WIDE || which == STEP_PACKED) {
+        // envs per CTA: one CTA per SM when the launch fits a single wave; the packed kernel also serves the other sizes
+        const int lanes = which == STEP_PACKED ? 2 : 1;
         int per;
+        if (a.n <= (int64_t)h->num_sms * 512 && a.n >= (int64_t)h->num_sms * 64) per = (int)((a.n + h->num_sms - 1) / h->num_sms);
+        else per = a.n < (int64_t)h->num_sms * 64 ? 64 : 256;        // packed only
+        per = (per + 3) / 4 * 4;
         QuadArgs aw = a;
-        if (h->chaining) {
-            // chained steps: 128-env CTAs (= one state tile, 64 threads, 4 resident per SM) so that CTAs of consecutive
-            // launches share an SM; the block -> env mapping is the same for every launch of the handle
-            per = kTileEnvs;
-            aw.chain_started = h->chain_flags;
-            aw.chain_done = h->chain_flags + h->chain_grid;
-        } else if (a.n <= (int64_t)h->num_sms * 64) per = 64;
-        else if (a.n <= (int64_t)h->num_sms * 128) per = 128;
-        else if (a.n <= (int64_t)h->num_sms * 512) per = (int)(((a.n + h->num_sms - 1) / h->num_sms + 3) / 4 * 4);
-        else per = 256;
-        if (!h->chaining && h->step_per > 0 && a.n > (int64_t)h->num_sms * 128) per = (h->step_per + 3) / 4 * 4;
-        if (per > 512) per = 512;
         aw.per_cta = per;
-        aw.stagger_ns = h->stagger_ns;
         cfg.gridDim = dim3((unsigned)((a.n + per - 1) / per));
-        cfg.blockDim = dim3((unsigned)((per / 2 + 31) / 32 * 32));
+        cfg.blockDim = dim3((unsigned)((per / lanes + 31) / 32 * 32));
         cfg.dynamicSmemBytes = (size_t)per * kMaxObs * 4 * 2;
-        if (h->chaining && h->chain_minb == 6) {
-            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 64, 6>, h->c, aw));
-            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 64, 6>, h->c, aw));
-        } else if (h->chaining) {
-            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 64, 4>, h->c, aw));
-            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 64, 4>, h->c, aw));
+        if (which == STEP_PACKED) {
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false>, h->c, aw));
         } else {
-            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<true, 256, 1>, h->c, aw));
-            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step2_kernel<false, 256, 1>, h->c, aw));
+            if (h->c.simple) MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_wide_kernel<true>, h->c, aw));
+            else MGB_CUDA(cudaLaunchKernelEx(&cfg, quad_step_wide_kernel<false>, h->c, aw));
         }
     } else {
-        const unsigned blocks = (unsigned)((a.n + kThreads - 1) / kThreads);
-        cfg.gridDim = dim3(blocks);
-        cfg.blockDim = dim3(kThreads);
         // single wave (<= ~8 resident CTAs per SM) -> latency-bound -> early target fetch; otherwise favour occupancy
         const bool early = blocks <= (unsigned)h->num_sms * 10u;
         if (h->c.simple) {
@@ -1701,33 +1657,14 @@ static int launch_step(mgb_quad *h, const QuadArgs &a, cudaStream_t st)
     return MGB_OK;
 }
 
-extern "C" int mgb_quad_set_chaining(mgb_quad *h, int on)
-{
-    MGB_REQUIRE(h, "null handle");
-    MgbDeviceGuard guard(h->device);
-    if (on && !h->chain_flags) {
-        h->chain_grid = (int)((h->n + kTileEnvs - 1) / kTileEnvs);
-        MGB_CUDA(cudaDeviceSynchronize());       // earlier launches of this handle may still trigger early: let them finish
-        MGB_CUDA(cudaMalloc(&h->chain_flags, sizeof(uint32_t) * 2 * (size_t)h->chain_grid));
-        MGB_CUDA(cudaMemset(h->chain_flags, 0, sizeof(uint32_t) * 2 * (size_t)h->chain_grid));
-        MGB_CUDA(cudaDeviceSynchronize());
-    }
-    if (on) h->chaining_ever = 1;
-    h->chaining = on ? 1 : 0;
-    return MGB_OK;
-}
-
 extern "C" const char *mgb_quad_step_kernel(const mgb_quad *h)
 {
     if (!h) return "";
     QuadArgs a = base_args(h);
     switch (choose_step_kernel(h, a)) {
-    case STEP_STREAM: return h->c.simple ? "quad_stream2_kernel<true>" : "quad_stream2_kernel<false>";
-    case STEP_PACKED:
-        if (h->chaining && h->chain_minb == 6)
-            return h->c.simple ? "quad_step2_kernel<true,64,6> (chained)" : "quad_step2_kernel<false,64,6> (chained)";
-        if (h->chaining) return h->c.simple ? "quad_step2_kernel<true,64,4> (chained)" : "quad_step2_kernel<false,64,4> (chained)";
-        return h->c.simple ? "quad_step2_kernel<true,256,1>" : "quad_step2_kernel<false,256,1>";
+    case STEP_STREAM: return h->c.simple ? "quad_stream_kernel<true>" : "quad_stream_kernel<false>";
+    case STEP_PACKED: return h->c.simple ? "quad_step2_kernel<true>" : "quad_step2_kernel<false>";
+    case STEP_WIDE: return h->c.simple ? "quad_step_wide_kernel<true>" : "quad_step_wide_kernel<false>";
     default: return h->c.simple ? "quad_step_kernel<true,.>" : "quad_step_kernel<false,.>";
     }
 }

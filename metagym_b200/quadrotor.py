@@ -398,13 +398,6 @@ class BatchedQuadrotor(object):
     def launch_count(self):
         return int(self._lib.mgb_quad_launch_count(self._h))
 
-    def set_chaining(self, on=True):
-        """Chained steps (mgb_quad_set_chaining): consecutive step() launches overlap on the GPU; each 128-env block of a
-        launch waits only for the same block of the previous launch.  Contract: the action tensor of a step was not
-        written by work enqueued after the previous step() (pre-generated action tables, one-step-ahead policies).
-        Results are bit-identical to unchained stepping."""
-        _lib.check(self._lib.mgb_quad_set_chaining(self._h, int(bool(on))))
-
     def step_kernel_name(self):
         """Name of the CUDA kernel a step() of this batch size launches (reporting only)."""
         return self._lib.mgb_quad_step_kernel(self._h).decode()

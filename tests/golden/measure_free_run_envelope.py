@@ -50,7 +50,30 @@ for name in RUNS:
         curve = np.concatenate([curve, np.zeros(len(errs) - len(curve))])
     curve[:len(errs)] = np.maximum(curve[:len(errs)], errs)
 mono = np.maximum.accumulate(curve)
-out = {"metric": "group_rel_err over obs[:16] (tests/util.py), GPU free run vs reference golden episodes",
+# ---- the same for test_random_batch_vs_oracle: 4096 envs, 20 free steps, actions U(-1, 16), vs the CPU oracle (mix mode)
+from oracle import quad_oracle as qo
+cfg = qo.make_cfg()
+batch = np.zeros(20)
+for task, dt in (("hovering_control", 0.01), ("velocity_control", 0.005), ("no_collision", 0.01)):
+    for n in (1, 127, 129, 4096):
+        rng = np.random.RandomState(1234 + n)
+        nt = 30
+        env = BatchedQuadrotor(task=task, num_envs=n, device=0, squeeze=False, dt=dt, nt=nt, seed=[0, 1, 2])
+        noise = rng.random_sample((n, 12))
+        env.reset(noise=noise)
+        state = qo.reset_state(None, noise)
+        ct = np.zeros(n, np.int32)
+        kw = {}
+        if task == "velocity_control":
+            kw = dict(targets=env.velocity_targets.cpu().numpy(), env2task=env.env2task.cpu().numpy())
+        for t in range(20):
+            act = rng.uniform(-1.0, 16.0, (n, 4)).astype(np.float32)
+            obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
+            o_ref = qo.env_step(cfg, state, ct, act, task, dt, nt, mode="mix", **kw)[0]
+            batch[t] = max(batch[t], group_rel_err(obs.cpu().numpy()[:, :16], o_ref[:, :16], OBS_GROUPS))
+        env.close()
+batch = np.maximum.accumulate(batch)
+out = {"random_batch_vs_oracle_running_max": [float(x) for x in batch],"metric": "group_rel_err over obs[:16] (tests/util.py), GPU free run vs reference golden episodes",
        "runs": RUNS, "curve_running_max": [float(x) for x in mono], "per_run_max": {k: float(max(v)) for k, v in per_run.items()},
        "per_run_len": {k: len(v) for k, v in per_run.items()}, "device": torch.cuda.get_device_name(0)}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -58,3 +81,4 @@ with open(os.path.join(ROOT, "gpurun_out", "free_run_envelope.json"), "w") as f:
     json.dump(out, f)
 print("steps", len(mono), "err@1,10,50,100,end:", [float(mono[min(i, len(mono) - 1)]) for i in (0, 9, 49, 99, len(mono) - 1)])
 print(out["per_run_max"])
+print("random batch vs oracle, err@1,5,10,20:", [float(batch[i]) for i in (0, 4, 9, 19)])

@@ -198,7 +198,10 @@ def test_multicast_rollout_outputs_equal_plain(torch_mod):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     r = subprocess.run([sys.executable, "-c", MC_CHILD % ROOT, str(port)], capture_output=True, text=True, timeout=600)
     if "NO_MULTICAST" in r.stdout:
-        pytest.skip("no multicast support here: " + r.stdout.strip()[-200:])
+        # shown as XFAIL (not a silent skip) on boxes whose driver offers no multicast object for a single GPU; the XM=2
+        # instantiations then have 2- and 8-GPU evidence only (profiles/r1_bench_mixed_8gpu.json, byte-for-byte check
+        # against an NCCL all-gather inside scripts/bench_mixed.py)
+        pytest.xfail("no NVSwitch multicast object on this box: " + r.stdout.strip()[-200:])
     assert r.returncode == 0 and "MC_OK" in r.stdout and "MISSING_CHECK" not in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 

@@ -17,6 +17,19 @@ pytestmark = pytest.mark.gpu
 RTOL_STEP = 1e-5
 
 
+def _envelope(key):
+    """Measured error-growth curves (tests/golden/measure_free_run_envelope.py, run on a B200): running max over the
+    recorded reference episodes / oracle batches of group_rel_err at step j.  Tests assert 2x the curve."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "free_run_envelope.json")) as f:
+        return np.asarray(json.load(f)[key], dtype=np.float64)
+
+
+def _tol(curve, j, floor=5e-7):
+    return max(2.0 * curve[min(j, len(curve) - 1)], floor)
+
+
 @pytest.fixture(scope="module")
 def torch_mod(cuda_device):
     import torch
@@ -105,7 +118,8 @@ def test_free_run_vs_reference(torch_mod, quad_golden, name):
         kw["seed"] = r["seed"]
     env = make_env(1, r["task"], **kw)
     ep = r["ep"]
-    for k in range(int(ep.max()) + 1):
+    curve = _envelope("curve_running_max")        # 3.9e-7 at step 1 ... 4.6e-6 at step 150 (the reference's own f32-vs-f64
+    for k in range(int(ep.max()) + 1):            # drift: 7e-6 at step 100)
         idx = np.nonzero(ep == k)[0]
         o0 = env.reset(noise=r["reset_noise"][k][None]).cpu().numpy()
         assert group_rel_err(o0[:, :16], r["reset_obs"][k][None, :16], OBS_GROUPS) < 1e-6
@@ -113,9 +127,9 @@ def test_free_run_vs_reference(torch_mod, quad_golden, name):
             assert np.abs(o0[0, 16:] - r["reset_obs"][k][16:]).max() < 1e-5
         for j, i in enumerate(idx):
             obs, rew, done, _ = env.step(torch.as_tensor(r["act"][i][None]).cuda())
-            tol = 5e-6 * (1 + j)
+            tol = _tol(curve, j)
             o = obs.cpu().numpy()
-            assert group_rel_err(o[:, :16], r["obs"][i][None, :16], OBS_GROUPS) < tol, (k, j)
+            assert group_rel_err(o[:, :16], r["obs"][i][None, :16], OBS_GROUPS) <= tol, (k, j)
             assert bool(done.cpu().numpy()[0]) == bool(r["done"][i]), (k, j)
             assert scalar_rel_err(rew.cpu().numpy(), r["rew"][i]) < max(tol, 1e-5), (k, j)
         _, ct = get_state(env)
@@ -140,12 +154,16 @@ def test_random_batch_vs_oracle(torch_mod, task, dt, n):
     kw = {}
     if task == "velocity_control":
         kw = dict(targets=env.velocity_targets.cpu().numpy(), env2task=env.env2task.cpu().numpy())
+    try:
+        batch_curve = _envelope("random_batch_vs_oracle_running_max")     # measured, asserted x2
+    except KeyError:
+        batch_curve = 1.5e-6 * (1 + np.arange(20))
     for t in range(20):
         act = rng.uniform(-1.0, 16.0, (n, 4)).astype(np.float32)
         obs, rew, done, _ = env.step(torch.as_tensor(act).cuda())
         o_ref, r_ref, d_ref, f_ref, _ = qo.env_step(cfg, state, ct, act, task, dt, nt, mode="mix", **kw)
-        tol = 3e-6 * (1 + t)
-        assert group_rel_err(obs.cpu().numpy()[:, :16], o_ref[:, :16], OBS_GROUPS) < tol, t
+        tol = _tol(batch_curve, t)
+        assert group_rel_err(obs.cpu().numpy()[:, :16], o_ref[:, :16], OBS_GROUPS) <= tol, t
         assert scalar_rel_err(rew.cpu().numpy(), r_ref) < max(tol, 1e-5), t
         assert np.array_equal(done.cpu().numpy(), d_ref.astype(bool)), t
     st, ct_gpu = get_state(env)
@@ -156,7 +174,7 @@ def test_random_batch_vs_oracle(torch_mod, task, dt, n):
 
 def test_benchmark_shape_vs_oracle(torch_mod):
     """BASELINE.json configs[2] exactly as bench.py runs it -- 65 536 envs, velocity_control, dt = 0.005, nt = 1000, 64
-    tasks, U(0.1, 15) actions, the packed one-CTA-per-SM kernel -- stepped 20 times against the CPU oracle DIRECTLY (no
+    tasks, U(0.1, 15) actions, the one-CTA-per-SM kernel -- stepped 20 times against the CPU oracle DIRECTLY (no
     chain through a smaller size).  Per-step error of every env, max over the batch."""
     torch = torch_mod
     from oracle import quad_oracle as qo
@@ -164,7 +182,7 @@ def test_benchmark_shape_vs_oracle(torch_mod):
     n, dt, nt = 65536, 0.005, 1000
     rng = np.random.RandomState(77)
     env = make_env(n, "velocity_control", dt=dt, nt=nt, seed=list(range(64)))
-    assert env.step_kernel_name().startswith("quad_step2_kernel")
+    assert env.step_kernel_name().startswith("quad_step_wide_kernel")
     noise = rng.random_sample((n, 12))
     env.reset(noise=noise)
     state = qo.reset_state(None, noise)
@@ -439,18 +457,17 @@ def test_auto_reset_publishes_first_obs_and_final_obs(torch_mod):
     env.close()
 
 
-def test_streaming_kernel_equals_scalar_kernel(torch_mod, monkeypatch):
-    """Multi-wave launches take the persistent TMA-pipelined packed kernel (quad_stream2_kernel); it must reproduce the
-    scalar one-env-per-thread kernel bit for bit, ragged last tile and auto-reset included (400 037 envs = 3125 full
-    tiles + 37, an odd count: the last pair has one live lane)."""
+def test_streaming_kernel_equals_tile_kernel(torch_mod, monkeypatch):
+    """Multi-wave launches take the persistent TMA-pipelined kernel (quad_stream_kernel); it must reproduce the plain
+    step kernel bit for bit, ragged last tile and auto-reset included (400 037 envs = 3125 full tiles + 37)."""
     torch = torch_mod
     N = 400037
     kw = dict(dt=0.005, nt=6, seed=list(range(16)), auto_reset=True, rng_seed=11)
     a = make_env(N, "velocity_control", **kw)                  # streaming kernel (default for this size)
-    assert a.step_kernel_name().startswith("quad_stream2_kernel")
-    monkeypatch.setenv("MGB_PACKED", "0")
-    b = make_env(N, "velocity_control", **kw)                  # scalar kernel
-    monkeypatch.delenv("MGB_PACKED")
+    assert a.step_kernel_name().startswith("quad_stream_kernel")
+    monkeypatch.setenv("MGB_STREAM_KERNEL", "0")
+    b = make_env(N, "velocity_control", **kw)                  # plain kernel
+    monkeypatch.delenv("MGB_STREAM_KERNEL")
     assert b.step_kernel_name().startswith("quad_step_kernel")
     g = torch.Generator(device="cuda").manual_seed(2)
     a.reset()
@@ -465,7 +482,34 @@ def test_streaming_kernel_equals_scalar_kernel(torch_mod, monkeypatch):
             assert torch.equal(a.final_observation[m], b.final_observation[m])
     s1, s2 = a.state_dict(), b.state_dict()
     assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
-    assert int(d1.sum()) > 0 or True
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("N", [9473, 65536, 70001])
+def test_wide_kernel_equals_tile_kernel(torch_mod, monkeypatch, N):
+    """Single-wave launches take the one-CTA-per-SM kernel (quad_step_wide_kernel); it must reproduce the 64-thread
+    tile kernel bit for bit (ragged sizes, auto-reset, terminal observations)."""
+    torch = torch_mod
+    kw = dict(dt=0.005, nt=5, seed=list(range(8)), auto_reset=True, rng_seed=4)
+    a = make_env(N, "velocity_control", **kw)
+    assert a.step_kernel_name().startswith("quad_step_wide_kernel")
+    monkeypatch.setenv("MGB_WIDE_KERNEL", "0")
+    b = make_env(N, "velocity_control", **kw)
+    monkeypatch.delenv("MGB_WIDE_KERNEL")
+    assert b.step_kernel_name().startswith("quad_step_kernel")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a.reset()
+    b.reset()
+    for t in range(8):
+        act = torch.rand((N, 4), device="cuda", generator=g) * 16.0 - 0.5
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        m = d1.bool()
+        assert torch.equal(a.final_observation[m], b.final_observation[m])
+    s1, s2 = a.state_dict(), b.state_dict()
+    assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
     a.close()
     b.close()
 
@@ -497,7 +541,7 @@ def test_rk4_integrator_vs_restatement(torch_mod, task, dt, rk4_steps):
 @pytest.mark.parametrize("task,dt", [("velocity_control", 0.005), ("hovering_control", 0.01), ("no_collision", 0.003)])
 @pytest.mark.parametrize("N", [1, 63, 9473, 65536, 70001, 151001])
 def test_packed_kernel_equals_scalar_kernel(torch_mod, monkeypatch, N, task, dt):
-    """The packed kernel (two envs per thread, FFMA2 / FADD2; quad_step2_kernel) must reproduce the scalar
+    """The packed variant (MGB_PACKED=1: two envs per thread, FFMA2 / FADD2; quad_step2_kernel) must reproduce the scalar
     one-env-per-thread instantiation of the same code bit for bit: ragged and odd sizes, auto-reset, terminal
     observations, fail codes, every task, and substep counts that do (5, 10) and do not (3) take the unrolled loop.
     Actions outside [0.1, 15] exercise the clamp; the long horizon lets hovering envs crash and velocity envs time out.
@@ -506,12 +550,13 @@ def test_packed_kernel_equals_scalar_kernel(torch_mod, monkeypatch, N, task, dt)
     kw = dict(dt=dt, nt=5, auto_reset=True, rng_seed=4)
     if task == "velocity_control":
         kw["seed"] = list(range(8))
+    monkeypatch.setenv("MGB_PACKED", "1")
     a = make_env(N, task, **kw)
-    assert a.step_kernel_name().startswith("quad_step2_kernel")
-    monkeypatch.setenv("MGB_PACKED", "0")
-    b = make_env(N, task, **kw)
     monkeypatch.delenv("MGB_PACKED")
-    assert b.step_kernel_name().startswith("quad_step_kernel")
+    if N > 1:
+        assert a.step_kernel_name().startswith("quad_step2_kernel")
+    b = make_env(N, task, **kw)
+    assert not b.step_kernel_name().startswith("quad_step2_kernel")
     g = torch.Generator(device="cuda").manual_seed(5)
     a.reset()
     b.reset()
@@ -526,63 +571,6 @@ def test_packed_kernel_equals_scalar_kernel(torch_mod, monkeypatch, N, task, dt)
         assert torch.equal(a.final_observation[m], b.final_observation[m])
     s1, s2 = a.state_dict(), b.state_dict()
     assert torch.equal(s1["state"], s2["state"]) and torch.equal(s1["ct"], s2["ct"])
-    a.close()
-    b.close()
-
-
-@pytest.mark.parametrize("N,task", [(65536, "velocity_control"), (151001, "velocity_control"), (4096, "hovering_control"),
-                                    (777, "no_collision")])
-def test_chained_steps_equal_unchained_steps(torch_mod, N, task):
-    """set_chaining(True): consecutive step launches overlap on the GPU (per-block tickets instead of the grid-wide wait).
-    Trajectories must be bit-identical to ordinary stepping -- eager back-to-back launches, a CUDA graph replayed several
-    times (tickets are taken on the device, so replays need no host-side epoch), other kernels of the same handle in
-    between (masked reset, state read), and switching chaining off again."""
-    torch = torch_mod
-    T = 48
-    kw = dict(dt=0.005, nt=7, auto_reset=True, rng_seed=6)
-    if task == "velocity_control":
-        kw["seed"] = list(range(5))
-    a = make_env(N, task, **kw)
-    b = make_env(N, task, **kw)
-    a.set_chaining(True)
-    assert "chained" in a.step_kernel_name()
-    g = torch.Generator(device="cuda").manual_seed(8)
-    acts = torch.rand((T, N, 4), device="cuda", generator=g) * 16.0 - 0.5
-    D = a.obs_dim
-    outs = []
-    for env in (a, b):
-        obs = torch.zeros((T, N, D), device="cuda")
-        rew = torch.zeros((T, N), device="cuda")
-        done = torch.zeros((T, N), dtype=torch.uint8, device="cuda")
-        env.reset()
-        for t in range(16):                                   # eager, back to back
-            env.step(acts[t], out=(obs[t], rew[t], done[t]))
-        mask = (torch.arange(N, device="cuda") % 3 == 0)
-        env.reset(mask=mask)                                  # an ordinary kernel of the same handle in between
-        st_mid = env.state_dict()["state"].clone()
-        stream = torch.cuda.Stream()
-        stream.wait_stream(torch.cuda.current_stream())       # torch side streams do not synchronise with the default one
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(stream):
-            env.step(acts[16], out=(obs[16], rew[16], done[16]))          # warm-up on the capture stream
-            stream.synchronize()
-            with torch.cuda.graph(graph, stream=stream):
-                for t in range(17, 25):
-                    env.step(acts[t], out=(obs[t], rew[t], done[t]))
-        torch.cuda.synchronize()
-        for _ in range(3):                                    # the same 8 launches three times: 24 more steps
-            graph.replay()
-        torch.cuda.synchronize()
-        if env is a:
-            env.set_chaining(False)                           # back to grid-wide waits: still consistent
-        for t in range(25, T):
-            env.step(acts[t], out=(obs[t], rew[t], done[t]))
-        torch.cuda.synchronize()
-        outs.append((obs, rew, done, st_mid, env.state_dict()))
-    for x, y in zip(outs[0][:4], outs[1][:4]):
-        assert torch.equal(x, y)
-    assert torch.equal(outs[0][4]["state"], outs[1][4]["state"]) and torch.equal(outs[0][4]["ct"], outs[1][4]["ct"])
-    assert int(outs[0][2].sum()) > 0
     a.close()
     b.close()
 
@@ -605,6 +593,7 @@ def test_packed_kernel_failing_env_does_not_disturb_its_pair_partner(torch_mod, 
     for packed in ("1", "0"):
         monkeypatch.setenv("MGB_PACKED", packed)
         env = make_env(n, "hovering_control", dt=0.01)
+        assert env.step_kernel_name().startswith("quad_step2_kernel") == (packed == "1")
         set_state(env, st, np.zeros(n, np.int32))
         o, r, d, _ = env.step(act)
         outs.append((o.clone(), r.clone(), d.clone(), env.fail_code.clone(), env.state_dict()["state"].clone()))
