@@ -676,9 +676,10 @@ def run_maze3d(ctx, sampler):
             # raycaster renders every frame; and the cost of set_task amortised over an episode of 200 steps
             many = fast_tasks(n, seed=5)
             env2 = BatchedMetaMazeDiscrete3D(resolution=(128, 128), max_steps=200, task_type="SURVIVAL", num_envs=n,
-                                             device=ctx.local_rank, squeeze=False, auto_reset=True, obs_dtype="uint8")
+                                             device=ctx.local_rank, squeeze=False, auto_reset=True, obs_dtype="uint8",
+                                             cache=False)
             t0 = time.perf_counter()
-            env2.set_task(many)
+            env2.set_task(many, env2task=np.arange(n))
             torch.cuda.synchronize(dev)
             st_many = time.perf_counter() - t0
             env2.reset()
@@ -686,11 +687,52 @@ def run_maze3d(ctx, sampler):
             t2 = _time_block_local(ctx, b2)
             us2 = t2["ms_per_step"] * 1e3
             extras["many_tasks"] = {"tasks": n, "us_per_step": us2, "value": n / us2 * 1e6, "unit": "env-steps/s",
-                                    "renderer": env2.renderer_name() if hasattr(env2, "renderer_name") else "direct",
+                                    "renderer": "direct float64 raycaster (maze3d_kernel<false>), one task per env",
                                     "set_task_s": st_many,
-                                    "amortised_value_200_step_episodes": n * 200 / (200 * us2 * 1e-6 + st_many),
                                     "frac_of_measured_hbm": n * MAZE3D_BYTES / us2 * 1e-3 / ctx.peak}
             del b2
+            # ---- per-episode task resampling: an env that finishes an episode gets a fresh task.
+            # (a) host samplers alone, (b) mgb_maze_update_tasks alone (stream-ordered, no device sync), (c) the loop:
+            # step, read `done`, re-task the finished envs with freshly sampled tasks
+            import random as _random
+            from metagym_b200 import MazeTaskSampler
+            rs = np.random.RandomState(11)
+            t0 = time.perf_counter()
+            fresh = [MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.35, rng=rs) for _ in range(256)]
+            rate_fast = 256 / (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            _ = [MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.35, seed=1000 + k) for k in range(32)]
+            rate_ref = 32 / (time.perf_counter() - t0)
+            ids = np.arange(256)
+            env2.update_tasks(ids, fresh)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for r in range(8):
+                env2.update_tasks((ids + 64 * r) % n, fresh)
+            host_s = time.perf_counter() - t0
+            torch.cuda.synchronize(dev)
+            rate_upd = 8 * 256 / (time.perf_counter() - t0)
+            steps_loop, retasked = 300, 0
+            pool, pi = fresh, 0
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for t in range(steps_loop):
+                _, _, d, _ = env2.step(acts[t % SLOTS])
+                fin = torch.nonzero(d).flatten().cpu().numpy()          # the learner reads `done` anyway
+                if fin.size:
+                    new = [pool[(pi + k) % len(pool)] for k in range(fin.size)]
+                    pi += fin.size
+                    env2.update_tasks(fin, new)
+                    retasked += int(fin.size)
+            torch.cuda.synchronize(dev)
+            dt_loop = time.perf_counter() - t0
+            extras["task_churn"] = {
+                "host_sampler_tasks_per_s": {"reference_streams": rate_ref, "rng_sampler": rate_fast},
+                "update_tasks_per_s": rate_upd, "update_tasks_host_s_per_call_of_256": host_s / 8,
+                "loop": {"steps": steps_loop, "envs": n, "retasked": retasked, "value": n * steps_loop / dt_loop,
+                         "unit": "env-steps/s", "tasks_per_s": retasked / dt_loop,
+                         "note": "step + done read-back + mgb_maze_update_tasks of the finished envs (tasks drawn from a "
+                                 "pre-sampled pool; sampling cost is the host_sampler line)"}}
             env2.close()
     else:
         env.close()

@@ -214,6 +214,23 @@ int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *walls_host, co
                       const double *food_rewards_host, const int32_t *food_interval_host,
                       const mgb_maze_task_scalars *scalars_host, const int32_t *env2task_host);
 
+/* MetaMazeDiscrete3D renderer choice.  enabled = 1 (default): static layers of every (task, cell, heading) are rendered once
+ * and memoised (pose cache, within MGB_MAZE_CACHE_GB), a step composes / copies; 0: every frame is ray-cast directly
+ * (ray_caster_utils.py:66-209 per frame, like the reference) -- the mode for task tables that change every episode. */
+int mgb_maze_set_cache(mgb_maze *h, int enabled);
+
+/* Per-episode task resampling (MazeBase.set_task on a fresh TaskConfig every episode, maze_base.py:19-38, at the scale of
+ * SURVEY.md 8f row 3): replace `count` entries of the table mgb_maze_set_task built -- task_slots_host [count] indices into
+ * it, the other arrays as for mgb_maze_set_task but [count] long -- STREAM-ORDERED and without any device synchronisation
+ * (one pinned-staged copy + three small kernels on `stream`).  Every env whose env2task entry is one of the replaced slots
+ * starts a new episode on its new task (agent at start, life = initial_life, food restored), like set_task + reset of that
+ * env; other envs are untouched.  The table's shape is fixed by mgb_maze_set_task: a replacement may not have more food
+ * cells than the table's largest task nor smaller cells than its smallest.  Needs the direct renderer (the pose cache
+ * memoises whole task tables): create the env with the cache off or with more tasks than the cache budget holds. */
+int mgb_maze_update_tasks(mgb_maze *h, int32_t count, const int32_t *task_slots_host, const int8_t *walls_host,
+                          const int8_t *texts_host, const double *food_rewards_host, const int32_t *food_interval_host,
+                          const mgb_maze_task_scalars *scalars_host, void *stream);
+
 /* MazeBase.reset (maze_base.py:40-63, maze_discrete_3d.py:39-49).  mask_dev NULL = all.  obs_dev NULL = skip. */
 int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_dev, void *stream);
 

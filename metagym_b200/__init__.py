@@ -8,8 +8,11 @@ Public surface (mirrors the reference's gym.Env classes with a leading batch axi
 All arithmetic runs in libmgb200.so (hand-written sm_100a CUDA, C ABI in include/mgb200.h); there is no CPU path.
 """
 from ._lib import MgbError  # noqa: F401
+from .registration import register_envs  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+register_envs()     # no-op without gym / gymnasium (metagym/quadrotor/__init__.py:20-32, metagym/metamaze/__init__.py:21-54)
 
 
 def __getattr__(name):

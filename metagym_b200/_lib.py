@@ -63,6 +63,8 @@ SIGNATURES = {
     "mgb_maze_obs_bytes_per_env": (c_i64, [vp]),
     "mgb_maze_set_textures": (ctypes.c_int, [vp, vp, c_i32, vp, c_i32]),
     "mgb_maze_set_task": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars), vp]),
+    "mgb_maze_set_cache": (ctypes.c_int, [vp, ctypes.c_int]),
+    "mgb_maze_update_tasks": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars), vp]),
     "mgb_maze_reset": (ctypes.c_int, [vp, vp, vp, vp]),
     "mgb_maze_step": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "mgb_maze_set_options": (ctypes.c_int, [vp, ctypes.c_int]),

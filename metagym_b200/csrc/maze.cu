@@ -78,6 +78,12 @@ struct MazeArgs {
     uint8_t *c_rgb8;             // [n_slots][H*V*3] finished uint8 pixel with EVERY food of the task present (baked)
     uint32_t *c_px_all;          // int32 mode: [n_slots][H*V] packed like c_px, every food present (baked)
     uint64_t *c_fmask;           // [n_slots][2] food slots that can change this pose's image at all
+    // variant frames (uint8 SURVIVAL): a pose whose image depends on k <= kVariantBits foods has all 2^k finished frames
+    // baked, so a step never recomputes a pixel -- it picks the frame of the foods currently visible
+    const int32_t *c_vbase;      // [n_slots] index of the pose's first extra frame in c_var8, or -1 (all-present frame only)
+    uint8_t *c_var8;             // [n_var_frames][H*V*3]; variant v of a pose = frame c_vbase + v, v = the visible foods'
+                                 // bits compacted in ascending slot order; the all-visible variant is c_rgb8[slot] itself
+    const void *bake_desc;       // bake mode over variant frames: [n_items] BakeDesc (slot, presence mask)
     int bake;                    // compose kernel: items are pose slots, output goes to c_rgb8 / c_px_all
     uint8_t *c_gsig;             // [n_slots][H*V/4] per 4-pixel group: signature of the foods that can tint it
     uint8_t *c_colhits;          // [n_slots][H]     transparent crossings recorded for the column
@@ -501,12 +507,24 @@ struct HitRec {                  // one transparent crossing of a column, 16 byt
     int16_t v_s, v_e;
     int32_t fid;                 // food slot of the crossed cell (pose cache: presence is decided per env, per step)
 };
-struct EnvDyn {                  // per env, per step: what the static pose layers must be combined with, 32 bytes
+struct EnvDyn {                  // per env, per step: what the static pose layers must be combined with, 40 bytes
     int32_t slot;                // pose-cache slot of (task, cell, heading)
     int32_t bar_end;             // life bar end column (python slice semantics already applied)
     uint64_t present[2];         // bit f: food slot f is currently visible
-    int32_t task, pad;
+    int32_t task, pad;           // pad: 8-bit signature of the missing foods that can tint this pose (0 = frame is final)
+    int32_t vframe, pad2;        // >= 0: finished frame c_var8[vframe]; -1: c_rgb8[slot] (+ the tints `pad` asks for)
 };
+struct BakeDesc {                // one variant frame to bake
+    int32_t slot, pad;
+    uint64_t present[2];
+};
+constexpr int kVariantBitsMax = 6;
+
+// finished uint8 frame the env's observation starts from
+__device__ __forceinline__ const uint8_t *frame_of(const MazeArgs &a, const EnvDyn &d, size_t frame_bytes)
+{
+    return d.vframe >= 0 ? a.c_var8 + (size_t)d.vframe * frame_bytes : a.c_rgb8 + (size_t)d.slot * frame_bytes;
+}
 
 __device__ __forceinline__ int trunc_i(double x) { return (int)x; }   // cvt.rzi: python/numba int()
 
@@ -1015,6 +1033,27 @@ __device__ __forceinline__ EnvDyn make_dyn(const MazeConst &c, const MazeArgs &a
     // baked "all present" frame + life bar
     const uint64_t *fm = a.c_fmask + (size_t)d.slot * 2;
     uint64_t miss = ((~d.present[0]) & fm[0]) | ((~d.present[1]) & fm[1]);      // fold 128 slots to (f & 7)
+    d.vframe = -1; d.pad2 = 0;
+    if (miss && a.c_vbase) {
+        const int vb = a.c_vbase[d.slot];
+        if (vb >= 0) {
+            // variant index = presence bits of the pose's foods, compacted in ascending slot order (all visible -> the
+            // c_rgb8 frame, handled by miss == 0 above)
+            int v = 0, bit = 0;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                uint64_t m = fm[w];
+                while (m) {
+                    const int f = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    v |= (int)((d.present[w] >> f) & 1ull) << bit;
+                    ++bit;
+                }
+            }
+            d.vframe = vb + v;
+            miss = 0;                    // the variant frame is final
+        }
+    }
     miss |= miss >> 32; miss |= miss >> 16; miss |= miss >> 8;
     d.pad = (int32_t)(miss & 0xFFu);
     return d;
@@ -1085,12 +1124,22 @@ __global__ void __launch_bounds__(256) maze3d_sig_kernel(const __grid_constant__
     }
 }
 
+// variant frames start as copies of the pose's STATIC frame (what the FILL render left in c_rgb8, before any tint is baked)
+__global__ void __launch_bounds__(256) maze3d_varinit_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a)
+{
+    const size_t frame16 = (size_t)c.res_h * c.res_v * 3 / 16;
+    const BakeDesc bd = reinterpret_cast<const BakeDesc *>(a.bake_desc)[blockIdx.x];
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.c_rgb8) + (size_t)bd.slot * frame16;
+    uint4 *dst = reinterpret_cast<uint4 *>(a.c_var8) + (size_t)blockIdx.x * frame16;
+    for (size_t i = threadIdx.x; i < frame16; i += blockDim.x) dst[i] = src[i];
+}
+
 constexpr int kComposeThreads = 256;
 
 // Work item = (env, image slice).  Pixels no missing food can tint are copied from the pose's baked all-present frame;
 // the others take the cached static layers (packed colour + in-wall flag, food slot under the pixel, crossing records
 // of the column) through the reference's float64 blend with the env's 128-bit food presence mask.
-__global__ void __launch_bounds__(kComposeThreads, 6) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
+__global__ void __launch_bounds__(kComposeThreads, 5) maze3d_compose_kernel(const __grid_constant__ MazeConst c,
                                                                          const __grid_constant__ MazeArgs a)
 {
     // persistent CTAs: work item = (env, one of kParts slices of its image); grid = resident CTA count, so there is
@@ -1108,7 +1157,12 @@ __global__ void __launch_bounds__(kComposeThreads, 6) maze3d_compose_kernel(cons
   auto fetch = [&](int64_t idx) -> EnvDyn {
       if (!a.bake) return reinterpret_cast<const EnvDyn *>(a.dyn)[idx];
       EnvDyn b;
-      b.slot = (int32_t)idx; b.bar_end = 0; b.present[0] = b.present[1] = ~0ull; b.task = a.poses[idx].x; b.pad = 0xFF;
+      b.slot = (int32_t)idx; b.bar_end = 0; b.present[0] = b.present[1] = ~0ull; b.pad = 0xFF; b.vframe = -1; b.pad2 = 0;
+      if (a.bake_desc) {               // variant frames: item = frame, its pose slot and presence mask come from the descriptor
+          const BakeDesc bd = reinterpret_cast<const BakeDesc *>(a.bake_desc)[idx];
+          b.slot = bd.slot; b.present[0] = bd.present[0]; b.present[1] = bd.present[1];
+      }
+      b.task = a.poses[b.slot].x;
       return b;
   };
   EnvDyn d_next;
@@ -1124,6 +1178,240 @@ __global__ void __launch_bounds__(kComposeThreads, 6) maze3d_compose_kernel(cons
     if (q_begin >= total_px) continue;
 #include "maze_compose_body.inc"
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused single-step kernel of the pose-cache path (uint8 frames): step logic + observation in ONE launch, the frame moved by
+// the TMA engine.  One CTA per env: thread 0 runs the step logic (action, evaluation rule, auto-reset, pose-cache lookup) and
+// immediately issues bulk copies (cp.async.bulk + mbarrier, 12 KB chunks) of the pose's baked all-present frame into shared
+// memory; as each chunk lands the CTA patches, in shared memory, the few 4-pixel groups a currently missing food can tint
+// (float64 blend of the cached static layers, exactly the compose kernel's slow path) and the life bar, and one bulk store
+// sends the chunk to `obs`.  The 49 KB of a frame are in flight without passing through registers (the compose kernel's 256
+// threads of dependent 16-byte loads were 48 % long-scoreboard stalls), the separate logic launch and its EnvDyn round trip
+// through global memory are gone, and four CTAs per SM overlap one env's logic latency with the others' copies.
+// Reference: maze_discrete_3d.py:51-81,113-127, maze_base.py:65-95, ray_caster_utils.py:66-209 (via the cached layers).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 128;
+constexpr int kStepChunkPx = 4096;          // pixels per bulk copy: 12 KB of uint8 RGB
+constexpr int kStepMaxChunks = 16;          // frames up to 65 536 pixels (192 KB) -- larger screens use the two-kernel path
+
+// one tinted 4-pixel group (4 consecutive rows of ONE screen column): cached static colour -> floor/ceiling tint ->
+// crossings of the column -> life bar (ray_caster_utils.py:118-205), packed to 12 uint8 (values above 255 clamp: MGB_OBS_U8).
+// Each crossing record of the column is loaded once for the four pixels (they share the column), in ascending order, so
+// every pixel sees the blends in the reference's order.
+__device__ __forceinline__ void compose_group_u8(const MazeConst &c, const EnvDyn &d, const uint32_t *gpx, const uint8_t *gfid,
+                                                 const uint8_t *colhits, const HitRec *ghits, const double *fval,
+                                                 bool survival, int q, int d_h, int d_v0, int lb_sx, int lb_sy, int lb_ey,
+                                                 uint32_t pk[3])
+{
+    const int V = c.res_v;
+    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(gpx + q));
+    const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t *>(gfid + q));
+    const int n_hits = colhits[d_h];
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    int rgb[4][3];
+    bool mark[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int d_v = d_v0 + k, f = (int)((f4 >> (8 * k)) & 0xFFu);
+        rgb[k][0] = (int)(w[k] & 1023u); rgb[k][1] = (int)((w[k] >> 10) & 1023u); rgb[k][2] = (int)((w[k] >> 20) & 1023u);
+        const bool in_wall = (w[k] >> 30) & 1u;
+        mark[k] = false;
+        if (f != 0xFF && ((d.present[f >> 6] >> (f & 63)) & 1ull)) {
+            const double tv = survival ? __ldg(fval + f) : 1.0;
+            if (d_v > V / 2 ? tv > 0.01 : tv > 0) {          // floor tests > 0.01 (:119), ceiling > 0 (:150)
+                if (!in_wall) blend(rgb[k], tv * 0.50 + 0.10);
+                mark[k] = true;
+            }
+        }
+    }
+    if (n_hits > 0 && !(mark[0] && mark[1] && mark[2] && mark[3])) {
+        const int4 *hits = reinterpret_cast<const int4 *>(ghits + (size_t)d_h * c.max_hits);
+        for (int j0 = 0; j0 < n_hits; j0 += 4) {                      // four records per round trip
+            int4 raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) raw[u] = __ldg(hits + (j0 + u < n_hits ? j0 + u : n_hits - 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u >= n_hits) break;
+                const double tf = __hiloint2double(raw[u].y, raw[u].x);
+                const int v_s = (int)(int16_t)(raw[u].z & 0xFFFF), v_e = (int)(int16_t)((uint32_t)raw[u].z >> 16), fid = raw[u].w;
+                if (!((d.present[fid >> 6] >> (fid & 63)) & 1ull)) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (!mark[k] && d_v0 + k >= v_s && d_v0 + k < v_e) blend(rgb[k], tf);
+            }
+        }
+    }
+    pk[0] = pk[1] = pk[2] = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int d_v = d_v0 + k;
+        if (survival && d_h >= lb_sx && d_h < d.bar_end && d_v >= lb_sy && d_v < lb_ey) { rgb[k][0] = 255; rgb[k][1] = 0; rgb[k][2] = 0; }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int idx = 3 * k + b;
+            pk[idx >> 2] |= (uint32_t)(rgb[k][b] > 255 ? 255 : rgb[k][b]) << (8 * (idx & 3));
+        }
+    }
+}
+
+constexpr int kStepBatch = 16;              // envs whose step logic one CTA runs side by side before moving their frames
+
+__global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __grid_constant__ MazeConst c,
+                                                                      const __grid_constant__ MazeArgs a)
+{
+    // Two CTAs per SM; CTA j owns the envs j, j + G, j + 2G, ... (G = grid size).  Per pass of up to kStepBatch envs:
+    //  (1) threads 0..B-1 run the step logic of the B envs SIDE BY SIDE (each is a chain of ~5 dependent L2 round trips:
+    //      one chain per frame would cost more than the frame's copy), leaving B EnvDyn records in shared memory;
+    //  (2) the B frames stream through two shared-memory frame buffers: while frame k is patched and stored, the bulk
+    //      loads of frame k + 1 are already in flight.
+    extern __shared__ __align__(128) uint8_t s_frames[];         // 2 x (H * V * 3 bytes)
+    __shared__ EnvDyn s_dyn[kStepBatch];
+    __shared__ __align__(8) uint64_t s_bar[2][kStepMaxChunks];
+    __shared__ int s_nslow;
+    __shared__ uint16_t s_slow[1024];                            // queued tinted groups of one chunk (group index in the chunk)
+    const int H = c.res_h, V = c.res_v, total_px = H * V;
+    const uint32_t frame_bytes = (uint32_t)total_px * 3u;
+    const int n_chunks = (total_px + kStepChunkPx - 1) / kStepChunkPx;
+    const bool survival = c.task_type == MGB_MAZE_SURVIVAL;
+    const int lb_sx = trunc_i(c.lb_sx), lb_sy = trunc_i(c.lb_sy);
+    int lb_ey = trunc_i(c.lb_sy + c.lb_w);
+    if (lb_ey > V) lb_ey = V;
+    const int tid = threadIdx.x;
+    const int v_shift = (V & (V - 1)) == 0 ? 31 - __clz(V) : -1;
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b)
+            for (int k = 0; k < n_chunks; ++k) mgb_mbar_init(&s_bar[b][k], 1);
+        mgb_fence_mbar_init();
+        s_nslow = 0;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+    uint32_t uses[2] = {0u, 0u};                                  // how often each frame buffer has been filled (mbarrier parity)
+    auto fetch = [&](const EnvDyn &dd, int buf) {                 // thread 0: the pose's baked frame, chunk by chunk
+        const uint8_t *g8 = frame_of(a, dd, frame_bytes);
+        for (int k = 0; k < n_chunks; ++k) {
+            const uint32_t off = (uint32_t)k * kStepChunkPx * 3u;
+            const uint32_t bytes = frame_bytes - off < kStepChunkPx * 3u ? frame_bytes - off : kStepChunkPx * 3u;
+            mgb_mbar_expect_tx(&s_bar[buf][k], bytes);
+            mgb_bulk_load(s_frames + (size_t)buf * frame_bytes + off, g8 + off, bytes, &s_bar[buf][k]);
+        }
+    };
+    for (int64_t base = blockIdx.x; base < a.n; base += (int64_t)gridDim.x * kStepBatch) {
+        const int64_t left = (a.n - base + gridDim.x - 1) / gridDim.x;
+        const int B = (int)(left < kStepBatch ? left : kStepBatch);
+        // ---- (1) step logic of the pass's envs, one thread each (what maze3d_logic_kernel does for the two-kernel path)
+        if (tid < B) {
+            const int64_t e = base + (int64_t)tid * gridDim.x;
+            const int task = a.env2task[e];
+            const uint8_t *blob = a.blobs + (int64_t)task * c.blob_bytes;
+            const int4 ag = a.agent[e];
+            Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
+            int32_t *eaten = a.eaten + e;
+            if (a.do_step) {
+                double reward;
+                int done;
+                maze_logic(c, blob, eaten, a.n_pad, s, a.act[e], reward, done);
+                a.rew[e] = reward;
+                a.done[e] = (uint8_t)done;
+                if (done && a.auto_reset) env_reset(c, blob, eaten, a.n_pad, s);
+                a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+                a.life[e] = s.life;
+            }
+            s_dyn[tid] = make_dyn(c, a, blob, task, s, eaten);
+        }
+        __syncthreads();
+        // ---- (2) the frames
+        if (tid == 0) {
+            mgb_bulk_wait_read<0>();                                   // the previous pass's stores have left the buffers
+            fetch(s_dyn[0], 0);
+        }
+        for (int it = 0; it < B; ++it) {
+            const int buf = it & 1;
+            const uint32_t parity = uses[buf] & 1u;
+            uses[buf] += 1u;
+            if (tid == 0 && it + 1 < B) {
+                mgb_bulk_wait_read<0>();                               // frame it-1 (other buffer) has been read by its stores
+                fetch(s_dyn[it + 1], buf ^ 1);
+            }
+            const int64_t e = base + (int64_t)it * gridDim.x;
+            const EnvDyn d = s_dyn[it];
+            uint8_t *s_frame = s_frames + (size_t)buf * frame_bytes;
+            const uint32_t miss_sig = (uint32_t)d.pad & 0xFFu;
+            const uint8_t *blob = a.blobs + (int64_t)d.task * c.blob_bytes;
+            const double *fval = reinterpret_cast<const double *>(blob + c.off_fval);
+            const uint32_t *gpx = a.c_px + (size_t)d.slot * total_px;
+            const uint8_t *gfid = a.c_fid + (size_t)d.slot * total_px;
+            const uint8_t *colhits = a.c_colhits + (size_t)d.slot * H;
+            const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)d.slot * H * c.max_hits;
+            const uint8_t *gsig = a.c_gsig + (size_t)d.slot * (total_px / 4);
+            uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * frame_bytes;
+            const uint32_t miss4 = miss_sig * 0x01010101u;
+            for (int k = 0; k < n_chunks; ++k) {
+                const int q0 = k * kStepChunkPx, q1 = q0 + kStepChunkPx < total_px ? q0 + kStepChunkPx : total_px;
+                const uint32_t off = (uint32_t)q0 * 3u, bytes = (uint32_t)(q1 - q0) * 3u;
+                // life bar columns inside this chunk (the bar is drawn last, maze_discrete_3d.py:118-126)
+                const int h0 = q0 / V, h1 = (q1 + V - 1) / V;          // columns [h0, h1) intersect the chunk
+                const int bh0 = lb_sx > h0 ? lb_sx : h0, bh1 = d.bar_end < h1 ? d.bar_end : h1;
+                const bool bar = survival && bh0 < bh1 && lb_sy < lb_ey;
+                const bool patch = miss_sig != 0 || bar;               // uniform over the CTA
+                if (patch) {
+                    if (miss_sig) {
+                        // queue the chunk's tinted groups (they cluster in a few columns, i.e. in a few signature words) ...
+                        for (int g4 = (q0 >> 4) + tid; g4 < (q1 >> 4); g4 += kStepThreads) {
+                            uint32_t hit = __ldg(reinterpret_cast<const uint32_t *>(gsig) + g4) & miss4;
+                            while (hit) {
+                                const int g = (__ffs(hit) - 1) >> 3;
+                                hit &= ~(0xFFu << (8 * g));
+                                s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)(((g4 << 2) + g) - (q0 >> 2));
+                            }
+                        }
+                        __syncthreads();
+                        const int n_slow = s_nslow;
+                        mgb_mbar_wait(&s_bar[buf][k], parity);
+                        // ... and share them out evenly: float64 blends of the cached static layers, written over the
+                        // baked pixels in shared memory
+                        for (int i = tid; i < n_slow; i += kStepThreads) {
+                            const int q = q0 + 4 * (int)s_slow[i];
+                            const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
+                            uint32_t pk[3];
+                            compose_group_u8(c, d, gpx, gfid, colhits, ghits, fval, survival, q, d_h, q - d_h * V, lb_sx, lb_sy,
+                                             lb_ey, pk);
+                            uint32_t *dst = reinterpret_cast<uint32_t *>(s_frame + (size_t)q * 3);
+                            dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
+                        }
+                        __syncthreads();                               // queue drained; the bar overwrites tinted pixels
+                        if (tid == 0) s_nslow = 0;
+                    } else {
+                        mgb_mbar_wait(&s_bar[buf][k], parity);
+                    }
+                    if (bar) {
+                        const int rows = lb_ey - lb_sy;
+                        for (int i = tid; i < (bh1 - bh0) * rows; i += kStepThreads) {
+                            const int d_h = bh0 + i / rows, d_v = lb_sy + i % rows;
+                            const int q = d_h * V + d_v;
+                            if (q >= q0 && q < q1) {
+                                uint8_t *px = s_frame + (size_t)q * 3;
+                                px[0] = 255; px[1] = 0; px[2] = 0;
+                            }
+                        }
+                    }
+                    mgb_fence_proxy_async();
+                    __syncthreads();
+                } else if (tid == 0) {
+                    mgb_mbar_wait(&s_bar[buf][k], parity);
+                }
+                if (tid == 0) {
+                    mgb_bulk_store(gobs + off, s_frame + off, bytes);
+                    mgb_bulk_commit();
+                }
+            }
+        }
+        __syncthreads();                                               // s_dyn is rewritten by the next pass
+    }
+    if (tid == 0) mgb_bulk_wait_read<0>();       // shared memory must outlive the copies
 }
 
 // T MetaMazeDiscrete3D steps in one launch (pose-cache path): one CTA per env; thread 0 runs the step logic and leaves the
@@ -1245,6 +1533,8 @@ struct mgb_maze {
     double *cori = nullptr;
     double *coltab_d = nullptr;
     // pose cache
+    int fused_step = 1;            // MGB_MAZE_FUSED_STEP=0: logic kernel + compose kernel instead of maze3d_step_kernel
+    size_t step_smem_set = 0, m2d_smem_set = 0;
     int cache_enabled = 1;         // MGB_MAZE_CACHE=0 disables (direct renderer only)
     double cache_budget_gb = 24.0; // MGB_MAZE_CACHE_GB
     bool cache_ready = false, cache_dirty = true;
@@ -1255,6 +1545,21 @@ struct mgb_maze {
     uint8_t *c_fid = nullptr, *c_colhits = nullptr, *c_rgb8 = nullptr;
     uint32_t *c_px_all = nullptr;
     uint64_t *c_fmask = nullptr;
+    uint8_t *task_flags = nullptr;            // [n_tasks] scratch of mgb_maze_update_tasks
+    int task_flags_n = 0;
+    bool cache_would_fit = true;              // last ensure_pose_cache decision (false: over budget -> direct renderer)
+    std::vector<double> cls_heights;          // eff-table classes of the current task table
+    double min_cell = 0.0;                    // smallest cell_size of the table (bounds the crossings a ray can record)
+    uint8_t *h_stage[2] = {nullptr, nullptr}; // pinned staging of mgb_maze_update_tasks (double-buffered)
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes[2] = {0, 0};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    int stage_next = 0;
+    int32_t *c_vbase = nullptr;
+    uint8_t *c_var8 = nullptr;
+    void *d_bake_desc = nullptr;
+    int64_t n_var_frames = 0;
+    int variant_bits = 4;          // MGB_MAZE_VARIANT_BITS: poses that depend on <= this many foods get all 2^k frames (0 = off)
     uint8_t *c_gsig = nullptr;
     HitRec *c_hits = nullptr;
     EnvDyn *dyn = nullptr;
@@ -1289,7 +1594,16 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     return off;
 }
 
+static MazeArgs maze_args(const mgb_maze *h);
+static MazeArgs maze_args_impl(const mgb_maze *h);
 static MazeArgs maze_args(const mgb_maze *h)
+{
+    MazeArgs a = maze_args_impl(h);
+    a.c_vbase = h->c_vbase;
+    a.c_var8 = h->c_var8;
+    return a;
+}
+static MazeArgs maze_args_impl(const mgb_maze *h)
 {
     MazeArgs a;
     memset(&a, 0, sizeof(a));
@@ -1340,6 +1654,12 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     cudaDeviceProp prop;
     MGB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    if (const char *ev = getenv("MGB_MAZE_FUSED_STEP")) h->fused_step = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_MAZE_VARIANT_BITS")) {
+        h->variant_bits = atoi(ev);
+        if (h->variant_bits < 0) h->variant_bits = 0;
+        if (h->variant_bits > kVariantBitsMax) h->variant_bits = kVariantBitsMax;
+    }
     if (const char *ev = getenv("MGB_MAZE_CACHE")) h->cache_enabled = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_CACHE_GB")) h->cache_budget_gb = atof(ev);
     MGB_CUDA(cudaMalloc(&h->agent, sizeof(int4) * h->n_pad));
@@ -1402,6 +1722,11 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig); cudaFree(h->hit_scratch);
     cudaFree(h->c_px_all); cudaFree(h->c_fmask);
+    cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc); cudaFree(h->task_flags);
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(h->h_stage[i]); cudaFree(h->d_stage[i]);
+        if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
+    }
     delete h;
 }
 
@@ -1418,6 +1743,16 @@ extern "C" int mgb_maze_set_options(mgb_maze *h, int auto_reset)
 {
     MGB_REQUIRE(h, "null handle");
     h->auto_reset = auto_reset ? 1 : 0;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_set_cache(mgb_maze *h, int enabled)
+{
+    MGB_REQUIRE(h, "null handle");
+    if ((h->cache_enabled != 0) != (enabled != 0)) {
+        h->cache_enabled = enabled ? 1 : 0;
+        h->cache_dirty = true;            // rebuilt (or dropped) at the next reset / step
+    }
     return MGB_OK;
 }
 
@@ -1447,10 +1782,58 @@ extern "C" int mgb_maze_set_textures(mgb_maze *h, const uint8_t *grounds_host, i
     return MGB_OK;
 }
 
+// One task of the table as the kernels read it: header, walls, textures, food slot of every cell, food values / intervals.
+// allow_new_class: set_task may open a new (agent_height, wall_height) class (it builds the eff tables afterwards); a
+// partial update may only join an existing class, otherwise the task's pixels compute eff themselves (cls = -1).
+static void fill_task_blob(const MazeConst &c, uint8_t *b, const int8_t *walls, const int8_t *texts, const double *food,
+                           const int32_t *interval, const mgb_maze_task_scalars &s, std::vector<double> &cls_heights,
+                           bool allow_new_class)
+{
+    const int nn = c.n * c.n;
+    TaskHdr hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.start[0] = s.start[0]; hd.start[1] = s.start[1]; hd.goal[0] = s.goal[0]; hd.goal[1] = s.goal[1];
+    hd.cell_size = s.cell_size; hd.wall_height = s.wall_height; hd.agent_height = s.agent_height;
+    hd.initial_life = s.initial_life; hd.max_life = s.max_life; hd.step_reward = s.step_reward;
+    hd.goal_reward = s.goal_reward;
+    {
+        int ex = 0;
+        const double t2c = c.text_size / s.cell_size;
+        hd.cell_pow2 = frexp(s.cell_size, &ex) == 0.5 ? 1 : 0;
+        hd.t2c_pow2 = frexp(t2c, &ex) == 0.5 ? 1 : 0;
+        hd.inv_cell = 1.0 / s.cell_size;
+        hd.inv_t2c = 1.0 / t2c;
+        hd.cls = -1;
+        for (size_t k = 0; k < cls_heights.size() / 2; ++k)
+            if (cls_heights[2 * k] == s.agent_height && cls_heights[2 * k + 1] == s.wall_height) hd.cls = (int)k;
+        if (hd.cls < 0 && allow_new_class && cls_heights.size() / 2 < 8) {
+            hd.cls = (int)(cls_heights.size() / 2);
+            cls_heights.push_back(s.agent_height);
+            cls_heights.push_back(s.wall_height);
+        }
+    }
+    int cnt = 0;
+    int8_t *fidx = reinterpret_cast<int8_t *>(b + c.off_fidx);
+    double *fval = reinterpret_cast<double *>(b + c.off_fval);
+    int32_t *fint = reinterpret_cast<int32_t *>(b + c.off_fint);
+    for (int k = 0; k < nn; ++k) {
+        b[c.off_walls + k] = (uint8_t)walls[k];
+        b[c.off_texts + k] = (uint8_t)texts[k];
+        const double fv = food[k];
+        if (fv > 0.0) {
+            fidx[k] = (int8_t)cnt; fval[cnt] = fv; fint[cnt] = interval[k];
+            ++cnt;
+        } else fidx[k] = -1;
+    }
+    hd.n_food = cnt;
+    memcpy(b, &hd, sizeof(hd));
+}
+
 extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *walls_host, const int8_t *texts_host,
                                  const double *food_rewards_host, const int32_t *food_interval_host,
                                  const mgb_maze_task_scalars *scalars_host, const int32_t *env2task_host)
 {
+    MgbRange nvtx_range("mgb_maze_set_task");
     MGB_REQUIRE(h && walls_host && texts_host && food_rewards_host && food_interval_host && scalars_host &&
                     env2task_host, "null argument");
     MGB_REQUIRE(n_tasks > 0, "n_tasks must be positive");
@@ -1478,6 +1861,7 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     // plus the start cell): that bounds the transparent crossings a column can record (ray_caster_utils.py:24-61).
     double min_cell = scalars_host[0].cell_size;
     for (int t = 1; t < n_tasks; ++t) min_cell = scalars_host[t].cell_size < min_cell ? scalars_host[t].cell_size : min_cell;
+    h->min_cell = min_cell;
     const int geo = (int)ceil(2.0 * c.max_vision / min_cell) + 3;
     int mh = f_max < geo ? f_max : geo;
     if (mh < 1) mh = 1;
@@ -1499,48 +1883,12 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     c.off_fint = (int)off;  off += (size_t)(f_max > 0 ? f_max : 1) * 4;
     c.blob_bytes = (int)((off + 15) / 16 * 16);
     std::vector<uint8_t> blobs((size_t)n_tasks * c.blob_bytes, 0);
-    std::vector<double> cls_heights;   // distinct (agent_height, wall_height) pairs, at most 8 get an eff table
-    for (int t = 0; t < n_tasks; ++t) {
-        uint8_t *b = blobs.data() + (size_t)t * c.blob_bytes;
-        TaskHdr hd;
-        memset(&hd, 0, sizeof(hd));
-        const mgb_maze_task_scalars &s = scalars_host[t];
-        hd.start[0] = s.start[0]; hd.start[1] = s.start[1]; hd.goal[0] = s.goal[0]; hd.goal[1] = s.goal[1];
-        hd.cell_size = s.cell_size; hd.wall_height = s.wall_height; hd.agent_height = s.agent_height;
-        hd.initial_life = s.initial_life; hd.max_life = s.max_life; hd.step_reward = s.step_reward;
-        hd.goal_reward = s.goal_reward;
-        {
-            int ex = 0;
-            const double t2c = c.text_size / s.cell_size;
-            hd.cell_pow2 = frexp(s.cell_size, &ex) == 0.5 ? 1 : 0;
-            hd.t2c_pow2 = frexp(t2c, &ex) == 0.5 ? 1 : 0;
-            hd.inv_cell = 1.0 / s.cell_size;
-            hd.inv_t2c = 1.0 / t2c;
-            hd.cls = -1;
-            for (size_t k = 0; k < cls_heights.size() / 2; ++k)
-                if (cls_heights[2 * k] == s.agent_height && cls_heights[2 * k + 1] == s.wall_height) hd.cls = (int)k;
-            if (hd.cls < 0 && cls_heights.size() / 2 < 8) {
-                hd.cls = (int)(cls_heights.size() / 2);
-                cls_heights.push_back(s.agent_height);
-                cls_heights.push_back(s.wall_height);
-            }
-        }
-        int cnt = 0;
-        int8_t *fidx = reinterpret_cast<int8_t *>(b + c.off_fidx);
-        double *fval = reinterpret_cast<double *>(b + c.off_fval);
-        int32_t *fint = reinterpret_cast<int32_t *>(b + c.off_fint);
-        for (int k = 0; k < nn; ++k) {
-            b[c.off_walls + k] = (uint8_t)walls_host[(size_t)t * nn + k];
-            b[c.off_texts + k] = (uint8_t)texts_host[(size_t)t * nn + k];
-            const double fv = food_rewards_host[(size_t)t * nn + k];
-            if (fv > 0.0) {
-                fidx[k] = (int8_t)cnt; fval[cnt] = fv; fint[cnt] = food_interval_host[(size_t)t * nn + k];
-                ++cnt;
-            } else fidx[k] = -1;
-        }
-        hd.n_food = cnt;
-        memcpy(b, &hd, sizeof(hd));
-    }
+    std::vector<double> &cls_heights = h->cls_heights;   // distinct (agent_height, wall_height) pairs, at most 8 get an eff table
+    cls_heights.clear();
+    for (int t = 0; t < n_tasks; ++t)
+        fill_task_blob(c, blobs.data() + (size_t)t * c.blob_bytes, walls_host + (size_t)t * nn, texts_host + (size_t)t * nn,
+                       food_rewards_host + (size_t)t * nn, food_interval_host + (size_t)t * nn, scalars_host[t], cls_heights,
+                       true);
     if (c.kind != MGB_MAZE_2D) {
         for (int t = 0; t < n_tasks; ++t)
             for (int k = 0; k < nn; ++k) {
@@ -1556,6 +1904,8 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     MGB_CUDA(cudaMemcpy(h->env2task, env2task_host, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice));
     h->n_tasks = n_tasks;
     h->has_task = true;
+    cudaFree(h->task_flags); h->task_flags = nullptr; h->task_flags_n = 0;
+    h->cache_would_fit = true;
     // pose list of the cache: every free cell (the agent can never stand inside a wall, maze_discrete_3d.py:63-65) x 4
     h->host_poses.clear();
     h->host_pose_index.assign((size_t)n_tasks * nn * 4, -1);
@@ -1594,6 +1944,114 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     maze_reset_kernel<<<(unsigned)((h->n + 255) / 256), 256>>>(c, a);
     MGB_CUDA(cudaDeviceSynchronize());
     h->launches += 1;
+    return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Partial, stream-ordered task replacement (per-episode task resampling, SURVEY.md 8f row 3 / maze_base.py:19-38)
+// ---------------------------------------------------------------------------------------------------------------
+// staging layout: [count] int32 table slots | pad to 16 | [count] blobs
+__global__ void maze_scatter_tasks_kernel(const __grid_constant__ MazeConst c, uint8_t *blobs, const uint8_t *stage, int count,
+                                          uint8_t *task_flags)
+{
+    const int32_t *slots = reinterpret_cast<const int32_t *>(stage);
+    const uint4 *src = reinterpret_cast<const uint4 *>(stage + (((size_t)count * 4 + 15) / 16) * 16) + (size_t)blockIdx.x * (c.blob_bytes / 16);
+    uint4 *dst = reinterpret_cast<uint4 *>(blobs + (size_t)slots[blockIdx.x] * c.blob_bytes);
+    for (int i = threadIdx.x; i < c.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) task_flags[slots[blockIdx.x]] = 1;
+}
+// envs whose task was replaced start a new episode on it (set_task leaves an env at its start state, maze_env.py:44-50)
+__global__ void maze_reset_flagged_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a,
+                                          const uint8_t *task_flags)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const int task = a.env2task[e];
+    if (!task_flags[task]) return;
+    const uint8_t *blob = a.blobs + (int64_t)task * c.blob_bytes;
+    Env s;
+    env_reset(c, blob, a.eaten + e, a.n_pad, s);
+    a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+    a.life[e] = s.life;
+    if (c.kind == MGB_MAZE_CONTINUOUS_3D) {             // get_cell_center(start), heading 0 (maze_base.py:41,50)
+        const TaskHdr *th = blob_hdr(blob);
+        a.cpos[e] = make_float2((float)(s.gx * th->cell_size + 0.5 * th->cell_size),
+                                (float)(s.gy * th->cell_size + 0.5 * th->cell_size));
+        a.cori[e] = 0.0;
+    }
+}
+__global__ void maze_clear_flags_kernel(uint8_t *task_flags, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_flags[i] = 0;
+}
+
+extern "C" int mgb_maze_update_tasks(mgb_maze *h, int32_t count, const int32_t *task_slots_host, const int8_t *walls_host,
+                                     const int8_t *texts_host, const double *food_rewards_host,
+                                     const int32_t *food_interval_host, const mgb_maze_task_scalars *scalars_host,
+                                     void *stream)
+{
+    MgbRange nvtx_range("mgb_maze_update_tasks");
+    MGB_REQUIRE(h && task_slots_host && walls_host && texts_host && food_rewards_host && food_interval_host && scalars_host,
+                "null argument");
+    MGB_REQUIRE(count > 0, "count must be positive");
+    MGB_REQUIRE(h->has_task, "call mgb_maze_set_task first (it sizes the task table)");
+    MgbDeviceGuard guard(h->device);
+    MazeConst &c = h->c;
+    MGB_REQUIRE(!(c.kind == MGB_MAZE_DISCRETE_3D && h->cache_enabled && !h->host_poses.empty() && h->cache_would_fit),
+                "partial task updates need the direct renderer: create the env with the pose cache off (MGB_MAZE_CACHE=0 / "
+                "cache=False) -- the cache memoises whole task tables");
+    const int n = c.n, nn = n * n;
+    for (int t = 0; t < count; ++t) {
+        MGB_REQUIRE(task_slots_host[t] >= 0 && task_slots_host[t] < h->n_tasks, "task slot out of range");
+        int cnt = 0;
+        for (int k = 0; k < nn; ++k) {
+            cnt += food_rewards_host[(size_t)t * nn + k] > 0.0 ? 1 : 0;
+            const int id = texts_host[(size_t)t * nn + k];
+            MGB_REQUIRE(c.kind == MGB_MAZE_2D || (id >= 0 && (!h->has_tex || id < c.n_tex)), "cell_texts refers to a texture that is not loaded");
+        }
+        MGB_REQUIRE(cnt <= c.f_max, "a replacement task may not have more food cells than the largest task of set_task");
+        const mgb_maze_task_scalars &s = scalars_host[t];
+        MGB_REQUIRE(s.start[0] >= 0 && s.start[0] < n && s.start[1] >= 0 && s.start[1] < n, "start outside the maze");
+        MGB_REQUIRE(s.goal[0] >= 0 && s.goal[0] < n && s.goal[1] >= 0 && s.goal[1] < n, "goal outside the maze");
+        MGB_REQUIRE(s.agent_height < s.wall_height && s.agent_height > 0, "the agent height must be > 0 and < wall height");
+        MGB_REQUIRE(s.cell_size >= h->min_cell, "a replacement task may not have smaller cells than the table's smallest");
+    }
+    // pinned staging, double-buffered: the host waits only for the COPY of the call before last, never for the device
+    const int sb = h->stage_next;
+    h->stage_next ^= 1;
+    const size_t head = (((size_t)count * 4 + 15) / 16) * 16, need = head + (size_t)count * c.blob_bytes;
+    if (!h->stage_done[sb]) MGB_CUDA(cudaEventCreateWithFlags(&h->stage_done[sb], cudaEventDisableTiming));
+    else MGB_CUDA(cudaEventSynchronize(h->stage_done[sb]));
+    if (need > h->stage_bytes[sb]) {
+        cudaFreeHost(h->h_stage[sb]); cudaFree(h->d_stage[sb]);
+        h->h_stage[sb] = nullptr; h->d_stage[sb] = nullptr; h->stage_bytes[sb] = 0;
+        const size_t cap = need * 2;
+        MGB_CUDA(cudaMallocHost(&h->h_stage[sb], cap));
+        MGB_CUDA(cudaMalloc(&h->d_stage[sb], cap));
+        h->stage_bytes[sb] = cap;
+    }
+    if (!h->task_flags) {
+        MGB_CUDA(cudaMalloc(&h->task_flags, (size_t)h->n_tasks));
+        MGB_CUDA(cudaMemset(h->task_flags, 0, (size_t)h->n_tasks));
+        h->task_flags_n = h->n_tasks;
+    }
+    uint8_t *hs = h->h_stage[sb];
+    memset(hs, 0, need);
+    memcpy(hs, task_slots_host, (size_t)count * 4);
+    for (int t = 0; t < count; ++t)
+        fill_task_blob(c, hs + head + (size_t)t * c.blob_bytes, walls_host + (size_t)t * nn, texts_host + (size_t)t * nn,
+                       food_rewards_host + (size_t)t * nn, food_interval_host + (size_t)t * nn, scalars_host[t], h->cls_heights,
+                       false);
+    cudaStream_t st = (cudaStream_t)stream;
+    MGB_CUDA(cudaMemcpyAsync(h->d_stage[sb], hs, need, cudaMemcpyHostToDevice, st));
+    MGB_CUDA(cudaEventRecord(h->stage_done[sb], st));
+    maze_scatter_tasks_kernel<<<(unsigned)count, 128, 0, st>>>(c, h->blobs, h->d_stage[sb], count, h->task_flags);
+    MazeArgs a = maze_args(h);
+    maze_reset_flagged_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, st>>>(c, a, h->task_flags);
+    maze_clear_flags_kernel<<<(unsigned)((h->n_tasks + 255) / 256), 256, 0, st>>>(h->task_flags, h->n_tasks);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 3;
     return MGB_OK;
 }
 
@@ -1655,14 +2113,15 @@ static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStre
 static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
 {
     if (!h->cache_dirty) return MGB_OK;
-    h->cache_dirty = false;
     h->cache_ready = false;
     MazeConst &c = h->c;
-    if (!h->cache_enabled || c.kind != MGB_MAZE_DISCRETE_3D || h->host_poses.empty()) return MGB_OK;
+    if (!h->cache_enabled || c.kind != MGB_MAZE_DISCRETE_3D || h->host_poses.empty()) { h->cache_dirty = false; return MGB_OK; }
     const size_t slots = h->host_poses.size(), px = (size_t)c.res_h * c.res_v;
     const double bytes = (double)slots * (px * (c.obs_dtype == MGB_OBS_U8 ? 8.0 : 12.0) + px / 4.0 + 16.0 +
                                           c.res_h * (1.0 + (double)c.max_hits * sizeof(HitRec)));
-    if (bytes > h->cache_budget_gb * 1e9) return MGB_OK;
+    if (bytes > h->cache_budget_gb * 1e9) { h->cache_dirty = false; h->cache_would_fit = false; return MGB_OK; }   // a decision, not a failure
+    // From here on a failure (capture in progress, out of memory) leaves cache_dirty set: the next call retries instead of
+    // silently rendering every frame with the slow direct renderer (round-1 advice).
     // cudaMalloc/cudaFree synchronise; a capture in progress cannot build the cache
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
@@ -1672,6 +2131,8 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig);
     cudaFree(h->c_px_all); cudaFree(h->c_fmask);
+    cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc);
+    h->c_vbase = nullptr; h->c_var8 = nullptr; h->d_bake_desc = nullptr; h->n_var_frames = 0;
     h->c_px_all = nullptr; h->c_fmask = nullptr;
     h->poses = nullptr; h->pose_index = nullptr; h->c_px = nullptr; h->c_fid = nullptr; h->c_colhits = nullptr;
     h->c_hits = nullptr; h->dyn = nullptr; h->c_rgb8 = nullptr; h->c_gsig = nullptr;
@@ -1704,10 +2165,73 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
         maze3d_sig_kernel<<<(unsigned)slots, 256, 0, st>>>(c, a);
         MGB_CUDA(cudaGetLastError());
         if (h->c_px_all) MGB_CUDA(cudaMemcpyAsync(h->c_px_all, h->c_px, slots * px * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        // ---- variant frames: every pose whose image depends on k <= variant_bits foods gets its other 2^k - 1 finished
+        // frames too (the all-visible one is c_rgb8[slot]); bits = the pose's foods in ascending slot order
+        std::vector<BakeDesc> descs;
+        if (h->variant_bits > 0 && c.obs_dtype == MGB_OBS_U8 && c.task_type == MGB_MAZE_SURVIVAL && (px * 3) % 16 == 0) {
+            std::vector<uint64_t> fm(slots * 2);
+            MGB_CUDA(cudaStreamSynchronize(st));
+            MGB_CUDA(cudaMemcpy(fm.data(), h->c_fmask, slots * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            auto popc = [](uint64_t x) { int n = 0; while (x) { x &= x - 1; ++n; } return n; };
+            int bits = h->variant_bits;
+            const double room = h->cache_budget_gb * 1e9 - bytes;
+            size_t frames = 0;
+            for (; bits > 0; --bits) {                     // largest k whose frames fit the cache budget
+                frames = 0;
+                for (size_t sl = 0; sl < slots; ++sl) {
+                    const int k = popc(fm[2 * sl]) + popc(fm[2 * sl + 1]);
+                    if (k >= 1 && k <= bits) frames += ((size_t)1 << k) - 1;
+                }
+                if ((double)frames * (double)(px * 3) <= room) break;
+            }
+            if (bits > 0 && frames > 0) {
+                std::vector<int32_t> vbase(slots, -1);
+                descs.reserve(frames);
+                for (size_t sl = 0; sl < slots; ++sl) {
+                    const int k = popc(fm[2 * sl]) + popc(fm[2 * sl + 1]);
+                    if (k < 1 || k > bits) continue;
+                    vbase[sl] = (int32_t)descs.size();
+                    for (int v = 0; v < (1 << k) - 1; ++v) {
+                        BakeDesc bd;
+                        bd.slot = (int32_t)sl; bd.pad = 0;
+                        bd.present[0] = ~fm[2 * sl]; bd.present[1] = ~fm[2 * sl + 1];   // foods this pose never shows: irrelevant
+                        int bit = 0;
+                        for (int w = 0; w < 2; ++w) {
+                            uint64_t m = fm[2 * sl + w];
+                            while (m) {
+                                const uint64_t low = m & (~m + 1);
+                                m &= m - 1;
+                                if ((v >> bit) & 1) bd.present[w] |= low;
+                                ++bit;
+                            }
+                        }
+                        descs.push_back(bd);
+                    }
+                }
+                MGB_CUDA(cudaMalloc(&h->c_vbase, slots * sizeof(int32_t)));
+                MGB_CUDA(cudaMalloc(&h->c_var8, descs.size() * px * 3));
+                MGB_CUDA(cudaMalloc(&h->d_bake_desc, descs.size() * sizeof(BakeDesc)));
+                MGB_CUDA(cudaMemcpy(h->c_vbase, vbase.data(), slots * sizeof(int32_t), cudaMemcpyHostToDevice));
+                MGB_CUDA(cudaMemcpy(h->d_bake_desc, descs.data(), descs.size() * sizeof(BakeDesc), cudaMemcpyHostToDevice));
+                h->n_var_frames = (int64_t)descs.size();
+                MazeArgs av = a;
+                av.c_var8 = h->c_var8; av.bake_desc = h->d_bake_desc;
+                maze3d_varinit_kernel<<<(unsigned)descs.size(), 256, 0, st>>>(c, av);      // static colours first ...
+                MGB_CUDA(cudaGetLastError());
+            }
+        }
         a.bake = 1;
         a.do_parts = 1;
         maze3d_compose_kernel<<<(unsigned)slots, kComposeThreads, 0, st>>>(c, a);
         MGB_CUDA(cudaGetLastError());
+        if (!descs.empty()) {                               // ... then each variant's tints (compose kernel, bake mode)
+            MazeArgs av = a;
+            av.n = (int64_t)descs.size();
+            av.c_rgb8 = h->c_var8; av.bake_desc = h->d_bake_desc;
+            maze3d_compose_kernel<<<(unsigned)descs.size(), kComposeThreads, 0, st>>>(c, av);
+            MGB_CUDA(cudaGetLastError());
+            h->launches += 2;
+        }
         a.bake = 0;
         h->launches += 2;
     } else {
@@ -1716,6 +2240,7 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     MGB_CUDA(cudaStreamSynchronize(st));
     h->n_poses = (int64_t)slots;
     h->cache_ready = true;
+    h->cache_dirty = false;
     h->launches += 1;
     return MGB_OK;
 }
@@ -1726,6 +2251,11 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
     if (c.kind == MGB_MAZE_2D) {
         const int W = 2 * c.view_grid + 1;
         const size_t sm = (size_t)k2dThreads * W * W * 4;
+        if (sm > 48 * 1024 && sm > h->m2d_smem_set) {      // view_grid >= 5: above the default dynamic shared-memory limit
+            MGB_REQUIRE(sm <= 200 * 1024, "view_grid too large for the 2-D observation tile");
+            MGB_CUDA(cudaFuncSetAttribute(maze2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            h->m2d_smem_set = sm;
+        }
         maze2d_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, st>>>(c, a);
     } else {
         int rc = ensure_pose_cache(h, st);
@@ -1735,6 +2265,34 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
             a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
             a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
     a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
+            // uint8 frames whose columns are whole 16-pixel runs: ONE fused launch (logic + TMA-moved frame)
+            const size_t frame_bytes = (size_t)c.res_h * c.res_v * 3;
+            if (h->fused_step && c.obs_dtype == MGB_OBS_U8 && (c.res_v & 15) == 0 && ((size_t)c.res_h * c.res_v) % 128 == 0 &&
+                frame_bytes <= (size_t)kStepMaxChunks * kStepChunkPx * 3 && 2 * frame_bytes + 4096 <= 220 * 1024 &&
+                (reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0) {
+                if (2 * frame_bytes > 40 * 1024 && h->step_smem_set == 0) {
+                    MGB_CUDA(cudaFuncSetAttribute(maze3d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    h->step_smem_set = 220 * 1024;
+                }
+                // two CTAs per SM when two double-buffered frames each fit (128x128: 4 x 48 KB), else one
+                const int per_sm = 4 * frame_bytes + 8192 <= 220 * 1024 ? 2 : 1;
+                const int64_t grid = (int64_t)h->num_sms * per_sm;
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3((unsigned)(h->n < grid ? h->n : grid));
+                cfg.blockDim = dim3(kStepThreads);
+                cfg.dynamicSmemBytes = 2 * frame_bytes;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                MGB_CUDA(cudaLaunchKernelEx(&cfg, maze3d_step_kernel, c, a));
+                MGB_CUDA(cudaGetLastError());
+                h->launches += 1;
+                return MGB_OK;
+            }
             maze3d_logic_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
             MGB_CUDA(cudaGetLastError());
             {
@@ -1768,6 +2326,7 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
 
 extern "C" int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_dev, void *stream)
 {
+    MgbRange nvtx_range("mgb_maze_reset");
     MGB_REQUIRE(h, "null handle");
     int rc = maze_ready(h);
     if (rc) return rc;
@@ -1788,6 +2347,7 @@ extern "C" int mgb_maze_reset(mgb_maze *h, const uint8_t *mask_dev, void *obs_de
 extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, uint64_t act_seed, int32_t *act_out_dev,
                                 void *obs_dev, double *rew_dev, uint8_t *done_dev, void *stream)
 {
+    MgbRange nvtx_range("mgb_maze_rollout");
     MGB_REQUIRE(h, "null handle");
     MGB_REQUIRE(T > 0, "T must be positive");
     MGB_REQUIRE(h->c.kind == MGB_MAZE_2D || h->c.kind == MGB_MAZE_DISCRETE_3D,
@@ -1881,6 +2441,7 @@ extern "C" int mgb_maze_set_multicast(mgb_maze *h, int64_t byte_delta)
 extern "C" int mgb_maze_step_continuous(mgb_maze *h, const float *act_dev, void *obs_dev, double *rew_dev,
                                         uint8_t *done_dev, void *stream)
 {
+    MgbRange nvtx_range("mgb_maze_step_continuous");
     MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
     MGB_REQUIRE(h->c.kind == MGB_MAZE_CONTINUOUS_3D, "mgb_maze_step_continuous needs a MGB_MAZE_CONTINUOUS_3D handle");
     int rc = maze_ready(h);
@@ -1915,6 +2476,7 @@ extern "C" int mgb_maze_pose(mgb_maze *h, float *pos_dev, double *ori_dev, void 
 extern "C" int mgb_maze_step(mgb_maze *h, const int32_t *act_dev, void *obs_dev, double *rew_dev, uint8_t *done_dev,
                              void *stream)
 {
+    MgbRange nvtx_range("mgb_maze_step");
     MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
     MGB_REQUIRE(h->c.kind != MGB_MAZE_CONTINUOUS_3D, "use mgb_maze_step_continuous for the continuous maze");
     int rc = maze_ready(h);

@@ -5,9 +5,18 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <nvtx3/nvToolsExt.h>      // header-only; a no-op unless a profiler (nsys / ncu --nvtx) is attached
+
 #include "mgb200.h"
 
 void mgb_set_error(const char *fmt, ...);
+
+// NVTX range over one C-ABI call (tracing): shows the host-side extent of every entry point on a
+// profiler timeline.  Costs a few nanoseconds when nothing is attached.
+struct MgbRange {
+    explicit MgbRange(const char *name) { nvtxRangePushA(name); }
+    ~MgbRange() { nvtxRangePop(); }
+};
 
 #define MGB_CUDA(call)                                                                                   \
     do {                                                                                                 \

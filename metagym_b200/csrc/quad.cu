@@ -1555,6 +1555,7 @@ static int check_ready(const mgb_quad *h)
 
 extern "C" int mgb_quad_make_targets(mgb_quad *h, const float *act_dev, int32_t n_tasks, float *tbl_dev, void *stream)
 {
+    MgbRange nvtx_range("mgb_quad_make_targets");
     MGB_REQUIRE(h && act_dev && tbl_dev, "null argument");
     MGB_REQUIRE(n_tasks > 0, "n_tasks must be positive");
     MgbDeviceGuard guard(h->device);
@@ -1570,6 +1571,7 @@ extern "C" int mgb_quad_make_targets(mgb_quad *h, const float *act_dev, int32_t 
 extern "C" int mgb_quad_reset(mgb_quad *h, const uint8_t *mask_dev, const double *noise_dev, float *obs_dev,
                               void *stream)
 {
+    MgbRange nvtx_range("mgb_quad_reset");
     MGB_REQUIRE(h, "null handle");
     int rc = check_ready(h);
     if (rc) return rc;
@@ -1672,6 +1674,7 @@ extern "C" const char *mgb_quad_step_kernel(const mgb_quad *h)
 extern "C" int mgb_quad_step(mgb_quad *h, const float *act_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev,
                              int32_t *fail_dev, float *final_obs_dev, void *stream)
 {
+    MgbRange nvtx_range("mgb_quad_step");
     MGB_REQUIRE(h && act_dev && obs_dev && rew_dev && done_dev, "null argument");
     MGB_REQUIRE((reinterpret_cast<uintptr_t>(act_dev) & 15u) == 0, "act_dev must be 16-byte aligned");
     int rc = check_ready(h);
@@ -1686,6 +1689,7 @@ extern "C" int mgb_quad_step(mgb_quad *h, const float *act_dev, float *obs_dev, 
 extern "C" int mgb_quad_rollout(mgb_quad *h, int32_t T, const float *act_dev, uint64_t act_seed, float *act_out_dev,
                                 float *obs_dev, float *rew_dev, uint8_t *done_dev, void *stream)
 {
+    MgbRange nvtx_range("mgb_quad_rollout");
     MGB_REQUIRE(h, "null handle");
     MGB_REQUIRE(T > 0, "T must be positive");
     MGB_REQUIRE((reinterpret_cast<uintptr_t>(act_dev) & 15u) == 0, "act_dev must be 16-byte aligned");
@@ -1786,6 +1790,7 @@ static void *pinned_device_alias(const void *p)
 extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs_host, float *rew_host,
                                   uint8_t *done_host, int32_t *fail_host, float *final_obs_host, void *stream)
 {
+    MgbRange nvtx_range("mgb_quad_step_host");
     MGB_REQUIRE(h && act_host && obs_host && rew_host && done_host, "null argument");
     int rc = check_ready(h);
     if (rc) return rc;
@@ -1852,6 +1857,7 @@ extern "C" int mgb_quad_step_host(mgb_quad *h, const float *act_host, float *obs
 
 extern "C" int mgb_quad_state(mgb_quad *h, float *state_dev, int32_t *ct_dev, int load, void *stream)
 {
+    MgbRange nvtx_range("mgb_quad_state");
     MGB_REQUIRE(h && state_dev, "null argument");
     MgbDeviceGuard guard(h->device);
     QuadArgs a = base_args(h);

@@ -281,6 +281,33 @@ class _BatchedMazeBase(object):
         self.need_set_task = False
         self.need_reset = True
 
+    def update_tasks(self, task_slots, task_configs):
+        """Per-episode task resampling: replace entries `task_slots` of the task table by `task_configs`, stream-ordered
+        and without a device synchronisation (mgb_maze_update_tasks).  Envs flying a replaced slot restart on the new task.
+        With set_task(tasks) of one task per env (env2task = arange), `update_tasks(env_ids, new_tasks)` re-tasks exactly
+        those envs.  Needs the direct renderer (cache=False / more tasks than the pose-cache budget)."""
+        slots = np.ascontiguousarray(np.asarray(task_slots, dtype=np.int32).reshape(-1))
+        tasks = [task_configs] if hasattr(task_configs, "cell_walls") else list(task_configs)
+        K = len(tasks)
+        assert slots.shape == (K,), "one task per slot"
+        walls = np.ascontiguousarray(np.stack([np.asarray(t.cell_walls) for t in tasks]).astype(np.int8))
+        texts = np.ascontiguousarray(np.stack([np.asarray(t.cell_texts) for t in tasks]).astype(np.int8))
+        food = np.ascontiguousarray(np.stack([np.asarray(t.food_rewards, dtype=np.float64) for t in tasks]))
+        itv = np.ascontiguousarray(np.stack([np.asarray(t.food_interval) for t in tasks]).astype(np.int32))
+        assert walls.shape[1:] == (self._n_cells, self._n_cells), "all tasks of one batch must share the maze size"
+        sc = (_lib.MazeTaskScalars * K)()
+        for k, t in enumerate(tasks):
+            assert t.agent_height < t.wall_height and t.agent_height > 0, "the agent height must be > 0 and < wall height"
+            sc[k].start[:] = [int(t.start[0]), int(t.start[1])]
+            sc[k].goal[:] = [int(t.goal[0]), int(t.goal[1])]
+            sc[k].cell_size, sc[k].wall_height, sc[k].agent_height = t.cell_size, t.wall_height, t.agent_height
+            sc[k].initial_life, sc[k].max_life = t.initial_life, t.max_life
+            sc[k].step_reward, sc[k].goal_reward = t.step_reward, t.goal_reward
+        _lib.check(self._lib.mgb_maze_update_tasks(self._h, K, slots.ctypes.data, walls.ctypes.data, texts.ctypes.data,
+                                                   food.ctypes.data, itv.ctypes.data, sc, self._stream()))
+        for k, sl in enumerate(slots):
+            self.tasks[int(sl)] = tasks[k]
+
     def sample_task(self, **kwargs):
         """Convenience: draw one task with the host sampler (reference usage: MazeTaskSampler(...), test.py:12)."""
         return MazeTaskSampler(**kwargs)
@@ -434,7 +461,7 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
 
     def __init__(self, enable_render=False, render_scale=480, resolution=(320, 320), max_steps=5000,
                  task_type="SURVIVAL", num_envs=1, device=0, auto_reset=False, env_index_base=0, squeeze=True,
-                 obs_dtype="int32", textures=None, max_vision_range=12.0, fol_angle=0.6 * PI):
+                 obs_dtype="int32", textures=None, max_vision_range=12.0, fol_angle=0.6 * PI, cache=None):
         if enable_render:
             raise NotImplementedError("enable_render=True needs a display; the batched engine is headless")
         self.enable_render = False
@@ -442,6 +469,7 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
         assert obs_dtype in ("int32", "uint8")
         self.obs_dtype = obs_dtype
         self.max_vision_range, self.fol_angle = max_vision_range, fol_angle
+        self.cache = cache                  # None: library default (on, MGB_MAZE_CACHE); False: direct renderer only
         self.textures = textures if textures is not None else synthetic_textures(seed=0)
         self._setup(num_envs, device, task_type, max_steps, auto_reset, env_index_base, squeeze)
         torch = self._torch
@@ -468,6 +496,8 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
         return self._rollout(T, actions, act_seed, want_actions, out)
 
     def _after_create(self):
+        if self.cache is not None:
+            _lib.check(self._lib.mgb_maze_set_cache(self._h, int(bool(self.cache))))
         grounds = np.ascontiguousarray(self.textures[0], dtype=np.uint8)
         ceil = np.ascontiguousarray(self.textures[1], dtype=np.uint8)
         ts = grounds.shape[1]

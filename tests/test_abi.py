@@ -93,3 +93,26 @@ def test_host_config_parsing_agrees_with_the_oracle():
     del bad["thrust"]
     with pytest.raises(RuntimeError, match="Error in loading configuration"):
         build_cfg(bad, 0.01, 10, "hovering_control", 1.0)
+
+
+def test_gym_registration_ids_match_the_reference():
+    """quadrotor/__init__.py:20-32 and metamaze/__init__.py:21-54 register four ids on import; register_envs() registers the
+    same ids with the same default kwargs (enable_render off: headless) on whatever `register` it is given."""
+    from metagym_b200.registration import SPECS, register_envs
+    seen = {}
+
+    class Reg(object):
+        @staticmethod
+        def register(id, entry_point, kwargs):
+            seen[id] = (entry_point, kwargs)
+
+    ids = register_envs(Reg)
+    assert ids == ["quadrotor-v0", "meta-maze-continuous-3D-v0", "meta-maze-discrete-3D-v0", "meta-maze-2D-v0"]
+    assert seen["quadrotor-v0"][1] == {"dt": 0.01, "nt": 1000, "seed": 0, "task": "no_collision", "map_file": None,
+                                       "simulator_conf": None, "healthy_reward": 1.0}
+    assert seen["meta-maze-discrete-3D-v0"][1]["max_steps"] == 200 and seen["meta-maze-2D-v0"][1]["view_grid"] == 1
+    assert seen["meta-maze-continuous-3D-v0"][1]["resolution"] == (256, 256)
+    import importlib
+    for _, entry, _ in SPECS:                      # every entry point resolves to a class of this package
+        mod, cls = entry.split(":")
+        assert hasattr(importlib.import_module(mod), cls)

@@ -191,6 +191,115 @@ def test_pose_cache_equals_direct_render_at_config4_shape(torch_mod, maze_golden
     b.close()
 
 
+@pytest.mark.parametrize("res,task_type", [((128, 128), "SURVIVAL"), ((64, 48), "SURVIVAL"), ((96, 80), "ESCAPE"),
+                                           ((256, 256), "SURVIVAL")])
+def test_fused_step_kernel_equals_two_kernel_path(torch_mod, maze_golden, textures, monkeypatch, res, task_type):
+    """uint8 frames take maze3d_step_kernel (logic + TMA-moved baked frame + in-smem patches, one launch); it must equal the
+    logic + compose kernel pair bit for bit: partial last chunk (64x48 = one 9 KB chunk), many chunks (256x256 = 16),
+    tinted groups under the life bar, auto-reset, reset() frames."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 20, g["tasks15.scalars"][k]) for k in range(6)]
+    N = 300
+    kw = dict(resolution=res, max_steps=50, task_type=task_type, squeeze=False, auto_reset=True, obs_dtype="uint8",
+              textures=textures, num_envs=N)
+    monkeypatch.setenv("MGB_MAZE_FUSED_STEP", "1")
+    a = BatchedMetaMazeDiscrete3D(**kw)
+    monkeypatch.setenv("MGB_MAZE_FUSED_STEP", "0")
+    b = BatchedMetaMazeDiscrete3D(**kw)
+    monkeypatch.delenv("MGB_MAZE_FUSED_STEP")
+    for e in (a, b):
+        e.set_task(tasks)
+    assert torch.equal(a.reset(), b.reset())
+    gen = torch.Generator(device="cuda").manual_seed(13)
+    changed = 0
+    for t in range(70):
+        act = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2), (t, int((o1 != o2).sum()))
+        assert torch.equal(r1, r2) and torch.equal(d1, d2)
+        changed += int(d1.sum())
+    assert changed > 0
+    ag1, l1 = a.agent_state()
+    ag2, l2 = b.agent_state()
+    assert torch.equal(ag1, ag2) and torch.equal(l1, l2)
+    a.close()
+    b.close()
+
+
+def test_maze2d_large_view_grid(torch_mod, maze_golden):
+    """view_grid = 5: the 2-D step kernel needs 62 KB of dynamic shared memory (round-1 advice: the attribute was only
+    raised on the rollout path, every step()/reset() failed with 'invalid argument')."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D
+    from oracle.maze_oracle import OracleMaze
+    g = maze_golden
+    task = task_from_arrays(g["tasks15.walls"][0], g["tasks15.texts"][0], g["tasks15.food"][0], g["tasks15.interval"][0] // 10,
+                            g["tasks15.scalars"][0])
+    env = BatchedMetaMaze2D(max_steps=30, task_type="SURVIVAL", view_grid=5, num_envs=3, squeeze=False)
+    ora = OracleMaze("2D", "SURVIVAL", 30, 5)
+    env.set_task(task)
+    ora.set_task(task)
+    assert np.array_equal(env.reset().cpu().numpy()[0], ora.reset())
+    rs = np.random.RandomState(2)
+    for t in range(12):
+        act = int(rs.randint(4))
+        obs, rew, done, _ = env.step(torch.full((3,), act, device="cuda", dtype=torch.int32))
+        o2, r2, d2, _ = ora.step(act)
+        assert np.array_equal(obs.cpu().numpy()[2], o2) and float(rew[1]) == r2 and bool(done[0]) == d2
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["2D", "3D"])
+def test_update_tasks_equals_fresh_env(torch_mod, maze_golden, textures, kind):
+    """Per-episode task resampling: update_tasks() on a subset of slots (stream-ordered, no device sync) must leave the batch
+    exactly where a fresh env with the final task table, reset on those envs, would be -- the untouched envs keep their
+    episodes, the re-tasked envs restart, and every later step matches the oracle of each env's current task."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D
+    from oracle.maze_oracle import OracleMaze
+    g = maze_golden
+    pool = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                             g["tasks15.interval"][k] // 10, g["tasks15.scalars"][k]) for k in range(8)]
+    N = 12
+    if kind == "2D":
+        env = BatchedMetaMaze2D(max_steps=30, task_type="SURVIVAL", view_grid=1, num_envs=N, squeeze=False)
+        oras = [OracleMaze("2D", "SURVIVAL", 30, 1) for _ in range(N)]
+    else:
+        env = BatchedMetaMazeDiscrete3D(resolution=(32, 24), max_steps=30, task_type="SURVIVAL", num_envs=N, squeeze=False,
+                                        textures=textures, cache=False)
+        oras = [OracleMaze("3D", "SURVIVAL", 30, 1, (32, 24), textures=textures) for _ in range(N)]
+    cur = [pool[i % 4] for i in range(N)]                       # one table slot per env
+    env.set_task(cur, env2task=np.arange(N))
+    obs = env.reset().cpu().numpy()
+    for i, o in enumerate(oras):
+        o.set_task(cur[i])
+        assert np.array_equal(obs[i], o.reset())
+    rs = np.random.RandomState(4)
+    for t in range(40):
+        if t in (7, 8, 19, 33):                                  # re-task a few envs between steps, twice in a row too
+            ids = rs.choice(N, size=4, replace=False)
+            new = [pool[4 + int(rs.randint(4))] for _ in ids]
+            env.update_tasks(ids, new)
+            for i, nt in zip(ids, new):
+                oras[i].set_task(nt)
+                oras[i].reset()
+        act = rs.randint(0, 4, size=N)
+        obs, rew, done, _ = env.step(torch.as_tensor(act, dtype=torch.int32).cuda())
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for i, o in enumerate(oras):
+            o2, r2, d2, _ = o.step(int(act[i]))
+            assert np.array_equal(obs[i], o2) and rew[i] == r2 and bool(done[i]) == d2, (t, i)
+            if d2:
+                o.reset()
+        if done.any():
+            env.reset(mask=torch.as_tensor(done).cuda())
+    env.close()
+
+
 def test_config4_shape_properties(torch_mod, maze_golden, textures):
     """BASELINE config 4 shape per GPU (1024 envs, 15x15, 128x128, uint8): sharding invariance + determinism."""
     torch = torch_mod
