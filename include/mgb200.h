@@ -219,6 +219,11 @@ int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *walls_host, co
  * (ray_caster_utils.py:66-209 per frame, like the reference) -- the mode for task tables that change every episode. */
 int mgb_maze_set_cache(mgb_maze *h, int enabled);
 
+/* Pose-cache statistics after the first reset/step (reporting only): out[0] cached poses, out[1] extra variant frames,
+ * out[2] variant bits in use (poses whose image depends on k <= bits foods have all 2^k finished frames), out[3] bytes,
+ * out[4..12] poses by k (0..7, and 8 = eight or more), out[13] 1 if the cache is in use. */
+int mgb_maze_cache_info(const mgb_maze *h, int64_t out[16]);
+
 /* Per-episode task resampling (MazeBase.set_task on a fresh TaskConfig every episode, maze_base.py:19-38, at the scale of
  * SURVEY.md 8f row 3): replace `count` entries of the table mgb_maze_set_task built -- task_slots_host [count] indices into
  * it, the other arrays as for mgb_maze_set_task but [count] long -- STREAM-ORDERED and without any device synchronisation

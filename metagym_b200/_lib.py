@@ -64,6 +64,7 @@ SIGNATURES = {
     "mgb_maze_set_textures": (ctypes.c_int, [vp, vp, c_i32, vp, c_i32]),
     "mgb_maze_set_task": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars), vp]),
     "mgb_maze_set_cache": (ctypes.c_int, [vp, ctypes.c_int]),
+    "mgb_maze_cache_info": (ctypes.c_int, [vp, vp]),
     "mgb_maze_update_tasks": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars), vp]),
     "mgb_maze_reset": (ctypes.c_int, [vp, vp, vp, vp]),
     "mgb_maze_step": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),

@@ -518,7 +518,7 @@ struct BakeDesc {                // one variant frame to bake
     int32_t slot, pad;
     uint64_t present[2];
 };
-constexpr int kVariantBitsMax = 6;
+constexpr int kVariantBitsMax = 7;
 
 // finished uint8 frame the env's observation starts from
 __device__ __forceinline__ const uint8_t *frame_of(const MazeArgs &a, const EnvDyn &d, size_t frame_bytes)
@@ -1193,7 +1193,6 @@ __global__ void __launch_bounds__(kComposeThreads, 5) maze3d_compose_kernel(cons
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStepThreads = 128;
 constexpr int kStepChunkPx = 4096;          // pixels per bulk copy: 12 KB of uint8 RGB
-constexpr int kStepMaxChunks = 16;          // frames up to 65 536 pixels (192 KB) -- larger screens use the two-kernel path
 
 // one tinted 4-pixel group (4 consecutive rows of ONE screen column): cached static colour -> floor/ceiling tint ->
 // crossings of the column -> life bar (ray_caster_utils.py:118-205), packed to 12 uint8 (values above 255 clamp: MGB_OBS_U8).
@@ -1257,18 +1256,22 @@ __device__ __forceinline__ void compose_group_u8(const MazeConst &c, const EnvDy
 }
 
 constexpr int kStepBatch = 16;              // envs whose step logic one CTA runs side by side before moving their frames
+constexpr int kStepSlots = 8;               // 12 KB chunk slots of a CTA's shared-memory ring (7 bulk loads in flight)
 
 __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __grid_constant__ MazeConst c,
                                                                       const __grid_constant__ MazeArgs a)
 {
     // Two CTAs per SM; CTA j owns the envs j, j + G, j + 2G, ... (G = grid size).  Per pass of up to kStepBatch envs:
-    //  (1) threads 0..B-1 run the step logic of the B envs SIDE BY SIDE (each is a chain of ~5 dependent L2 round trips:
+    //  (1) threads 0..B-1 run the step logic of the B envs SIDE BY SIDE (each is a chain of ~4 dependent L2 round trips:
     //      one chain per frame would cost more than the frame's copy), leaving B EnvDyn records in shared memory;
-    //  (2) the B frames stream through two shared-memory frame buffers: while frame k is patched and stored, the bulk
-    //      loads of frame k + 1 are already in flight.
-    extern __shared__ __align__(128) uint8_t s_frames[];         // 2 x (H * V * 3 bytes)
+    //  (2) the B frames stream, 12 KB chunk by chunk, through a ring of kStepSlots shared-memory slots: warp 0 waits for
+    //      chunk u, draws the life bar into it, sends it to `obs` with one bulk store, and -- as soon as the store of chunk
+    //      u - 1 has left its slot -- issues the bulk load of chunk u + 7 into it, so seven loads stay in flight across
+    //      frame boundaries.  The other warps only join for the rare frames that still need float64 tints (poses whose
+    //      image depends on more foods than have variant frames).
+    extern __shared__ __align__(128) uint8_t s_ring[];           // kStepSlots x 12 KB
     __shared__ EnvDyn s_dyn[kStepBatch];
-    __shared__ __align__(8) uint64_t s_bar[2][kStepMaxChunks];
+    __shared__ __align__(8) uint64_t s_bar[kStepSlots];
     __shared__ int s_nslow;
     __shared__ uint16_t s_slow[1024];                            // queued tinted groups of one chunk (group index in the chunk)
     const int H = c.res_h, V = c.res_v, total_px = H * V;
@@ -1278,30 +1281,22 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
     const int lb_sx = trunc_i(c.lb_sx), lb_sy = trunc_i(c.lb_sy);
     int lb_ey = trunc_i(c.lb_sy + c.lb_w);
     if (lb_ey > V) lb_ey = V;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool warp0 = tid < 32;
     const int v_shift = (V & (V - 1)) == 0 ? 31 - __clz(V) : -1;
     asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b)
-            for (int k = 0; k < n_chunks; ++k) mgb_mbar_init(&s_bar[b][k], 1);
+        for (int k = 0; k < kStepSlots; ++k) mgb_mbar_init(&s_bar[k], 1);
         mgb_fence_mbar_init();
         s_nslow = 0;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
-    uint32_t uses[2] = {0u, 0u};                                  // how often each frame buffer has been filled (mbarrier parity)
-    auto fetch = [&](const EnvDyn &dd, int buf) {                 // thread 0: the pose's baked frame, chunk by chunk
-        const uint8_t *g8 = frame_of(a, dd, frame_bytes);
-        for (int k = 0; k < n_chunks; ++k) {
-            const uint32_t off = (uint32_t)k * kStepChunkPx * 3u;
-            const uint32_t bytes = frame_bytes - off < kStepChunkPx * 3u ? frame_bytes - off : kStepChunkPx * 3u;
-            mgb_mbar_expect_tx(&s_bar[buf][k], bytes);
-            mgb_bulk_load(s_frames + (size_t)buf * frame_bytes + off, g8 + off, bytes, &s_bar[buf][k]);
-        }
-    };
+    uint32_t g0 = 0;                                             // chunks this CTA has moved in earlier passes (ring position)
     for (int64_t base = blockIdx.x; base < a.n; base += (int64_t)gridDim.x * kStepBatch) {
         const int64_t left = (a.n - base + gridDim.x - 1) / gridDim.x;
         const int B = (int)(left < kStepBatch ? left : kStepBatch);
+        const int M = B * n_chunks;                               // chunks of this pass
         // ---- (1) step logic of the pass's envs, one thread each (what maze3d_logic_kernel does for the two-kernel path)
         if (tid < B) {
             const int64_t e = base + (int64_t)tid * gridDim.x;
@@ -1323,23 +1318,26 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
             s_dyn[tid] = make_dyn(c, a, blob, task, s, eaten);
         }
         __syncthreads();
-        // ---- (2) the frames
+        // chunk u of the pass: frame u / n_chunks, chunk u % n_chunks, ring slot (g0 + u) % kStepSlots
+        auto issue = [&](int u) {                                  // thread 0 only
+            const int it = u / n_chunks, k = u - it * n_chunks;
+            const uint32_t off = (uint32_t)k * kStepChunkPx * 3u;
+            const uint32_t bytes = frame_bytes - off < kStepChunkPx * 3u ? frame_bytes - off : kStepChunkPx * 3u;
+            const int slot = (int)((g0 + (uint32_t)u) % kStepSlots);
+            mgb_mbar_expect_tx(&s_bar[slot], bytes);
+            mgb_bulk_load(s_ring + (size_t)slot * (kStepChunkPx * 3), frame_of(a, s_dyn[it], frame_bytes) + off, bytes, &s_bar[slot]);
+        };
         if (tid == 0) {
-            mgb_bulk_wait_read<0>();                                   // the previous pass's stores have left the buffers
-            fetch(s_dyn[0], 0);
+            mgb_bulk_wait_read<0>();                               // the previous pass's stores have left the ring
+            for (int u = 0; u < kStepSlots - 1 && u < M; ++u) issue(u);
         }
         for (int it = 0; it < B; ++it) {
-            const int buf = it & 1;
-            const uint32_t parity = uses[buf] & 1u;
-            uses[buf] += 1u;
-            if (tid == 0 && it + 1 < B) {
-                mgb_bulk_wait_read<0>();                               // frame it-1 (other buffer) has been read by its stores
-                fetch(s_dyn[it + 1], buf ^ 1);
-            }
+            __syncthreads();                                       // frame boundary: nobody runs more than a frame ahead of warp 0
             const int64_t e = base + (int64_t)it * gridDim.x;
             const EnvDyn d = s_dyn[it];
-            uint8_t *s_frame = s_frames + (size_t)buf * frame_bytes;
-            const uint32_t miss_sig = (uint32_t)d.pad & 0xFFu;
+            const uint32_t miss_sig = (uint32_t)d.pad & 0xFFu;     // != 0: some groups need the float64 path (uniform)
+            uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * frame_bytes;
+            if (!warp0 && !miss_sig) continue;
             const uint8_t *blob = a.blobs + (int64_t)d.task * c.blob_bytes;
             const double *fval = reinterpret_cast<const double *>(blob + c.off_fval);
             const uint32_t *gpx = a.c_px + (size_t)d.slot * total_px;
@@ -1347,69 +1345,72 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
             const uint8_t *colhits = a.c_colhits + (size_t)d.slot * H;
             const HitRec *ghits = reinterpret_cast<const HitRec *>(a.c_hits) + (size_t)d.slot * H * c.max_hits;
             const uint8_t *gsig = a.c_gsig + (size_t)d.slot * (total_px / 4);
-            uint8_t *gobs = reinterpret_cast<uint8_t *>(a.obs) + (size_t)e * frame_bytes;
             const uint32_t miss4 = miss_sig * 0x01010101u;
             for (int k = 0; k < n_chunks; ++k) {
+                const int u = it * n_chunks + k;
+                const uint32_t gu = g0 + (uint32_t)u;
+                const int slot = (int)(gu % kStepSlots);
+                const uint32_t parity = (gu / kStepSlots) & 1u;
+                uint8_t *s_chunk = s_ring + (size_t)slot * (kStepChunkPx * 3);
                 const int q0 = k * kStepChunkPx, q1 = q0 + kStepChunkPx < total_px ? q0 + kStepChunkPx : total_px;
                 const uint32_t off = (uint32_t)q0 * 3u, bytes = (uint32_t)(q1 - q0) * 3u;
-                // life bar columns inside this chunk (the bar is drawn last, maze_discrete_3d.py:118-126)
-                const int h0 = q0 / V, h1 = (q1 + V - 1) / V;          // columns [h0, h1) intersect the chunk
-                const int bh0 = lb_sx > h0 ? lb_sx : h0, bh1 = d.bar_end < h1 ? d.bar_end : h1;
-                const bool bar = survival && bh0 < bh1 && lb_sy < lb_ey;
-                const bool patch = miss_sig != 0 || bar;               // uniform over the CTA
-                if (patch) {
-                    if (miss_sig) {
-                        // queue the chunk's tinted groups (they cluster in a few columns, i.e. in a few signature words) ...
-                        for (int g4 = (q0 >> 4) + tid; g4 < (q1 >> 4); g4 += kStepThreads) {
-                            uint32_t hit = __ldg(reinterpret_cast<const uint32_t *>(gsig) + g4) & miss4;
-                            while (hit) {
-                                const int g = (__ffs(hit) - 1) >> 3;
-                                hit &= ~(0xFFu << (8 * g));
-                                s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)(((g4 << 2) + g) - (q0 >> 2));
-                            }
+                if (miss_sig) {
+                    // whole CTA: queue the chunk's tinted groups (they cluster in a few columns) ...
+                    for (int g4 = (q0 >> 4) + tid; g4 < (q1 >> 4); g4 += kStepThreads) {
+                        uint32_t hit = __ldg(reinterpret_cast<const uint32_t *>(gsig) + g4) & miss4;
+                        while (hit) {
+                            const int g = (__ffs(hit) - 1) >> 3;
+                            hit &= ~(0xFFu << (8 * g));
+                            s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)(((g4 << 2) + g) - (q0 >> 2));
                         }
-                        __syncthreads();
-                        const int n_slow = s_nslow;
-                        mgb_mbar_wait(&s_bar[buf][k], parity);
-                        // ... and share them out evenly: float64 blends of the cached static layers, written over the
-                        // baked pixels in shared memory
-                        for (int i = tid; i < n_slow; i += kStepThreads) {
-                            const int q = q0 + 4 * (int)s_slow[i];
-                            const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
-                            uint32_t pk[3];
-                            compose_group_u8(c, d, gpx, gfid, colhits, ghits, fval, survival, q, d_h, q - d_h * V, lb_sx, lb_sy,
-                                             lb_ey, pk);
-                            uint32_t *dst = reinterpret_cast<uint32_t *>(s_frame + (size_t)q * 3);
-                            dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
-                        }
-                        __syncthreads();                               // queue drained; the bar overwrites tinted pixels
-                        if (tid == 0) s_nslow = 0;
-                    } else {
-                        mgb_mbar_wait(&s_bar[buf][k], parity);
                     }
-                    if (bar) {
+                    __syncthreads();
+                    const int n_slow = s_nslow;
+                    mgb_mbar_wait(&s_bar[slot], parity);
+                    // ... and share them out evenly: float64 blends of the cached static layers over the baked pixels
+                    for (int i = tid; i < n_slow; i += kStepThreads) {
+                        const int q = q0 + 4 * (int)s_slow[i];
+                        const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
+                        uint32_t pk[3];
+                        compose_group_u8(c, d, gpx, gfid, colhits, ghits, fval, survival, q, d_h, q - d_h * V, lb_sx, lb_sy, lb_ey, pk);
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(s_chunk + (size_t)(q - q0) * 3);
+                        dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
+                    }
+                    mgb_fence_proxy_async();
+                    __syncthreads();                               // tints done before the bar is drawn over them / the store
+                    if (tid == 0) s_nslow = 0;
+                }
+                if (warp0) {
+                    if (!miss_sig) mgb_mbar_wait(&s_bar[slot], parity);
+                    // life bar columns inside this chunk (drawn last, maze_discrete_3d.py:118-126)
+                    const int h0 = q0 / V, h1 = (q1 + V - 1) / V;      // columns [h0, h1) intersect the chunk
+                    const int bh0 = lb_sx > h0 ? lb_sx : h0, bh1 = d.bar_end < h1 ? d.bar_end : h1;
+                    if (survival && bh0 < bh1 && lb_sy < lb_ey) {
                         const int rows = lb_ey - lb_sy;
-                        for (int i = tid; i < (bh1 - bh0) * rows; i += kStepThreads) {
+                        for (int i = lane; i < (bh1 - bh0) * rows; i += 32) {
                             const int d_h = bh0 + i / rows, d_v = lb_sy + i % rows;
                             const int q = d_h * V + d_v;
                             if (q >= q0 && q < q1) {
-                                uint8_t *px = s_frame + (size_t)q * 3;
+                                uint8_t *px = s_chunk + (size_t)(q - q0) * 3;
                                 px[0] = 255; px[1] = 0; px[2] = 0;
                             }
                         }
+                        mgb_fence_proxy_async();
                     }
-                    mgb_fence_proxy_async();
-                    __syncthreads();
-                } else if (tid == 0) {
-                    mgb_mbar_wait(&s_bar[buf][k], parity);
-                }
-                if (tid == 0) {
-                    mgb_bulk_store(gobs + off, s_frame + off, bytes);
-                    mgb_bulk_commit();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mgb_bulk_store(gobs + off, s_chunk, bytes);
+                        mgb_bulk_commit();
+                        if (u + kStepSlots - 1 < M) {
+                            mgb_bulk_wait_read<1>();               // the store of chunk u - 1 has left its slot ...
+                            issue(u + kStepSlots - 1);             // ... which is the slot of chunk u + 7
+                        }
+                    }
                 }
             }
         }
-        __syncthreads();                                               // s_dyn is rewritten by the next pass
+        g0 += (uint32_t)M;
+        __syncthreads();                                           // s_dyn is rewritten by the next pass
     }
     if (tid == 0) mgb_bulk_wait_read<0>();       // shared memory must outlive the copies
 }
@@ -1533,6 +1534,7 @@ struct mgb_maze {
     double *cori = nullptr;
     double *coltab_d = nullptr;
     // pose cache
+    int step_pdl = 1;              // MGB_MAZE_PDL=0: no programmatic dependent launch between consecutive fused steps
     int fused_step = 1;            // MGB_MAZE_FUSED_STEP=0: logic kernel + compose kernel instead of maze3d_step_kernel
     size_t step_smem_set = 0, m2d_smem_set = 0;
     int cache_enabled = 1;         // MGB_MAZE_CACHE=0 disables (direct renderer only)
@@ -1559,7 +1561,10 @@ struct mgb_maze {
     uint8_t *c_var8 = nullptr;
     void *d_bake_desc = nullptr;
     int64_t n_var_frames = 0;
-    int variant_bits = 4;          // MGB_MAZE_VARIANT_BITS: poses that depend on <= this many foods get all 2^k frames (0 = off)
+    int64_t k_hist[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // poses by the number of foods their image depends on (8 = 8 or more)
+    int variant_bits_used = 0;
+    double cache_bytes = 0.0;
+    int variant_bits = 7;          // MGB_MAZE_VARIANT_BITS: poses that depend on <= this many foods get all 2^k frames (0 = off)
     uint8_t *c_gsig = nullptr;
     HitRec *c_hits = nullptr;
     EnvDyn *dyn = nullptr;
@@ -1655,6 +1660,7 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     MGB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     if (const char *ev = getenv("MGB_MAZE_FUSED_STEP")) h->fused_step = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_MAZE_PDL")) h->step_pdl = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_VARIANT_BITS")) {
         h->variant_bits = atoi(ev);
         if (h->variant_bits < 0) h->variant_bits = 0;
@@ -1743,6 +1749,19 @@ extern "C" int mgb_maze_set_options(mgb_maze *h, int auto_reset)
 {
     MGB_REQUIRE(h, "null handle");
     h->auto_reset = auto_reset ? 1 : 0;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_cache_info(const mgb_maze *h, int64_t out[16])
+{
+    MGB_REQUIRE(h && out, "null argument");
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    out[0] = h->cache_ready ? h->n_poses : 0;
+    out[1] = h->cache_ready ? h->n_var_frames : 0;
+    out[2] = h->variant_bits_used;
+    out[3] = (int64_t)h->cache_bytes;
+    for (int k = 0; k < 9; ++k) out[4 + k] = h->k_hist[k];
+    out[13] = h->cache_ready ? 1 : 0;
     return MGB_OK;
 }
 
@@ -2173,6 +2192,11 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
             MGB_CUDA(cudaStreamSynchronize(st));
             MGB_CUDA(cudaMemcpy(fm.data(), h->c_fmask, slots * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
             auto popc = [](uint64_t x) { int n = 0; while (x) { x &= x - 1; ++n; } return n; };
+            for (int k = 0; k < 9; ++k) h->k_hist[k] = 0;
+            for (size_t sl = 0; sl < slots; ++sl) {
+                const int k = popc(fm[2 * sl]) + popc(fm[2 * sl + 1]);
+                h->k_hist[k < 8 ? k : 8] += 1;
+            }
             int bits = h->variant_bits;
             const double room = h->cache_budget_gb * 1e9 - bytes;
             size_t frames = 0;
@@ -2184,6 +2208,7 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
                 }
                 if ((double)frames * (double)(px * 3) <= room) break;
             }
+            h->variant_bits_used = bits;
             if (bits > 0 && frames > 0) {
                 std::vector<int32_t> vbase(slots, -1);
                 descs.reserve(frames);
@@ -2239,6 +2264,7 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     }
     MGB_CUDA(cudaStreamSynchronize(st));
     h->n_poses = (int64_t)slots;
+    h->cache_bytes = bytes + (double)h->n_var_frames * (double)(px * 3);
     h->cache_ready = true;
     h->cache_dirty = false;
     h->launches += 1;
@@ -2268,24 +2294,23 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
             // uint8 frames whose columns are whole 16-pixel runs: ONE fused launch (logic + TMA-moved frame)
             const size_t frame_bytes = (size_t)c.res_h * c.res_v * 3;
             if (h->fused_step && c.obs_dtype == MGB_OBS_U8 && (c.res_v & 15) == 0 && ((size_t)c.res_h * c.res_v) % 128 == 0 &&
-                frame_bytes <= (size_t)kStepMaxChunks * kStepChunkPx * 3 && 2 * frame_bytes + 4096 <= 220 * 1024 &&
+                frame_bytes <= (size_t)64 * kStepChunkPx * 3 &&
                 (reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0) {
-                if (2 * frame_bytes > 40 * 1024 && h->step_smem_set == 0) {
-                    MGB_CUDA(cudaFuncSetAttribute(maze3d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                    h->step_smem_set = 220 * 1024;
+                const size_t ring_bytes = (size_t)kStepSlots * kStepChunkPx * 3;       // 96 KB: two CTAs per SM
+                if (h->step_smem_set == 0) {
+                    MGB_CUDA(cudaFuncSetAttribute(maze3d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+                    h->step_smem_set = ring_bytes;
                 }
-                // two CTAs per SM when two double-buffered frames each fit (128x128: 4 x 48 KB), else one
-                const int per_sm = 4 * frame_bytes + 8192 <= 220 * 1024 ? 2 : 1;
-                const int64_t grid = (int64_t)h->num_sms * per_sm;
+                const int64_t grid = (int64_t)h->num_sms * 2;
                 cudaLaunchConfig_t cfg;
                 memset(&cfg, 0, sizeof(cfg));
                 cfg.gridDim = dim3((unsigned)(h->n < grid ? h->n : grid));
                 cfg.blockDim = dim3(kStepThreads);
-                cfg.dynamicSmemBytes = 2 * frame_bytes;
+                cfg.dynamicSmemBytes = ring_bytes;
                 cfg.stream = st;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                attr[0].val.programmaticStreamSerializationAllowed = h->step_pdl ? 1 : 0;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
                 MGB_CUDA(cudaLaunchKernelEx(&cfg, maze3d_step_kernel, c, a));

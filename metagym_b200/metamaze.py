@@ -495,6 +495,14 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
             raise NotImplementedError("fused rollout: MetaMaze2D and MetaMazeDiscrete3D")
         return self._rollout(T, actions, act_seed, want_actions, out)
 
+    def cache_info(self):
+        """Pose-cache statistics (valid after the first reset()/step()): dict(poses, variant_frames, variant_bits, bytes,
+        poses_by_food_count [k = 0..7, >= 8], in_use)."""
+        out = (ctypes.c_int64 * 16)()
+        _lib.check(self._lib.mgb_maze_cache_info(self._h, out))
+        return {"poses": int(out[0]), "variant_frames": int(out[1]), "variant_bits": int(out[2]), "bytes": int(out[3]),
+                "poses_by_food_count": [int(out[4 + k]) for k in range(9)], "in_use": bool(out[13])}
+
     def _after_create(self):
         if self.cache is not None:
             _lib.check(self._lib.mgb_maze_set_cache(self._h, int(bool(self.cache))))
