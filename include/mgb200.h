@@ -171,6 +171,7 @@ const char *mgb_quad_step_kernel(const mgb_quad *h);
 
 #define MGB_OBS_U8 0  /* min(value, 255) as uint8 (3-D only; reference values can reach ~350 on near-floor pixels) */
 #define MGB_OBS_I32 1 /* exact reference values as int32 (ray_caster_utils.py:79)                                 */
+#define MGB_OBS_F32 2 /* the same exact values as float32: the dtype observation_space declares (maze_env.py:37-39)  */
 
 /* Scalars of one TaskConfig (maze_task.py:15-17,176-190). */
 typedef struct mgb_maze_task_scalars {

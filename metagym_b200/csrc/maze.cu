@@ -527,6 +527,9 @@ __device__ __forceinline__ const uint8_t *frame_of(const MazeArgs &a, const EnvD
 }
 
 __device__ __forceinline__ int trunc_i(double x) { return (int)x; }   // cvt.rzi: python/numba int()
+// 32-bit observation word of a pixel value: the integer itself (MGB_OBS_I32, what the reference's array holds) or the same
+// value as float32 (MGB_OBS_F32, the dtype the reference's observation_space declares, maze_env.py:37-39)
+#define MGB_OBS_WORD(c, v) ((c).obs_dtype == MGB_OBS_F32 ? __float_as_int((float)(v)) : (v))
 
 // rgb = light * (alpha * FAR_RGB + (1 - alpha) * texel), FAR_RGB = 0 (ray_caster_utils.py:7,118)
 __device__ __forceinline__ void shade(int rgb[3], double light, double oma, uint32_t texel)
@@ -967,7 +970,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                         buf[p * 3 + 2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
                     } else {
                         int32_t *o = reinterpret_cast<int32_t *>(buf) + p * 3;
-                        o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
+                        o[0] = MGB_OBS_WORD(c, rgb[0]); o[1] = MGB_OBS_WORD(c, rgb[1]); o[2] = MGB_OBS_WORD(c, rgb[2]);
                     }
                 }
             }
@@ -1256,7 +1259,8 @@ __device__ __forceinline__ void compose_group_u8(const MazeConst &c, const EnvDy
 }
 
 constexpr int kStepBatch = 16;              // envs whose step logic one CTA runs side by side before moving their frames
-constexpr int kStepSlots = 8;               // 12 KB chunk slots of a CTA's shared-memory ring (7 bulk loads in flight)
+constexpr int kStepSlots = 8;               // 12 KB chunk slots of a CTA's shared-memory ring
+constexpr int kStepSlack = 3;               // bulk stores that may still be reading their slot (=> 5 bulk loads in flight)
 
 __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __grid_constant__ MazeConst c,
                                                                       const __grid_constant__ MazeArgs a)
@@ -1266,8 +1270,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
     //      one chain per frame would cost more than the frame's copy), leaving B EnvDyn records in shared memory;
     //  (2) the B frames stream, 12 KB chunk by chunk, through a ring of kStepSlots shared-memory slots: warp 0 waits for
     //      chunk u, draws the life bar into it, sends it to `obs` with one bulk store, and -- as soon as the store of chunk
-    //      u - 1 has left its slot -- issues the bulk load of chunk u + 7 into it, so seven loads stay in flight across
-    //      frame boundaries.  The other warps only join for the rare frames that still need float64 tints (poses whose
+    //      u - 3 has left its slot -- issues the bulk load of chunk u + 5 into it, so five loads and three stores stay in
+    //      flight across frame boundaries.  The other warps only join for the rare frames that still need float64 tints (poses whose
     //      image depends on more foods than have variant frames).
     extern __shared__ __align__(128) uint8_t s_ring[];           // kStepSlots x 12 KB
     __shared__ EnvDyn s_dyn[kStepBatch];
@@ -1329,7 +1333,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
         };
         if (tid == 0) {
             mgb_bulk_wait_read<0>();                               // the previous pass's stores have left the ring
-            for (int u = 0; u < kStepSlots - 1 && u < M; ++u) issue(u);
+            for (int u = 0; u < kStepSlots - kStepSlack && u < M; ++u) issue(u);
         }
         for (int it = 0; it < B; ++it) {
             __syncthreads();                                       // frame boundary: nobody runs more than a frame ahead of warp 0
@@ -1401,9 +1405,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                     if (lane == 0) {
                         mgb_bulk_store(gobs + off, s_chunk, bytes);
                         mgb_bulk_commit();
-                        if (u + kStepSlots - 1 < M) {
-                            mgb_bulk_wait_read<1>();               // the store of chunk u - 1 has left its slot ...
-                            issue(u + kStepSlots - 1);             // ... which is the slot of chunk u + 7
+                        if (u + kStepSlots - kStepSlack < M) {
+                            mgb_bulk_wait_read<kStepSlack>();      // the store of chunk u - 3 has left its slot ...
+                            issue(u + kStepSlots - kStepSlack);    // ... which is the slot of chunk u + 5
                         }
                     }
                 }
@@ -1635,7 +1639,8 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     if (cfg->kind == MGB_MAZE_2D) MGB_REQUIRE(cfg->view_grid >= 0 && cfg->view_grid <= 8, "view_grid out of range");
     if (cfg->kind != MGB_MAZE_2D) {
         MGB_REQUIRE(cfg->res_h > 0 && cfg->res_h <= 1024 && cfg->res_v > 0 && cfg->res_v <= 1024, "resolution out of range");
-        MGB_REQUIRE(cfg->obs_dtype == MGB_OBS_U8 || cfg->obs_dtype == MGB_OBS_I32, "invalid obs_dtype");
+        MGB_REQUIRE(cfg->obs_dtype == MGB_OBS_U8 || cfg->obs_dtype == MGB_OBS_I32 || cfg->obs_dtype == MGB_OBS_F32,
+                    "invalid obs_dtype");
         MGB_REQUIRE(cfg->max_vision > 0 && cfg->l_focal > 0 && cfg->text_size > 0 && cfg->fov > 0, "invalid optics");
     }
     int ndev = 0;

@@ -455,7 +455,8 @@ class BatchedMetaMaze2D(_BatchedMazeBase):
 
 class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
     """MetaMazeDiscrete3D(enable_render, render_scale, resolution, max_steps, task_type) x num_envs
-    (maze_env.py:16-42).  obs_dtype: 'int32' = exact reference values, 'uint8' = min(value, 255).
+    (maze_env.py:16-42).  obs_dtype: 'int32' = exact reference values (what the reference's array holds), 'float32' = the
+    same values in the dtype the reference's observation_space declares (maze_env.py:37-39), 'uint8' = min(value, 255).
     textures: (grounds uint8 [n_tex,64,64,3], ceil uint8 [64,64,3]); default = procedural set."""
     KIND = 1
 
@@ -466,7 +467,7 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
             raise NotImplementedError("enable_render=True needs a display; the batched engine is headless")
         self.enable_render = False
         self.resolution = (int(resolution[0]), int(resolution[1]))
-        assert obs_dtype in ("int32", "uint8")
+        assert obs_dtype in ("int32", "uint8", "float32")
         self.obs_dtype = obs_dtype
         self.max_vision_range, self.fol_angle = max_vision_range, fol_angle
         self.cache = cache                  # None: library default (on, MGB_MAZE_CACHE); False: direct renderer only
@@ -475,15 +476,15 @@ class BatchedMetaMazeDiscrete3D(_BatchedMazeBase):
         torch = self._torch
         h, v = self.resolution
         self.observation_space = Box(low=0, high=256, shape=(h, v, 3), dtype=np.float32)     # maze_env.py:37-39
-        self._obs = torch.empty((self.num_envs, h, v, 3), dtype=torch.int32 if obs_dtype == "int32" else torch.uint8,
-                                device=self.device)
+        self._obs = torch.empty((self.num_envs, h, v, 3), device=self.device,
+                                dtype={"int32": torch.int32, "uint8": torch.uint8, "float32": torch.float32}[obs_dtype])
 
     def _make_cfg(self, n_cells):
         cfg = _lib.MazeCfg()
         cfg.kind, cfg.task_type = 1, {"SURVIVAL": 0, "ESCAPE": 1}[self.task_type]
         cfg.n_cells, cfg.max_steps, cfg.view_grid = n_cells, self.max_steps, 0
         cfg.res_h, cfg.res_v = self.resolution
-        cfg.obs_dtype = 1 if self.obs_dtype == "int32" else 0
+        cfg.obs_dtype = {"uint8": 0, "int32": 1, "float32": 2}[self.obs_dtype]
         cfg.max_vision, cfg.fov = self.max_vision_range, self.fol_angle       # maze_discrete_3d.py:22-23
         cfg.l_focal, cfg.text_size = 0.20, 1.0                                # maze_discrete_3d.py:116
         return cfg

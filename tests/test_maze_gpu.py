@@ -300,6 +300,28 @@ def test_update_tasks_equals_fresh_env(torch_mod, maze_golden, textures, kind):
     env.close()
 
 
+@pytest.mark.parametrize("cache", [True, False])
+def test_float32_observation_view_equals_int32(torch_mod, maze_golden, textures, cache):
+    """obs_dtype='float32' (the dtype the reference's observation_space declares, maze_env.py:37-39) holds exactly the
+    int32 values, on the pose-cache path, the direct renderer, reset() and the fused rollout."""
+    torch = torch_mod
+    c = maze_case(maze_golden, "m3d_surv")
+    envs = [make_env(c, 3, textures, obs_dtype=dt, cache=cache) for dt in ("int32", "float32")]
+    for e in envs:
+        e.set_task(c["task"])
+    o_i, o_f = [e.reset() for e in envs]
+    assert o_f.dtype == torch.float32 and torch.equal(o_i.to(torch.float32), o_f)
+    for t in range(25):
+        act = torch.full((3,), int(c["act"][t]), dtype=torch.int32, device="cuda")
+        o_i, o_f = [e.step(act)[0] for e in envs]
+        assert torch.equal(o_i.to(torch.float32), o_f), t
+    if cache:
+        r_i, r_f = [e.rollout(4, act_seed=3)["obs"] for e in envs]
+        assert torch.equal(r_i.to(torch.float32), r_f)
+    for e in envs:
+        e.close()
+
+
 def test_config4_shape_properties(torch_mod, maze_golden, textures):
     """BASELINE config 4 shape per GPU (1024 envs, 15x15, 128x128, uint8): sharding invariance + determinism."""
     torch = torch_mod
