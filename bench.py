@@ -726,7 +726,33 @@ def run_maze3d(ctx, sampler):
                     retasked += int(fin.size)
             torch.cuda.synchronize(dev)
             dt_loop = time.perf_counter() - t0
+            # (d) the same loop with the DEVICE sampler: no host round trip at all (mgb_maze_resample_tasks(done))
+            for t in range(20):
+                _, _, d, _ = env2.step(acts[t % SLOTS])
+                env2.resample_tasks(d, seed=5, allow_loops=True, crowd_ratio=0.35)
+            torch.cuda.synchronize(dev)
+            ndone = torch.zeros((), dtype=torch.int64, device=dev)
+            ctx.e0.record()
+            for t in range(steps_loop):
+                _, _, d, _ = env2.step(acts[t % SLOTS])
+                env2.resample_tasks(d, seed=5, allow_loops=True, crowd_ratio=0.35)
+                ndone += d.sum()
+            ctx.e1.record()
+            torch.cuda.synchronize(dev)
+            ms_dev = ctx.e0.elapsed_time(ctx.e1)
+            # sampler alone: every env resampled at once
+            ctx.e0.record()
+            for _ in range(10):
+                env2.resample_tasks(None, seed=6, allow_loops=True, crowd_ratio=0.35)
+            ctx.e1.record()
+            torch.cuda.synchronize(dev)
+            rate_dev = 10 * n / (ctx.e0.elapsed_time(ctx.e1) * 1e-3)
             extras["task_churn"] = {
+                "device_sampler_tasks_per_s": rate_dev,
+                "device_loop": {"steps": steps_loop, "envs": n, "retasked": int(ndone), "value": n * steps_loop / (ms_dev * 1e-3),
+                                "unit": "env-steps/s", "tasks_per_s": int(ndone) / (ms_dev * 1e-3),
+                                "note": "step + mgb_maze_resample_tasks(done): finished envs get a maze drawn on the device "
+                                        "(one kernel, stream-ordered, no host synchronisation)"},
                 "host_sampler_tasks_per_s": {"reference_streams": rate_ref, "rng_sampler": rate_fast},
                 "update_tasks_per_s": rate_upd, "update_tasks_host_s_per_call_of_256": host_s / 8,
                 "loop": {"steps": steps_loop, "envs": n, "retasked": retasked, "value": n * steps_loop / dt_loop,

@@ -215,6 +215,29 @@ int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *walls_host, co
                       const double *food_rewards_host, const int32_t *food_interval_host,
                       const mgb_maze_task_scalars *scalars_host, const int32_t *env2task_host);
 
+/* MazeTaskSampler keyword arguments (maze_task.py:41-54; defaults in metagym_b200/metamaze.py). */
+typedef struct mgb_maze_sampler_cfg {
+    int32_t allow_loops, n_texts, food_interval, pad;
+    double cell_size, wall_height, agent_height, step_reward;
+    double goal_reward;         /* <= 0: the reference's default -sqrt(n) * n * step_reward (maze_task.py:163-166) */
+    double food_reward, initial_life, max_life, food_density, crowd_ratio;
+} mgb_maze_sampler_cfg;
+
+/* Per-episode task resampling ON THE DEVICE (maze_task.py:41-190 at the scale of SURVEY.md 8f row 3): every env e with
+ * mask_dev[e] != 0 (NULL: all envs) gets a freshly drawn maze written into its task-table slot and starts an episode on
+ * it; one kernel, stream-ordered, no host involvement (typical use: mask = the `done` array of the previous step).  Draws
+ * come from a counter-based generator keyed by (seed, global env index, how often the env has been resampled), so results
+ * do not depend on sharding.  The distribution family is MazeTaskSampler's (spanning tree of the room lattice, loops down
+ * to crowd_ratio, textures, start/goal, thinned food); it is NOT sample-identical to the reference, which draws from
+ * Python's and numpy's global MT19937 streams.  Needs one table slot per env (mgb_maze_set_task with an injective
+ * env2task) and the direct renderer; food cells per task are capped at the table's largest task. */
+int mgb_maze_resample_tasks(mgb_maze *h, const uint8_t *mask_dev, const mgb_maze_sampler_cfg *cfg, uint64_t seed,
+                            void *stream);
+
+/* Read tasks back from the table (synchronous; inspection / tests): arrays as for mgb_maze_set_task, [count] long. */
+int mgb_maze_get_tasks(mgb_maze *h, int32_t count, const int32_t *task_slots_host, int8_t *walls_host, int8_t *texts_host,
+                       double *food_rewards_host, int32_t *food_interval_host, mgb_maze_task_scalars *scalars_host);
+
 /* MetaMazeDiscrete3D renderer choice.  enabled = 1 (default): static layers of every (task, cell, heading) are rendered once
  * and memoised (pose cache, within MGB_MAZE_CACHE_GB), a step composes / copies; 0: every frame is ray-cast directly
  * (ray_caster_utils.py:66-209 per frame, like the reference) -- the mode for task tables that change every episode. */

@@ -34,6 +34,14 @@ class MazeTaskScalars(ctypes.Structure):
                 ("goal_reward", c_f64)]
 
 
+class MazeSamplerCfg(ctypes.Structure):
+    """mgb_maze_sampler_cfg (include/mgb200.h)."""
+    _fields_ = [("allow_loops", c_i32), ("n_texts", c_i32), ("food_interval", c_i32), ("pad", c_i32),
+                ("cell_size", c_f64), ("wall_height", c_f64), ("agent_height", c_f64), ("step_reward", c_f64),
+                ("goal_reward", c_f64), ("food_reward", c_f64), ("initial_life", c_f64), ("max_life", c_f64),
+                ("food_density", c_f64), ("crowd_ratio", c_f64)]
+
+
 class MazeCfg(ctypes.Structure):
     """mgb_maze_cfg (include/mgb200.h)."""
     _fields_ = [("kind", c_i32), ("task_type", c_i32), ("n_cells", c_i32), ("max_steps", c_i32),
@@ -63,6 +71,8 @@ SIGNATURES = {
     "mgb_maze_obs_bytes_per_env": (c_i64, [vp]),
     "mgb_maze_set_textures": (ctypes.c_int, [vp, vp, c_i32, vp, c_i32]),
     "mgb_maze_set_task": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars), vp]),
+    "mgb_maze_resample_tasks": (ctypes.c_int, [vp, vp, ctypes.POINTER(MazeSamplerCfg), c_u64, vp]),
+    "mgb_maze_get_tasks": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars)]),
     "mgb_maze_set_cache": (ctypes.c_int, [vp, ctypes.c_int]),
     "mgb_maze_cache_info": (ctypes.c_int, [vp, vp]),
     "mgb_maze_update_tasks": (ctypes.c_int, [vp, c_i32, vp, vp, vp, vp, vp, ctypes.POINTER(MazeTaskScalars), vp]),

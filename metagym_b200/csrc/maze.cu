@@ -1551,6 +1551,8 @@ struct mgb_maze {
     uint8_t *c_fid = nullptr, *c_colhits = nullptr, *c_rgb8 = nullptr;
     uint32_t *c_px_all = nullptr;
     uint64_t *c_fmask = nullptr;
+    uint32_t *task_epoch = nullptr;           // [n_pad] how often each env's task has been resampled on the device
+    bool slot_per_env = false;                // env2task is injective: every env owns its task-table slot
     uint8_t *task_flags = nullptr;            // [n_tasks] scratch of mgb_maze_update_tasks
     int task_flags_n = 0;
     bool cache_would_fit = true;              // last ensure_pose_cache decision (false: over budget -> direct renderer)
@@ -1733,7 +1735,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig); cudaFree(h->hit_scratch);
     cudaFree(h->c_px_all); cudaFree(h->c_fmask);
-    cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc); cudaFree(h->task_flags);
+    cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc); cudaFree(h->task_flags); cudaFree(h->task_epoch);
     for (int i = 0; i < 2; ++i) {
         cudaFreeHost(h->h_stage[i]); cudaFree(h->d_stage[i]);
         if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
@@ -1880,6 +1882,14 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     }
     MGB_REQUIRE(f_max <= 127, "at most 127 food cells per task are supported");
     for (int e = 0; e < h->n; ++e) MGB_REQUIRE(env2task_host[e] >= 0 && env2task_host[e] < n_tasks, "env2task out of range");
+    {
+        std::vector<uint8_t> used((size_t)n_tasks, 0);
+        h->slot_per_env = true;
+        for (int e = 0; e < h->n; ++e) {
+            if (used[env2task_host[e]]) { h->slot_per_env = false; break; }
+            used[env2task_host[e]] = 1;
+        }
+    }
     c.f_max = f_max;
     // A ray is followed for max_vision at most, i.e. through <= 2 * max_vision / cell_size + 2 cells (one per DDA step
     // plus the start cell): that bounds the transparent crossings a column can record (ray_caster_utils.py:24-61).
@@ -1969,6 +1979,170 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
     MGB_CUDA(cudaDeviceSynchronize());
     h->launches += 1;
     return MGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-side task sampler: per-episode task resampling without the host.  Measured motivation
+// (bench.py --workload maze3d, task_churn): 1024 envs finish ~26 000 episodes/s on the direct renderer, the host samplers
+// deliver 700 (reference random streams) to 4 200 (numpy RandomState) tasks/s.  This kernel draws a fresh maze per finished
+// env -- one thread per env, Philox keyed by (seed, global env index, resample count) -- from the same distribution family
+// as MazeTaskSampler(rng=...) (metagym_b200/metamaze.py; the reference's maze_task.py:41-190 draws from Python's and
+// numpy's global MT19937 streams, which a device cannot replay: parity here is distributional and structural, asserted
+// in tests/test_maze_gpu.py: rooms on odd coordinates, border walls, a spanning tree of the room lattice by randomised
+// Kruskal, loops knocked out down to crowd_ratio, textures 1..n_texts-1 on walls, start/goal rooms > 0.45 n apart, food
+// values clip(U * food_reward, 0.1, food_reward) thinned by 0.9 per round until their sum is <= (n-1)^2 food_density).
+// ---------------------------------------------------------------------------------------------------------------
+struct SamplerCfg {          // mgb_maze_sampler_cfg + derived fields
+    int allow_loops, n_texts, food_interval, cls;
+    double cell_size, wall_height, agent_height, step_reward, goal_reward, food_reward, initial_life, max_life, food_density,
+        crowd_ratio;
+};
+struct PhiloxStream {
+    uint2 key;
+    uint4 ctr;
+    uint4 buf;
+    int have;
+    __device__ uint32_t next()
+    {
+        if (have == 0) { buf = mgb_philox4x32_10(ctr, key); ctr.z += 1u; have = 4; }
+        const uint32_t v = have == 4 ? buf.x : (have == 3 ? buf.y : (have == 2 ? buf.z : buf.w));
+        --have;
+        return v;
+    }
+    __device__ double uniform() { return (double)(next() >> 8) * (1.0 / 16777216.0); }
+    __device__ int below(int n) { return (int)(((uint64_t)next() * (uint64_t)n) >> 32); }     // uniform in [0, n)
+};
+#define MGB_STREAM_SAMPLER 0x300u
+
+__global__ void __launch_bounds__(32) maze_sample_tasks_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a,
+                                                               uint8_t *blobs, const uint8_t *mask, uint32_t *epoch,
+                                                               const __grid_constant__ SamplerCfg sc, uint64_t seed)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    if (mask && !mask[e]) return;
+    const int n = c.n, nn = n * n, m = (n - 1) / 2;
+    const uint32_t ep = epoch[e] + 1u;
+    epoch[e] = ep;
+    const int64_t genv = a.env_base + e;
+    PhiloxStream rng;
+    rng.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    rng.ctr = make_uint4((uint32_t)genv, ep, 0u, MGB_STREAM_SAMPLER + (uint32_t)((uint64_t)genv >> 32));
+    rng.have = 0;
+    uint8_t walls[kMaxN * kMaxN];
+    uint8_t parent[((kMaxN - 1) / 2) * ((kMaxN - 1) / 2)];
+    uint16_t order[kMaxN * kMaxN];
+    for (int k = 0; k < nn; ++k) walls[k] = 1;
+    for (int i = 1; i < n; i += 2)
+        for (int j = 1; j < n; j += 2) walls[i * n + j] = 0;
+    for (int k = 0; k < m * m; ++k) parent[k] = (uint8_t)k;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    // ---- random spanning tree of the room lattice (Kruskal over shuffled edges); edge id = 2 * room + dir
+    int ne = 0;
+    for (int ra = 0; ra < m; ++ra)
+        for (int rb = 0; rb < m; ++rb) {
+            if (ra + 1 < m) order[ne++] = (uint16_t)(2 * (ra * m + rb));
+            if (rb + 1 < m) order[ne++] = (uint16_t)(2 * (ra * m + rb) + 1);
+        }
+    for (int k = ne - 1; k > 0; --k) { const int j = rng.below(k + 1); const uint16_t t = order[k]; order[k] = order[j]; order[j] = t; }
+    for (int k = 0; k < ne; ++k) {
+        const int room = order[k] >> 1, dir = order[k] & 1, ra = room / m, rb = room % m;
+        const int other = dir == 0 ? (ra + 1) * m + rb : ra * m + rb + 1;
+        const int x = find(room), y = find(other);
+        if (x != y) {
+            parent[x] = (uint8_t)y;
+            if (dir == 0) walls[(2 * ra + 2) * n + 2 * rb + 1] = 0; else walls[(2 * ra + 1) * n + 2 * rb + 2] = 0;
+        }
+    }
+    // ---- loops: knock interior walls out (in random order, only next to a free cell) down to crowd_ratio
+    if (sc.allow_loops) {
+        int standing = 0, nc = 0;
+        for (int i = 1; i < n - 1; ++i)
+            for (int j = 1; j < n - 1; ++j)
+                if (walls[i * n + j]) { ++standing; order[nc++] = (uint16_t)(i * n + j); }
+        const double budget = (double)((n - 2) * (n - 2)) * sc.crowd_ratio;
+        for (int k = nc - 1; k > 0; --k) { const int j = rng.below(k + 1); const uint16_t t = order[k]; order[k] = order[j]; order[j] = t; }
+        for (int k = 0; k < nc && (double)standing > budget; ++k) {
+            const int cell = order[k];
+            if (!walls[cell - n] || !walls[cell + n] || !walls[cell - 1] || !walls[cell + 1]) { walls[cell] = 0; --standing; }
+        }
+    }
+    // ---- blob
+    uint8_t *b = blobs + (size_t)a.env2task[e] * c.blob_bytes;
+    for (int k = 0; k < nn; ++k) {
+        b[c.off_walls + k] = walls[k];
+        const int tx = 1 + rng.below(sc.n_texts - 1);                          // randint(1, n_texts)
+        b[c.off_texts + k] = walls[k] ? (uint8_t)tx : 0;
+    }
+    const int sx = rng.below(m) * 2 + 1, sy = rng.below(m) * 2 + 1;
+    int gx = n - 2, gy = n - 2;
+    for (int t = 0; t < m * m; ++t) {
+        const int ex = rng.below(m) * 2 + 1, ey = rng.below(m) * 2 + 1;
+        const double dx = ex - sx, dy = ey - sy;
+        if (sqrt(dx * dx + dy * dy) > 0.45 * n) { gx = ex; gy = ey; break; }
+    }
+    // food: float values kept in `order` as 16-bit fixed point would lose the distribution -> recompute by thinning masks
+    // value[k] is drawn once, survival is thinned round by round; the per-cell values live in the blob's fval area only at
+    // the end, so keep them in registers-free form: alive flags in walls[] bit 1, values re-derived from a second stream
+    PhiloxStream vr = rng;
+    vr.ctr.w ^= 0x5A5A0000u; vr.ctr.z = 0u; vr.have = 0;                      // independent stream for the values
+    double total = 0.0;
+    int alive = 0;
+    for (int k = 0; k < nn; ++k) {
+        double v = vr.uniform() * sc.food_reward;
+        v = v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
+        if (!(walls[k] & 1)) { walls[k] |= 2; total += v; ++alive; }
+    }
+    const double expected = (double)((n - 1) * (n - 1)) * sc.food_density;
+    while (total > expected || alive > c.f_max) {                             // food *= (rand < 0.90) per round
+        PhiloxStream v2 = rng;
+        v2.ctr.w ^= 0x5A5A0000u; v2.ctr.z = 0u; v2.have = 0;
+        total = 0.0; alive = 0;
+        for (int k = 0; k < nn; ++k) {
+            double v = v2.uniform() * sc.food_reward;
+            v = v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
+            const bool keep = rng.uniform() < 0.90;
+            if (walls[k] & 2) {
+                if (keep) { total += v; ++alive; } else walls[k] &= ~2;
+            }
+        }
+    }
+    int8_t *fidx = reinterpret_cast<int8_t *>(b + c.off_fidx);
+    double *fval = reinterpret_cast<double *>(b + c.off_fval);
+    int32_t *fint = reinterpret_cast<int32_t *>(b + c.off_fint);
+    {
+        PhiloxStream v2 = rng;
+        v2.ctr.w ^= 0x5A5A0000u; v2.ctr.z = 0u; v2.have = 0;
+        int cnt = 0;
+        for (int k = 0; k < nn; ++k) {
+            double v = v2.uniform() * sc.food_reward;
+            v = v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
+            if (walls[k] & 2) { fidx[k] = (int8_t)cnt; fval[cnt] = v; fint[cnt] = sc.food_interval; ++cnt; }
+            else fidx[k] = -1;
+        }
+        TaskHdr hd;
+        hd.start[0] = sx; hd.start[1] = sy; hd.goal[0] = gx; hd.goal[1] = gy;
+        hd.cell_size = sc.cell_size; hd.wall_height = sc.wall_height; hd.agent_height = sc.agent_height;
+        hd.initial_life = sc.initial_life; hd.max_life = sc.max_life; hd.step_reward = sc.step_reward;
+        hd.goal_reward = sc.goal_reward;
+        hd.n_food = cnt; hd.cls = sc.cls;
+        int ex = 0;
+        const double t2c = c.text_size / sc.cell_size;
+        hd.cell_pow2 = frexp(sc.cell_size, &ex) == 0.5 ? 1 : 0;
+        hd.t2c_pow2 = frexp(t2c, &ex) == 0.5 ? 1 : 0;
+        hd.inv_cell = 1.0 / sc.cell_size;
+        hd.inv_t2c = 1.0 / t2c;
+        *reinterpret_cast<TaskHdr *>(b) = hd;
+    }
+    // ---- the env starts an episode on its new task (set_task + reset of that env, maze_env.py:44-57)
+    Env s;
+    env_reset(c, b, a.eaten + e, a.n_pad, s);
+    a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
+    a.life[e] = s.life;
+    if (c.kind == MGB_MAZE_CONTINUOUS_3D) {
+        a.cpos[e] = make_float2((float)(s.gx * sc.cell_size + 0.5 * sc.cell_size), (float)(s.gy * sc.cell_size + 0.5 * sc.cell_size));
+        a.cori[e] = 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -2076,6 +2250,81 @@ extern "C" int mgb_maze_update_tasks(mgb_maze *h, int32_t count, const int32_t *
     maze_clear_flags_kernel<<<(unsigned)((h->n_tasks + 255) / 256), 256, 0, st>>>(h->task_flags, h->n_tasks);
     MGB_CUDA(cudaGetLastError());
     h->launches += 3;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_resample_tasks(mgb_maze *h, const uint8_t *mask_dev, const mgb_maze_sampler_cfg *cfg, uint64_t seed,
+                                       void *stream)
+{
+    MgbRange nvtx_range("mgb_maze_resample_tasks");
+    MGB_REQUIRE(h && cfg, "null argument");
+    MGB_REQUIRE(h->has_task, "call mgb_maze_set_task first (it sizes the task table)");
+    MGB_REQUIRE(h->slot_per_env, "device resampling needs one task-table slot per env (mgb_maze_set_task with n_tasks >= n_envs "
+                                 "and an injective env2task)");
+    MgbDeviceGuard guard(h->device);
+    MazeConst &c = h->c;
+    MGB_REQUIRE(!(c.kind == MGB_MAZE_DISCRETE_3D && h->cache_enabled && !h->host_poses.empty() && h->cache_would_fit),
+                "device resampling needs the direct renderer: create the env with the pose cache off (cache=False)");
+    MGB_REQUIRE(c.n % 2 == 1 && c.n > 6, "Cell Numbers can only be odd, minimum 7 (maze_task.py:57-58)");
+    MGB_REQUIRE(cfg->step_reward < 0, "step_reward must be < 0 (maze_task.py:59)");
+    MGB_REQUIRE(cfg->agent_height < cfg->wall_height && cfg->agent_height > 0, "the agent height must be > 0 and < wall height");
+    MGB_REQUIRE(cfg->cell_size >= h->min_cell, "resampled tasks may not have smaller cells than the table's smallest");
+    MGB_REQUIRE(cfg->n_texts >= 2 && (c.kind == MGB_MAZE_2D || !h->has_tex || cfg->n_texts <= c.n_tex), "n_texts out of range");
+    MGB_REQUIRE(cfg->food_reward > 0 && cfg->food_density >= 0 && cfg->crowd_ratio >= 0, "invalid sampler parameters");
+    SamplerCfg sc;
+    sc.allow_loops = cfg->allow_loops; sc.n_texts = cfg->n_texts; sc.food_interval = cfg->food_interval;
+    sc.cell_size = cfg->cell_size; sc.wall_height = cfg->wall_height; sc.agent_height = cfg->agent_height;
+    sc.step_reward = cfg->step_reward;
+    sc.goal_reward = cfg->goal_reward > 0 ? cfg->goal_reward : -sqrt((double)c.n) * c.n * cfg->step_reward;   // maze_task.py:163-166
+    sc.food_reward = cfg->food_reward; sc.initial_life = cfg->initial_life; sc.max_life = cfg->max_life;
+    sc.food_density = cfg->food_density; sc.crowd_ratio = cfg->crowd_ratio;
+    sc.cls = -1;
+    for (size_t k = 0; k < h->cls_heights.size() / 2; ++k)
+        if (h->cls_heights[2 * k] == cfg->agent_height && h->cls_heights[2 * k + 1] == cfg->wall_height) sc.cls = (int)k;
+    if (!h->task_epoch) {
+        MGB_CUDA(cudaMalloc(&h->task_epoch, sizeof(uint32_t) * (size_t)h->n_pad));
+        MGB_CUDA(cudaMemset(h->task_epoch, 0, sizeof(uint32_t) * (size_t)h->n_pad));
+    }
+    MazeArgs a = maze_args(h);
+    maze_sample_tasks_kernel<<<(unsigned)((h->n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(c, a, h->blobs, mask_dev, h->task_epoch,
+                                                                                        sc, seed);
+    MGB_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MGB_OK;
+}
+
+extern "C" int mgb_maze_get_tasks(mgb_maze *h, int32_t count, const int32_t *task_slots_host, int8_t *walls_host,
+                                  int8_t *texts_host, double *food_rewards_host, int32_t *food_interval_host,
+                                  mgb_maze_task_scalars *scalars_host)
+{
+    MGB_REQUIRE(h && task_slots_host && walls_host && texts_host && food_rewards_host && food_interval_host && scalars_host,
+                "null argument");
+    MGB_REQUIRE(h->has_task && count > 0, "no task table");
+    MgbDeviceGuard guard(h->device);
+    MGB_CUDA(cudaDeviceSynchronize());
+    const MazeConst &c = h->c;
+    const int nn = c.n * c.n;
+    std::vector<uint8_t> blob((size_t)c.blob_bytes);
+    for (int t = 0; t < count; ++t) {
+        MGB_REQUIRE(task_slots_host[t] >= 0 && task_slots_host[t] < h->n_tasks, "task slot out of range");
+        MGB_CUDA(cudaMemcpy(blob.data(), h->blobs + (size_t)task_slots_host[t] * c.blob_bytes, blob.size(), cudaMemcpyDeviceToHost));
+        TaskHdr hd;
+        memcpy(&hd, blob.data(), sizeof(hd));
+        const int8_t *fidx = reinterpret_cast<const int8_t *>(blob.data() + c.off_fidx);
+        const double *fval = reinterpret_cast<const double *>(blob.data() + c.off_fval);
+        const int32_t *fint = reinterpret_cast<const int32_t *>(blob.data() + c.off_fint);
+        for (int k = 0; k < nn; ++k) {
+            walls_host[(size_t)t * nn + k] = (int8_t)blob[c.off_walls + k];
+            texts_host[(size_t)t * nn + k] = (int8_t)blob[c.off_texts + k];
+            const int f = fidx[k];
+            food_rewards_host[(size_t)t * nn + k] = f >= 0 ? fval[f] : 0.0;
+            food_interval_host[(size_t)t * nn + k] = f >= 0 ? fint[f] : 0;
+        }
+        mgb_maze_task_scalars &s = scalars_host[t];
+        s.start[0] = hd.start[0]; s.start[1] = hd.start[1]; s.goal[0] = hd.goal[0]; s.goal[1] = hd.goal[1];
+        s.cell_size = hd.cell_size; s.wall_height = hd.wall_height; s.agent_height = hd.agent_height;
+        s.initial_life = hd.initial_life; s.max_life = hd.max_life; s.step_reward = hd.step_reward; s.goal_reward = hd.goal_reward;
+    }
     return MGB_OK;
 }
 

@@ -308,6 +308,42 @@ class _BatchedMazeBase(object):
         for k, sl in enumerate(slots):
             self.tasks[int(sl)] = tasks[k]
 
+    def resample_tasks(self, mask=None, seed=0, allow_loops=True, cell_size=2.0, wall_height=3.2, agent_height=1.6,
+                       step_reward=-0.01, goal_reward=None, food_reward=0.50, initial_life=1.0, max_life=2.0,
+                       food_density=0.010, food_interval=100, crowd_ratio=0.0, n_texts=7):
+        """Per-episode task resampling on the device (mgb_maze_resample_tasks): every env with mask[e] != 0 (None: all)
+        gets a freshly drawn maze (MazeTaskSampler's keyword arguments and distribution family; counter-based draws keyed
+        by (seed, global env index, resample count)) and restarts on it.  One stream-ordered kernel; typical use:
+        `obs, rew, done, _ = env.step(a); env.resample_tasks(done)`.  Needs set_task() with one table slot per env
+        (env2task = arange) and the direct renderer (cache=False)."""
+        m = None
+        if mask is not None:
+            m = self._torch.as_tensor(mask, device=self.device).to(self._torch.uint8).contiguous()
+        cfg = _lib.MazeSamplerCfg()
+        cfg.allow_loops, cfg.n_texts, cfg.food_interval = int(bool(allow_loops)), int(n_texts), int(food_interval)
+        cfg.cell_size, cfg.wall_height, cfg.agent_height = cell_size, wall_height, agent_height
+        cfg.step_reward, cfg.goal_reward = step_reward, (0.0 if goal_reward is None else goal_reward)
+        cfg.food_reward, cfg.initial_life, cfg.max_life = food_reward, initial_life, max_life
+        cfg.food_density, cfg.crowd_ratio = food_density, crowd_ratio
+        _lib.check(self._lib.mgb_maze_resample_tasks(self._h, _lib.ptr(m), ctypes.byref(cfg), int(seed), self._stream()))
+        self.need_reset = False
+
+    def get_tasks(self, task_slots):
+        """Tasks currently in the table slots `task_slots` (synchronous read-back) -> list of TaskConfig."""
+        slots = np.ascontiguousarray(np.asarray(task_slots, dtype=np.int32).reshape(-1))
+        K, n = int(slots.size), self._n_cells
+        walls = np.empty((K, n, n), np.int8); texts = np.empty((K, n, n), np.int8)
+        food = np.empty((K, n, n), np.float64); itv = np.empty((K, n, n), np.int32)
+        sc = (_lib.MazeTaskScalars * K)()
+        _lib.check(self._lib.mgb_maze_get_tasks(self._h, K, slots.ctypes.data, walls.ctypes.data, texts.ctypes.data,
+                                                food.ctypes.data, itv.ctypes.data, sc))
+        return [TaskConfig(start=(int(sc[k].start[0]), int(sc[k].start[1])), goal=(int(sc[k].goal[0]), int(sc[k].goal[1])),
+                           cell_walls=walls[k].astype(np.int32), cell_texts=texts[k].astype(np.int64),
+                           cell_size=sc[k].cell_size, step_reward=sc[k].step_reward, goal_reward=sc[k].goal_reward,
+                           wall_height=sc[k].wall_height, agent_height=sc[k].agent_height,
+                           initial_life=sc[k].initial_life, max_life=sc[k].max_life, food_rewards=food[k],
+                           food_interval=itv[k]) for k in range(K)]
+
     def sample_task(self, **kwargs):
         """Convenience: draw one task with the host sampler (reference usage: MazeTaskSampler(...), test.py:12)."""
         return MazeTaskSampler(**kwargs)

@@ -322,6 +322,129 @@ def test_float32_observation_view_equals_int32(torch_mod, maze_golden, textures,
         e.close()
 
 
+def _connected(walls):
+    """All free cells reachable from one of them (4-neighbourhood)."""
+    free = np.argwhere(walls == 0)
+    seen = {tuple(free[0])}
+    todo = [tuple(free[0])]
+    n = walls.shape[0]
+    while todo:
+        i, j = todo.pop()
+        for a, b in ((i - 1, j), (i + 1, j), (i, j - 1), (i, j + 1)):
+            if 0 <= a < n and 0 <= b < n and walls[a, b] == 0 and (a, b) not in seen:
+                seen.add((a, b))
+                todo.append((a, b))
+    return len(seen) == len(free)
+
+
+def test_device_task_sampler_structure_and_distribution(torch_mod, maze_golden, textures):
+    """mgb_maze_resample_tasks draws mazes on the device.  The reference sampler (maze_task.py:41-190) consumes Python's and
+    numpy's global MT19937 streams, so parity is structural and distributional (parity of this row is 'unpinned' by
+    construction): every sampled task satisfies the invariants the reference's construction guarantees, and the batch
+    statistics match MazeTaskSampler(rng=...) -- the host sampler of the same distribution family -- within sampling
+    noise.  Draws are keyed by (seed, global env index, resample count): deterministic and sharding-invariant."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, MazeTaskSampler
+    N, n = 600, 15
+    rs = np.random.RandomState(0)
+    seed_tasks = [MazeTaskSampler(n=n, allow_loops=True, crowd_ratio=0.35, food_density=0.03, rng=rs) for _ in range(8)]
+    fmax = max(int((np.asarray(t.food_rewards) > 0).sum()) for t in seed_tasks)
+    kw = dict(allow_loops=True, crowd_ratio=0.35, food_density=0.010, food_interval=50)
+
+    def sampled(base, seed):
+        env = BatchedMetaMaze2D(max_steps=50, task_type="SURVIVAL", view_grid=1, num_envs=N, squeeze=False, env_index_base=base)
+        env.set_task([seed_tasks[i % 8] for i in range(N)], env2task=np.arange(N))
+        env.reset()
+        env.resample_tasks(None, seed=seed, **kw)
+        out = env.get_tasks(np.arange(N))
+        ag, life = env.agent_state()
+        env.close()
+        return out, ag.cpu().numpy(), life.cpu().numpy()
+
+    tasks, ag, life = sampled(0, 7)
+    m = (n - 1) // 2
+    dens, nfood = [], []
+    for k, t in enumerate(tasks):
+        w = np.asarray(t.cell_walls)
+        assert w[0].all() and w[-1].all() and w[:, 0].all() and w[:, -1].all()            # closed border
+        assert (w[1:n:2, 1:n:2] == 0).all()                                                # rooms on odd coordinates
+        assert _connected(w)                                                               # spanning tree (+ loops)
+        inner = w[1:-1, 1:-1]
+        assert inner.sum() <= max(0.35 * inner.size, 0) + 1e-9 or inner.sum() <= (n - 2) ** 2 - (2 * m * m - 1)
+        tx = np.asarray(t.cell_texts)
+        assert (tx[w == 0] == 0).all() and (tx[w > 0] >= 1).all() and (tx[w > 0] <= 6).all()
+        sx, sy = t.start
+        gx, gy = t.goal
+        assert sx % 2 == 1 and sy % 2 == 1 and w[sx, sy] == 0 and w[gx, gy] == 0
+        assert (gx, gy) == (n - 2, n - 2) or np.hypot(gx - sx, gy - sy) > 0.45 * n
+        f = np.asarray(t.food_rewards)
+        assert (f[w > 0] == 0).all() and ((f == 0) | ((f >= 0.10) & (f <= 0.50))).all()
+        assert f.sum() <= (n - 1) ** 2 * 0.010 + 1e-12 and (f > 0).sum() <= fmax
+        itv = np.asarray(t.food_interval)
+        assert (itv[f > 0] == 50).all() and (itv[f == 0] == 0).all()
+        assert tuple(ag[k][:2]) == (sx, sy) and ag[k][3] == 0 and life[k] == t.initial_life   # env restarted on its task
+        assert abs(t.goal_reward - (np.sqrt(n) * n * 0.01)) < 1e-12                       # maze_task.py:163-166 default
+        dens.append(inner.mean())
+        nfood.append((f > 0).sum())
+    # distribution: against the host sampler of the same family
+    host = [MazeTaskSampler(n=n, rng=rs, **{k2: v for k2, v in kw.items()}) for _ in range(N)]
+    h_dens = [np.asarray(t.cell_walls)[1:-1, 1:-1].mean() for t in host]
+    h_food = [(np.asarray(t.food_rewards) > 0).sum() for t in host]
+    assert abs(np.mean(dens) - np.mean(h_dens)) < 0.01, (np.mean(dens), np.mean(h_dens))
+    assert abs(np.mean(nfood) - np.mean(h_food)) < 0.35, (np.mean(nfood), np.mean(h_food))
+    assert len({np.asarray(t.cell_walls).tobytes() for t in tasks}) > 0.95 * N            # all different mazes
+    # determinism and sharding invariance: the same global envs draw the same tasks in a differently sharded batch
+    again, _, _ = sampled(0, 7)
+    assert all(np.array_equal(a.cell_walls, b.cell_walls) and np.array_equal(a.food_rewards, b.food_rewards)
+               for a, b in zip(tasks, again))
+    shifted, _, _ = sampled(100, 7)
+    assert all(np.array_equal(tasks[100 + i].cell_walls, shifted[i].cell_walls) for i in range(N - 100))
+    other, _, _ = sampled(0, 8)
+    assert sum(np.array_equal(a.cell_walls, b.cell_walls) for a, b in zip(tasks, other)) < 5
+
+
+@pytest.mark.parametrize("kind", ["2D", "3D"])
+def test_device_resampled_tasks_step_like_the_oracle(torch_mod, maze_golden, textures, kind):
+    """Episodes on device-sampled tasks: after each resample_tasks(done) the re-tasked envs' tasks are read back and given to
+    an oracle instance; every later observation / reward / done must match it bit for bit (the blobs the sampler writes are
+    exactly what the step and render kernels consume)."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D, MazeTaskSampler
+    from oracle.maze_oracle import OracleMaze
+    N = 10
+    rs = np.random.RandomState(3)
+    init = [MazeTaskSampler(n=15, allow_loops=True, crowd_ratio=0.3, food_density=0.05, food_interval=5, rng=rs) for _ in range(N)]
+    if kind == "2D":
+        env = BatchedMetaMaze2D(max_steps=12, task_type="SURVIVAL", view_grid=2, num_envs=N, squeeze=False)
+        oras = [OracleMaze("2D", "SURVIVAL", 12, 2) for _ in range(N)]
+    else:
+        env = BatchedMetaMazeDiscrete3D(resolution=(32, 32), max_steps=12, task_type="SURVIVAL", num_envs=N, squeeze=False,
+                                        textures=textures, cache=False)
+        oras = [OracleMaze("3D", "SURVIVAL", 12, 1, (32, 32), textures=textures) for _ in range(N)]
+    env.set_task(init, env2task=np.arange(N))
+    obs = env.reset().cpu().numpy()
+    for i, o in enumerate(oras):
+        o.set_task(init[i])
+        assert np.array_equal(obs[i], o.reset())
+    retasked = 0
+    for t in range(40):
+        act = rs.randint(0, 4, size=N)
+        obs, rew, done, _ = env.step(torch.as_tensor(act, dtype=torch.int32).cuda())
+        obs, rew, done_h = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for i, o in enumerate(oras):
+            o2, r2, d2, _ = o.step(int(act[i]))
+            assert np.array_equal(obs[i], o2) and rew[i] == r2 and bool(done_h[i]) == d2, (t, i)
+        if done_h.any():
+            env.resample_tasks(done, seed=21, allow_loops=True, crowd_ratio=0.3, food_density=0.05, food_interval=5)
+            ids = np.nonzero(done_h)[0]
+            for i, nt in zip(ids, env.get_tasks(ids)):
+                oras[i].set_task(nt)
+                oras[i].reset()
+                retasked += 1
+    assert retasked >= N
+    env.close()
+
+
 def test_config4_shape_properties(torch_mod, maze_golden, textures):
     """BASELINE config 4 shape per GPU (1024 envs, 15x15, 128x128, uint8): sharding invariance + determinism."""
     torch = torch_mod
