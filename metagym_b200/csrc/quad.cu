@@ -397,9 +397,12 @@ __device__ __forceinline__ bool integrate(const QuadConst &c, VState<T> &s, cons
     // registers, measured 3 % faster than unrolled)
     if (N == 1 && c.substeps % 5 == 0) {
 #pragma unroll 1
-        for (int k = 0; k < c.substeps && !failed; k += 5) {
-#pragma unroll
-            for (int u = 0; u < 5; ++u) MGB_QUAD_ONE_SUBSTEP()
+        for (int k = 0; k < c.substeps; k += 5) {      // five copies written out (a `break` leaves this loop): nvcc does not
+            MGB_QUAD_ONE_SUBSTEP()                      // unroll the body by pragma once it contains the per-lane loops
+            MGB_QUAD_ONE_SUBSTEP()
+            MGB_QUAD_ONE_SUBSTEP()
+            MGB_QUAD_ONE_SUBSTEP()
+            MGB_QUAD_ONE_SUBSTEP()
         }
     } else {
 #pragma unroll 1
