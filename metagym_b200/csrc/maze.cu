@@ -564,7 +564,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     // ---- shared memory carve-up (mirrors maze3d_smem_bytes on the host)
     size_t off = 0;
     uint32_t *s_tex = reinterpret_cast<uint32_t *>(smem + off);          off = align_up(off + (size_t)tex_words * 4, 128);
-    uint8_t *s_blob = smem + off;                                         off = align_up(off + c.blob_bytes, 128);
+    uint8_t *s_blob2[2];                                                  // this env's tile + the next env's, in flight
+    s_blob2[0] = smem + off;                                              off = align_up(off + c.blob_bytes, 128);
+    s_blob2[1] = smem + off;                                              off = align_up(off + c.blob_bytes, 128);
     double *s_transp = reinterpret_cast<double *>(smem + off);           off = align_up(off + (size_t)n * n * 8, 128);
     ColRec *s_col = reinterpret_cast<ColRec *>(smem + off);              off = align_up(off + (size_t)H * sizeof(ColRec), 128);
     RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
@@ -575,14 +577,15 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     const int run_bytes = c.run_px * px_bytes;                           // 768
     const int n_slots = c.obs_dtype == MGB_OBS_U8 ? 2 : 1;               // int32 runs are 4x larger: single slot
     uint8_t *s_out = smem + off;                                          off = align_up(off + (size_t)(kRenderThreads / 32) * n_slots * run_bytes, 128);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 16;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 32;
     int *s_env = reinterpret_cast<int *>(smem + off);                    // [0..3] gx gy ori steps, [4] lifebar end
     double *s_pose = reinterpret_cast<double *>(smem + off + 32);         // continuous maze: x, y, sin(ori), cos(ori)
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         mgb_mbar_init(&s_bar[0], 1);   // textures
-        mgb_mbar_init(&s_bar[1], 1);   // task blob
+        mgb_mbar_init(&s_bar[1], 1);   // task blob, buffer 0
+        mgb_mbar_init(&s_bar[2], 1);   // task blob, buffer 1
         mgb_fence_mbar_init();
     }
     __syncthreads();
@@ -596,20 +599,27 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                           &s_bar[0]);
         }
     }
-    uint32_t blob_phase = 0;
+    uint32_t blob_phase = 0;      // bit b: parity of buffer b's mbarrier
+    int blob_cur = 0;
     bool tex_ready = false;
     int run_parity = 0;
 
+    // ---- maze tiles (walls, texture ids, food table) arrive by TMA one env ahead of their use
+    auto load_blob = [&](int64_t e, int b) {
+        const int task_id = FILL ? a.poses[e].x : a.env2task[e];
+        const uint8_t *src = a.blobs + (int64_t)task_id * c.blob_bytes;
+        mgb_mbar_expect_tx(&s_bar[1 + b], (uint32_t)c.blob_bytes);
+        mgb_bulk_load(b ? s_blob2[1] : s_blob2[0], src, (uint32_t)c.blob_bytes, &s_bar[1 + b]);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < a.n) load_blob(blockIdx.x, 0);
+
     for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x) {
-        // ---- stage this env's maze tile (walls, textures ids, food table) by TMA
-        if (tid == 0) {
-            const int task_id = FILL ? a.poses[e].x : a.env2task[e];
-            const uint8_t *src = a.blobs + (int64_t)task_id * c.blob_bytes;
-            mgb_mbar_expect_tx(&s_bar[1], (uint32_t)c.blob_bytes);
-            mgb_bulk_load(s_blob, src, (uint32_t)c.blob_bytes, &s_bar[1]);
-        }
-        mgb_mbar_wait(&s_bar[1], blob_phase);
-        blob_phase ^= 1u;
+        uint8_t *s_blob = blob_cur ? s_blob2[1] : s_blob2[0];
+        mgb_mbar_wait(&s_bar[1 + blob_cur], (blob_phase >> blob_cur) & 1u);
+        blob_phase ^= 1u << blob_cur;
+        // the other buffer was last read before the barrier that closed the previous env
+        if (tid == 0 && e + gridDim.x < a.n) load_blob(e + gridDim.x, blob_cur ^ 1);
+        blob_cur ^= 1;
         const TaskHdr *th = blob_hdr(s_blob);
 
         // ---- step logic (one thread), then publish agent pose to the CTA
@@ -1065,6 +1075,9 @@ __device__ __forceinline__ EnvDyn make_dyn(const MazeConst &c, const MazeArgs &a
 // ---------------------------------------------------------------------------------------------------------------
 // Pose cache path: step logic (one thread per env) + compose (static pose layers x current food state -> observation)
 // ---------------------------------------------------------------------------------------------------------------
+// DYN = false: step logic only, ahead of the direct renderer (which then runs with do_step = 0): the per-env logic is a
+// chain of dependent L2 round trips that one thread of a 512-thread CTA would otherwise walk once per env, serially.
+template <bool DYN>
 __global__ void maze3d_logic_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1085,8 +1098,10 @@ __global__ void maze3d_logic_kernel(const __grid_constant__ MazeConst c, const _
         a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
         a.life[e] = s.life;
     }
-    const EnvDyn d = make_dyn(c, a, blob, task, s, eaten);
-    reinterpret_cast<EnvDyn *>(a.dyn)[e] = d;
+    if (DYN) {
+        const EnvDyn d = make_dyn(c, a, blob, task, s, eaten);
+        reinterpret_cast<EnvDyn *>(a.dyn)[e] = d;
+    }
 }
 
 // per pose slot, after the FILL render: (1) c_fmask = the food slots that can change this pose's image at all (under a
@@ -1595,13 +1610,14 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     size_t off = 0;
     off = up(off + (size_t)(c.n_tex + 1) * c.ts * c.ts * 4, 128);
     off = up(off + c.blob_bytes, 128);
+    off = up(off + c.blob_bytes, 128);
     off = up(off + (size_t)c.n * c.n * 8, 128);
     off = up(off + (size_t)c.res_h * sizeof(ColRec), 128);
     off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
     if (!c.hits_in_global) off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     off = up(off + (size_t)(kRenderThreads / 32) * (c.obs_dtype == MGB_OBS_U8 ? 2 : 1) * c.run_px * px, 128);
-    off += 16 + 32 + 32;
+    off += 32 + 32 + 32;
     return off;
 }
 
@@ -2572,7 +2588,7 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
                 h->launches += 1;
                 return MGB_OK;
             }
-            maze3d_logic_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
+            maze3d_logic_kernel<true><<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
             MGB_CUDA(cudaGetLastError());
             {
                 static int ctas_per_sm = 0;
@@ -2594,6 +2610,12 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
             }
             h->launches += 1;
         } else {
+            if (a.do_step && c.kind == MGB_MAZE_DISCRETE_3D) {     // logic for all envs in parallel, then render only
+                maze3d_logic_kernel<false><<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
+                MGB_CUDA(cudaGetLastError());
+                h->launches += 1;
+                a.do_step = 0;
+            }
             rc = launch_render<false>(h, a, (unsigned)(h->n < h->num_sms ? h->n : h->num_sms), st);
             if (rc) return rc;
         }
