@@ -901,6 +901,95 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const double *efft = (c.n_cls > 0 && th->cls >= 0) ? a.efftab + (size_t)th->cls * total_px : nullptr;
         const double fog_from = 0.4999 * c.max_vision;
         const double dts = (double)ts;
+        // Exact integer texel / cell indices.  With cell_size = 2^a, text_size = 2^b (a >= b) and ts = 2^m, every scaling in
+        //   texel = trunc(ts * frac((cell/text) * frac(x / cell)))   (floor, ray_caster_utils.py:106-112)
+        //   texel = trunc(ts * frac(x / text))                        (ceiling, :140-144),   cell = trunc(x / cell)
+        // is by a power of two and every frac() is exact, so for x >= 0 all three equal integer functions of
+        // t = trunc(x * ts / text): texel = t mod ts, cell = t >> log2(ts * cell / text).  One multiply and one conversion per
+        // axis instead of three multiplies, two floors, two subtractions and two conversions; pixels with a negative
+        // coordinate (the reference truncates those toward zero) and tasks with other sizes take the original expressions.
+        const bool fast_ix = cell_p2 && t2c_p2 && text_p2 && (ts & (ts - 1)) == 0 && cell_size >= c.text_size;
+        const double tex_scale = dts * c.inv_text;
+        int cell_shift = 0;
+        { int ex = 0; frexp(tex_scale * cell_size, &ex); cell_shift = ex - 1; }
+        const int ts_mask = ts - 1;
+        const double ix_lim = 1073741824.0 / tex_scale;                        // t < 2^30
+
+        // floor / ceiling pixel (ray_caster_utils.py:94-153).  Returns true when a transparent cell tinted it (`mark`).
+        auto fc_px = [&](int d_v, const ColRec &cr, const double *effc, int rgb[3]) -> bool {
+            bool mark = false;
+            const RowRec rr = s_row[d_v];
+            if (rr.kind == 0) return false;
+            const double eff = effc ? __ldg(effc + d_v) : rr.distance / cr.cos_hp;
+            // alpha = clip(2 eff / max_vision - 1, 0, 1) is exactly 0 while 2 eff / max_vision < 1; the margin keeps the
+            // shortcut independent of the division's rounding
+            double fog = 0.0;
+            if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
+            const double hit_x = eff * cr.cos_abs + pos_x;
+            const double hit_y = eff * cr.sin_abs + pos_y;
+            const bool fastpx = fast_ix && hit_x >= 0.0 && hit_y >= 0.0 && hit_x < ix_lim && hit_y < ix_lim;
+            int i, j, tu = 0, tv_ = 0;                                        // cell, texel coordinates (fast path)
+            double ci = 0.0, cj = 0.0;
+            if (fastpx) {
+                const int tx = trunc_i(hit_x * tex_scale), ty = trunc_i(hit_y * tex_scale);
+                i = tx >> cell_shift; j = ty >> cell_shift;
+                tu = tx & ts_mask; tv_ = ty & ts_mask;
+            } else {
+                ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
+                cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
+                i = trunc_i(ci); j = trunc_i(cj);
+            }
+            const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
+            if (rr.kind == 1) {                                               // floor, :103-126
+                if (inside) {
+                    const int text_id = texts[i * n + j];
+                    if (!fastpx) {
+                        double d_i = ci - floor(ci), d_j = cj - floor(cj);
+                        d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
+                        d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
+                        d_i -= floor(d_i); d_j -= floor(d_j);
+                        d_i *= dts; d_j *= dts;
+                        tu = trunc_i(d_i); tv_ = trunc_i(d_j);
+                    }
+                    shade(rgb, rr.light, 1.0 - fog * rr.light, s_tex[(text_id * ts + tu) * ts + tv_]);
+                    const double tv = s_transp[i * n + j];
+                    if (tv > 0.01) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+                }
+            } else {                                                          // ceiling, :137-153
+                if (!fastpx) {
+                    const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
+                    const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
+                    double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                    d_i *= dts; d_j *= dts;
+                    tu = trunc_i(d_i); tv_ = trunc_i(d_j);
+                }
+                shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + tu) * ts + tv_]);
+                if (inside) {
+                    const double tv = s_transp[i * n + j];
+                    if (tv > 0) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
+                }
+            }
+            return mark;
+        };
+        // wall pixel (:184-189)
+        auto wall_px = [&](int d_v, const ColRec &cr, int rgb[3]) {
+            const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
+            double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
+            d_j -= floor(d_j);
+            shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
+        };
+        const bool out_u8 = c.obs_dtype == MGB_OBS_U8;
+        auto store_px = [&](uint8_t *buf, int p, const int rgb[3]) {
+            if (out_u8) {
+                buf[p * 3 + 0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
+                buf[p * 3 + 1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
+                buf[p * 3 + 2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
+            } else {
+                int32_t *o = reinterpret_cast<int32_t *>(buf) + p * 3;
+                o[0] = MGB_OBS_WORD(c, rgb[0]); o[1] = MGB_OBS_WORD(c, rgb[1]); o[2] = MGB_OBS_WORD(c, rgb[2]);
+            }
+        };
+
         const int cols_per_run = c.run_px / V > 0 ? c.run_px / V : 1;
         const int n_runs = (H + cols_per_run - 1) / cols_per_run;
         for (int run = warp; run < n_runs; run += n_warps) {
@@ -913,75 +1002,48 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             for (int cc = 0; cc < ncol; ++cc) {
                 const int d_h = h0 + cc;
                 const ColRec cr = s_col[d_h];                              // warp-uniform
-                const HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
                 const bool bar_col = has_bar && d_h >= lb_sx && d_h < lb_ex;
                 const double *effc = efft ? efft + (size_t)d_h * V : nullptr;
+                if (cr.n_hits == 0) {
+                    // Column without transparent crossings: every pixel is EITHER wall OR floor/ceiling.  The two kinds are
+                    // walked separately -- the wall span [ws, we), then the remaining rows as one compacted index range --
+                    // so that a warp pass runs one code path with (almost) all lanes instead of both paths half empty.
+                    int ws = 0, we = 0;
+                    if (cr.wall) {
+                        ws = cr.v_s < 0 ? 0 : (cr.v_s > V ? V : cr.v_s);
+                        we = cr.v_e < ws ? ws : (cr.v_e > V ? V : cr.v_e);
+                    }
+                    for (int d_v = ws + lane; d_v < we; d_v += 32) {
+                        int rgb[3];
+                        wall_px(d_v, cr, rgb);
+                        if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+                        store_px(buf, cc * V + d_v, rgb);
+                    }
+                    const int span = we - ws, rest = V - span;
+                    for (int k = lane; k < rest; k += 32) {
+                        const int d_v = k < ws ? k : k + span;
+                        int rgb[3] = {0, 0, 0};
+                        fc_px(d_v, cr, effc, rgb);
+                        if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+                        store_px(buf, cc * V + d_v, rgb);
+                    }
+                    continue;
+                }
+                const HitRec *hits = s_hit + (size_t)d_h * c.max_hits;
                 for (int d_v = lane; d_v < V; d_v += 32) {
                     int rgb[3] = {0, 0, 0};
                     bool mark = false;
                     const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
-                    if (!in_wall || cr.n_hits > 0) {
-                        const RowRec rr = s_row[d_v];
-                        if (rr.kind != 0) {
-                            const double eff = effc ? __ldg(effc + d_v) : rr.distance / cr.cos_hp;
-                            // alpha = clip(2 eff / max_vision - 1, 0, 1) is exactly 0 while 2 eff / max_vision < 1; the
-                            // margin keeps the shortcut independent of the division's rounding
-                            double fog = 0.0;
-                            if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
-                            const double hit_x = eff * cr.cos_abs + pos_x;
-                            const double hit_y = eff * cr.sin_abs + pos_y;
-                            const double ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
-                            const double cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
-                            const int i = trunc_i(ci), j = trunc_i(cj);
-                            const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
-                            if (rr.kind == 1) {                               // floor, :103-126
-                                if (inside) {
-                                    double d_i = ci - floor(ci), d_j = cj - floor(cj);
-                                    const int text_id = texts[i * n + j];
-                                    d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
-                                    d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
-                                    d_i -= floor(d_i); d_j -= floor(d_j);
-                                    d_i *= dts; d_j *= dts;
-                                    shade(rgb, rr.light, 1.0 - fog * rr.light,
-                                          s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
-                                    const double tv = s_transp[i * n + j];
-                                    if (tv > 0.01) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
-                                }
-                            } else {                                          // ceiling, :137-153
-                                const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
-                                const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
-                                double d_i = fi - floor(fi), d_j = fj - floor(fj);
-                                d_i *= dts; d_j *= dts;
-                                shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
-                                if (inside) {
-                                    const double tv = s_transp[i * n + j];
-                                    if (tv > 0) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
-                                }
-                            }
-                        }
-                    }
-                    if (in_wall) {                                            // wall texel, :184-189
-                        const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
-                        double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
-                        d_j -= floor(d_j);
-                        shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
-                    }
-                    if (cr.n_hits > 0 && !mark) {                             // transparent overlays, :191-205
+                    mark = fc_px(d_v, cr, effc, rgb);     // also under a wall: `mark` decides about the overlays below
+                    if (in_wall) wall_px(d_v, cr, rgb);
+                    if (!mark) {                                              // transparent overlays, :191-205
                         for (int k = 0; k < cr.n_hits; ++k)
                             if (d_v >= hits[k].v_s && d_v < hits[k].v_e) blend(rgb, hits[k].tf);
                     }
                     if (bar_col && d_v >= lb_sy && d_v < lb_ey) {             // life bar, maze_discrete_3d.py:118-126
                         rgb[0] = 255; rgb[1] = 0; rgb[2] = 0;
                     }
-                    const int p = cc * V + d_v;
-                    if (c.obs_dtype == MGB_OBS_U8) {
-                        buf[p * 3 + 0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
-                        buf[p * 3 + 1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
-                        buf[p * 3 + 2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
-                    } else {
-                        int32_t *o = reinterpret_cast<int32_t *>(buf) + p * 3;
-                        o[0] = MGB_OBS_WORD(c, rgb[0]); o[1] = MGB_OBS_WORD(c, rgb[1]); o[2] = MGB_OBS_WORD(c, rgb[2]);
-                    }
+                    store_px(buf, cc * V + d_v, rgb);
                 }
             }
             uint8_t *dst = gobs + (size_t)h0 * V * px_bytes;

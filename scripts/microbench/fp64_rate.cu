@@ -2,6 +2,7 @@
 //   DFMA / DMUL / DADD / DADD.RZ, F2I.F64.TRUNC, I2F.F64, FRND.F64.FLOOR, the float64 division sequence, and FFMA as the yardstick.
 // Every thread runs 8 independent chains, 16 warps per SM sub-partition-quad (512 threads), one CTA per SM, so the numbers are
 // issue/pipe throughput, not latency.  Printed unit: lane-operations per clock per SM.
+// Second table: latency of a dependent chain (one warp, one chain per thread), cycles per chain step.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_rate.bin fp64_rate.cu
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -9,6 +10,10 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 constexpr int CH = 8;
+// conversions through inline PTX so that the compiler cannot fold (int)(double)(int)x chains
+__device__ __forceinline__ int f2i(double x) { int r; asm volatile("cvt.rzi.s32.f64 %0, %1;" : "=r"(r) : "d"(x)); return r; }
+__device__ __forceinline__ double i2f(int x) { double r; asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(r) : "r"(x)); return r; }
+__device__ __forceinline__ double frnd(double x) { double r; asm volatile("cvt.rmi.f64.f64 %0, %1;" : "=d"(r) : "d"(x)); return r; }
 enum { M_DFMA, M_DMUL, M_DADD, M_DADD_RZ, M_F2I, M_I2F, M_FRND, M_DDIV, M_FFMA, M_MAGIC_TRUNC, M_COUNT };
 static const char *kNames[M_COUNT] = {"DFMA", "DMUL", "DADD", "DADD.RZ", "F2I.F64.TRUNC (+I2F.F64 back)", "I2F.F64 (+F2I back)",
                                      "FRND.F64.FLOOR", "float64 division", "FFMA (float32)", "trunc via DADD.RZ + 2^52"};
@@ -33,9 +38,9 @@ template <int MODE> __global__ void __launch_bounds__(512, 1) rate_kernel(double
                 else if (MODE == M_DMUL) acc[k] = __dmul_rn(acc[k], a);
                 else if (MODE == M_DADD) acc[k] = __dadd_rn(acc[k], b);
                 else if (MODE == M_DADD_RZ) acc[k] = __dadd_rz(acc[k], b);
-                else if (MODE == M_F2I) acc[k] = (double)((int)acc[k] + 1);
-                else if (MODE == M_I2F) acc[k] = (double)((int)acc[k] ^ 3);
-                else if (MODE == M_FRND) acc[k] = floor(acc[k]) + 0.0;      // the add is folded by nothing: -0 semantics
+                else if (MODE == M_F2I) acc[k] = i2f(f2i(acc[k]));
+                else if (MODE == M_I2F) acc[k] = i2f(f2i(acc[k]) ^ 3);
+                else if (MODE == M_FRND) acc[k] = frnd(acc[k]);
                 else if (MODE == M_DDIV) acc[k] = acc[k] / a;
                 else if (MODE == M_FFMA) facc[k] = fmaf(facc[k], (float)a, (float)b);
                 else if (MODE == M_MAGIC_TRUNC)
@@ -49,6 +54,46 @@ template <int MODE> __global__ void __launch_bounds__(512, 1) rate_kernel(double
     for (int k = 0; k < CH; ++k) s += acc[k] + facc[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE> __global__ void latency_kernel(double *out, long long *cycles, int iters, double a, double b)
+{
+    double acc = threadIdx.x * 0.37 + 1.5;
+    float facc = (float)acc;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (MODE == M_DFMA) acc = fma(acc, a, b);
+            else if (MODE == M_DMUL) acc = __dmul_rn(acc, a);
+            else if (MODE == M_DADD) acc = __dadd_rn(acc, b);
+            else if (MODE == M_DADD_RZ) acc = __dadd_rz(acc, b);
+            else if (MODE == M_F2I) acc = i2f(f2i(acc));
+            else if (MODE == M_I2F) acc = i2f(f2i(acc) ^ 3);
+            else if (MODE == M_FRND) acc = frnd(acc);
+            else if (MODE == M_DDIV) acc = acc / a;
+            else if (MODE == M_FFMA) facc = fmaf(facc, (float)a, (float)b);
+            else if (MODE == M_MAGIC_TRUNC) acc = __hiloint2double(0x40200000, __double2loint(__dadd_rz(acc, 4503599627370496.0)));
+        }
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = acc + facc;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int MODE> static void run_latency(double *out, long long *cyc)
+{
+    const int iters = 500;
+    const double a = (MODE == M_DDIV) ? 1.0000001 : 0.999999, b = 1.0e-3;
+    latency_kernel<MODE><<<1, 32>>>(out, cyc, iters, a, b);
+    CK(cudaDeviceSynchronize());
+    latency_kernel<MODE><<<1, 32>>>(out, cyc, iters, a, b);
+    CK(cudaDeviceSynchronize());
+    long long h = 0;
+    CK(cudaMemcpy(&h, cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    printf("%-34s %8.1f cycles per dependent step (%s)\n", kNames[MODE], (double)h / (iters * 16.0),
+           kOps[MODE] == 2 ? "two conversions (+ xor)" : MODE == M_FRND ? "one instruction" : MODE == M_MAGIC_TRUNC ? "DADD.RZ + mov" : "one instruction");
 }
 
 template <int MODE> static void run(double *out, long long *cyc, int sms)
@@ -94,5 +139,15 @@ int main()
     run<M_FRND>(out, cyc, sms);
     run<M_DDIV>(out, cyc, sms);
     run<M_MAGIC_TRUNC>(out, cyc, sms);
+    printf("latency, one warp, one chain:\n");
+    run_latency<M_FFMA>(out, cyc);
+    run_latency<M_DFMA>(out, cyc);
+    run_latency<M_DMUL>(out, cyc);
+    run_latency<M_DADD>(out, cyc);
+    run_latency<M_F2I>(out, cyc);
+    run_latency<M_I2F>(out, cyc);
+    run_latency<M_FRND>(out, cyc);
+    run_latency<M_DDIV>(out, cyc);
+    run_latency<M_MAGIC_TRUNC>(out, cyc);
     return 0;
 }
