@@ -29,6 +29,7 @@ namespace {
 constexpr int kMaxN = 31;
 constexpr int kNever = INT_MIN / 2;
 constexpr int kRenderThreads = 512;
+constexpr int kWallIlp = 2;         // wall rows per lane in flight (direct renderer)
 constexpr int kMaxHitsCap = 48;
 
 struct TaskHdr {                 // 112 bytes, head of every task blob
@@ -51,6 +52,7 @@ struct MazeConst {
     int text_pow2;               // text_size is a power of two
     double inv_text;
     int n_cls;                   // height classes with a precomputed eff table (0 = compute per pixel)
+    int wall_ilp;                // direct renderer: wall rows per lane computed as independent chains (dev switch MGB_MAZE_WALL_ILP)
     int hits_in_global;          // large screens: the per-column crossing lists live in a global scratch, not smem
     int blob_bytes;              // bytes of one task blob (multiple of 16)
     int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
@@ -570,6 +572,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     double *s_transp = reinterpret_cast<double *>(smem + off);           off = align_up(off + (size_t)n * n * 8, 128);
     ColRec *s_col = reinterpret_cast<ColRec *>(smem + off);              off = align_up(off + (size_t)H * sizeof(ColRec), 128);
     RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
+    double *s_rowc = reinterpret_cast<double *>(smem + off);             off = align_up(off + (size_t)V * 8, 128);
     HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);
     if (c.hits_in_global) s_hit = reinterpret_cast<HitRec *>(a.hit_scratch) + (size_t)blockIdx.x * H * c.max_hits;
     else off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
@@ -582,6 +585,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     double *s_pose = reinterpret_cast<double *>(smem + off + 32);         // continuous maze: x, y, sin(ori), cos(ori)
 
     const int tid = threadIdx.x;
+    // screen-row centre above the horizon, half_v - (d_v + 0.5) * pixel_size: the wall texel's row term (:184), pose independent
+    for (int d_v = tid; d_v < V; d_v += blockDim.x) s_rowc[d_v] = c.half_v - (d_v + 0.5) * c.pixel_size;
     if (tid == 0) {
         mgb_mbar_init(&s_bar[0], 1);   // textures
         mgb_mbar_init(&s_bar[1], 1);   // task blob, buffer 0
@@ -915,12 +920,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const int ts_mask = ts - 1;
         const double ix_lim = 1073741824.0 / tex_scale;                        // t < 2^30
 
-        // floor / ceiling pixel (ray_caster_utils.py:94-153).  Returns true when a transparent cell tinted it (`mark`).
-        auto fc_px = [&](int d_v, const ColRec &cr, const double *effc, int rgb[3]) -> bool {
+        // floor / ceiling pixel (ray_caster_utils.py:94-153) at effective distance `eff`.  Returns true when a transparent
+        // cell tinted it (`mark`).  Floor and ceiling rows share ONE instruction stream on the integer-index path (selects
+        // for texture id, fog weight and tint threshold): a warp pass that holds both kinds does not run two code paths.
+        auto fc_px = [&](const RowRec &rr, double eff, const ColRec &cr, int rgb[3]) -> bool {
             bool mark = false;
-            const RowRec rr = s_row[d_v];
             if (rr.kind == 0) return false;
-            const double eff = effc ? __ldg(effc + d_v) : rr.distance / cr.cos_hp;
             // alpha = clip(2 eff / max_vision - 1, 0, 1) is exactly 0 while 2 eff / max_vision < 1; the margin keeps the
             // shortcut independent of the division's rounding
             double fog = 0.0;
@@ -928,42 +933,44 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             const double hit_x = eff * cr.cos_abs + pos_x;
             const double hit_y = eff * cr.sin_abs + pos_y;
             const bool fastpx = fast_ix && hit_x >= 0.0 && hit_y >= 0.0 && hit_x < ix_lim && hit_y < ix_lim;
-            int i, j, tu = 0, tv_ = 0;                                        // cell, texel coordinates (fast path)
-            double ci = 0.0, cj = 0.0;
             if (fastpx) {
                 const int tx = trunc_i(hit_x * tex_scale), ty = trunc_i(hit_y * tex_scale);
-                i = tx >> cell_shift; j = ty >> cell_shift;
-                tu = tx & ts_mask; tv_ = ty & ts_mask;
-            } else {
-                ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
-                cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
-                i = trunc_i(ci); j = trunc_i(cj);
+                const int i = tx >> cell_shift, j = ty >> cell_shift;
+                const int tu = tx & ts_mask, tv_ = ty & ts_mask;
+                const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
+                const bool is_floor = rr.kind == 1;
+                const int cell = inside ? i * n + j : 0;
+                const int text_id = is_floor ? (int)texts[cell] : c.n_tex;
+                // floor: 1 - alpha * light (:118), ceiling: 1 - alpha (:149); alpha * 1.0 == alpha exactly
+                const double oma = 1.0 - fog * (is_floor ? rr.light : 1.0);
+                shade(rgb, rr.light, oma, s_tex[(text_id * ts + tu) * ts + tv_]);
+                if (is_floor && !inside) { rgb[0] = 0; rgb[1] = 0; rgb[2] = 0; }   // the floor is drawn inside the maze only (:104)
+                const double tv = inside ? s_transp[cell] : 0.0;
+                if (tv > (is_floor ? 0.01 : 0.0)) { blend(rgb, tv * 0.50 + 0.10); mark = true; }      // :119-123, :150-153
+                return mark;
             }
+            const double ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
+            const double cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
+            const int i = trunc_i(ci), j = trunc_i(cj);
             const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
             if (rr.kind == 1) {                                               // floor, :103-126
                 if (inside) {
                     const int text_id = texts[i * n + j];
-                    if (!fastpx) {
-                        double d_i = ci - floor(ci), d_j = cj - floor(cj);
-                        d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
-                        d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
-                        d_i -= floor(d_i); d_j -= floor(d_j);
-                        d_i *= dts; d_j *= dts;
-                        tu = trunc_i(d_i); tv_ = trunc_i(d_j);
-                    }
-                    shade(rgb, rr.light, 1.0 - fog * rr.light, s_tex[(text_id * ts + tu) * ts + tv_]);
+                    double d_i = ci - floor(ci), d_j = cj - floor(cj);
+                    d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
+                    d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
+                    d_i -= floor(d_i); d_j -= floor(d_j);
+                    d_i *= dts; d_j *= dts;
+                    shade(rgb, rr.light, 1.0 - fog * rr.light, s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
                     const double tv = s_transp[i * n + j];
                     if (tv > 0.01) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
                 }
             } else {                                                          // ceiling, :137-153
-                if (!fastpx) {
-                    const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
-                    const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
-                    double d_i = fi - floor(fi), d_j = fj - floor(fj);
-                    d_i *= dts; d_j *= dts;
-                    tu = trunc_i(d_i); tv_ = trunc_i(d_j);
-                }
-                shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + tu) * ts + tv_]);
+                const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
+                const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
+                double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                d_i *= dts; d_j *= dts;
+                shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
                 if (inside) {
                     const double tv = s_transp[i * n + j];
                     if (tv > 0) { blend(rgb, tv * 0.50 + 0.10); mark = true; }
@@ -971,9 +978,13 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             }
             return mark;
         };
+        // effective distance of pixel (d_h, d_v): tabulated per height class, else the division itself (:97, :131)
+        auto eff_of = [&](const double *effc, int d_v, const ColRec &cr) -> double {
+            return effc ? __ldg(effc + d_v) : s_row[d_v].distance / cr.cos_hp;
+        };
         // wall pixel (:184-189)
         auto wall_px = [&](int d_v, const ColRec &cr, int rgb[3]) {
-            const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
+            const double local_v = s_rowc[d_v] * cr.ratio + vision_height;
             double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
             d_j -= floor(d_j);
             shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
@@ -1013,17 +1024,62 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                         ws = cr.v_s < 0 ? 0 : (cr.v_s > V ? V : cr.v_s);
                         we = cr.v_e < ws ? ws : (cr.v_e > V ? V : cr.v_e);
                     }
-                    for (int d_v = ws + lane; d_v < we; d_v += 32) {
-                        int rgb[3];
-                        wall_px(d_v, cr, rgb);
-                        if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
-                        store_px(buf, cc * V + d_v, rgb);
-                    }
                     const int span = we - ws, rest = V - span;
+                    // the floor/ceiling rows' distances come from L2: ask for the first two passes' worth now, use them after
+                    // the wall passes
+                    double eff_a = 0.0, eff_b = 0.0;
+                    {
+                        const int ka = lane, kb = lane + 32;
+                        if (ka < rest) eff_a = eff_of(effc, ka < ws ? ka : ka + span, cr);
+                        if (kb < rest) eff_b = eff_of(effc, kb < ws ? kb : kb + span, cr);
+                    }
+                    if (text_p2 && c.wall_ilp) {
+                        // kWallIlp rows per lane, computed as independent straight-line chains (a warp inside one float64
+                        // dependency chain issues an instruction every ~8 cycles: profiles/r2_fp64_rate.txt); rows past the
+                        // span are clamped for the arithmetic and not stored
+                        const uint32_t *tex_col = s_tex + (cr.text_id * ts + cr.ti) * ts;
+                        auto wall_rgb = [&](int d_v, int rgb[3]) {
+                            double d_j = (s_rowc[d_v] * cr.ratio + vision_height) * c.inv_text;
+                            d_j -= floor(d_j);
+                            shade(rgb, cr.light, cr.oma, tex_col[trunc_i(dts * d_j)]);
+                        };
+                        auto wall_out = [&](int d_v, int rgb[3]) {
+                            if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+                            store_px(buf, cc * V + d_v, rgb);
+                        };
+                        const int npass = (we - ws + 31) >> 5;
+                        int d0 = ws + lane, pass = 0;
+                        for (; pass + kWallIlp <= npass; pass += kWallIlp, d0 += 32 * kWallIlp) {
+                            int rgbs[kWallIlp][3];
+#pragma unroll
+                            for (int u = 0; u < kWallIlp; ++u) {
+                                const int d_v = d0 + 32 * u;
+                                wall_rgb(d_v < we ? d_v : we - 1, rgbs[u]);   // only the span's last pass can run past it
+                            }
+#pragma unroll
+                            for (int u = 0; u < kWallIlp; ++u)
+                                if (d0 + 32 * u < we) wall_out(d0 + 32 * u, rgbs[u]);
+                        }
+                        for (; pass < npass; ++pass, d0 += 32) {
+                            if (d0 < we) {
+                                int rgb[3];
+                                wall_rgb(d0, rgb);
+                                wall_out(d0, rgb);
+                            }
+                        }
+                    } else {
+                        for (int d_v = ws + lane; d_v < we; d_v += 32) {
+                            int rgb[3];
+                            wall_px(d_v, cr, rgb);
+                            if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+                            store_px(buf, cc * V + d_v, rgb);
+                        }
+                    }
                     for (int k = lane; k < rest; k += 32) {
                         const int d_v = k < ws ? k : k + span;
                         int rgb[3] = {0, 0, 0};
-                        fc_px(d_v, cr, effc, rgb);
+                        const double eff = k < 32 ? eff_a : (k < 64 ? eff_b : eff_of(effc, d_v, cr));
+                        fc_px(s_row[d_v], eff, cr, rgb);
                         if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
                         store_px(buf, cc * V + d_v, rgb);
                     }
@@ -1034,7 +1090,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                     int rgb[3] = {0, 0, 0};
                     bool mark = false;
                     const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
-                    mark = fc_px(d_v, cr, effc, rgb);     // also under a wall: `mark` decides about the overlays below
+                    mark = fc_px(s_row[d_v], eff_of(effc, d_v, cr), cr, rgb);   // also under a wall: `mark` decides about the overlays below
                     if (in_wall) wall_px(d_v, cr, rgb);
                     if (!mark) {                                              // transparent overlays, :191-205
                         for (int k = 0; k < cr.n_hits; ++k)
@@ -1676,6 +1732,7 @@ static size_t maze3d_smem_bytes(const MazeConst &c)
     off = up(off + (size_t)c.n * c.n * 8, 128);
     off = up(off + (size_t)c.res_h * sizeof(ColRec), 128);
     off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
+    off = up(off + (size_t)c.res_v * 8, 128);
     if (!c.hits_in_global) off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     off = up(off + (size_t)(kRenderThreads / 32) * (c.obs_dtype == MGB_OBS_U8 ? 2 : 1) * c.run_px * px, 128);
@@ -1746,6 +1803,8 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     h->num_sms = prop.multiProcessorCount;
     if (const char *ev = getenv("MGB_MAZE_FUSED_STEP")) h->fused_step = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_PDL")) h->step_pdl = atoi(ev) != 0;
+    h->c.wall_ilp = 1;
+    if (const char *ev = getenv("MGB_MAZE_WALL_ILP")) h->c.wall_ilp = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_VARIANT_BITS")) {
         h->variant_bits = atoi(ev);
         if (h->variant_bits < 0) h->variant_bits = 0;
