@@ -72,6 +72,7 @@ struct MazeArgs {
     const uint32_t *tex;         // packed 0x00BBGGRR, (n_tex + 1) * ts * ts, ceiling last
     const float *coltab;         // [4][3][res_h]: cos_hp, cos_abs, sin_abs per heading
     const double *efftab;        // [n_cls][res_h * res_v]: distance(d_v) / cos_hp(d_h), pose independent
+    const double *fogtab;        // [n_cls][res_h * res_v]: alpha = clip(2 eff / max_vision - 1, 0, 1) of that distance
     // pose cache (memoised static layers, see maze3d_compose_kernel)
     const int4 *poses;           // FILL: [n_slots] task, gx, gy, ori
     const int32_t *pose_index;   // [n_tasks][n*n*4] -> slot or -1
@@ -904,6 +905,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const double inv_cell = th->inv_cell, inv_t2c = th->inv_t2c;
         const bool cell_p2 = th->cell_pow2 != 0, t2c_p2 = th->t2c_pow2 != 0, text_p2 = c.text_pow2 != 0;
         const double *efft = (c.n_cls > 0 && th->cls >= 0) ? a.efftab + (size_t)th->cls * total_px : nullptr;
+        const double *fogt = efft ? a.fogtab + (size_t)th->cls * total_px : nullptr;
         const double fog_from = 0.4999 * c.max_vision;
         const double dts = (double)ts;
         // Exact integer texel / cell indices.  With cell_size = 2^a, text_size = 2^b (a >= b) and ts = 2^m, every scaling in
@@ -923,13 +925,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         // floor / ceiling pixel (ray_caster_utils.py:94-153) at effective distance `eff`.  Returns true when a transparent
         // cell tinted it (`mark`).  Floor and ceiling rows share ONE instruction stream on the integer-index path (selects
         // for texture id, fog weight and tint threshold): a warp pass that holds both kinds does not run two code paths.
-        auto fc_px = [&](const RowRec &rr, double eff, const ColRec &cr, int rgb[3]) -> bool {
+        auto fc_px = [&](const RowRec &rr, double eff, double fog, const ColRec &cr, int rgb[3]) -> bool {
             bool mark = false;
             if (rr.kind == 0) return false;
-            // alpha = clip(2 eff / max_vision - 1, 0, 1) is exactly 0 while 2 eff / max_vision < 1; the margin keeps the
-            // shortcut independent of the division's rounding
-            double fog = 0.0;
-            if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
             const double hit_x = eff * cr.cos_abs + pos_x;
             const double hit_y = eff * cr.sin_abs + pos_y;
             const bool fastpx = fast_ix && hit_x >= 0.0 && hit_y >= 0.0 && hit_x < ix_lim && hit_y < ix_lim;
@@ -982,6 +980,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         auto eff_of = [&](const double *effc, int d_v, const ColRec &cr) -> double {
             return effc ? __ldg(effc + d_v) : s_row[d_v].distance / cr.cos_hp;
         };
+        // alpha = clip(2 eff / max_vision - 1, 0, 1): tabulated with eff, else evaluated here.  It is exactly 0 while
+        // 2 eff / max_vision < 1; the margin keeps that shortcut independent of the division's rounding
+        auto fog_of = [&](const double *fogc, int d_v, double eff) -> double {
+            if (fogc) return __ldg(fogc + d_v);
+            return eff > fog_from ? fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0)) : 0.0;
+        };
         // wall pixel (:184-189)
         auto wall_px = [&](int d_v, const ColRec &cr, int rgb[3]) {
             const double local_v = s_rowc[d_v] * cr.ratio + vision_height;
@@ -1015,6 +1019,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 const ColRec cr = s_col[d_h];                              // warp-uniform
                 const bool bar_col = has_bar && d_h >= lb_sx && d_h < lb_ex;
                 const double *effc = efft ? efft + (size_t)d_h * V : nullptr;
+                const double *fogc = efft ? fogt + (size_t)d_h * V : nullptr;
                 if (cr.n_hits == 0) {
                     // Column without transparent crossings: every pixel is EITHER wall OR floor/ceiling.  The two kinds are
                     // walked separately -- the wall span [ws, we), then the remaining rows as one compacted index range --
@@ -1027,11 +1032,17 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                     const int span = we - ws, rest = V - span;
                     // the floor/ceiling rows' distances come from L2: ask for the first two passes' worth now, use them after
                     // the wall passes
-                    double eff_a = 0.0, eff_b = 0.0;
+                    double eff_a = 0.0, eff_b = 0.0, fog_a = 0.0, fog_b = 0.0;
                     {
                         const int ka = lane, kb = lane + 32;
-                        if (ka < rest) eff_a = eff_of(effc, ka < ws ? ka : ka + span, cr);
-                        if (kb < rest) eff_b = eff_of(effc, kb < ws ? kb : kb + span, cr);
+                        if (ka < rest) {
+                            const int d_v = ka < ws ? ka : ka + span;
+                            eff_a = eff_of(effc, d_v, cr); fog_a = fog_of(fogc, d_v, eff_a);
+                        }
+                        if (kb < rest) {
+                            const int d_v = kb < ws ? kb : kb + span;
+                            eff_b = eff_of(effc, d_v, cr); fog_b = fog_of(fogc, d_v, eff_b);
+                        }
                     }
                     if (text_p2 && c.wall_ilp) {
                         // kWallIlp rows per lane, computed as independent straight-line chains (a warp inside one float64
@@ -1079,7 +1090,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                         const int d_v = k < ws ? k : k + span;
                         int rgb[3] = {0, 0, 0};
                         const double eff = k < 32 ? eff_a : (k < 64 ? eff_b : eff_of(effc, d_v, cr));
-                        fc_px(s_row[d_v], eff, cr, rgb);
+                        const double fog = k < 32 ? fog_a : (k < 64 ? fog_b : fog_of(fogc, d_v, eff));
+                        fc_px(s_row[d_v], eff, fog, cr, rgb);
                         if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
                         store_px(buf, cc * V + d_v, rgb);
                     }
@@ -1090,7 +1102,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                     int rgb[3] = {0, 0, 0};
                     bool mark = false;
                     const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
-                    mark = fc_px(s_row[d_v], eff_of(effc, d_v, cr), cr, rgb);   // also under a wall: `mark` decides about the overlays below
+                    const double eff = eff_of(effc, d_v, cr);
+                    mark = fc_px(s_row[d_v], eff, fog_of(fogc, d_v, eff), cr, rgb);   // also under a wall: `mark` decides about the overlays below
                     if (in_wall) wall_px(d_v, cr, rgb);
                     if (!mark) {                                              // transparent overlays, :191-205
                         for (int k = 0; k < cr.n_hits; ++k)
@@ -1620,7 +1633,7 @@ __global__ void __launch_bounds__(kComposeThreads, 5) maze3d_rollout_kernel(cons
 // (ray_caster_utils.py:97-104,131-138) depends only on the screen, the optics and the two heights of a task, so it is
 // tabulated once per (agent_height, wall_height) class with the SAME float64 division the renderer would execute.
 __global__ void maze_efftab_kernel(const __grid_constant__ MazeConst c, const float *coltab, const double *cls_heights,
-                                   int n_cls, double *efftab)
+                                   int n_cls, double *efftab, double *fogtab)
 {
     const int H = c.res_h, V = c.res_v;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1637,7 +1650,10 @@ __global__ void maze_efftab_kernel(const __grid_constant__ MazeConst c, const fl
         const double v_screen = c.half_v - (d_v + 0.5) * c.pixel_size;
         distance = (ceil_height - vision_height) / v_screen * c.l_focal;
     }
-    efftab[idx] = distance / (double)coltab[d_h];     // cos_hp does not depend on the heading: use heading 0
+    const double eff = distance / (double)coltab[d_h];     // cos_hp does not depend on the heading: use heading 0
+    efftab[idx] = eff;
+    // the fog weight of that distance (ray_caster_utils.py:99,133), the expression the renderer evaluates when it has no table
+    fogtab[idx] = eff > 0.4999 * c.max_vision ? fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0)) : 0.0;
 }
 
 __global__ void maze_state_kernel(MazeArgs a, int32_t *agent_out, double *life_out)
@@ -1666,7 +1682,7 @@ struct mgb_maze {
     uint8_t *blobs = nullptr;
     uint32_t *tex = nullptr;
     float *coltab = nullptr;
-    double *efftab = nullptr;
+    double *efftab = nullptr, *fogtab = nullptr;
     float2 *cpos = nullptr;        // continuous maze pose
     double *cori = nullptr;
     double *coltab_d = nullptr;
@@ -1755,7 +1771,7 @@ static MazeArgs maze_args_impl(const mgb_maze *h)
     memset(&a, 0, sizeof(a));
     a.n = h->n; a.n_pad = h->n_pad; a.env_base = h->env_base;
     a.agent = h->agent; a.life = h->life; a.eaten = h->eaten; a.env2task = h->env2task; a.blobs = h->blobs;
-    a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.auto_reset = h->auto_reset;
+    a.tex = h->tex; a.coltab = h->coltab; a.efftab = h->efftab; a.fogtab = h->fogtab; a.auto_reset = h->auto_reset;
     a.cpos = h->cpos; a.cori = h->cori; a.coltab_d = h->coltab_d;
     a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
     a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
@@ -1868,7 +1884,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     MgbDeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->agent); cudaFree(h->life); cudaFree(h->eaten); cudaFree(h->env2task); cudaFree(h->blobs);
-    cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab); cudaFree(h->cpos); cudaFree(h->cori); cudaFree(h->coltab_d);
+    cudaFree(h->tex); cudaFree(h->coltab); cudaFree(h->efftab); cudaFree(h->fogtab); cudaFree(h->cpos); cudaFree(h->cori); cudaFree(h->coltab_d);
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig); cudaFree(h->hit_scratch);
     cudaFree(h->c_px_all); cudaFree(h->c_fmask);
@@ -2096,15 +2112,17 @@ extern "C" int mgb_maze_set_task(mgb_maze *h, int32_t n_tasks, const int8_t *wal
         }
     }
     cudaFree(h->efftab); h->efftab = nullptr;
+    cudaFree(h->fogtab); h->fogtab = nullptr;
     c.n_cls = 0;
     if (c.kind != MGB_MAZE_2D && !cls_heights.empty()) {
         const int n_cls = (int)(cls_heights.size() / 2);
         const size_t cells = (size_t)n_cls * c.res_h * c.res_v;
         double *d_heights = nullptr;
         MGB_CUDA(cudaMalloc(&h->efftab, cells * sizeof(double)));
+        MGB_CUDA(cudaMalloc(&h->fogtab, cells * sizeof(double)));
         MGB_CUDA(cudaMalloc(&d_heights, cls_heights.size() * sizeof(double)));
         MGB_CUDA(cudaMemcpy(d_heights, cls_heights.data(), cls_heights.size() * sizeof(double), cudaMemcpyHostToDevice));
-        maze_efftab_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(c, h->coltab, d_heights, n_cls, h->efftab);
+        maze_efftab_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(c, h->coltab, d_heights, n_cls, h->efftab, h->fogtab);
         MGB_CUDA(cudaDeviceSynchronize());
         cudaFree(d_heights);
         c.n_cls = n_cls;
