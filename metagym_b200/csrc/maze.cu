@@ -29,7 +29,6 @@ namespace {
 constexpr int kMaxN = 31;
 constexpr int kNever = INT_MIN / 2;
 constexpr int kRenderThreads = 512;
-constexpr int kWallIlp = 2;         // wall rows per lane in flight (direct renderer)
 constexpr int kMaxHitsCap = 48;
 
 struct TaskHdr {                 // 112 bytes, head of every task blob
@@ -52,7 +51,6 @@ struct MazeConst {
     int text_pow2;               // text_size is a power of two
     double inv_text;
     int n_cls;                   // height classes with a precomputed eff table (0 = compute per pixel)
-    int wall_ilp;                // direct renderer: wall rows per lane computed as independent chains (dev switch MGB_MAZE_WALL_ILP)
     int hits_in_global;          // large screens: the per-column crossing lists live in a global scratch, not smem
     int blob_bytes;              // bytes of one task blob (multiple of 16)
     int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
@@ -1044,47 +1042,11 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                             eff_b = eff_of(effc, d_v, cr); fog_b = fog_of(fogc, d_v, eff_b);
                         }
                     }
-                    if (text_p2 && c.wall_ilp) {
-                        // kWallIlp rows per lane, computed as independent straight-line chains (a warp inside one float64
-                        // dependency chain issues an instruction every ~8 cycles: profiles/r2_fp64_rate.txt); rows past the
-                        // span are clamped for the arithmetic and not stored
-                        const uint32_t *tex_col = s_tex + (cr.text_id * ts + cr.ti) * ts;
-                        auto wall_rgb = [&](int d_v, int rgb[3]) {
-                            double d_j = (s_rowc[d_v] * cr.ratio + vision_height) * c.inv_text;
-                            d_j -= floor(d_j);
-                            shade(rgb, cr.light, cr.oma, tex_col[trunc_i(dts * d_j)]);
-                        };
-                        auto wall_out = [&](int d_v, int rgb[3]) {
-                            if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
-                            store_px(buf, cc * V + d_v, rgb);
-                        };
-                        const int npass = (we - ws + 31) >> 5;
-                        int d0 = ws + lane, pass = 0;
-                        for (; pass + kWallIlp <= npass; pass += kWallIlp, d0 += 32 * kWallIlp) {
-                            int rgbs[kWallIlp][3];
-#pragma unroll
-                            for (int u = 0; u < kWallIlp; ++u) {
-                                const int d_v = d0 + 32 * u;
-                                wall_rgb(d_v < we ? d_v : we - 1, rgbs[u]);   // only the span's last pass can run past it
-                            }
-#pragma unroll
-                            for (int u = 0; u < kWallIlp; ++u)
-                                if (d0 + 32 * u < we) wall_out(d0 + 32 * u, rgbs[u]);
-                        }
-                        for (; pass < npass; ++pass, d0 += 32) {
-                            if (d0 < we) {
-                                int rgb[3];
-                                wall_rgb(d0, rgb);
-                                wall_out(d0, rgb);
-                            }
-                        }
-                    } else {
-                        for (int d_v = ws + lane; d_v < we; d_v += 32) {
-                            int rgb[3];
-                            wall_px(d_v, cr, rgb);
-                            if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
-                            store_px(buf, cc * V + d_v, rgb);
-                        }
+                    for (int d_v = ws + lane; d_v < we; d_v += 32) {
+                        int rgb[3];
+                        wall_px(d_v, cr, rgb);
+                        if (bar_col && d_v >= lb_sy && d_v < lb_ey) { rgb[0] = 255; rgb[1] = 0; rgb[2] = 0; }
+                        store_px(buf, cc * V + d_v, rgb);
                     }
                     for (int k = lane; k < rest; k += 32) {
                         const int d_v = k < ws ? k : k + span;
@@ -1819,8 +1781,6 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     h->num_sms = prop.multiProcessorCount;
     if (const char *ev = getenv("MGB_MAZE_FUSED_STEP")) h->fused_step = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_PDL")) h->step_pdl = atoi(ev) != 0;
-    h->c.wall_ilp = 1;
-    if (const char *ev = getenv("MGB_MAZE_WALL_ILP")) h->c.wall_ilp = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_VARIANT_BITS")) {
         h->variant_bits = atoi(ev);
         if (h->variant_bits < 0) h->variant_bits = 0;
