@@ -409,6 +409,8 @@ def run_quadrotor(ctx, sampler):
                "d2h_bytes_per_step": n * (D * 4 + 4 + 1), "steps": Ke, "timer": "host wall clock around the synchronous "
                "mgb_quad_step_host calls (pinned host buffers), max over ranks",
                "result_checksum": float(h_rew.double().sum())}
+        # bytes over PCIe per second per GPU, both directions (the kernel reads actions from / writes results to pinned host memory)
+        e2e["pcie_gbs_per_gpu"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) * Ke / dt_e * 1e-9
         assert bool(torch.isfinite(h_obs).all())
 
         # ---- fused T-step rollout kernel (state in registers), same buffers
@@ -669,6 +671,7 @@ def run_maze3d(ctx, sampler):
         e2e = {"value": n * world * Ke / dt_e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 4,
                "d2h_bytes_per_step": n * (128 * 128 * 3 + 8), "steps": Ke,
                "timer": "host wall clock, pinned buffers, copies + synchronize inside", "result_checksum": float(h_rew.sum())}
+        e2e["pcie_gbs_per_gpu"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) * Ke / dt_e * 1e-9
         del block
         env.close()
         if rank == 0:

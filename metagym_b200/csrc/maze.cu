@@ -1368,22 +1368,27 @@ __device__ __forceinline__ void compose_group_u8(const MazeConst &c, const EnvDy
 
 constexpr int kStepBatch = 16;              // envs whose step logic one CTA runs side by side before moving their frames
 constexpr int kStepSlots = 8;               // 12 KB chunk slots of a CTA's shared-memory ring
-constexpr int kStepSlack = 3;               // bulk stores that may still be reading their slot (=> 5 bulk loads in flight)
+constexpr int kStepSlack = 3;               // bulk stores that may still be reading their slot before it is handed back
 
 __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __grid_constant__ MazeConst c,
                                                                       const __grid_constant__ MazeArgs a)
 {
     // Two CTAs per SM; CTA j owns the envs j, j + G, j + 2G, ... (G = grid size).  Per pass of up to kStepBatch envs:
     //  (1) threads 0..B-1 run the step logic of the B envs SIDE BY SIDE (each is a chain of ~4 dependent L2 round trips:
-    //      one chain per frame would cost more than the frame's copy), leaving B EnvDyn records in shared memory;
-    //  (2) the B frames stream, 12 KB chunk by chunk, through a ring of kStepSlots shared-memory slots: warp 0 waits for
-    //      chunk u, draws the life bar into it, sends it to `obs` with one bulk store, and -- as soon as the store of chunk
-    //      u - 3 has left its slot -- issues the bulk load of chunk u + 5 into it, so five loads and three stores stay in
-    //      flight across frame boundaries.  The other warps only join for the rare frames that still need float64 tints (poses whose
-    //      image depends on more foods than have variant frames).
+    //      one chain per frame would cost more than the frame's copy), leaving B EnvDyn records + frame pointers in shared memory;
+    //  (2) the B frames stream, 12 KB chunk by chunk, through a ring of kStepSlots shared-memory slots.  Warp 1's lane 0 only
+    //      ISSUES bulk loads, up to kStepSlots chunks ahead, as the consumer hands slots back through their `empty`
+    //      mbarriers; warp 0 only consumes: waits for chunk u, draws the life bar into it, sends it to `obs` with one bulk
+    //      store and -- once the store of chunk u - kStepSlack has left its slot -- releases that slot.  Loads and stores stay
+    //      in flight across frame boundaries.  Warps 0, 2, 3 (named barrier 1, 96 threads) tint the rare frames that still need
+    //      float64 blends (poses whose image depends on more foods than have variant frames).
+    // The frame move is HBM-bound: scripts/microbench/framecopy.cu moves the same 1024 x 48 KB in 16.4 us (6.1 TB/s read + write)
+    // with ANY scheme -- this ring, LDG/STG.128, cudaMemcpy -- so the step costs launch gap + logic (~4 us) + that.
     extern __shared__ __align__(128) uint8_t s_ring[];           // kStepSlots x 12 KB
     __shared__ EnvDyn s_dyn[kStepBatch];
+    __shared__ const uint8_t *s_src[kStepBatch];                 // finished frame each env's observation starts from
     __shared__ __align__(8) uint64_t s_bar[kStepSlots];
+    __shared__ __align__(8) uint64_t s_empty[kStepSlots];
     __shared__ int s_nslow;
     __shared__ uint16_t s_slow[1024];                            // queued tinted groups of one chunk (group index in the chunk)
     const int H = c.res_h, V = c.res_v, total_px = H * V;
@@ -1398,7 +1403,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
     const int v_shift = (V & (V - 1)) == 0 ? 31 - __clz(V) : -1;
     asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
-        for (int k = 0; k < kStepSlots; ++k) mgb_mbar_init(&s_bar[k], 1);
+        for (int k = 0; k < kStepSlots; ++k) { mgb_mbar_init(&s_bar[k], 1); mgb_mbar_init(&s_empty[k], 1); }
         mgb_fence_mbar_init();
         s_nslow = 0;
     }
@@ -1427,24 +1432,31 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                 a.agent[e] = make_int4(s.gx, s.gy, s.ori, s.steps);
                 a.life[e] = s.life;
             }
-            s_dyn[tid] = make_dyn(c, a, blob, task, s, eaten);
+            const EnvDyn dd = make_dyn(c, a, blob, task, s, eaten);
+            s_dyn[tid] = dd;
+            s_src[tid] = frame_of(a, dd, frame_bytes);
         }
         __syncthreads();
-        // chunk u of the pass: frame u / n_chunks, chunk u % n_chunks, ring slot (g0 + u) % kStepSlots
-        auto issue = [&](int u) {                                  // thread 0 only
-            const int it = u / n_chunks, k = u - it * n_chunks;
-            const uint32_t off = (uint32_t)k * kStepChunkPx * 3u;
-            const uint32_t bytes = frame_bytes - off < kStepChunkPx * 3u ? frame_bytes - off : kStepChunkPx * 3u;
-            const int slot = (int)((g0 + (uint32_t)u) % kStepSlots);
-            mgb_mbar_expect_tx(&s_bar[slot], bytes);
-            mgb_bulk_load(s_ring + (size_t)slot * (kStepChunkPx * 3), frame_of(a, s_dyn[it], frame_bytes) + off, bytes, &s_bar[slot]);
-        };
-        if (tid == 0) {
-            mgb_bulk_wait_read<0>();                               // the previous pass's stores have left the ring
-            for (int u = 0; u < kStepSlots - kStepSlack && u < M; ++u) issue(u);
-        }
+        const bool producer = (tid >> 5) == 1;
+        const int t96 = tid < 32 ? tid : tid - 32;                 // index inside the consumer group (warps 0, 2, 3)
+        if (producer) {
+            if (lane == 0) {
+                int it = 0, k = 0;
+                for (int u = 0; u < M; ++u) {
+                    const uint32_t gu = g0 + (uint32_t)u;
+                    const int slot = (int)(gu % kStepSlots);
+                    const uint32_t use = gu / kStepSlots;           // how often this slot has been filled before
+                    if (use > 0) mgb_mbar_wait(&s_empty[slot], (use - 1) & 1u);
+                    const uint32_t off = (uint32_t)k * kStepChunkPx * 3u;
+                    const uint32_t bytes = frame_bytes - off < kStepChunkPx * 3u ? frame_bytes - off : kStepChunkPx * 3u;
+                    mgb_mbar_expect_tx(&s_bar[slot], bytes);
+                    mgb_bulk_load(s_ring + (size_t)slot * (kStepChunkPx * 3), s_src[it] + off, bytes, &s_bar[slot]);
+                    if (++k == n_chunks) { k = 0; ++it; }
+                }
+            }
+        } else {
         for (int it = 0; it < B; ++it) {
-            __syncthreads();                                       // frame boundary: nobody runs more than a frame ahead of warp 0
+            asm volatile("bar.sync 1, 96;" ::: "memory");          // frame boundary: nobody runs more than a frame ahead of warp 0
             const int64_t e = base + (int64_t)it * gridDim.x;
             const EnvDyn d = s_dyn[it];
             const uint32_t miss_sig = (uint32_t)d.pad & 0xFFu;     // != 0: some groups need the float64 path (uniform)
@@ -1468,7 +1480,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                 const uint32_t off = (uint32_t)q0 * 3u, bytes = (uint32_t)(q1 - q0) * 3u;
                 if (miss_sig) {
                     // whole CTA: queue the chunk's tinted groups (they cluster in a few columns) ...
-                    for (int g4 = (q0 >> 4) + tid; g4 < (q1 >> 4); g4 += kStepThreads) {
+                    for (int g4 = (q0 >> 4) + t96; g4 < (q1 >> 4); g4 += 96) {
                         uint32_t hit = __ldg(reinterpret_cast<const uint32_t *>(gsig) + g4) & miss4;
                         while (hit) {
                             const int g = (__ffs(hit) - 1) >> 3;
@@ -1476,11 +1488,11 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                             s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)(((g4 << 2) + g) - (q0 >> 2));
                         }
                     }
-                    __syncthreads();
+                    asm volatile("bar.sync 1, 96;" ::: "memory");
                     const int n_slow = s_nslow;
                     mgb_mbar_wait(&s_bar[slot], parity);
                     // ... and share them out evenly: float64 blends of the cached static layers over the baked pixels
-                    for (int i = tid; i < n_slow; i += kStepThreads) {
+                    for (int i = t96; i < n_slow; i += 96) {
                         const int q = q0 + 4 * (int)s_slow[i];
                         const int d_h = v_shift >= 0 ? (q >> v_shift) : q / V;
                         uint32_t pk[3];
@@ -1489,7 +1501,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                         dst[0] = pk[0]; dst[1] = pk[1]; dst[2] = pk[2];
                     }
                     mgb_fence_proxy_async();
-                    __syncthreads();                               // tints done before the bar is drawn over them / the store
+                    asm volatile("bar.sync 1, 96;" ::: "memory");  // tints done before the bar is drawn over them / the store
                     if (tid == 0) s_nslow = 0;
                 }
                 if (warp0) {
@@ -1498,14 +1510,14 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                     const int h0 = q0 / V, h1 = (q1 + V - 1) / V;      // columns [h0, h1) intersect the chunk
                     const int bh0 = lb_sx > h0 ? lb_sx : h0, bh1 = d.bar_end < h1 ? d.bar_end : h1;
                     if (survival && bh0 < bh1 && lb_sy < lb_ey) {
-                        const int rows = lb_ey - lb_sy;
-                        for (int i = lane; i < (bh1 - bh0) * rows; i += 32) {
-                            const int d_h = bh0 + i / rows, d_v = lb_sy + i % rows;
-                            const int q = d_h * V + d_v;
-                            if (q >= q0 && q < q1) {
-                                uint8_t *px = s_chunk + (size_t)(q - q0) * 3;
-                                px[0] = 255; px[1] = 0; px[2] = 0;
-                            }
+                        // one lane per column, rows walked in order: no integer division on the warp that feeds the ring
+                        for (int d_h = bh0 + lane; d_h < bh1; d_h += 32) {
+                            const int qc = d_h * V - q0;                // the column's first pixel, relative to the chunk
+                            int v0 = lb_sy, v1 = lb_ey;                 // rows whose pixel lies inside [q0, q1)
+                            if (qc + v0 < 0) v0 = -qc;
+                            if (qc + v1 > q1 - q0) v1 = q1 - q0 - qc;
+                            uint8_t *px = s_chunk + (size_t)(qc + v0) * 3;
+                            for (int d_v = v0; d_v < v1; ++d_v, px += 3) { px[0] = 255; px[1] = 0; px[2] = 0; }
                         }
                         mgb_fence_proxy_async();
                     }
@@ -1513,13 +1525,19 @@ __global__ void __launch_bounds__(kStepThreads, 2) maze3d_step_kernel(const __gr
                     if (lane == 0) {
                         mgb_bulk_store(gobs + off, s_chunk, bytes);
                         mgb_bulk_commit();
-                        if (u + kStepSlots - kStepSlack < M) {
-                            mgb_bulk_wait_read<kStepSlack>();      // the store of chunk u - 3 has left its slot ...
-                            issue(u + kStepSlots - kStepSlack);    // ... which is the slot of chunk u + 5
+                        if (u >= kStepSlack) {
+                            mgb_bulk_wait_read<kStepSlack>();      // the store of chunk u - 3 has left its slot: hand it back
+                            mgb_mbar_arrive(&s_empty[(int)((gu - kStepSlack) % kStepSlots)]);
                         }
                     }
                 }
             }
+        }
+        if (tid == 0) {                                            // the pass's last stores: wait for them, release their slots
+            mgb_bulk_wait_read<0>();
+            for (int u = (M > kStepSlack ? M - kStepSlack : 0); u < M; ++u)
+                mgb_mbar_arrive(&s_empty[(int)((g0 + (uint32_t)u) % kStepSlots)]);
+        }
         }
         g0 += (uint32_t)M;
         __syncthreads();                                           // s_dyn is rewritten by the next pass

@@ -192,6 +192,10 @@ __device__ __forceinline__ void mgb_mbar_expect_tx(uint64_t *bar, uint32_t bytes
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mgb_smem_addr(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mgb_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mgb_smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void mgb_bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -191,13 +191,17 @@ def test_pose_cache_equals_direct_render_at_config4_shape(torch_mod, maze_golden
     b.close()
 
 
-@pytest.mark.parametrize("res,task_type", [((128, 128), "SURVIVAL"), ((64, 48), "SURVIVAL"), ((96, 80), "ESCAPE"),
-                                           ((256, 256), "SURVIVAL")])
-def test_fused_step_kernel_equals_two_kernel_path(torch_mod, maze_golden, textures, monkeypatch, res, task_type):
+@pytest.mark.parametrize("res,task_type,vbits", [((128, 128), "SURVIVAL", None), ((64, 48), "SURVIVAL", None),
+                                                 ((96, 80), "ESCAPE", None), ((256, 256), "SURVIVAL", None),
+                                                 ((128, 128), "SURVIVAL", "0"), ((64, 48), "SURVIVAL", "2")])
+def test_fused_step_kernel_equals_two_kernel_path(torch_mod, maze_golden, textures, monkeypatch, res, task_type, vbits):
     """uint8 frames take maze3d_step_kernel (logic + TMA-moved baked frame + in-smem patches, one launch); it must equal the
     logic + compose kernel pair bit for bit: partial last chunk (64x48 = one 9 KB chunk), many chunks (256x256 = 16),
-    tinted groups under the life bar, auto-reset, reset() frames."""
+    tinted groups under the life bar, auto-reset, reset() frames.  vbits = MGB_MAZE_VARIANT_BITS: with 0 or 2 variant bits
+    most frames with an eaten food in view keep float64 tints, i.e. the kernel's three-warp tint group runs for real."""
     torch = torch_mod
+    if vbits is not None:
+        monkeypatch.setenv("MGB_MAZE_VARIANT_BITS", vbits)
     from metagym_b200 import BatchedMetaMazeDiscrete3D
     g = maze_golden
     tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
@@ -571,6 +575,48 @@ def test_continuous_maze_random_batch_vs_oracle(torch_mod, maze_golden, textures
             p2, a2 = oracles[e].pose
             assert np.array_equal(pos[e], p2) and ori[e] == a2, (t, e)
             assert np.array_equal(obs[e], o2), (t, e, int((obs[e] != o2).sum()))
+    env.close()
+
+
+@pytest.mark.parametrize("cell_size", [0.5, 1.0, 2.0, 4.0, 8.0, 3.0, 1.25])
+def test_direct_renderer_cell_size_family_vs_oracle(torch_mod, textures, cell_size):
+    """The direct renderer's integer texel / cell index path is taken for power-of-two cell sizes >= text_size (1.0); smaller
+    and non-power-of-two sizes take the reference expressions.  Each family member: 48 envs random-walk one sampled task
+    for 50 steps (most free poses get visited), every frame against the env's own oracle instance, bit for bit."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D, MazeTaskSampler
+    from oracle.maze_oracle import OracleMaze
+    rs = np.random.RandomState(int(cell_size * 100))
+    task = MazeTaskSampler(n=9, allow_loops=True, crowd_ratio=0.4, cell_size=cell_size, wall_height=1.6 * cell_size,
+                           agent_height=0.8 * cell_size, food_density=0.05, food_interval=7, rng=rs)
+    n, res, max_steps = 48, (48, 32), 30
+    env = BatchedMetaMazeDiscrete3D(resolution=res, max_steps=max_steps, num_envs=n, squeeze=False, auto_reset=True,
+                                    textures=textures, cache=False)
+    env.set_task(task)
+    oracles = []
+    for e in range(n):
+        o = OracleMaze("3D", "SURVIVAL", max_steps, 1, res, textures=textures)
+        o.set_task(task)
+        oracles.append(o)
+    obs = env.reset().cpu().numpy()
+    for e in range(n):
+        assert np.array_equal(obs[e], oracles[e].reset())
+    poses = set()
+    for t in range(50):
+        act = rs.randint(0, 4, n)
+        obs, rew, done, _ = env.step(torch.as_tensor(act, dtype=torch.int32).cuda())
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        ag = env.agent_state()[0].cpu().numpy() if hasattr(env, "agent_state") else None
+        for e in range(n):
+            o2, r2, d2, _ = oracles[e].step(int(act[e]))
+            assert rew[e] == r2 and bool(done[e]) == d2, (t, e)
+            if d2:
+                o2 = oracles[e].reset()
+            assert np.array_equal(obs[e], o2), (cell_size, t, e)
+            if ag is not None:
+                poses.add((int(ag[e][0]), int(ag[e][1]), int(ag[e][2])))
+    if ag is not None:
+        assert len(poses) >= 40, len(poses)
     env.close()
 
 
