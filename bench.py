@@ -782,7 +782,14 @@ def run_maze3d(ctx, sampler):
                          "frac": achieved / ctx.peak, "traffic": ncu_traffic("maze3d_step")[0],
                          "traffic_source": ncu_traffic("maze3d_step")[1], "peak_source": ctx.peak_src,
                          "kernel": "maze3d_step_kernel", "bytes_per_env_step": MAZE3D_BYTES, "envs_per_launch": n,
-                         "us_per_launch": us},
+                         "us_per_launch": us,
+                         # the pose-cache design READS a finished 48 KB frame per env as well as writing one: what the kernel
+                         # really moves, and the measured floor of just moving it (scripts/microbench/framecopy.cu: 16.4 us
+                         # for 1024 frames with a TMA ring, LDG/STG.128 or cudaMemcpy alike = 6.1 TB/s read + write)
+                         "moved_bytes_per_env_step": MAZE3D_BYTES + 128 * 128 * 3,
+                         "frac_of_moved_bytes": n * (MAZE3D_BYTES + 128 * 128 * 3) / us * 1e-3 / ctx.peak,
+                         "frame_move_floor_us_per_1024_envs": 16.4,
+                         "floor_source": "profiles/r2_framecopy.txt"},
             "gpu_launches": tm["timed_steps"] * launches_per_step, "clocks": clocks}
     if e2e is not None:
         line["e2e"] = e2e
