@@ -9,4 +9,4 @@ ncu --set full --clock-control none --import-source on -k regex:quad_stream -s 6
 MGB_PACKED=1 ncu --set full --clock-control none --import-source on -k regex:quad_step2 -s 12 -c 1 -o gpurun_out/prof_r2_quad_step2_packed_65k python scripts/profile_quad.py 65536 20 > gpurun_out/ncu_r2_q3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:maze3d_step_kernel -s 150 -c 1 -o gpurun_out/prof_r2_maze3d_step_1024 python scripts/profile_maze.py 1024 200 > gpurun_out/ncu_r2_m1.log 2>&1
 MGB_MAZE_CACHE=0 ncu --set full --clock-control none --import-source on -k regex:maze3d_kernel -s 4 -c 1 -o gpurun_out/prof_r2_maze3d_direct_1024 python scripts/profile_maze.py 1024 8 > gpurun_out/ncu_r2_m2.log 2>&1
-tail -2 gpurun_out/ncu_r2_*.log
+for f in gpurun_out/ncu_r2_*.log; do tail -n 2 "$f"; done
