@@ -2147,110 +2147,134 @@ struct PhiloxStream {
 };
 #define MGB_STREAM_SAMPLER 0x300u
 
-__global__ void __launch_bounds__(32) maze_sample_tasks_kernel(const __grid_constant__ MazeConst c, const __grid_constant__ MazeArgs a,
-                                                               uint8_t *blobs, const uint8_t *mask, uint32_t *epoch,
-                                                               const __grid_constant__ SamplerCfg sc, uint64_t seed)
+constexpr int kSamplerWarps = 4;
+// One WARP per env.  Lane 0 carves the maze (randomised Kruskal + loop knock-out are sequential by nature; their working set
+// lives in shared memory); textures, food values and the food thinning rounds are counter-based per cell -- Philox keyed by
+// (seed; global env, resample count, cell, purpose) -- so the 32 lanes take cells side by side.  A task costs ~50 us of one
+// warp instead of ~1.7 ms of one thread (the thinning alone was 20 rounds x n^2 serial draws).
+__global__ void __launch_bounds__(32 * kSamplerWarps) maze_sample_tasks_kernel(const __grid_constant__ MazeConst c,
+                                                                              const __grid_constant__ MazeArgs a,
+                                                                              uint8_t *blobs, const uint8_t *mask, uint32_t *epoch,
+                                                                              const __grid_constant__ SamplerCfg sc, uint64_t seed)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n) return;
+    __shared__ uint8_t s_walls[kSamplerWarps][kMaxN * kMaxN];      // bit 0 wall, bit 1 food alive
+    __shared__ uint8_t s_parent[kSamplerWarps][((kMaxN - 1) / 2) * ((kMaxN - 1) / 2)];
+    __shared__ uint16_t s_order[kSamplerWarps][kMaxN * kMaxN];
+    __shared__ uint32_t s_val[kSamplerWarps][kMaxN * kMaxN];       // 24-bit draw behind every cell's food value
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * kSamplerWarps + w;
+    if (e >= a.n) return;                                          // warp-uniform exits: no block-wide barrier below
     if (mask && !mask[e]) return;
+    uint8_t *walls = s_walls[w];
+    uint8_t *parent = s_parent[w];
+    uint16_t *order = s_order[w];
+    uint32_t *val = s_val[w];
     const int n = c.n, nn = n * n, m = (n - 1) / 2;
     const uint32_t ep = epoch[e] + 1u;
-    epoch[e] = ep;
+    __syncwarp();
+    if (lane == 0) epoch[e] = ep;
     const int64_t genv = a.env_base + e;
-    PhiloxStream rng;
-    rng.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    rng.ctr = make_uint4((uint32_t)genv, ep, 0u, MGB_STREAM_SAMPLER + (uint32_t)((uint64_t)genv >> 32));
-    rng.have = 0;
-    uint8_t walls[kMaxN * kMaxN];
-    uint8_t parent[((kMaxN - 1) / 2) * ((kMaxN - 1) / 2)];
-    uint16_t order[kMaxN * kMaxN];
-    for (int k = 0; k < nn; ++k) walls[k] = 1;
-    for (int i = 1; i < n; i += 2)
-        for (int j = 1; j < n; j += 2) walls[i * n + j] = 0;
-    for (int k = 0; k < m * m; ++k) parent[k] = (uint8_t)k;
-    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    // ---- random spanning tree of the room lattice (Kruskal over shuffled edges); edge id = 2 * room + dir
-    int ne = 0;
-    for (int ra = 0; ra < m; ++ra)
-        for (int rb = 0; rb < m; ++rb) {
-            if (ra + 1 < m) order[ne++] = (uint16_t)(2 * (ra * m + rb));
-            if (rb + 1 < m) order[ne++] = (uint16_t)(2 * (ra * m + rb) + 1);
-        }
-    for (int k = ne - 1; k > 0; --k) { const int j = rng.below(k + 1); const uint16_t t = order[k]; order[k] = order[j]; order[j] = t; }
-    for (int k = 0; k < ne; ++k) {
-        const int room = order[k] >> 1, dir = order[k] & 1, ra = room / m, rb = room % m;
-        const int other = dir == 0 ? (ra + 1) * m + rb : ra * m + rb + 1;
-        const int x = find(room), y = find(other);
-        if (x != y) {
-            parent[x] = (uint8_t)y;
-            if (dir == 0) walls[(2 * ra + 2) * n + 2 * rb + 1] = 0; else walls[(2 * ra + 1) * n + 2 * rb + 2] = 0;
-        }
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t hi = (uint32_t)((uint64_t)genv >> 32);
+    // per-cell draws: ctr = (env, resample count, cell, purpose)
+    auto cell_draw = [&](int k, uint32_t purpose) { return mgb_philox4x32_10(make_uint4((uint32_t)genv, ep, (uint32_t)k, purpose + hi), key); };
+    const uint32_t P_TEX = MGB_STREAM_SAMPLER + 0x10u, P_VAL = MGB_STREAM_SAMPLER + 0x20u, P_KEEP = MGB_STREAM_SAMPLER + 0x1000u;
+    for (int k = lane; k < nn; k += 32) {
+        const int i = k / n, j = k - i * n;
+        walls[k] = ((i & 1) && (j & 1)) ? 0 : 1;
     }
-    // ---- loops: knock interior walls out (in random order, only next to a free cell) down to crowd_ratio
-    if (sc.allow_loops) {
-        int standing = 0, nc = 0;
-        for (int i = 1; i < n - 1; ++i)
-            for (int j = 1; j < n - 1; ++j)
-                if (walls[i * n + j]) { ++standing; order[nc++] = (uint16_t)(i * n + j); }
-        const double budget = (double)((n - 2) * (n - 2)) * sc.crowd_ratio;
-        for (int k = nc - 1; k > 0; --k) { const int j = rng.below(k + 1); const uint16_t t = order[k]; order[k] = order[j]; order[j] = t; }
-        for (int k = 0; k < nc && (double)standing > budget; ++k) {
-            const int cell = order[k];
-            if (!walls[cell - n] || !walls[cell + n] || !walls[cell - 1] || !walls[cell + 1]) { walls[cell] = 0; --standing; }
-        }
-    }
-    // ---- blob
-    uint8_t *b = blobs + (size_t)a.env2task[e] * c.blob_bytes;
-    for (int k = 0; k < nn; ++k) {
-        b[c.off_walls + k] = walls[k];
-        const int tx = 1 + rng.below(sc.n_texts - 1);                          // randint(1, n_texts)
-        b[c.off_texts + k] = walls[k] ? (uint8_t)tx : 0;
-    }
-    const int sx = rng.below(m) * 2 + 1, sy = rng.below(m) * 2 + 1;
-    int gx = n - 2, gy = n - 2;
-    for (int t = 0; t < m * m; ++t) {
-        const int ex = rng.below(m) * 2 + 1, ey = rng.below(m) * 2 + 1;
-        const double dx = ex - sx, dy = ey - sy;
-        if (sqrt(dx * dx + dy * dy) > 0.45 * n) { gx = ex; gy = ey; break; }
-    }
-    // food: float values kept in `order` as 16-bit fixed point would lose the distribution -> recompute by thinning masks
-    // value[k] is drawn once, survival is thinned round by round; the per-cell values live in the blob's fval area only at
-    // the end, so keep them in registers-free form: alive flags in walls[] bit 1, values re-derived from a second stream
-    PhiloxStream vr = rng;
-    vr.ctr.w ^= 0x5A5A0000u; vr.ctr.z = 0u; vr.have = 0;                      // independent stream for the values
-    double total = 0.0;
-    int alive = 0;
-    for (int k = 0; k < nn; ++k) {
-        double v = vr.uniform() * sc.food_reward;
-        v = v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
-        if (!(walls[k] & 1)) { walls[k] |= 2; total += v; ++alive; }
-    }
-    const double expected = (double)((n - 1) * (n - 1)) * sc.food_density;
-    while (total > expected || alive > c.f_max) {                             // food *= (rand < 0.90) per round
-        PhiloxStream v2 = rng;
-        v2.ctr.w ^= 0x5A5A0000u; v2.ctr.z = 0u; v2.have = 0;
-        total = 0.0; alive = 0;
-        for (int k = 0; k < nn; ++k) {
-            double v = v2.uniform() * sc.food_reward;
-            v = v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
-            const bool keep = rng.uniform() < 0.90;
-            if (walls[k] & 2) {
-                if (keep) { total += v; ++alive; } else walls[k] &= ~2;
+    for (int k = lane; k < m * m; k += 32) parent[k] = (uint8_t)k;
+    __syncwarp();
+    int sx = 1, sy = 1, gx = n - 2, gy = n - 2;
+    if (lane == 0) {
+        PhiloxStream rng;                                            // the sequential stream of the carving steps
+        rng.key = key;
+        rng.ctr = make_uint4((uint32_t)genv, ep, 0u, MGB_STREAM_SAMPLER + hi);
+        rng.have = 0;
+        auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+        // ---- random spanning tree of the room lattice (Kruskal over shuffled edges); edge id = 2 * room + dir
+        int ne = 0;
+        for (int ra = 0; ra < m; ++ra)
+            for (int rb = 0; rb < m; ++rb) {
+                if (ra + 1 < m) order[ne++] = (uint16_t)(2 * (ra * m + rb));
+                if (rb + 1 < m) order[ne++] = (uint16_t)(2 * (ra * m + rb) + 1);
+            }
+        for (int k = ne - 1; k > 0; --k) { const int j = rng.below(k + 1); const uint16_t t = order[k]; order[k] = order[j]; order[j] = t; }
+        for (int k = 0; k < ne; ++k) {
+            const int room = order[k] >> 1, dir = order[k] & 1, ra = room / m, rb = room % m;
+            const int other = dir == 0 ? (ra + 1) * m + rb : ra * m + rb + 1;
+            const int x = find(room), y = find(other);
+            if (x != y) {
+                parent[x] = (uint8_t)y;
+                if (dir == 0) walls[(2 * ra + 2) * n + 2 * rb + 1] = 0; else walls[(2 * ra + 1) * n + 2 * rb + 2] = 0;
             }
         }
+        // ---- loops: knock interior walls out (in random order, only next to a free cell) down to crowd_ratio
+        if (sc.allow_loops) {
+            int standing = 0, nc = 0;
+            for (int i = 1; i < n - 1; ++i)
+                for (int j = 1; j < n - 1; ++j)
+                    if (walls[i * n + j]) { ++standing; order[nc++] = (uint16_t)(i * n + j); }
+            const double budget = (double)((n - 2) * (n - 2)) * sc.crowd_ratio;
+            for (int k = nc - 1; k > 0; --k) { const int j = rng.below(k + 1); const uint16_t t = order[k]; order[k] = order[j]; order[j] = t; }
+            for (int k = 0; k < nc && (double)standing > budget; ++k) {
+                const int cell = order[k];
+                if (!walls[cell - n] || !walls[cell + n] || !walls[cell - 1] || !walls[cell + 1]) { walls[cell] = 0; --standing; }
+            }
+        }
+        // ---- start / goal (maze_task.py:153-160: rooms, goal far enough from the start)
+        sx = rng.below(m) * 2 + 1; sy = rng.below(m) * 2 + 1;
+        for (int t = 0; t < m * m; ++t) {
+            const int ex = rng.below(m) * 2 + 1, ey = rng.below(m) * 2 + 1;
+            const double dx = ex - sx, dy = ey - sy;
+            if (sqrt(dx * dx + dy * dy) > 0.45 * n) { gx = ex; gy = ey; break; }
+        }
     }
+    __syncwarp();
+    // ---- textures + food values, one cell per lane and pass
+    uint8_t *b = blobs + (size_t)a.env2task[e] * c.blob_bytes;
+    auto value_of = [&](uint32_t u24) {                               // clip(food_reward * U, 0.10, food_reward)
+        const double v = (double)u24 * (1.0 / 16777216.0) * sc.food_reward;
+        return v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
+    };
+    double total = 0.0;
+    int alive = 0;
+    for (int k = lane; k < nn; k += 32) {
+        const uint4 r = cell_draw(k, P_TEX);
+        const int tx = 1 + (int)(((uint64_t)r.x * (uint64_t)(sc.n_texts - 1)) >> 32);      // randint(1, n_texts)
+        const bool wall = walls[k] & 1;
+        b[c.off_walls + k] = wall ? 1 : 0;
+        b[c.off_texts + k] = wall ? (uint8_t)tx : 0;
+        const uint32_t u24 = cell_draw(k, P_VAL).x >> 8;
+        val[k] = u24;
+        if (!wall) { walls[k] |= 2; total += value_of(u24); ++alive; }
+    }
+    auto warp_sum = [&](double &t, int &cnt) {                        // fixed butterfly: the same sum on every lane
+        for (int o = 16; o > 0; o >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    };
+    warp_sum(total, alive);
+    // ---- thinning: food *= (rand < 0.90) per round until the total value and the slot count fit (maze_task.py:176-180)
+    const double expected = (double)((n - 1) * (n - 1)) * sc.food_density;
+    for (uint32_t round = 0; total > expected || alive > c.f_max; ++round) {
+        total = 0.0; alive = 0;
+        for (int k = lane; k < nn; k += 32) {
+            if (!(walls[k] & 2)) continue;
+            const uint4 r = cell_draw(k, P_KEEP + (round >> 2));
+            const uint32_t x = (round & 3u) == 0 ? r.x : ((round & 3u) == 1 ? r.y : ((round & 3u) == 2 ? r.z : r.w));
+            if ((double)(x >> 8) * (1.0 / 16777216.0) < 0.90) { total += value_of(val[k]); ++alive; }
+            else walls[k] &= ~2;
+        }
+        warp_sum(total, alive);
+    }
+    __syncwarp();
     int8_t *fidx = reinterpret_cast<int8_t *>(b + c.off_fidx);
     double *fval = reinterpret_cast<double *>(b + c.off_fval);
     int32_t *fint = reinterpret_cast<int32_t *>(b + c.off_fint);
+    if (lane != 0) return;
     {
-        PhiloxStream v2 = rng;
-        v2.ctr.w ^= 0x5A5A0000u; v2.ctr.z = 0u; v2.have = 0;
         int cnt = 0;
-        for (int k = 0; k < nn; ++k) {
-            double v = v2.uniform() * sc.food_reward;
-            v = v < 0.10 ? 0.10 : (v > sc.food_reward ? sc.food_reward : v);
-            if (walls[k] & 2) { fidx[k] = (int8_t)cnt; fval[cnt] = v; fint[cnt] = sc.food_interval; ++cnt; }
+        for (int k = 0; k < nn; ++k) {                                 // food slots numbered in cell order
+            if (walls[k] & 2) { fidx[k] = (int8_t)cnt; fval[cnt] = value_of(val[k]); fint[cnt] = sc.food_interval; ++cnt; }
             else fidx[k] = -1;
         }
         TaskHdr hd;
@@ -2419,7 +2443,7 @@ extern "C" int mgb_maze_resample_tasks(mgb_maze *h, const uint8_t *mask_dev, con
         MGB_CUDA(cudaMemset(h->task_epoch, 0, sizeof(uint32_t) * (size_t)h->n_pad));
     }
     MazeArgs a = maze_args(h);
-    maze_sample_tasks_kernel<<<(unsigned)((h->n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(c, a, h->blobs, mask_dev, h->task_epoch,
+    maze_sample_tasks_kernel<<<(unsigned)((h->n + kSamplerWarps - 1) / kSamplerWarps), 32 * kSamplerWarps, 0, (cudaStream_t)stream>>>(c, a, h->blobs, mask_dev, h->task_epoch,
                                                                                         sc, seed);
     MGB_CUDA(cudaGetLastError());
     h->launches += 1;
