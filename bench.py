@@ -333,10 +333,14 @@ class Ctx(object):
         K = block.K
         block.replay(max(1, -(-W // block.steps_per_replay())))
         probe = self.timed(lambda: block.replay(1))
-        R = max(1, int(math.ceil(MIN_TIMED_MS / max(probe, 1e-3))))
-        t_wall0 = time.time()
-        ms = self.timed(lambda: block.replay(R))
-        t_wall1 = time.time()
+        R = max(1, int(math.ceil(1.05 * MIN_TIMED_MS / max(probe, 1e-3))))
+        for _ in range(4):
+            t_wall0 = time.time()
+            ms = self.timed(lambda: block.replay(R))      # max over ranks: every rank sees the same ms and takes the same branch
+            t_wall1 = time.time()
+            if ms >= MIN_TIMED_MS:
+                break
+            R = int(math.ceil(R * 1.25 * MIN_TIMED_MS / max(ms, 1e-3)))   # a lone replay over-estimates: re-time with more
         steps = R * block.steps_per_replay()
         return {"ms": ms, "timed_steps": steps, "repeats": R * block.blocks_per_replay, "ms_per_step": ms / steps,
                 "t_wall0": t_wall0, "t_wall1": t_wall1, "K": K}
@@ -611,7 +615,7 @@ def _time_block_local(ctx, block):
     torch.cuda.synchronize(ctx.dev)
     ctx.e0.record(); block.replay(1); ctx.e1.record()
     torch.cuda.synchronize(ctx.dev)
-    R = max(1, int(math.ceil(MIN_TIMED_MS / max(ctx.e0.elapsed_time(ctx.e1), 1e-3))))
+    R = max(1, int(math.ceil(1.2 * MIN_TIMED_MS / max(ctx.e0.elapsed_time(ctx.e1), 1e-3))))
     ctx.e0.record(); block.replay(R); ctx.e1.record()
     torch.cuda.synchronize(ctx.dev)
     ms = ctx.e0.elapsed_time(ctx.e1)
@@ -837,7 +841,7 @@ def run_mixed(ctx, sampler):
     for _ in range(max(2, -(-W // T))):
         collect(plain.views)
     probe = ctx.timed(lambda: collect(plain.views))
-    reps = max(chunks, int(math.ceil(MIN_TIMED_MS / max(probe, 1e-3))))
+    reps = max(chunks, int(math.ceil(1.3 * MIN_TIMED_MS / max(probe, 1e-3))))      # a lone probe over-estimates a chunk
     ms_none = ctx.timed(lambda: [collect(plain.views) for _ in range(reps)])
     results = {"no_exchange": {"value": (NQ + NM) * world * T * reps / (ms_none * 1e-3), "ms_per_chunk": ms_none / reps}}
     how = "none (1 GPU: the chunk is already where the learner is)"
