@@ -29,6 +29,7 @@ namespace {
 constexpr int kMaxN = 31;
 constexpr int kNever = INT_MIN / 2;
 constexpr int kRenderThreads = 512;
+constexpr int kGeoThreads = 128;            // direct renderer, pipelined: threads that prepare the next env's records
 constexpr int kMaxHitsCap = 48;
 
 struct TaskHdr {                 // 112 bytes, head of every task blob
@@ -51,6 +52,7 @@ struct MazeConst {
     int text_pow2;               // text_size is a power of two
     double inv_text;
     int n_cls;                   // height classes with a precomputed eff table (0 = compute per pixel)
+    int pipe;                    // direct renderer: two record sets, geometry of env e + 1 under the pixels of env e
     int hits_in_global;          // large screens: the per-column crossing lists live in a global scratch, not smem
     int blob_bytes;              // bytes of one task blob (multiple of 16)
     int off_walls, off_texts, off_fidx, off_fval, off_fint;   // offsets inside a blob
@@ -565,23 +567,38 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
     // ---- shared memory carve-up (mirrors maze3d_smem_bytes on the host)
     size_t off = 0;
     uint32_t *s_tex = reinterpret_cast<uint32_t *>(smem + off);          off = align_up(off + (size_t)tex_words * 4, 128);
-    uint8_t *s_blob2[2];                                                  // this env's tile + the next env's, in flight
-    s_blob2[0] = smem + off;                                              off = align_up(off + c.blob_bytes, 128);
-    s_blob2[1] = smem + off;                                              off = align_up(off + c.blob_bytes, 128);
-    double *s_transp = reinterpret_cast<double *>(smem + off);           off = align_up(off + (size_t)n * n * 8, 128);
-    ColRec *s_col = reinterpret_cast<ColRec *>(smem + off);              off = align_up(off + (size_t)H * sizeof(ColRec), 128);
-    RowRec *s_row = reinterpret_cast<RowRec *>(smem + off);              off = align_up(off + (size_t)V * sizeof(RowRec), 128);
+    // record sets: [0] always, [1] when the direct renderer pipelines geometry of env e + 1 under the pixels of env e (c.pipe)
+    const int nbuf = (!FILL && c.pipe) ? 2 : 1;
+    uint8_t *s_blob2[2];
+    double *s_transp2[2];
+    ColRec *s_col2[2];
+    RowRec *s_row2[2];
+    HitRec *s_hit2[2];
+    for (int b = 0; b < 2; ++b) {                                         // maze tiles: always two (this env's + the next one's in flight)
+        s_blob2[b] = smem + off;                                          off = align_up(off + c.blob_bytes, 128);
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (b < nbuf) {
+            s_transp2[b] = reinterpret_cast<double *>(smem + off);       off = align_up(off + (size_t)n * n * 8, 128);
+            s_col2[b] = reinterpret_cast<ColRec *>(smem + off);          off = align_up(off + (size_t)H * sizeof(ColRec), 128);
+            s_row2[b] = reinterpret_cast<RowRec *>(smem + off);          off = align_up(off + (size_t)V * sizeof(RowRec), 128);
+            if (c.hits_in_global) s_hit2[b] = reinterpret_cast<HitRec *>(a.hit_scratch) + ((size_t)blockIdx.x * nbuf + b) * H * c.max_hits;
+            else { s_hit2[b] = reinterpret_cast<HitRec *>(smem + off); off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128); }
+        } else {
+            s_transp2[b] = s_transp2[0]; s_col2[b] = s_col2[0]; s_row2[b] = s_row2[0]; s_hit2[b] = s_hit2[0];
+        }
+    }
     double *s_rowc = reinterpret_cast<double *>(smem + off);             off = align_up(off + (size_t)V * 8, 128);
-    HitRec *s_hit = reinterpret_cast<HitRec *>(smem + off);
-    if (c.hits_in_global) s_hit = reinterpret_cast<HitRec *>(a.hit_scratch) + (size_t)blockIdx.x * H * c.max_hits;
-    else off = align_up(off + (size_t)H * c.max_hits * sizeof(HitRec), 128);
     const int px_bytes = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     const int run_bytes = c.run_px * px_bytes;                           // 768
     const int n_slots = c.obs_dtype == MGB_OBS_U8 ? 2 : 1;               // int32 runs are 4x larger: single slot
     uint8_t *s_out = smem + off;                                          off = align_up(off + (size_t)(kRenderThreads / 32) * n_slots * run_bytes, 128);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + off);          off += 32;
-    int *s_env = reinterpret_cast<int *>(smem + off);                    // [0..3] gx gy ori steps, [4] lifebar end
-    double *s_pose = reinterpret_cast<double *>(smem + off + 32);         // continuous maze: x, y, sin(ori), cos(ori)
+    int *s_env2[2];                                                       // [0..3] gx gy ori steps, [4] lifebar end
+    double *s_pose2[2];                                                   // continuous maze: x, y, sin(ori), cos(ori)
+    s_env2[0] = reinterpret_cast<int *>(smem + off);      s_pose2[0] = reinterpret_cast<double *>(smem + off + 32);
+    s_env2[1] = reinterpret_cast<int *>(smem + off + 64); s_pose2[1] = reinterpret_cast<double *>(smem + off + 96);
+    int *s_runctr = reinterpret_cast<int *>(smem + off + 128);            // [b]: next column run of record set b (pipelined mode)
 
     const int tid = threadIdx.x;
     // screen-row centre above the horizon, half_v - (d_v + 0.5) * pixel_size: the wall texel's row term (:184), pose independent
@@ -604,7 +621,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         }
     }
     uint32_t blob_phase = 0;      // bit b: parity of buffer b's mbarrier
-    int blob_cur = 0;
     bool tex_ready = false;
     int run_parity = 0;
 
@@ -615,24 +631,33 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         mgb_mbar_expect_tx(&s_bar[1 + b], (uint32_t)c.blob_bytes);
         mgb_bulk_load(b ? s_blob2[1] : s_blob2[0], src, (uint32_t)c.blob_bytes, &s_bar[1 + b]);
     };
-    if (tid == 0 && (int64_t)blockIdx.x < a.n) load_blob(blockIdx.x, 0);
 
-    for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x) {
-        uint8_t *s_blob = blob_cur ? s_blob2[1] : s_blob2[0];
-        mgb_mbar_wait(&s_bar[1 + blob_cur], (blob_phase >> blob_cur) & 1u);
-        blob_phase ^= 1u << blob_cur;
-        // the other buffer was last read before the barrier that closed the previous env
-        if (tid == 0 && e + gridDim.x < a.n) load_blob(e + gridDim.x, blob_cur ^ 1);
-        blob_cur ^= 1;
+    // ---- per-env geometry: tile, pose, transparent map, row table, one DDA ray per column -> record set `b`.  Run by `gn`
+    // threads (gt = index among them) that synchronise among themselves: the whole CTA (__syncthreads), or -- pipelined
+    // direct renderer -- the first kGeoThreads threads (named barrier 2) while every warp paints the previous env.
+    // Tile buffer bb: loaded here (pipelined mode: the other buffer is being read by the pixel warps), or already requested by
+    // the previous call, which prefetches `next_e` into the other buffer after its own wait (sequential mode).
+    auto geometry = [&](int64_t e, int b, int bb, int gt, int gn, bool named, bool load_here, int64_t next_e) {
+        auto gsync = [&]() { if (named) asm volatile("bar.sync 2, %0;" ::"n"(kGeoThreads) : "memory"); else __syncthreads(); };
+        uint8_t *s_blob = (bb ? s_blob2[1] : s_blob2[0]);
+        double *s_transp = (b ? s_transp2[1] : s_transp2[0]);
+        ColRec *s_col = (b ? s_col2[1] : s_col2[0]);
+        RowRec *s_row = (b ? s_row2[1] : s_row2[0]);
+        HitRec *s_hit = (b ? s_hit2[1] : s_hit2[0]);
+        int *s_env = (b ? s_env2[1] : s_env2[0]);
+        double *s_pose = (b ? s_pose2[1] : s_pose2[0]);
+        if (gt == 0) { if (load_here) load_blob(e, bb); s_runctr[b] = 0; }
+        mgb_mbar_wait(&s_bar[1 + bb], (blob_phase >> bb) & 1u);
+        blob_phase ^= 1u << bb;
+        if (gt == 0 && next_e >= 0) load_blob(next_e, bb ^ 1);
         const TaskHdr *th = blob_hdr(s_blob);
-
         // ---- step logic (one thread), then publish agent pose to the CTA
         if (FILL) {
-            if (tid == 0) {
+            if (gt == 0) {
                 const int4 ps = a.poses[e];
                 s_env[0] = ps.y; s_env[1] = ps.z; s_env[2] = ps.w; s_env[3] = 0; s_env[4] = 0;
             }
-        } else if (tid == 0) {
+        } else if (gt == 0) {
             const int4 ag = a.agent[e];
             Env s = {ag.x, ag.y, ag.z, ag.w, a.life[e]};
             int32_t *eaten = a.eaten + e;
@@ -675,7 +700,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             if (ex > H) ex = H;
             s_env[4] = ex;
         }
-        __syncthreads();
+        gsync();
         const int gx = s_env[0], gy = s_env[1], ori = s_env[2], steps = s_env[3];
         const double cell_size = th->cell_size, vision_height = th->agent_height, ceil_height = th->wall_height;
         const bool cont_pose = !FILL && c.kind == MGB_MAZE_CONTINUOUS_3D;
@@ -684,7 +709,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const double text_to_cell = c.text_size / cell_size;
 
         // ---- transparent map + row table
-        for (int k = tid; k < n * n; k += blockDim.x) {
+        for (int k = gt; k < n * n; k += gn) {
             double v;
             if (c.task_type == MGB_MAZE_SURVIVAL) {
                 if (FILL) {   // static superset: every food cell at its full value
@@ -694,7 +719,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             } else v = (k == th->goal[0] * n + th->goal[1]) ? 1.0 : 0.0;
             s_transp[k] = v;
         }
-        for (int d_v = tid; d_v < V; d_v += blockDim.x) {
+        for (int d_v = gt; d_v < V; d_v += gn) {
             RowRec r;
             r.kind = 0; r.distance = 0.0; r.light = 0.0; r.pad = 0;
             if (d_v > V / 2) {                                       // floor rows, ray_caster_utils.py:95-101
@@ -710,13 +735,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             }
             s_row[d_v] = r;
         }
-        __syncthreads();
-
+        gsync();
         // ---- one ray per column: DDA_2D (ray_caster_utils.py:11-62) + wall span set-up (:156-182)
         const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
         const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
         const float *ct = a.coltab + (size_t)(cont_pose ? 0 : ori) * 3 * H;
-        for (int d_h = tid; d_h < H; d_h += blockDim.x) {
+        for (int d_h = gt; d_h < H; d_h += gn) {
             ColRec cr;
             cr.cos_hp = (double)ct[d_h];
             if (cont_pose) {     // float64 heading: tables from the float64 sin/cos, stored as float32 (:82-92)
@@ -818,76 +842,29 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 for (int k = 0; k < cr.n_hits; ++k) gh[k] = hits[k];
             }
         }
-        if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
-        __syncthreads();
+    };
+    // ---- pixels of env e from record set b (direct renderer).  dyn: warps pull column runs from a shared counter (the
+    // geometry warps join late), else run = warp, warp + n_warps, ...
+    auto pixels = [&](int64_t e, int b, int bb, bool dyn) {
+        uint8_t *s_blob = (bb ? s_blob2[1] : s_blob2[0]);
+        double *s_transp = (b ? s_transp2[1] : s_transp2[0]);
+        ColRec *s_col = (b ? s_col2[1] : s_col2[0]);
+        RowRec *s_row = (b ? s_row2[1] : s_row2[0]);
+        HitRec *s_hit = (b ? s_hit2[1] : s_hit2[0]);
+        int *s_env = (b ? s_env2[1] : s_env2[0]);
+        double *s_pose = (b ? s_pose2[1] : s_pose2[0]);
+        const TaskHdr *th = blob_hdr(s_blob);
+        const int gx = s_env[0], gy = s_env[1], ori = s_env[2], steps = s_env[3];
+        const double cell_size = th->cell_size, vision_height = th->agent_height, ceil_height = th->wall_height;
+        const bool cont_pose = !FILL && c.kind == MGB_MAZE_CONTINUOUS_3D;
+        const double pos_x = cont_pose ? s_pose[0] : gx * cell_size + 0.5 * cell_size;   // get_cell_center, maze_base.py:194-197
+        const double pos_y = cont_pose ? s_pose[1] : gy * cell_size + 0.5 * cell_size;
+        const double text_to_cell = c.text_size / cell_size;
 
-        if (FILL) {
-            // ---- static layers of this pose: colour before any transparency (wall colour wins inside the wall span),
-            // the food slot of the floor / ceiling cell under every pixel, one word + one byte per pixel, coalesced
-            const int total_px = H * V;
-            const double inv_cell = th->inv_cell, inv_t2c = th->inv_t2c;
-            const bool cell_p2 = th->cell_pow2 != 0, t2c_p2 = th->t2c_pow2 != 0, text_p2 = c.text_pow2 != 0;
-            const double *efft = (c.n_cls > 0 && th->cls >= 0) ? a.efftab + (size_t)th->cls * total_px : nullptr;
-            const double fog_from = 0.4999 * c.max_vision;
-            const double dts = (double)ts;
-            const int8_t *fidx = reinterpret_cast<const int8_t *>(s_blob + c.off_fidx);
-            const int goal_cell = th->goal[0] * n + th->goal[1];
-            uint32_t *gpx = a.c_px + (size_t)e * total_px;
-            uint8_t *gfid = a.c_fid + (size_t)e * total_px;
-            for (int q = tid; q < total_px; q += blockDim.x) {
-                const int d_h = q / V, d_v = q - d_h * V;
-                const ColRec &cr = s_col[d_h];
-                const RowRec &rr = s_row[d_v];
-                int rgb[3] = {0, 0, 0};
-                int fid = 0xFF;
-                const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
-                if (rr.kind != 0 && (!in_wall || cr.n_hits > 0)) {
-                    const double eff = efft ? __ldg(efft + q) : rr.distance / cr.cos_hp;
-                    double fog = 0.0;
-                    if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
-                    const double hit_x = eff * cr.cos_abs + pos_x;
-                    const double hit_y = eff * cr.sin_abs + pos_y;
-                    const double ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
-                    const double cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
-                    const int i = trunc_i(ci), j = trunc_i(cj);
-                    const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
-                    if (inside) {
-                        if (c.task_type == MGB_MAZE_SURVIVAL) { const int f = fidx[i * n + j]; if (f >= 0) fid = f; }
-                        else if (i * n + j == goal_cell) fid = 0;
-                    }
-                    if (rr.kind == 1) {
-                        if (inside) {
-                            double d_i = ci - floor(ci), d_j = cj - floor(cj);
-                            const int text_id = texts[i * n + j];
-                            d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
-                            d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
-                            d_i -= floor(d_i); d_j -= floor(d_j);
-                            d_i *= dts; d_j *= dts;
-                            shade(rgb, rr.light, 1.0 - fog * rr.light,
-                                  s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
-                        } else fid = 0xFF;
-                    } else {
-                        const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
-                        const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
-                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
-                        d_i *= dts; d_j *= dts;
-                        shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
-                    }
-                }
-                if (in_wall) {
-                    const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
-                    double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
-                    d_j -= floor(d_j);
-                    shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
-                }
-                gpx[q] = (uint32_t)rgb[0] | ((uint32_t)rgb[1] << 10) | ((uint32_t)rgb[2] << 20) | (in_wall ? (1u << 30) : 0u);
-                gfid[q] = (uint8_t)fid;
-                uint8_t *g8 = a.c_rgb8 + ((size_t)e * total_px + q) * 3;
-                g8[0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
-                g8[1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
-                g8[2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
-            }
-        } else {
+        const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
+        const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
+        const float *ct = a.coltab + (size_t)(cont_pose ? 0 : ori) * 3 * H;
+        if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
         // ---- pixels.  Each WARP owns runs of whole screen columns (c.run_px / V of them, 768 B of output): the column
         // record is warp-uniform (one broadcast read, held in registers), lanes take rows d_v = lane, lane + 32, ...,
         // write into the warp's private staging slot, and lane 0 issues ONE bulk (TMA) store per run; the slot is
@@ -1005,7 +982,13 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
 
         const int cols_per_run = c.run_px / V > 0 ? c.run_px / V : 1;
         const int n_runs = (H + cols_per_run - 1) / cols_per_run;
-        for (int run = warp; run < n_runs; run += n_warps) {
+        auto next_run = [&](int prev) {
+            if (!dyn) return prev < 0 ? warp : prev + n_warps;
+            int r = 0;
+            if (lane == 0) r = atomicAdd(&s_runctr[b], 1);
+            return __shfl_sync(0xffffffffu, r, 0);
+        };
+        for (int run = next_run(-1); run < n_runs; run = next_run(run)) {
             uint8_t *buf = s_out + ((size_t)warp * n_slots + (n_slots == 2 ? run_parity : 0)) * run_bytes;
             const int h0 = run * cols_per_run;
             const int ncol = H - h0 < cols_per_run ? H - h0 : cols_per_run;
@@ -1092,8 +1075,119 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
             }
             run_parity ^= 1;
         }
+    };
+    // ---- FILL: static layers of pose e (record set 0)
+    auto fill_pixels = [&](int64_t e, int bb) {
+        const int b = 0;
+        uint8_t *s_blob = (bb ? s_blob2[1] : s_blob2[0]);
+        double *s_transp = (b ? s_transp2[1] : s_transp2[0]);
+        ColRec *s_col = (b ? s_col2[1] : s_col2[0]);
+        RowRec *s_row = (b ? s_row2[1] : s_row2[0]);
+        HitRec *s_hit = (b ? s_hit2[1] : s_hit2[0]);
+        int *s_env = (b ? s_env2[1] : s_env2[0]);
+        double *s_pose = (b ? s_pose2[1] : s_pose2[0]);
+        const TaskHdr *th = blob_hdr(s_blob);
+        const int gx = s_env[0], gy = s_env[1], ori = s_env[2], steps = s_env[3];
+        const double cell_size = th->cell_size, vision_height = th->agent_height, ceil_height = th->wall_height;
+        const bool cont_pose = !FILL && c.kind == MGB_MAZE_CONTINUOUS_3D;
+        const double pos_x = cont_pose ? s_pose[0] : gx * cell_size + 0.5 * cell_size;   // get_cell_center, maze_base.py:194-197
+        const double pos_y = cont_pose ? s_pose[1] : gy * cell_size + 0.5 * cell_size;
+        const double text_to_cell = c.text_size / cell_size;
+
+        const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
+        const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
+        const float *ct = a.coltab + (size_t)(cont_pose ? 0 : ori) * 3 * H;
+            // ---- static layers of this pose: colour before any transparency (wall colour wins inside the wall span),
+            // the food slot of the floor / ceiling cell under every pixel, one word + one byte per pixel, coalesced
+            const int total_px = H * V;
+            const double inv_cell = th->inv_cell, inv_t2c = th->inv_t2c;
+            const bool cell_p2 = th->cell_pow2 != 0, t2c_p2 = th->t2c_pow2 != 0, text_p2 = c.text_pow2 != 0;
+            const double *efft = (c.n_cls > 0 && th->cls >= 0) ? a.efftab + (size_t)th->cls * total_px : nullptr;
+            const double fog_from = 0.4999 * c.max_vision;
+            const double dts = (double)ts;
+            const int8_t *fidx = reinterpret_cast<const int8_t *>(s_blob + c.off_fidx);
+            const int goal_cell = th->goal[0] * n + th->goal[1];
+            uint32_t *gpx = a.c_px + (size_t)e * total_px;
+            uint8_t *gfid = a.c_fid + (size_t)e * total_px;
+            for (int q = tid; q < total_px; q += blockDim.x) {
+                const int d_h = q / V, d_v = q - d_h * V;
+                const ColRec &cr = s_col[d_h];
+                const RowRec &rr = s_row[d_v];
+                int rgb[3] = {0, 0, 0};
+                int fid = 0xFF;
+                const bool in_wall = cr.wall && d_v >= cr.v_s && d_v < cr.v_e;
+                if (rr.kind != 0 && (!in_wall || cr.n_hits > 0)) {
+                    const double eff = efft ? __ldg(efft + q) : rr.distance / cr.cos_hp;
+                    double fog = 0.0;
+                    if (eff > fog_from) fog = fmin(1.0, fmax(2.0 * eff / c.max_vision - 1.0, 0.0));
+                    const double hit_x = eff * cr.cos_abs + pos_x;
+                    const double hit_y = eff * cr.sin_abs + pos_y;
+                    const double ci = cell_p2 ? hit_x * inv_cell : hit_x / cell_size;
+                    const double cj = cell_p2 ? hit_y * inv_cell : hit_y / cell_size;
+                    const int i = trunc_i(ci), j = trunc_i(cj);
+                    const bool inside = (unsigned)i < (unsigned)n && (unsigned)j < (unsigned)n;
+                    if (inside) {
+                        if (c.task_type == MGB_MAZE_SURVIVAL) { const int f = fidx[i * n + j]; if (f >= 0) fid = f; }
+                        else if (i * n + j == goal_cell) fid = 0;
+                    }
+                    if (rr.kind == 1) {
+                        if (inside) {
+                            double d_i = ci - floor(ci), d_j = cj - floor(cj);
+                            const int text_id = texts[i * n + j];
+                            d_i = t2c_p2 ? d_i * inv_t2c : d_i / text_to_cell;
+                            d_j = t2c_p2 ? d_j * inv_t2c : d_j / text_to_cell;
+                            d_i -= floor(d_i); d_j -= floor(d_j);
+                            d_i *= dts; d_j *= dts;
+                            shade(rgb, rr.light, 1.0 - fog * rr.light,
+                                  s_tex[(text_id * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                        } else fid = 0xFF;
+                    } else {
+                        const double fi = text_p2 ? hit_x * c.inv_text : hit_x / c.text_size;
+                        const double fj = text_p2 ? hit_y * c.inv_text : hit_y / c.text_size;
+                        double d_i = fi - floor(fi), d_j = fj - floor(fj);
+                        d_i *= dts; d_j *= dts;
+                        shade(rgb, rr.light, 1.0 - fog, s_tex[(c.n_tex * ts + trunc_i(d_i)) * ts + trunc_i(d_j)]);
+                    }
+                }
+                if (in_wall) {
+                    const double local_v = (c.half_v - (d_v + 0.5) * c.pixel_size) * cr.ratio + vision_height;
+                    double d_j = text_p2 ? local_v * c.inv_text : local_v / c.text_size;
+                    d_j -= floor(d_j);
+                    shade(rgb, cr.light, cr.oma, s_tex[(cr.text_id * ts + cr.ti) * ts + trunc_i(dts * d_j)]);
+                }
+                gpx[q] = (uint32_t)rgb[0] | ((uint32_t)rgb[1] << 10) | ((uint32_t)rgb[2] << 20) | (in_wall ? (1u << 30) : 0u);
+                gfid[q] = (uint8_t)fid;
+                uint8_t *g8 = a.c_rgb8 + ((size_t)e * total_px + q) * 3;
+                g8[0] = (uint8_t)(rgb[0] > 255 ? 255 : rgb[0]);
+                g8[1] = (uint8_t)(rgb[1] > 255 ? 255 : rgb[1]);
+                g8[2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
+            }
+    };
+    if (FILL || !c.pipe) {
+        int bb = 0;
+        if (tid == 0 && (int64_t)blockIdx.x < a.n) load_blob(blockIdx.x, 0);
+        for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x, bb ^= 1) {
+            // the other tile buffer was last read before the barrier that closed the previous env: prefetch into it
+            geometry(e, 0, bb, tid, blockDim.x, false, false, e + gridDim.x < a.n ? e + gridDim.x : -1);
+            if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
+            __syncthreads();
+            if (FILL) fill_pixels(e, bb);
+            else pixels(e, 0, bb, false);
+            __syncthreads();   // s_col / s_row / s_transp / s_blob are rewritten by the next env
         }
-        __syncthreads();   // s_col / s_row / s_transp / s_blob are rewritten by the next env
+    } else {
+        // Software pipeline over the CTA's envs: the first kGeoThreads threads prepare env e + 1 (record set b ^ 1) and then
+        // join the other warps, which have been painting env e (record set b) since the last barrier.
+        int b = 0;
+        int64_t e = blockIdx.x;
+        if (e < a.n && tid < kGeoThreads) geometry(e, 0, 0, tid, kGeoThreads, true, true, -1);
+        __syncthreads();
+        for (; e < a.n; e += gridDim.x, b ^= 1) {
+            const int64_t en = e + gridDim.x;
+            if (tid < kGeoThreads && en < a.n) geometry(en, b ^ 1, b ^ 1, tid, kGeoThreads, true, true, -1);
+            pixels(e, b, b, true);
+            __syncthreads();
+        }
     }
     if (!tex_ready && tid == 0) mgb_mbar_wait(&s_bar[0], 0);   // never leave a TMA load in flight
     if ((tid & 31) == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copies; the kernel boundary flushes the writes
@@ -1668,6 +1762,7 @@ struct mgb_maze {
     double *coltab_d = nullptr;
     // pose cache
     int step_pdl = 1;              // MGB_MAZE_PDL=0: no programmatic dependent launch between consecutive fused steps
+    int render_pipe = 1;           // MGB_MAZE_RENDER_PIPE=0: direct renderer without the geometry / pixel software pipeline
     int fused_step = 1;            // MGB_MAZE_FUSED_STEP=0: logic kernel + compose kernel instead of maze3d_step_kernel
     size_t step_smem_set = 0, m2d_smem_set = 0;
     int cache_enabled = 1;         // MGB_MAZE_CACHE=0 disables (direct renderer only)
@@ -1718,21 +1813,24 @@ struct mgb_maze {
     MgbMirrorWindow mir_win;     // mgb_maze_set_mirror_window
 };
 
-static size_t maze3d_smem_bytes(const MazeConst &c)
+static size_t maze3d_smem_bytes(const MazeConst &c, bool fill)
 {
     auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
     size_t off = 0;
     off = up(off + (size_t)(c.n_tex + 1) * c.ts * c.ts * 4, 128);
+    const int nbuf = (!fill && c.pipe) ? 2 : 1;
     off = up(off + c.blob_bytes, 128);
     off = up(off + c.blob_bytes, 128);
-    off = up(off + (size_t)c.n * c.n * 8, 128);
-    off = up(off + (size_t)c.res_h * sizeof(ColRec), 128);
-    off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
+    for (int b = 0; b < nbuf; ++b) {
+        off = up(off + (size_t)c.n * c.n * 8, 128);
+        off = up(off + (size_t)c.res_h * sizeof(ColRec), 128);
+        off = up(off + (size_t)c.res_v * sizeof(RowRec), 128);
+        if (!c.hits_in_global) off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
+    }
     off = up(off + (size_t)c.res_v * 8, 128);
-    if (!c.hits_in_global) off = up(off + (size_t)c.res_h * c.max_hits * sizeof(HitRec), 128);
     const size_t px = c.obs_dtype == MGB_OBS_U8 ? 3 : 12;
     off = up(off + (size_t)(kRenderThreads / 32) * (c.obs_dtype == MGB_OBS_U8 ? 2 : 1) * c.run_px * px, 128);
-    off += 32 + 32 + 32;
+    off += 32 + 128 + 16;
     return off;
 }
 
@@ -1799,6 +1897,7 @@ extern "C" int mgb_maze_create(mgb_maze **out, int64_t n_envs, const mgb_maze_cf
     h->num_sms = prop.multiProcessorCount;
     if (const char *ev = getenv("MGB_MAZE_FUSED_STEP")) h->fused_step = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_PDL")) h->step_pdl = atoi(ev) != 0;
+    if (const char *ev = getenv("MGB_MAZE_RENDER_PIPE")) h->render_pipe = atoi(ev) != 0;
     if (const char *ev = getenv("MGB_MAZE_VARIANT_BITS")) {
         h->variant_bits = atoi(ev);
         if (h->variant_bits < 0) h->variant_bits = 0;
@@ -2499,11 +2598,15 @@ template <bool FILL>
 static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStream_t st)
 {
     MazeConst &c = h->c;
-    c.hits_in_global = 0;
-    size_t sm = maze3d_smem_bytes(c);
-    if (sm > 227 * 1024) {          // e.g. the reference's default 256x256 / 320x320 screens: spill the hit lists
-        c.hits_in_global = 1;
-        sm = maze3d_smem_bytes(c);
+    // shared-memory plan, most wanted first: (direct renderer) two record sets with the crossing lists in shared memory,
+    // two record sets with the lists in a global scratch, then one record set (the only plan of the FILL pass)
+    size_t sm = 0;
+    const int plans[4][2] = {{1, 0}, {1, 1}, {0, 0}, {0, 1}};           // {pipe, hits_in_global}
+    for (int k = 0; k < 4; ++k) {
+        if (plans[k][0] && (FILL || !h->render_pipe)) continue;
+        c.pipe = plans[k][0]; c.hits_in_global = plans[k][1];
+        sm = maze3d_smem_bytes(c, FILL);
+        if (sm <= 227 * 1024) break;
     }
     if (sm > 227 * 1024) {
         mgb_set_error("3-D maze needs %zu bytes of shared memory per CTA (> 227 KB): reduce textures/resolution", sm);
@@ -2511,7 +2614,7 @@ static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStre
     }
     MazeArgs a2 = a;
     if (c.hits_in_global) {
-        const size_t need = (size_t)grid * c.res_h * c.max_hits * sizeof(HitRec);
+        const size_t need = (size_t)grid * (c.pipe ? 2 : 1) * c.res_h * c.max_hits * sizeof(HitRec);
         if (need > h->hit_scratch_bytes) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
