@@ -1163,31 +1163,31 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
                 g8[2] = (uint8_t)(rgb[2] > 255 ? 255 : rgb[2]);
             }
     };
-    if (FILL || !c.pipe) {
-        int bb = 0;
-        if (tid == 0 && (int64_t)blockIdx.x < a.n) load_blob(blockIdx.x, 0);
-        for (int64_t e = blockIdx.x; e < a.n; e += gridDim.x, bb ^= 1) {
-            // the other tile buffer was last read before the barrier that closed the previous env: prefetch into it
-            geometry(e, 0, bb, tid, blockDim.x, false, false, e + gridDim.x < a.n ? e + gridDim.x : -1);
+    // ONE loop for both orders (one call site per phase keeps the kernel's code size down):
+    //   sequential (FILL, or no room for two record sets): geometry(e) by the whole CTA, barrier, pixels(e), barrier;
+    //   pipelined: the first kGeoThreads threads prepare env e + 1 (record set b ^ 1) and then join the other warps, which
+    //   have been painting env e (record set b) since the last barrier; the first trip only prepares.
+    const bool pipe = !FILL && c.pipe;
+    const int64_t stride = gridDim.x;
+    int b = 0, bb = 0;
+    if (!pipe && tid == 0 && (int64_t)blockIdx.x < a.n) load_blob(blockIdx.x, 0);
+    for (int64_t e_pix = pipe ? (int64_t)blockIdx.x - stride : (int64_t)blockIdx.x; e_pix < a.n; e_pix += stride) {
+        const int64_t e_geo = pipe ? e_pix + stride : e_pix;
+        if (e_geo < a.n && (!pipe || tid < kGeoThreads)) {
+            // sequential: the other tile buffer was last read before the barrier that closed the previous env: prefetch into it
+            geometry(e_geo, pipe ? b ^ 1 : 0, pipe ? b ^ 1 : bb, tid, pipe ? kGeoThreads : (int)blockDim.x, pipe, pipe,
+                     (!pipe && e_geo + stride < a.n) ? e_geo + stride : -1);
+        }
+        if (!pipe) {
             if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
             __syncthreads();
-            if (FILL) fill_pixels(e, bb);
-            else pixels(e, 0, bb, false);
-            __syncthreads();   // s_col / s_row / s_transp / s_blob are rewritten by the next env
         }
-    } else {
-        // Software pipeline over the CTA's envs: the first kGeoThreads threads prepare env e + 1 (record set b ^ 1) and then
-        // join the other warps, which have been painting env e (record set b) since the last barrier.
-        int b = 0;
-        int64_t e = blockIdx.x;
-        if (e < a.n && tid < kGeoThreads) geometry(e, 0, 0, tid, kGeoThreads, true, true, -1);
-        __syncthreads();
-        for (; e < a.n; e += gridDim.x, b ^= 1) {
-            const int64_t en = e + gridDim.x;
-            if (tid < kGeoThreads && en < a.n) geometry(en, b ^ 1, b ^ 1, tid, kGeoThreads, true, true, -1);
-            pixels(e, b, b, true);
-            __syncthreads();
+        if (e_pix >= 0) {
+            if (FILL) fill_pixels(e_pix, bb);
+            else pixels(e_pix, pipe ? b : 0, pipe ? b : bb, pipe);
         }
+        __syncthreads();   // the record set / tile just painted from is rewritten next
+        b ^= 1; bb ^= 1;   // pipelined: the set prepared in this trip is painted in the next one
     }
     if (!tex_ready && tid == 0) mgb_mbar_wait(&s_bar[0], 0);   // never leave a TMA load in flight
     if ((tid & 31) == 0) mgb_bulk_wait_read<0>();   // smem must outlive the copies; the kernel boundary flushes the writes
