@@ -21,4 +21,4 @@ for k in quad_step_wide_kernel quad_stream_kernel quad_step2_kernel quad_rollout
          "UBLKCP $(grep -c UBLKCP $f || true), SYNCS $(grep -c SYNCS $f || true), FFMA2 $(grep -c FFMA2 $f || true)," \
          "DFMA/DMUL/DADD $(grep -cE 'DFMA|DMUL|DADD' $f || true), UTC*MMA $(grep -cE 'UTC[A-Z]*MMA' $f || true)"
 done | tee "profiles/sass/${pfx}_summary.txt"
-for k in quad_step2_kernel quad_rollout_kernel maze3d_compose_kernel maze3d_kernel; do gzip -f "profiles/sass/${pfx}_$k.sass"; done
+for k in quad_step2_kernel quad_rollout_kernel maze3d_compose_kernel maze3d_kernel; do gzip -nf "profiles/sass/${pfx}_$k.sass"; done
