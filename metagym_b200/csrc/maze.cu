@@ -1806,6 +1806,9 @@ struct mgb_maze {
     int auto_reset = 0;
     bool has_task = false, has_tex = false;
     size_t smem3d = 0;
+    int render_attr_set[2] = {0, 0};   // maze3d_kernel<false / true>: shared-memory opt-in raised by this handle
+    int compose_ctas_per_sm = 0;       // occupancy of maze3d_compose_kernel (queried once per handle)
+    int compose_persistent = -1;       // MGB_COMPOSE_PERSISTENT
     int num_sms = 0;
     int64_t launches = 0;
     uint32_t t_base = 0;
@@ -2594,6 +2597,19 @@ static int maze_ready(const mgb_maze *h)
     return MGB_OK;
 }
 
+// Raise a kernel's dynamic shared-memory opt-in to everything the device allows next to the kernel's static shared memory.
+// The value does not depend on the calling handle, so handles (and host threads) cannot undo each other's setting.
+template <class F> static cudaError_t maze_allow_max_dynamic_smem(F *kernel)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 template <bool FILL>
 static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStream_t st)
 {
@@ -2629,11 +2645,11 @@ static int launch_render(mgb_maze *h, const MazeArgs &a, unsigned grid, cudaStre
         }
         a2.hit_scratch = h->hit_scratch;
     }
-    // the opt-in limit is a property of the kernel (per device), shared by every handle: only ever raise it
-    static size_t g_smem_limit[64] = {0};
-    if (sm > g_smem_limit[h->device & 63]) {
-        MGB_CUDA(cudaFuncSetAttribute(maze3d_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        g_smem_limit[h->device & 63] = sm;
+    // The opt-in limit is a property of the kernel on a device, shared by every handle: each handle raises it once to the
+    // device maximum (the same value from every handle and thread, so there is no ordering to get wrong and no global state).
+    if (!h->render_attr_set[FILL ? 1 : 0]) {
+        MGB_CUDA(maze_allow_max_dynamic_smem(maze3d_kernel<FILL>));
+        h->render_attr_set[FILL ? 1 : 0] = 1;
     }
     h->smem3d = sm;
     maze3d_kernel<FILL><<<grid, kRenderThreads, sm, st>>>(c, a2);
@@ -2793,7 +2809,7 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
         const size_t sm = (size_t)k2dThreads * W * W * 4;
         if (sm > 48 * 1024 && sm > h->m2d_smem_set) {      // view_grid >= 5: above the default dynamic shared-memory limit
             MGB_REQUIRE(sm <= 200 * 1024, "view_grid too large for the 2-D observation tile");
-            MGB_CUDA(cudaFuncSetAttribute(maze2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            MGB_CUDA(maze_allow_max_dynamic_smem(maze2d_kernel));   // the device maximum: the same value from every handle
             h->m2d_smem_set = sm;
         }
         maze2d_kernel<<<(unsigned)((h->n + k2dThreads - 1) / k2dThreads), k2dThreads, sm, st>>>(c, a);
@@ -2812,7 +2828,7 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
                 (reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0) {
                 const size_t ring_bytes = (size_t)kStepSlots * kStepChunkPx * 3;       // 96 KB: two CTAs per SM
                 if (h->step_smem_set == 0) {
-                    MGB_CUDA(cudaFuncSetAttribute(maze3d_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+                    MGB_CUDA(maze_allow_max_dynamic_smem(maze3d_step_kernel));
                     h->step_smem_set = ring_bytes;
                 }
                 const int64_t grid = (int64_t)h->num_sms * 2;
@@ -2835,7 +2851,7 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
             maze3d_logic_kernel<true><<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(c, a);
             MGB_CUDA(cudaGetLastError());
             {
-                static int ctas_per_sm = 0;
+                int &ctas_per_sm = h->compose_ctas_per_sm;
                 if (!ctas_per_sm) {
                     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, maze3d_compose_kernel, kComposeThreads, 0) !=
                             cudaSuccess || ctas_per_sm < 1) ctas_per_sm = 4;
@@ -2845,7 +2861,7 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
                 parts = parts < 1 ? 1 : (parts > 4 ? 4 : parts);
                 a.do_parts = (int)parts;
                 int64_t items = h->n * parts;
-                static int persistent = -1;
+                int &persistent = h->compose_persistent;
                 if (persistent < 0) { const char *ev = getenv("MGB_COMPOSE_PERSISTENT"); persistent = ev ? atoi(ev) : 0; }   // measured: plain grid 65/295 us vs persistent 72/319 us (1024/8192 envs)
                 if (!persistent) items = items < resident ? items : 0x7fffffff;   // plain grid: one CTA per item
                 if (!persistent) { maze3d_compose_kernel<<<(unsigned)(h->n * parts), kComposeThreads, 0, st>>>(c, a); }
@@ -2923,7 +2939,7 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
         const size_t qbytes = ((size_t)h->c.res_h * h->c.res_v / 4 + 1) * sizeof(int);
         MGB_REQUIRE(qbytes <= 200 * 1024, "screen too large for the fused rollout's group queue");
         if (qbytes > 40 * 1024)
-            MGB_CUDA(cudaFuncSetAttribute(maze3d_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qbytes));
+            MGB_CUDA(maze_allow_max_dynamic_smem(maze3d_rollout_kernel));
         maze3d_rollout_kernel<<<(unsigned)(h->n < resident ? h->n : resident), kComposeThreads, qbytes, st>>>(h->c, a);
         MGB_CUDA(cudaGetLastError());
         h->t_base += (uint32_t)T;
@@ -2934,9 +2950,9 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
     const size_t sm = (size_t)2 * k2dThreads * W * W * 4;
     const unsigned blocks = (unsigned)((h->n + k2dThreads - 1) / k2dThreads);
     if (sm > 48 * 1024) {
-        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        MGB_CUDA(cudaFuncSetAttribute(maze2d_rollout_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        MGB_CUDA(maze_allow_max_dynamic_smem(maze2d_rollout_kernel<0>));
+        MGB_CUDA(maze_allow_max_dynamic_smem(maze2d_rollout_kernel<1>));
+        MGB_CUDA(maze_allow_max_dynamic_smem(maze2d_rollout_kernel<2>));
     }
     if (h->mir.count == MGB_MIRROR_MULTICAST) {
         MGB_REQUIRE(h->n % 4 == 0, "multicast outputs need num_envs % 4 == 0");
