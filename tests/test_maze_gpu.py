@@ -578,6 +578,43 @@ def test_continuous_maze_random_batch_vs_oracle(torch_mod, maze_golden, textures
     env.close()
 
 
+def test_handles_with_different_shared_memory_needs_interleave(torch_mod, maze_golden, textures):
+    """Handles are independent: kernels' shared-memory opt-ins are device-wide properties, so a handle that needs little must
+    not lower what a handle that needs a lot has set.  Big and small screens / view grids are stepped alternately and must
+    reproduce what each gives when it runs alone."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMaze2D, BatchedMetaMazeDiscrete3D
+    g = maze_golden
+    tasks = [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                              g["tasks15.interval"][k] // 10, g["tasks15.scalars"][k]) for k in range(2)]
+    acts = torch.randint(0, 4, (12, 8), device="cuda", dtype=torch.int32, generator=torch.Generator(device="cuda").manual_seed(3))
+
+    def make(kind, arg):
+        if kind == "3D":
+            e = BatchedMetaMazeDiscrete3D(resolution=arg, max_steps=30, num_envs=8, squeeze=False, auto_reset=True,
+                                          obs_dtype="uint8", textures=textures, cache=False)
+        else:
+            e = BatchedMetaMaze2D(max_steps=30, view_grid=arg, num_envs=8, squeeze=False, auto_reset=True)
+        e.set_task(tasks)
+        return e
+
+    specs = [("3D", (256, 256)), ("3D", (32, 32)), ("2D", 6), ("2D", 1), ("3D", (128, 128))]
+    alone = []
+    for kind, arg in specs:
+        e = make(kind, arg)
+        frames = [e.reset().clone()] + [e.step(acts[t])[0].clone() for t in range(12)]
+        alone.append(frames)
+        e.close()
+    envs = [make(kind, arg) for kind, arg in specs]
+    for k in (0, 1, 2, 3, 4):                    # big first, then small: the small one must not shrink the big one's limit
+        assert torch.equal(envs[k].reset(), alone[k][0])
+    for t in range(12):
+        for k in (1, 0, 3, 2, 4):
+            assert torch.equal(envs[k].step(acts[t])[0], alone[k][t + 1]), (t, specs[k])
+    for e in envs:
+        e.close()
+
+
 @pytest.mark.parametrize("cell_size", [0.5, 1.0, 2.0, 4.0, 8.0, 3.0, 1.25])
 def test_direct_renderer_cell_size_family_vs_oracle(torch_mod, textures, cell_size):
     """The direct renderer's integer texel / cell index path is taken for power-of-two cell sizes >= text_size (1.0); smaller
