@@ -1761,7 +1761,7 @@ struct mgb_maze {
     double *cori = nullptr;
     double *coltab_d = nullptr;
     // pose cache
-    int step_pdl = 1;              // MGB_MAZE_PDL=0: no programmatic dependent launch between consecutive fused steps
+    int step_pdl = 0;              // MGB_MAZE_PDL=1: programmatic dependent launch between consecutive fused steps (measured 1 % slower)
     int render_pipe = 1;           // MGB_MAZE_RENDER_PIPE=0: direct renderer without the geometry / pixel software pipeline
     int fused_step = 1;            // MGB_MAZE_FUSED_STEP=0: logic kernel + compose kernel instead of maze3d_step_kernel
     size_t step_smem_set = 0, m2d_smem_set = 0;
