@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const double pos_x = cont_pose ? s_pose[0] : gx * cell_size + 0.5 * cell_size;   // get_cell_center, maze_base.py:194-197
         const double pos_y = cont_pose ? s_pose[1] : gy * cell_size + 0.5 * cell_size;
         const double text_to_cell = c.text_size / cell_size;
+        (void)text_to_cell;
 
         // ---- transparent map + row table
         for (int k = gt; k < n * n; k += gn) {
@@ -864,6 +865,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
         const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
         const float *ct = a.coltab + (size_t)(cont_pose ? 0 : ori) * 3 * H;
+        (void)walls; (void)steps; (void)ct; (void)ceil_height; (void)text_to_cell; (void)s_transp; (void)s_hit; (void)s_col; (void)s_env;   // the two pixel paths share one preamble
         if (!tex_ready) { mgb_mbar_wait(&s_bar[0], 0); tex_ready = true; }
         // ---- pixels.  Each WARP owns runs of whole screen columns (c.run_px / V of them, 768 B of output): the column
         // record is warp-uniform (one broadcast read, held in registers), lanes take rows d_v = lane, lane + 32, ...,
@@ -1097,6 +1099,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) maze3d_kernel(const __grid_
         const int8_t *walls = reinterpret_cast<const int8_t *>(s_blob + c.off_walls);
         const int8_t *texts = reinterpret_cast<const int8_t *>(s_blob + c.off_texts);
         const float *ct = a.coltab + (size_t)(cont_pose ? 0 : ori) * 3 * H;
+        (void)walls; (void)steps; (void)ct; (void)ceil_height; (void)text_to_cell; (void)s_transp; (void)s_hit; (void)s_col; (void)s_env;   // the two pixel paths share one preamble
             // ---- static layers of this pose: colour before any transparency (wall colour wins inside the wall span),
             // the food slot of the floor / ceiling cell under every pixel, one word + one byte per pixel, coalesced
             const int total_px = H * V;
