@@ -76,6 +76,7 @@ struct MazeArgs {
     // pose cache (memoised static layers, see maze3d_compose_kernel)
     const int4 *poses;           // FILL: [n_slots] task, gx, gy, ori
     const int32_t *pose_index;   // [n_tasks][n*n*4] -> slot or -1
+    const void *pose_rec;        // [n_tasks][n*n*4] PoseRec (pose_index + c_fmask + c_vbase merged), nullptr: use the three tables
     uint32_t *c_px;              // [n_slots][H*V]   10-bit R | G<<10 | B<<20 | in_wall<<30
     uint8_t *c_fid;              // [n_slots][H*V]   food slot of the floor/ceiling cell under the pixel, 0xFF none
     uint8_t *c_rgb8;             // [n_slots][H*V*3] finished uint8 pixel with EVERY food of the task present (baked)
@@ -516,6 +517,14 @@ struct EnvDyn {                  // per env, per step: what the static pose laye
     uint64_t present[2];         // bit f: food slot f is currently visible
     int32_t task, pad;           // pad: 8-bit signature of the missing foods that can tint this pose (0 = frame is final)
     int32_t vframe, pad2;        // >= 0: finished frame c_var8[vframe]; -1: c_rgb8[slot] (+ the tints `pad` asks for)
+};
+// what make_dyn needs to know about a pose, in ONE 32-byte record indexed like pose_index (two 16-byte loads issued together
+// instead of the dependent chain pose_index -> c_fmask[slot] -> c_vbase[slot])
+struct PoseRec {
+    int32_t slot;                // pose-cache slot, -1: wall cell (never an agent pose)
+    int32_t vbase;               // first variant frame of the pose, -1: none
+    uint64_t fmask[2];           // food slots that can change this pose's image
+    uint64_t pad;
 };
 struct BakeDesc {                // one variant frame to bake
     int32_t slot, pad;
@@ -1203,7 +1212,19 @@ __device__ __forceinline__ EnvDyn make_dyn(const MazeConst &c, const MazeArgs &a
 {
     const TaskHdr *th = blob_hdr(blob);
     EnvDyn d;
-    d.slot = a.pose_index[(size_t)task * c.n * c.n * 4 + (s.gx * c.n + s.gy) * 4 + s.ori];
+    const size_t pose = (size_t)task * c.n * c.n * 4 + (s.gx * c.n + s.gy) * 4 + s.ori;
+    uint64_t fm[2];
+    int vb = -1;
+    bool have_vb = false;
+    if (a.pose_rec) {                  // one record: nothing below waits for a second round trip
+        const int4 *r = reinterpret_cast<const int4 *>(reinterpret_cast<const PoseRec *>(a.pose_rec) + pose);
+        const int4 r0 = __ldg(r), r1 = __ldg(r + 1);
+        d.slot = r0.x; vb = r0.y; have_vb = true;
+        fm[0] = ((uint64_t)(uint32_t)r0.w << 32) | (uint32_t)r0.z;
+        fm[1] = ((uint64_t)(uint32_t)r1.y << 32) | (uint32_t)r1.x;
+    } else {
+        d.slot = a.pose_index[pose];
+    }
     d.task = task; d.pad = 0;
     d.present[0] = d.present[1] = 0;
     if (c.task_type == MGB_MAZE_SURVIVAL) {
@@ -1234,11 +1255,11 @@ __device__ __forceinline__ EnvDyn make_dyn(const MazeConst &c, const MazeArgs &a
     }
     // 8-bit signature of the foods that can show in this pose but are currently missing; 0 -> the whole frame is the
     // baked "all present" frame + life bar
-    const uint64_t *fm = a.c_fmask + (size_t)d.slot * 2;
+    if (!a.pose_rec) { fm[0] = a.c_fmask[(size_t)d.slot * 2]; fm[1] = a.c_fmask[(size_t)d.slot * 2 + 1]; }
     uint64_t miss = ((~d.present[0]) & fm[0]) | ((~d.present[1]) & fm[1]);      // fold 128 slots to (f & 7)
     d.vframe = -1; d.pad2 = 0;
-    if (miss && a.c_vbase) {
-        const int vb = a.c_vbase[d.slot];
+    if (miss && (have_vb || a.c_vbase)) {
+        if (!have_vb) vb = a.c_vbase[d.slot];
         if (vb >= 0) {
             // variant index = presence bits of the pose's foods, compacted in ascending slot order (all visible -> the
             // c_rgb8 frame, handled by miss == 0 above)
@@ -1791,6 +1812,7 @@ struct mgb_maze {
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     int stage_next = 0;
     int32_t *c_vbase = nullptr;
+    void *pose_rec = nullptr;      // PoseRec table, built after the variant frames
     uint8_t *c_var8 = nullptr;
     void *d_bake_desc = nullptr;
     int64_t n_var_frames = 0;
@@ -1846,6 +1868,7 @@ static MazeArgs maze_args(const mgb_maze *h)
 {
     MazeArgs a = maze_args_impl(h);
     a.c_vbase = h->c_vbase;
+    a.pose_rec = h->pose_rec;
     a.c_var8 = h->c_var8;
     return a;
 }
@@ -1972,6 +1995,7 @@ extern "C" void mgb_maze_destroy(mgb_maze *h)
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig); cudaFree(h->hit_scratch);
     cudaFree(h->c_px_all); cudaFree(h->c_fmask);
     cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc); cudaFree(h->task_flags); cudaFree(h->task_epoch);
+    cudaFree(h->pose_rec);
     for (int i = 0; i < 2; ++i) {
         cudaFreeHost(h->h_stage[i]); cudaFree(h->d_stage[i]);
         if (h->stage_done[i]) cudaEventDestroy(h->stage_done[i]);
@@ -2600,6 +2624,20 @@ static int maze_ready(const mgb_maze *h)
     return MGB_OK;
 }
 
+// pose_index + c_fmask + c_vbase -> one PoseRec per (task, cell, heading)
+__global__ void maze_pose_rec_kernel(const int32_t *pose_index, const uint64_t *fmask, const int32_t *vbase, PoseRec *rec, int64_t count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    PoseRec r;
+    r.slot = pose_index[i]; r.vbase = -1; r.fmask[0] = r.fmask[1] = 0; r.pad = 0;
+    if (r.slot >= 0) {
+        r.fmask[0] = fmask[(size_t)r.slot * 2]; r.fmask[1] = fmask[(size_t)r.slot * 2 + 1];
+        if (vbase) r.vbase = vbase[r.slot];
+    }
+    rec[i] = r;
+}
+
 // Raise a kernel's dynamic shared-memory opt-in to everything the device allows next to the kernel's static shared memory.
 // The value does not depend on the calling handle, so handles (and host threads) cannot undo each other's setting.
 template <class F> static cudaError_t maze_allow_max_dynamic_smem(F *kernel)
@@ -2683,7 +2721,8 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
     cudaFree(h->poses); cudaFree(h->pose_index); cudaFree(h->c_px); cudaFree(h->c_fid); cudaFree(h->c_colhits);
     cudaFree(h->c_hits); cudaFree(h->dyn); cudaFree(h->c_rgb8); cudaFree(h->c_gsig);
     cudaFree(h->c_px_all); cudaFree(h->c_fmask);
-    cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc);
+    cudaFree(h->c_vbase); cudaFree(h->c_var8); cudaFree(h->d_bake_desc); cudaFree(h->pose_rec);
+    h->pose_rec = nullptr;
     h->c_vbase = nullptr; h->c_var8 = nullptr; h->d_bake_desc = nullptr; h->n_var_frames = 0;
     h->c_px_all = nullptr; h->c_fmask = nullptr;
     h->poses = nullptr; h->pose_index = nullptr; h->c_px = nullptr; h->c_fid = nullptr; h->c_colhits = nullptr;
@@ -2794,6 +2833,13 @@ static int ensure_pose_cache(mgb_maze *h, cudaStream_t st)
         h->launches += 2;
     } else {
         MGB_CUDA(cudaMemsetAsync(h->c_fmask, 0xFF, slots * 2 * sizeof(uint64_t), st));
+    }
+    {   // merged per-pose records for the step logic (after c_fmask and c_vbase are final)
+        const int64_t count = (int64_t)h->host_pose_index.size();
+        MGB_CUDA(cudaMalloc(&h->pose_rec, (size_t)count * sizeof(PoseRec)));
+        maze_pose_rec_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(h->pose_index, h->c_fmask, h->c_vbase,
+                                                                            reinterpret_cast<PoseRec *>(h->pose_rec), count);
+        MGB_CUDA(cudaGetLastError());
     }
     MGB_CUDA(cudaStreamSynchronize(st));
     h->n_poses = (int64_t)slots;
