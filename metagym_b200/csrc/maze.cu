@@ -2869,7 +2869,8 @@ static int launch_observe(mgb_maze *h, MazeArgs &a, cudaStream_t st)
             // memoised path: integer step logic, then compose static pose layers with the current food state
             a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
             a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
-    a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
+            a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
+            a.c_vbase = h->c_vbase; a.c_var8 = h->c_var8; a.pose_rec = h->pose_rec;   // (re)built by ensure_pose_cache just above
             // uint8 frames whose columns are whole 16-pixel runs: ONE fused launch (logic + TMA-moved frame)
             const size_t frame_bytes = (size_t)c.res_h * c.res_v * 3;
             if (h->fused_step && c.obs_dtype == MGB_OBS_U8 && (c.res_v & 15) == 0 && ((size_t)c.res_h * c.res_v) % 128 == 0 &&
@@ -2983,6 +2984,7 @@ extern "C" int mgb_maze_rollout(mgb_maze *h, int32_t T, const int32_t *act_dev, 
         a.poses = h->poses; a.pose_index = h->pose_index; a.c_px = h->c_px; a.c_fid = h->c_fid;
         a.c_colhits = h->c_colhits; a.c_hits = h->c_hits; a.dyn = h->dyn; a.c_rgb8 = h->c_rgb8; a.c_gsig = h->c_gsig;
         a.c_px_all = h->c_px_all; a.c_fmask = h->c_fmask;
+        a.c_vbase = h->c_vbase; a.c_var8 = h->c_var8; a.pose_rec = h->pose_rec;
         a.bake = 0;
         const int64_t resident = (int64_t)h->num_sms * 5;          // __launch_bounds__(256, 5): 48 registers, no spills
         const size_t qbytes = ((size_t)h->c.res_h * h->c.res_v / 4 + 1) * sizeof(int);

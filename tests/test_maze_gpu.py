@@ -578,6 +578,41 @@ def test_continuous_maze_random_batch_vs_oracle(torch_mod, maze_golden, textures
     env.close()
 
 
+@pytest.mark.parametrize("cache", [True, False])
+def test_set_task_again_on_the_same_handle(torch_mod, maze_golden, textures, cache):
+    """set_task() on a handle that already ran (the reference's meta-RL loop: sample_task / set_task / reset per
+    episode, maze_env.py:44-57) rebuilds the task table and the pose cache -- every device table of the old cache is freed.
+    The envs must behave exactly like a fresh handle given the second task list (use-after-rebuild regression)."""
+    torch = torch_mod
+    from metagym_b200 import BatchedMetaMazeDiscrete3D
+    g = maze_golden
+    def tasks_of(ks):
+        return [task_from_arrays(g["tasks15.walls"][k], g["tasks15.texts"][k], g["tasks15.food"][k],
+                                 g["tasks15.interval"][k] // 20, g["tasks15.scalars"][k]) for k in ks]
+    first, second = tasks_of([0, 1, 2, 3, 4, 5]), tasks_of([5, 3, 1])
+    kw = dict(resolution=(128, 128), max_steps=40, squeeze=False, auto_reset=True, obs_dtype="uint8", textures=textures,
+              num_envs=96, cache=None if cache else False)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.randint(0, 4, (30, 96), device="cuda", generator=gen, dtype=torch.int32)
+    a = BatchedMetaMazeDiscrete3D(**kw)
+    a.set_task(first); a.reset()
+    for t in range(10):
+        a.step(acts[t])
+    a.set_task(second)                      # different table size: every cache array changes size and address
+    b = BatchedMetaMazeDiscrete3D(**kw)
+    b.set_task(second)
+    assert torch.equal(a.reset(), b.reset())
+    for t in range(30):
+        o1, r1, d1, _ = a.step(acts[t])
+        o2, r2, d2, _ = b.step(acts[t])
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    a.set_task(first); a.reset()            # and back again
+    a.step(acts[0])
+    torch.cuda.synchronize()
+    a.close()
+    b.close()
+
+
 def test_handles_with_different_shared_memory_needs_interleave(torch_mod, maze_golden, textures):
     """Handles are independent: kernels' shared-memory opt-ins are device-wide properties, so a handle that needs little must
     not lower what a handle that needs a lot has set.  Big and small screens / view grids are stepped alternately and must
